@@ -1,0 +1,705 @@
+/* ORACLE (test infrastructure, NOT product code).
+ *
+ * CPU restatement of the batched-polynomial-commitment hot path that sits under `prove()` in the
+ * reference (call sites: wormhole/prover/src/lib.rs:171-175,
+ * wormhole/aggregator/src/private_batch/prover/lib.rs:326-330,
+ * wormhole/aggregator/src/public_batch/prover/lib.rs:301-305).  The arithmetic lives in the
+ * crates.io dependency qp-plonky2 / -core / -field =1.5.5 (Cargo.toml:20, Cargo.lock:839-903),
+ * which is absent from /root/reference; this file restates upstream plonky2's published algorithm
+ * as written down in SURVEY.md Appendix A:
+ *   A.2 field/src/{fft,polynomial}.rs          -> orc_fft / orc_ifft / orc_coset_fft
+ *   A.3 plonky2/src/hash/poseidon*.rs          -> orc_poseidon_naive / orc_poseidon
+ *   A.4 plonky2/src/hash/hashing.rs            -> orc_hash_no_pad / orc_hash_or_noop / orc_two_to_one
+ *   A.5 plonky2/src/hash/merkle_tree.rs, fri/oracle.rs -> orc_merkle_* / orc_batch_*
+ *   A.6 plonky2/src/iop/challenger.rs          -> orc_challenger_*
+ *   A.7/A.8 plonky2/src/fri/{oracle,prover,verifier,reduction_strategies}.rs -> orc_fri_*
+ * FRI parameters used by the reference: rate_bits 3, cap_height 4, pow 16, 28 queries,
+ * ConstantArityBits(4,5) (wormhole/circuit/src/profile.rs:168-174).
+ *
+ * PARITY STATUS: "parity unpinned" beyond the Poseidon permutation KATs (see oracle.h).
+ *
+ * The FRI prover here works in the COEFFICIENT domain exactly like upstream (reduce_with_powers on
+ * coefficient chunks, then coset_fft); the CUDA product folds in the VALUE domain, so agreement
+ * between the two is a real cross-check, not a tautology.  orc_fri_verify restates the verifier.
+ */
+#include "oracle.h"
+#include "goldilocks.h"
+#include "poseidon_rc.h"
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }
+uint64_t orc_gl_inv(uint64_t a) { return gl_inv(a); }
+uint64_t orc_gl_exp(uint64_t a, uint64_t e) { return gl_exp(a, e); }
+uint64_t orc_gl_root_of_unity(unsigned log_n) { return gl_root_of_unity(log_n); }
+
+/* ------------------------------------------------------------------------------------------
+ * Poseidon-12: width 12, rate 8, x^7, 4 full + 22 partial + 4 full rounds.
+ * ------------------------------------------------------------------------------------------ */
+static const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const uint64_t MDS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static inline uint64_t sbox7(uint64_t x) {
+    uint64_t x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x, x2);
+    return gl_mul(x3, x4);
+}
+
+/* out[r] = sum_i CIRC[i]*s[(i+r)%12] + DIAG[r]*s[r]; products are < 2^70 so a u128 accumulator is exact. */
+static inline void mds_layer(uint64_t s[12]) {
+    uint64_t out[12];
+    for (int r = 0; r < 12; r++) {
+        u128 acc = (u128)MDS_DIAG[r] * s[r];
+        for (int i = 0; i < 12; i++) acc += (u128)MDS_CIRC[i] * s[(i + r) % 12];
+        out[r] = gl_reduce128(acc);
+    }
+    memcpy(s, out, sizeof out);
+}
+
+void orc_poseidon_naive(uint64_t s[12]) {
+    for (int r = 0; r < 30; r++) {
+        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_RC[12 * r + i]);
+        if (r < 4 || r >= 26) {
+            for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+        } else {
+            s[0] = sbox7(s[0]);
+        }
+        mds_layer(s);
+    }
+}
+
+/* Same function with the 22 partial rounds in sparse form (constants derived by
+ * tools/gen_poseidon_constants.py: derive_fast_partial; equivalence is checked there and in tests). */
+void orc_poseidon(uint64_t s[12]) {
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], POSEIDON_RC[12 * r + i]));
+        mds_layer(s);
+    }
+    {
+        uint64_t t[11];
+        for (int i = 0; i < 11; i++) {
+            u128 acc = 0; /* 11 products < 2^128 each: accumulate with explicit carry folding */
+            uint64_t carry = 0;
+            for (int j = 0; j < 11; j++) {
+                u128 p = (u128)POSEIDON_PARTIAL_INIT[11 * i + j] * s[1 + j];
+                u128 n = acc + p;
+                if (n < acc) carry++;
+                acc = n;
+            }
+            /* acc + carry*2^128 ; 2^128 = (2^64)^2 = (2^32-1)^2 mod p */
+            uint64_t r = gl_reduce128(acc);
+            if (carry) r = gl_add(r, gl_mul(carry, gl_mul(GL_EPSILON, GL_EPSILON)));
+            t[i] = r;
+        }
+        memcpy(s + 1, t, sizeof t);
+    }
+    for (int r = 0; r < 22; r++) {
+        uint64_t x0 = sbox7(gl_add(s[0], POSEIDON_PARTIAL_K[r]));
+        u128 acc = (u128)25 * x0;
+        uint64_t carry = 0;
+        for (int i = 0; i < 11; i++) {
+            u128 p = (u128)POSEIDON_PARTIAL_VHAT[11 * r + i] * s[1 + i];
+            u128 n = acc + p;
+            if (n < acc) carry++;
+            acc = n;
+        }
+        uint64_t d = gl_reduce128(acc);
+        if (carry) d = gl_add(d, gl_mul(carry, gl_mul(GL_EPSILON, GL_EPSILON)));
+        for (int i = 0; i < 11; i++) s[1 + i] = gl_add(s[1 + i], gl_mul(POSEIDON_PARTIAL_W[11 * r + i], x0));
+        s[0] = d;
+    }
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POSEIDON_PARTIAL_POST[i]);
+    for (int r = 26; r < 30; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], POSEIDON_RC[12 * r + i]));
+        mds_layer(s);
+    }
+}
+
+/* hash_no_pad: overwrite-mode sponge, rate 8, no padding, output state[0..4]. */
+void orc_hash_no_pad(const uint64_t* in, size_t n, uint64_t out[4]) {
+    uint64_t st[12] = {0};
+    for (size_t off = 0; off < n; off += 8) {
+        size_t len = n - off < 8 ? n - off : 8;
+        memcpy(st, in + off, len * sizeof(uint64_t));
+        orc_poseidon(st);
+    }
+    memcpy(out, st, 4 * sizeof(uint64_t));
+}
+
+void orc_hash_or_noop(const uint64_t* in, size_t n, uint64_t out[4]) {
+    if (n <= 4) {
+        memset(out, 0, 4 * sizeof(uint64_t));
+        memcpy(out, in, n * sizeof(uint64_t));
+    } else {
+        orc_hash_no_pad(in, n, out);
+    }
+}
+
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    uint64_t st[12] = {0};
+    memcpy(st, l, 32);
+    memcpy(st + 4, r, 32);
+    orc_poseidon(st);
+    memcpy(out, st, 32);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FFT.  values[i] = sum_j coeffs[j] * w^(ij); natural order in and out.
+ * ------------------------------------------------------------------------------------------ */
+static inline size_t bitrev(size_t x, unsigned bits) {
+    size_t r = 0;
+    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+static void fft_base_inplace(uint64_t* a, unsigned log_n, uint64_t root) {
+    size_t n = (size_t)1 << log_n;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = bitrev(i, log_n);
+        if (i < j) { uint64_t t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+    for (unsigned s = 1; s <= log_n; s++) {
+        size_t m = (size_t)1 << s, half = m >> 1;
+        uint64_t wm = gl_exp(root, n >> s);
+        for (size_t k = 0; k < n; k += m) {
+            uint64_t w = 1;
+            for (size_t j = 0; j < half; j++) {
+                uint64_t t = gl_mul(w, a[k + j + half]), u = a[k + j];
+                a[k + j] = gl_add(u, t);
+                a[k + j + half] = gl_sub(u, t);
+                w = gl_mul(w, wm);
+            }
+        }
+    }
+}
+
+void orc_fft(uint64_t* a, unsigned log_n) { fft_base_inplace(a, log_n, gl_root_of_unity(log_n)); }
+
+void orc_ifft(uint64_t* a, unsigned log_n) {
+    size_t n = (size_t)1 << log_n;
+    fft_base_inplace(a, log_n, gl_inv(gl_root_of_unity(log_n)));
+    uint64_t ninv = gl_inv((uint64_t)n % GL_P);
+    for (size_t i = 0; i < n; i++) a[i] = gl_mul(a[i], ninv);
+}
+
+void orc_coset_fft(uint64_t* a, unsigned log_n, uint64_t shift) {
+    size_t n = (size_t)1 << log_n;
+    uint64_t s = 1;
+    for (size_t i = 0; i < n; i++) { a[i] = gl_mul(a[i], s); s = gl_mul(s, shift); }
+    orc_fft(a, log_n);
+}
+
+/* extension-field polynomials: the transform is F-linear, so run it per coordinate */
+static void ext_coset_fft(ext2* a, unsigned log_n, uint64_t shift) {
+    size_t n = (size_t)1 << log_n;
+    uint64_t* t = (uint64_t*)malloc(n * sizeof(uint64_t));
+    for (int c = 0; c < 2; c++) {
+        for (size_t i = 0; i < n; i++) t[i] = c ? a[i].b : a[i].a;
+        orc_coset_fft(t, log_n, shift);
+        for (size_t i = 0; i < n; i++) { if (c) a[i].b = t[i]; else a[i].a = t[i]; }
+    }
+    free(t);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * MerkleTree::new(leaves, cap_height)
+ * ------------------------------------------------------------------------------------------ */
+struct orc_tree {
+    size_t num_leaves, leaf_len;
+    unsigned cap_height, log_leaves, num_levels; /* levels[0] = leaf digests ... levels[num_levels-1] = cap */
+    uint64_t* leaves;                             /* owned copy, row-major */
+    uint64_t** levels;
+};
+
+static unsigned log2_strict(size_t n) {
+    unsigned l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+orc_tree* orc_merkle_new(const uint64_t* leaves, size_t num_leaves, size_t leaf_len, unsigned cap_height) {
+    unsigned ll = log2_strict(num_leaves);
+    if (((size_t)1 << ll) != num_leaves || cap_height > ll) return NULL;
+    orc_tree* t = (orc_tree*)calloc(1, sizeof *t);
+    t->num_leaves = num_leaves; t->leaf_len = leaf_len; t->cap_height = cap_height; t->log_leaves = ll;
+    t->num_levels = ll - cap_height + 1;
+    t->leaves = (uint64_t*)malloc(num_leaves * leaf_len * sizeof(uint64_t) + 8);
+    memcpy(t->leaves, leaves, num_leaves * leaf_len * sizeof(uint64_t));
+    t->levels = (uint64_t**)calloc(t->num_levels, sizeof(uint64_t*));
+    t->levels[0] = (uint64_t*)malloc(num_leaves * 4 * sizeof(uint64_t));
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < num_leaves; i++) orc_hash_or_noop(t->leaves + i * leaf_len, leaf_len, t->levels[0] + 4 * i);
+    for (unsigned l = 1; l < t->num_levels; l++) {
+        size_t cnt = num_leaves >> l;
+        t->levels[l] = (uint64_t*)malloc(cnt * 4 * sizeof(uint64_t));
+        const uint64_t* prev = t->levels[l - 1];
+        uint64_t* cur = t->levels[l];
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < cnt; i++) orc_two_to_one(prev + 8 * i, prev + 8 * i + 4, cur + 4 * i);
+    }
+    return t;
+}
+
+void orc_merkle_free(orc_tree* t) {
+    if (!t) return;
+    for (unsigned l = 0; l < t->num_levels; l++) free(t->levels[l]);
+    free(t->levels); free(t->leaves); free(t);
+}
+
+size_t orc_merkle_cap(const orc_tree* t, uint64_t* out) {
+    size_t words = ((size_t)4) << t->cap_height;
+    memcpy(out, t->levels[t->num_levels - 1], words * sizeof(uint64_t));
+    return words;
+}
+
+size_t orc_merkle_prove(const orc_tree* t, size_t leaf_index, uint64_t* siblings) {
+    size_t idx = leaf_index;
+    for (unsigned l = 0; l + 1 < t->num_levels; l++) {
+        memcpy(siblings + 4 * l, t->levels[l] + 4 * (idx ^ 1), 32);
+        idx >>= 1;
+    }
+    return t->num_levels - 1;
+}
+
+const uint64_t* orc_merkle_leaf(const orc_tree* t, size_t leaf_index) { return t->leaves + leaf_index * t->leaf_len; }
+
+/* verify_merkle_proof_to_cap */
+int orc_merkle_verify(const uint64_t* leaf, size_t leaf_len, size_t leaf_index, const uint64_t* cap,
+                      unsigned cap_height, const uint64_t* siblings, size_t num_siblings) {
+    uint64_t cur[4], nxt[4];
+    size_t idx = leaf_index;
+    orc_hash_or_noop(leaf, leaf_len, cur);
+    for (size_t k = 0; k < num_siblings; k++) {
+        if (idx & 1) orc_two_to_one(siblings + 4 * k, cur, nxt); else orc_two_to_one(cur, siblings + 4 * k, nxt);
+        memcpy(cur, nxt, 32);
+        idx >>= 1;
+    }
+    if (idx >= ((size_t)1 << cap_height)) return -1;
+    return memcmp(cur, cap + 4 * idx, 32) == 0 ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * PolynomialBatch::from_values / from_coeffs
+ * ------------------------------------------------------------------------------------------ */
+struct orc_batch {
+    unsigned log_n, rate_bits, cap_height;
+    size_t num_cols, salt_cols;
+    uint64_t* coeffs; /* num_cols x n, column-major, natural order */
+    orc_tree* tree;   /* leaves: L rows x (num_cols+salt_cols), row j = LDE point bitrev(j) */
+};
+
+static orc_batch* batch_from_coeffs_owned(uint64_t* coeffs, unsigned log_n, size_t num_cols, unsigned rate_bits,
+                                          unsigned cap_height, const uint64_t* salt) {
+    size_t n = (size_t)1 << log_n, L = n << rate_bits;
+    unsigned log_L = log_n + rate_bits;
+    size_t salt_cols = salt ? 4 : 0, width = num_cols + salt_cols;
+    uint64_t* leaves = (uint64_t*)malloc(L * width * sizeof(uint64_t));
+#pragma omp parallel
+    {
+        uint64_t* col = (uint64_t*)malloc(L * sizeof(uint64_t));
+#pragma omp for schedule(dynamic, 1)
+        for (size_t c = 0; c < num_cols; c++) {
+            /* lde: zero-pad to L; coset_fft with shift g; then transpose + reverse_index_bits */
+            memcpy(col, coeffs + c * n, n * sizeof(uint64_t));
+            memset(col + n, 0, (L - n) * sizeof(uint64_t));
+            orc_coset_fft(col, log_L, GL_GENERATOR);
+            for (size_t i = 0; i < L; i++) leaves[bitrev(i, log_L) * width + c] = col[i];
+        }
+        free(col);
+    }
+    for (size_t s = 0; s < salt_cols; s++)
+        for (size_t i = 0; i < L; i++) leaves[bitrev(i, log_L) * width + num_cols + s] = salt[s * L + i];
+    orc_batch* b = (orc_batch*)calloc(1, sizeof *b);
+    b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->num_cols = num_cols; b->salt_cols = salt_cols; b->coeffs = coeffs;
+    b->tree = orc_merkle_new(leaves, L, width, cap_height);
+    free(leaves);
+    if (!b->tree) { free(b->coeffs); free(b); return NULL; }
+    return b;
+}
+
+orc_batch* orc_batch_from_coeffs(const uint64_t* cols, unsigned log_n, size_t num_cols, unsigned rate_bits,
+                                 unsigned cap_height, const uint64_t* salt) {
+    size_t n = (size_t)1 << log_n;
+    uint64_t* coeffs = (uint64_t*)malloc(num_cols * n * sizeof(uint64_t) + 8);
+    memcpy(coeffs, cols, num_cols * n * sizeof(uint64_t));
+    return batch_from_coeffs_owned(coeffs, log_n, num_cols, rate_bits, cap_height, salt);
+}
+
+orc_batch* orc_batch_from_values(const uint64_t* cols, unsigned log_n, size_t num_cols, unsigned rate_bits,
+                                 unsigned cap_height, const uint64_t* salt) {
+    size_t n = (size_t)1 << log_n;
+    uint64_t* coeffs = (uint64_t*)malloc(num_cols * n * sizeof(uint64_t) + 8);
+    memcpy(coeffs, cols, num_cols * n * sizeof(uint64_t));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < num_cols; c++) orc_ifft(coeffs + c * n, log_n);
+    return batch_from_coeffs_owned(coeffs, log_n, num_cols, rate_bits, cap_height, salt);
+}
+
+void orc_batch_free(orc_batch* b) {
+    if (!b) return;
+    orc_merkle_free(b->tree); free(b->coeffs); free(b);
+}
+const orc_tree* orc_batch_tree(const orc_batch* b) { return b->tree; }
+const uint64_t* orc_batch_coeffs(const orc_batch* b) { return b->coeffs; }
+size_t orc_batch_leaf_len(const orc_batch* b) { return b->num_cols + b->salt_cols; }
+
+void orc_batch_eval_ext(const orc_batch* b, const uint64_t point[2], uint64_t* out) {
+    size_t n = (size_t)1 << b->log_n;
+    ext2 z = {point[0], point[1]};
+    for (size_t c = 0; c < b->num_cols; c++) {
+        const uint64_t* p = b->coeffs + c * n;
+        ext2 acc = {0, 0};
+        for (size_t i = n; i-- > 0;) acc = ext_add(ext_mul(acc, z), ext_from(p[i]));
+        out[2 * c] = acc.a; out[2 * c + 1] = acc.b;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Challenger
+ * ------------------------------------------------------------------------------------------ */
+void orc_challenger_init(orc_challenger* c) { memset(c, 0, sizeof *c); }
+
+static void duplexing(orc_challenger* c) {
+    for (uint32_t i = 0; i < c->in_len; i++) c->state[i] = c->in[i];
+    c->in_len = 0;
+    orc_poseidon(c->state);
+    memcpy(c->out, c->state, 8 * sizeof(uint64_t));
+    c->out_len = 8;
+}
+
+void orc_challenger_observe(orc_challenger* c, const uint64_t* elems, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        c->out_len = 0;
+        c->in[c->in_len++] = elems[i];
+        if (c->in_len == 8) duplexing(c);
+    }
+}
+
+void orc_challenger_get(orc_challenger* c, uint64_t* out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        if (c->in_len > 0 || c->out_len == 0) duplexing(c);
+        out[i] = c->out[--c->out_len];
+    }
+}
+
+static ext2 challenger_get_ext(orc_challenger* c) {
+    uint64_t v[2];
+    orc_challenger_get(c, v, 2);
+    ext2 r = {v[0], v[1]};
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FRI
+ * ------------------------------------------------------------------------------------------ */
+void orc_fri_params_constant_arity(orc_fri_params* p, unsigned log_n, unsigned rate_bits, unsigned cap_height,
+                                   unsigned pow_bits, unsigned num_queries, unsigned arity_bits,
+                                   unsigned final_poly_bits) {
+    memset(p, 0, sizeof *p);
+    p->rate_bits = rate_bits; p->cap_height = cap_height; p->pow_bits = pow_bits; p->num_queries = num_queries;
+    unsigned d = log_n;
+    while (d > final_poly_bits && d + rate_bits - arity_bits >= cap_height && p->num_rounds < ORC_MAX_FRI_ROUNDS) {
+        p->arity_bits[p->num_rounds++] = arity_bits;
+        d -= arity_bits;
+    }
+}
+
+size_t orc_fri_proof_words(const orc_fri_params* p, unsigned log_n, unsigned num_oracles, const uint32_t* leaf_lens) {
+    unsigned log_L = log_n + p->rate_bits;
+    size_t w = (size_t)p->num_rounds * (((size_t)4) << p->cap_height);
+    size_t per_q = 0;
+    for (unsigned o = 0; o < num_oracles; o++) per_q += leaf_lens[o] + 4 * (size_t)(log_L - p->cap_height);
+    unsigned lg = log_L, deg = log_n;
+    for (unsigned r = 0; r < p->num_rounds; r++) {
+        lg -= p->arity_bits[r]; deg -= p->arity_bits[r];
+        per_q += (((size_t)2) << p->arity_bits[r]) + 4 * (size_t)(lg - p->cap_height);
+    }
+    w += per_q * p->num_queries;
+    w += ((size_t)2) << deg;
+    return w + 1;
+}
+
+static int pow_ok(uint64_t response, unsigned pow_bits) {
+    /* leading_zeros(response) >= pow_bits + (64 - bits(p)) with bits(p) = 64 */
+    return pow_bits == 0 ? 1 : (response >> (64 - pow_bits)) == 0;
+}
+
+int orc_fri_prove(const orc_batch* const* oracles, unsigned num_oracles, const orc_fri_instance* inst,
+                  const orc_fri_params* p, orc_challenger* ch, uint64_t pow_witness_in, uint64_t* proof_out) {
+    unsigned log_n = oracles[0]->log_n;
+    size_t n = (size_t)1 << log_n;
+    unsigned log_L = log_n + p->rate_bits;
+    size_t L = (size_t)1 << log_L;
+    for (unsigned o = 0; o < num_oracles; o++)
+        if (oracles[o]->log_n != log_n || oracles[o]->rate_bits != p->rate_bits) return -1;
+
+    /* PolynomialBatch::prove_openings */
+    ext2 alpha = challenger_get_ext(ch);
+    ext2* final_poly = (ext2*)calloc(L, sizeof(ext2));
+    size_t pi = 0;
+    for (uint32_t b = 0; b < inst->num_batches; b++) {
+        uint32_t k = inst->batch_sizes[b];
+        ext2 point = {inst->points[2 * b], inst->points[2 * b + 1]};
+        /* composition = sum_j alpha^j * poly_j   (ReducingFactor::reduce_polys_base) */
+        ext2* comp = (ext2*)calloc(n, sizeof(ext2));
+        ext2 apow = {1, 0};
+        for (uint32_t j = 0; j < k; j++, pi++) {
+            const orc_batch* ob = oracles[inst->poly_oracle[pi]];
+            if (inst->poly_index[pi] >= ob->num_cols) { free(comp); free(final_poly); return -2; }
+            const uint64_t* poly = ob->coeffs + (size_t)inst->poly_index[pi] * n;
+            for (size_t i = 0; i < n; i++) comp[i] = ext_add(comp[i], ext_scale(apow, poly[i]));
+            apow = ext_mul(apow, alpha);
+        }
+        /* quotient = (comp(X) - comp(z)) / (X - z)  (divide_by_linear), padded back with a zero */
+        ext2* quot = (ext2*)calloc(n, sizeof(ext2));
+        ext2 acc = {0, 0};
+        for (size_t i = n; i-- > 0;) {
+            /* bs (reversed scan): acc = acc*z + c_i ; bs[i] holds the accumulator AFTER coefficient i;
+             * upstream pops the last (i=0) and reverses: quotient[i-1] = accumulator after coefficient i. */
+            acc = ext_add(ext_mul(acc, point), comp[i]);
+            if (i > 0) quot[i - 1] = acc;
+        }
+        /* final_poly = final_poly * alpha^k + quotient  (shift_poly with count = k) */
+        ext2 shift = ext_exp(alpha, k);
+        for (size_t i = 0; i < n; i++) final_poly[i] = ext_add(ext_mul(final_poly[i], shift), quot[i]);
+        free(comp); free(quot);
+    }
+    /* lde + coset_fft(g) */
+    ext2* coeffs = final_poly; /* length L, zero padded beyond n */
+    ext2* values = (ext2*)malloc(L * sizeof(ext2));
+    memcpy(values, coeffs, L * sizeof(ext2));
+    ext_coset_fft(values, log_L, GL_GENERATOR);
+
+    /* fri_committed_trees */
+    orc_tree* trees[ORC_MAX_FRI_ROUNDS];
+    size_t len = L;
+    unsigned lg = log_L;
+    uint64_t shift = GL_GENERATOR;
+    uint64_t* out = proof_out;
+    for (unsigned r = 0; r < p->num_rounds; r++) {
+        unsigned ab = p->arity_bits[r];
+        size_t arity = (size_t)1 << ab;
+        /* reverse_index_bits_in_place(values); leaves = chunks of `arity` flattened */
+        uint64_t* leaves = (uint64_t*)malloc(len * 2 * sizeof(uint64_t));
+        for (size_t i = 0; i < len; i++) {
+            size_t j = bitrev(i, lg);
+            leaves[2 * j] = values[i].a; leaves[2 * j + 1] = values[i].b;
+        }
+        trees[r] = orc_merkle_new(leaves, len >> ab, 2 * arity, p->cap_height);
+        free(leaves);
+        if (!trees[r]) return -3;
+        size_t cw = orc_merkle_cap(trees[r], out);
+        orc_challenger_observe(ch, out, cw);
+        out += cw;
+        ext2 beta = challenger_get_ext(ch);
+        /* coeffs <- [reduce_with_powers(chunk, beta) for chunk in coeffs.chunks(arity)] */
+        size_t nl = len >> ab;
+        for (size_t i = 0; i < nl; i++) {
+            ext2 acc = {0, 0};
+            for (size_t k = arity; k-- > 0;) acc = ext_add(ext_mul(acc, beta), coeffs[i * arity + k]);
+            coeffs[i] = acc;
+        }
+        shift = gl_exp(shift, arity);
+        len = nl; lg -= ab;
+        memcpy(values, coeffs, len * sizeof(ext2));
+        ext_coset_fft(values, lg, shift);
+    }
+    size_t final_len = len >> p->rate_bits;
+    /* query-phase output comes before final_poly in the flat layout: remember where things go */
+    uint64_t* final_words = (uint64_t*)malloc(final_len * 2 * sizeof(uint64_t));
+    for (size_t i = 0; i < final_len; i++) { final_words[2 * i] = coeffs[i].a; final_words[2 * i + 1] = coeffs[i].b; }
+    orc_challenger_observe(ch, final_words, 2 * final_len);
+
+    /* fri_proof_of_work */
+    uint64_t witness = pow_witness_in;
+    if (witness == UINT64_MAX) {
+        for (witness = 0;; witness++) {
+            orc_challenger c2 = *ch;
+            orc_challenger_observe(&c2, &witness, 1);
+            uint64_t resp;
+            orc_challenger_get(&c2, &resp, 1);
+            if (pow_ok(resp, p->pow_bits)) break;
+        }
+    }
+    orc_challenger_observe(ch, &witness, 1);
+    uint64_t resp;
+    orc_challenger_get(ch, &resp, 1);
+    if (!pow_ok(resp, p->pow_bits)) return -4;
+
+    /* fri_prover_query_rounds */
+    for (uint32_t q = 0; q < p->num_queries; q++) {
+        uint64_t x;
+        orc_challenger_get(ch, &x, 1);
+        size_t x_index = (size_t)(x % L);
+        for (unsigned o = 0; o < num_oracles; o++) {
+            const orc_tree* t = oracles[o]->tree;
+            memcpy(out, orc_merkle_leaf(t, x_index), t->leaf_len * sizeof(uint64_t));
+            out += t->leaf_len;
+            out += 4 * orc_merkle_prove(t, x_index, out);
+        }
+        for (unsigned r = 0; r < p->num_rounds; r++) {
+            unsigned ab = p->arity_bits[r];
+            const orc_tree* t = trees[r];
+            memcpy(out, orc_merkle_leaf(t, x_index >> ab), t->leaf_len * sizeof(uint64_t));
+            out += t->leaf_len;
+            out += 4 * orc_merkle_prove(t, x_index >> ab, out);
+            x_index >>= ab;
+        }
+    }
+    memcpy(out, final_words, final_len * 2 * sizeof(uint64_t));
+    out += 2 * final_len;
+    *out++ = witness;
+    free(final_words); free(values); free(final_poly);
+    for (unsigned r = 0; r < p->num_rounds; r++) orc_merkle_free(trees[r]);
+    return 0;
+}
+
+/* compute_evaluation: interpolate {(x*g^i, P(x*g^i))} over the arity-sized coset and evaluate at beta */
+static ext2 compute_evaluation(uint64_t x, size_t x_index_within_coset, unsigned arity_bits, const ext2* evals_in,
+                               ext2 beta) {
+    size_t arity = (size_t)1 << arity_bits;
+    uint64_t g = gl_root_of_unity(arity_bits);
+    ext2 evals[1 << 8];
+    uint64_t pts[1 << 8];
+    for (size_t i = 0; i < arity; i++) evals[bitrev(i, arity_bits)] = evals_in[i];
+    size_t rev = bitrev(x_index_within_coset, arity_bits);
+    uint64_t coset_start = gl_mul(x, gl_exp(g, arity - rev));
+    uint64_t y = 1;
+    for (size_t i = 0; i < arity; i++) { pts[i] = gl_mul(coset_start, y); y = gl_mul(y, g); }
+    /* Lagrange interpolation at beta (the interpolant is unique, so any formula gives the same element) */
+    ext2 sum = {0, 0};
+    for (size_t i = 0; i < arity; i++) {
+        ext2 num = {1, 0};
+        uint64_t den = 1;
+        for (size_t j = 0; j < arity; j++) {
+            if (j == i) continue;
+            num = ext_mul(num, ext_sub(beta, ext_from(pts[j])));
+            den = gl_mul(den, gl_sub(pts[i], pts[j]));
+        }
+        sum = ext_add(sum, ext_mul(evals[i], ext_scale(num, gl_inv(den))));
+    }
+    return sum;
+}
+
+int orc_fri_verify(unsigned log_n, unsigned num_oracles, const uint32_t* leaf_lens, const uint64_t* caps,
+                   const orc_fri_instance* inst, const uint64_t* openings, const orc_fri_params* p,
+                   orc_challenger* ch, const uint64_t* proof) {
+    unsigned log_L = log_n + p->rate_bits;
+    size_t L = (size_t)1 << log_L;
+    size_t cap_words = ((size_t)4) << p->cap_height;
+    /* locate the sections of the flat proof */
+    const uint64_t* round_caps = proof;
+    const uint64_t* queries = proof + p->num_rounds * cap_words;
+    size_t total = orc_fri_proof_words(p, log_n, num_oracles, leaf_lens);
+    unsigned deg = log_n;
+    for (unsigned r = 0; r < p->num_rounds; r++) deg -= p->arity_bits[r];
+    size_t final_len = (size_t)1 << deg;
+    const uint64_t* final_words = proof + total - 1 - 2 * final_len;
+    uint64_t pow_witness = proof[total - 1];
+
+    /* fri_challenges */
+    ext2 alpha = challenger_get_ext(ch);
+    ext2 betas[ORC_MAX_FRI_ROUNDS];
+    for (unsigned r = 0; r < p->num_rounds; r++) {
+        orc_challenger_observe(ch, round_caps + r * cap_words, cap_words);
+        betas[r] = challenger_get_ext(ch);
+    }
+    orc_challenger_observe(ch, final_words, 2 * final_len);
+    orc_challenger_observe(ch, &pow_witness, 1);
+    uint64_t resp;
+    orc_challenger_get(ch, &resp, 1);
+    if (!pow_ok(resp, p->pow_bits)) return -10;
+
+    /* PrecomputedReducedOpenings: reduce(values) = sum_j alpha^j v_j per batch */
+    ext2 reduced[64];
+    if (inst->num_batches > 64) return -11;
+    {
+        size_t pi = 0;
+        for (uint32_t b = 0; b < inst->num_batches; b++) {
+            ext2 acc = {0, 0};
+            uint32_t k = inst->batch_sizes[b];
+            for (uint32_t j = k; j-- > 0;) {
+                ext2 v = {openings[2 * (pi + j)], openings[2 * (pi + j) + 1]};
+                acc = ext_add(ext_mul(acc, alpha), v);
+            }
+            reduced[b] = acc;
+            pi += k;
+        }
+    }
+    size_t cap_off[64];
+    {
+        size_t o = 0;
+        for (unsigned i = 0; i < num_oracles; i++) { cap_off[i] = o; o += cap_words; }
+    }
+    const uint64_t* qp = queries;
+    for (uint32_t q = 0; q < p->num_queries; q++) {
+        uint64_t x;
+        orc_challenger_get(ch, &x, 1);
+        size_t x_index = (size_t)(x % L);
+        /* fri_verify_initial_proof */
+        const uint64_t* rows[64];
+        for (unsigned o = 0; o < num_oracles; o++) {
+            rows[o] = qp;
+            const uint64_t* sib = qp + leaf_lens[o];
+            size_t ns = log_L - p->cap_height;
+            if (orc_merkle_verify(rows[o], leaf_lens[o], x_index, caps + cap_off[o], p->cap_height, sib, ns)) return -20;
+            qp = sib + 4 * ns;
+        }
+        uint64_t subgroup_x = gl_mul(GL_GENERATOR, gl_exp(gl_root_of_unity(log_L), bitrev(x_index, log_L)));
+        /* fri_combine_initial */
+        ext2 sum = {0, 0};
+        {
+            size_t pi = 0;
+            for (uint32_t b = 0; b < inst->num_batches; b++) {
+                uint32_t k = inst->batch_sizes[b];
+                ext2 point = {inst->points[2 * b], inst->points[2 * b + 1]};
+                ext2 acc = {0, 0};
+                for (uint32_t j = k; j-- > 0;) {
+                    uint64_t v = rows[inst->poly_oracle[pi + j]][inst->poly_index[pi + j]];
+                    acc = ext_add(ext_mul(acc, alpha), ext_from(v));
+                }
+                ext2 numer = ext_sub(acc, reduced[b]);
+                ext2 denom = ext_sub(ext_from(subgroup_x), point);
+                sum = ext_mul(sum, ext_exp(alpha, k));
+                sum = ext_add(sum, ext_mul(numer, ext_inv(denom)));
+                pi += k;
+            }
+        }
+        ext2 old_eval = sum;
+        unsigned lg = log_L;
+        for (unsigned r = 0; r < p->num_rounds; r++) {
+            unsigned ab = p->arity_bits[r];
+            size_t arity = (size_t)1 << ab;
+            const ext2* evals = (const ext2*)qp;
+            size_t coset_index = x_index >> ab, within = x_index & (arity - 1);
+            if (!ext_eq(evals[within], old_eval)) return -30 - (int)r;
+            old_eval = compute_evaluation(subgroup_x, within, ab, evals, betas[r]);
+            lg -= ab;
+            const uint64_t* sib = qp + 2 * arity;
+            size_t ns = lg - p->cap_height;
+            if (orc_merkle_verify(qp, 2 * arity, coset_index, round_caps + r * cap_words, p->cap_height, sib, ns)) return -50 - (int)r;
+            qp = sib + 4 * ns;
+            for (unsigned k = 0; k < ab; k++) subgroup_x = gl_sqr(subgroup_x);
+            x_index = coset_index;
+        }
+        /* final_poly.eval(subgroup_x) == old_eval */
+        ext2 acc = {0, 0};
+        for (size_t i = final_len; i-- > 0;) {
+            ext2 c = {final_words[2 * i], final_words[2 * i + 1]};
+            acc = ext_add(ext_scale(acc, subgroup_x), c);
+        }
+        if (!ext_eq(acc, old_eval)) return -70;
+    }
+    return 0;
+}
