@@ -1,0 +1,204 @@
+/* qpzk.h -- C ABI of libqpzk.so, the B200 (sm_100a) backend for the batched polynomial commitment
+ * under plonky2's `prove()` as used by Quantus-Network/qp-zk-circuits.
+ *
+ * This is the drop-in boundary.  The reference reaches the hot path only through
+ * `ProverCircuitData::prove` / `CircuitData::prove`:
+ *     wormhole/prover/src/lib.rs:171-175
+ *     wormhole/aggregator/src/private_batch/prover/lib.rs:326-330
+ *     wormhole/aggregator/src/public_batch/prover/lib.rs:301-305
+ * and `CircuitBuilder::build*` (wormhole/circuit/src/circuit.rs:206-216), which call, inside the
+ * un-vendored crate qp-plonky2 =1.5.5 (Cargo.toml:20), the functions each entry point below replaces.
+ * INTEGRATION.md shows the Rust `-sys` binding a maintainer adds to a `[patch.crates-io]` fork.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative QPZK_E* code on failure; qpzk_last_error() gives a
+ *    thread-local message.  No C++ exception or abort crosses this boundary.
+ *  - field elements are canonical Goldilocks values (< p = 2^64 - 2^32 + 1), little-endian uint64_t;
+ *    extension elements are two consecutive words [a0, a1] (a0 + a1*X, X^2 = 7).
+ *    Non-canonical inputs are rejected by the *_checked variants only; outputs are always canonical.
+ *  - host pointers are owned by the caller and only read/written during the call; device memory is
+ *    owned by the library behind opaque handles.  Functions suffixed _dev take DEVICE pointers.
+ *  - one qpzk_ctx = one device + one CUDA stream; a context must not be used from two threads at
+ *    once, distinct contexts are independent (multi-GPU = one context per device).
+ *  - randomness (salts, PoW witness policy) is always caller-controlled, so runs are reproducible.
+ *  - there is NO CPU fallback: if the device or the kernels are unavailable the call fails.
+ */
+#ifndef QPZK_H
+#define QPZK_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define QPZK_OK 0
+#define QPZK_EINVAL (-1)   /* bad argument (shape, cap_height > log2(leaves), null pointer, ...) */
+#define QPZK_ECUDA (-2)    /* CUDA runtime error (message has the CUDA error string) */
+#define QPZK_ENOMEM (-3)   /* device allocation failed */
+#define QPZK_EPOW (-4)     /* caller-supplied PoW witness does not satisfy the difficulty */
+#define QPZK_EINTERNAL (-5)
+
+#define QPZK_SALT_SIZE 4          /* plonky2 SALT_SIZE: blinding columns appended to each leaf */
+#define QPZK_MAX_FRI_ROUNDS 16
+#define QPZK_MAX_ORACLES 8
+#define QPZK_MAX_FRI_BATCHES 8
+#define QPZK_POW_SEARCH UINT64_MAX /* pow_witness_in value meaning "grind the minimum witness" */
+
+typedef struct qpzk_ctx qpzk_ctx;
+typedef struct qpzk_batch qpzk_batch;           /* PolynomialBatch and/or MerkleTree, device resident */
+typedef struct qpzk_challenger qpzk_challenger; /* Challenger<F, PoseidonHash>, device resident */
+
+const char* qpzk_last_error(void);
+const char* qpzk_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int qpzk_ctx_create(int device, qpzk_ctx** out);
+/* Same, but enqueue on an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx** out);
+void qpzk_ctx_destroy(qpzk_ctx* ctx);
+int qpzk_ctx_synchronize(qpzk_ctx* ctx);
+/* Zero wire/LDE buffers before they are released (secret hygiene, reference
+ * wormhole/circuit/src/sensitive.rs:1-16).  Default: on. */
+int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on);
+/* Stage timing with CUDA events on the context stream.  After a commit:
+ *   ms[0]=iNTT  ms[1]=LDE passes  ms[2]=leaf hashing  ms[3]=Merkle levels  (0 when a stage did not run) */
+int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on);
+int qpzk_ctx_last_commit_timing(qpzk_ctx* ctx, float ms[4]);
+/* number of kernel launches issued through this context since creation */
+uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx);
+
+/* ---- PolynomialBatch::from_values / from_coeffs --------------------------------------------------
+ * Replaces qp-plonky2 `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing,
+ * fft_root_table)` and `::from_coeffs(...)`: per column iFFT, zero-padded
+ * coset FFT with shift g, transpose, reverse_index_bits, MerkleTree::new.
+ *   cols: num_cols x 2^log_n words, column-major (one polynomial after another).
+ *   salt: NULL (blinding = false) or QPZK_SALT_SIZE x 2^(log_n+rate_bits) words, column-major, the
+ *         blinding values for LDE index i (natural order) -- what upstream draws from its RNG.
+ * The batch keeps: coefficients, the leaf matrix (row j = LDE point bitrev(j), num_cols+salt words),
+ * all digests, the cap. */
+int qpzk_commit_from_values(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out);
+int qpzk_commit_from_coeffs(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out);
+int qpzk_commit_from_values_dev(qpzk_ctx* ctx, const uint64_t* cols_dev, uint32_t log_n, uint32_t num_cols,
+                                uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev,
+                                qpzk_batch** out);
+int qpzk_commit_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* cols_dev, uint32_t log_n, uint32_t num_cols,
+                                uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev,
+                                qpzk_batch** out);
+/* Coset-split commitment for one commitment spread over several GPUs: compute only
+ * the leaf blocks [coset_begin, coset_begin+coset_count) (each block = 2^log_n consecutive leaves =
+ * one Merkle subtree) from the full coefficient matrix.  coset_count must be a power of two dividing
+ * 2^rate_bits and cap_height >= rate_bits - log2(coset_count).  The resulting batch's "cap" is the slice
+ * [coset_begin * 2^cap_height / 2^rate_bits, ...) of the full cap; leaf indices are local to the slice. */
+int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t log_n,
+                                       uint32_t num_cols, uint32_t rate_bits, uint32_t cap_height,
+                                       uint32_t coset_begin, uint32_t coset_count, qpzk_batch** out);
+/* column iNTT only (values -> coefficients), used by the coset-split path before the all-gather */
+int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint64_t* coeffs_dev, uint32_t log_n,
+                          uint32_t num_cols);
+
+/* ---- MerkleTree::new(leaves, cap_height) / .cap / .prove / .leaves -------------------------------
+ * leaves: num_leaves x leaf_len words, row-major.  num_leaves must be a power of two, cap_height <= log2. */
+int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,
+                    uint32_t cap_height, qpzk_batch** out);
+int qpzk_merkle_new_dev(qpzk_ctx* ctx, const uint64_t* leaves_dev, uint64_t num_leaves, uint32_t leaf_len,
+                        uint32_t cap_height, qpzk_batch** out);
+
+void qpzk_batch_free(qpzk_batch* b);
+uint64_t qpzk_batch_num_leaves(const qpzk_batch* b);
+uint32_t qpzk_batch_leaf_len(const qpzk_batch* b);   /* num_cols + salt */
+uint32_t qpzk_batch_cap_len(const qpzk_batch* b);    /* number of cap digests */
+/* cap: cap_len x 4 words, order = subtree index */
+int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out);
+/* polynomials (coefficients): num_cols x 2^log_n, column-major, natural order */
+int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out);
+/* leaf rows [first_row, first_row+num_rows): num_rows x leaf_len words.
+ * get_lde_values(i, step) of upstream is row bitrev(i*step) without the salt words. */
+int qpzk_batch_rows(const qpzk_batch* b, uint64_t first_row, uint64_t num_rows, uint64_t* out);
+/* digests of tree level `level` (0 = leaf digests): (num_leaves >> level) x 4 words */
+int qpzk_batch_digests(const qpzk_batch* b, uint32_t level, uint64_t* out);
+/* MerkleTree::prove for k leaf indices: rows = k x leaf_len, siblings = k x (log2(num_leaves)-cap_height) x 4 */
+int qpzk_batch_open(const qpzk_batch* b, const uint64_t* idx, uint32_t k, uint64_t* rows, uint64_t* siblings);
+/* evaluate every (unsalted) polynomial at an extension point: out = num_cols x 2 words.
+ * (OpeningSet::new / eval_commitment) */
+int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t point[2], uint64_t* out);
+/* device views for zero-copy consumers (quotient evaluation, next tier): valid until qpzk_batch_free */
+const uint64_t* qpzk_batch_leaves_dev(const qpzk_batch* b);
+const uint64_t* qpzk_batch_coeffs_dev(const qpzk_batch* b);
+
+/* ---- Challenger<F, PoseidonHash> ----------------------------------------------------------------- */
+typedef struct {
+    uint64_t sponge_state[12];
+    uint64_t input_buffer[8];
+    uint64_t output_buffer[8];
+    uint32_t input_len;
+    uint32_t output_len;
+} qpzk_challenger_state;
+
+int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out);
+void qpzk_challenger_free(qpzk_challenger* ch);
+int qpzk_challenger_observe(qpzk_challenger* ch, const uint64_t* elems, uint32_t n); /* observe_elements */
+int qpzk_challenger_observe_cap(qpzk_challenger* ch, const qpzk_batch* b);           /* device to device */
+int qpzk_challenger_get(qpzk_challenger* ch, uint64_t* out, uint32_t n);             /* get_n_challenges */
+int qpzk_challenger_export(qpzk_challenger* ch, qpzk_challenger_state* out);
+int qpzk_challenger_import(qpzk_challenger* ch, const qpzk_challenger_state* in);
+
+/* ---- FRI: PolynomialBatch::prove_openings --------------------------------------------------------- */
+typedef struct {
+    uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds;
+    uint32_t num_rounds;                            /* reduction_arity_bits.len() */
+    uint32_t arity_bits[QPZK_MAX_FRI_ROUNDS];
+} qpzk_fri_params;
+
+/* FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits)
+ * (the reference uses (4, 5): wormhole/circuit/src/profile.rs:168-174) */
+int qpzk_fri_params_constant_arity(qpzk_fri_params* p, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
+                                   uint32_t proof_of_work_bits, uint32_t num_query_rounds, uint32_t arity_bits,
+                                   uint32_t final_poly_bits);
+
+/* FriInstanceInfo: batches[b] opens polynomials (poly_oracle[k], poly_index[k]) at points[b]. */
+typedef struct {
+    uint32_t num_batches;
+    const uint64_t* points;       /* num_batches x 2 */
+    const uint32_t* batch_sizes;  /* num_batches */
+    const uint32_t* poly_oracle;  /* sum(batch_sizes) */
+    const uint32_t* poly_index;   /* sum(batch_sizes) */
+} qpzk_fri_instance;
+
+/* Flat FriProof layout (uint64 words), R = num_rounds, H = 2^cap_height, L = 2^(log_n+rate_bits):
+ *   commit_phase_merkle_caps : R x H x 4
+ *   query_round_proofs       : num_query_rounds x {
+ *        for each oracle o : leaf row (leaf_len[o]) , siblings (log2 L - cap_height) x 4
+ *        for each round r  : evals 2^arity_bits[r] x 2 , siblings (log2(L_r) - arity_bits[r] - cap_height) x 4 }
+ *   final_poly               : 2^(log_n - sum arity_bits) x 2
+ *   pow_witness              : 1
+ * (uncompressed proof, field order of upstream FriProof::to_bytes) */
+size_t qpzk_fri_proof_words(const qpzk_fri_params* p, uint32_t log_n, uint32_t num_oracles,
+                            const uint32_t* leaf_lens);
+
+/* prove_openings(instance, oracles, challenger, fri_params): draws alpha from the challenger, builds the
+ * batch-opening polynomial, runs the commit phase, proof of work and query phase, leaves the challenger
+ * in the same state upstream would.  openings_out (optional, may be NULL) receives the opened values in
+ * instance order (sum(batch_sizes) x 2 words).  pow_witness_in: QPZK_POW_SEARCH or a witness to use. */
+int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
+                   const qpzk_fri_instance* instance, const qpzk_fri_params* params, qpzk_challenger* ch,
+                   uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out);
+
+/* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------------- */
+/* IMAD.WIDE throughput: returns 32x32+64 multiply-adds per second measured over `iters` dependent-chain
+ * iterations on every SM. */
+int qpzk_bench_imad(qpzk_ctx* ctx, uint32_t iters, double* imad_per_sec);
+/* Poseidon permutations per second (state in registers, no memory traffic) */
+int qpzk_bench_poseidon(qpzk_ctx* ctx, uint32_t perms_per_thread, double* perms_per_sec);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,956 @@
+// C ABI of libqpzk.so (declared in include/qpzk.h): contexts, root-power tables, the commit pipeline
+// (iNTT -> coset LDE -> leaf hashing -> Merkle levels), openings, challenger and the FRI prover driver.
+// Host code here only plans passes, owns device buffers and enqueues kernels on the context stream; all
+// field arithmetic on data runs in the kernels of ntt.cu / hash.cu / fri.cu.  There is no CPU fallback.
+//
+// Replaces the host-side orchestration of qp-plonky2 =1.5.5 `PolynomialBatch::{from_values,from_coeffs,
+// prove_openings}`, `MerkleTree::new`, `fri_proof` (reference call sites
+// wormhole/prover/src/lib.rs:171-175 and the two aggregator provers).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/qpzk.h"
+#include "goldilocks.cuh"
+#include "internal.cuh"
+
+using namespace qpzk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(e_ == cudaErrorMemoryAllocation ? QPZK_ENOMEM : QPZK_ECUDA, buf_);              \
+        }                                                                                              \
+    } while (0)
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                  \
+    }                                                              \
+    catch (const std::bad_alloc&) { return fail(QPZK_ENOMEM, "host allocation failed"); } \
+    catch (const std::exception& ex) { return fail(QPZK_EINTERNAL, ex.what()); }          \
+    catch (...) { return fail(QPZK_EINTERNAL, "unknown exception"); }
+
+struct PowTables {
+    uint64_t *lo = nullptr, *hi = nullptr;  // device
+    uint64_t hi_size = 0;
+};
+struct CosetTables {
+    uint64_t *lo = nullptr, *hi = nullptr;  // device, [cosets][TW_LO_SIZE] / [cosets][hi_size]
+    uint64_t hi_size = 0;
+};
+
+struct qpzk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    bool zeroize = true;
+    bool timing = false;
+    cudaEvent_t ev[5] = {};
+    bool ev_valid[5] = {};
+    uint64_t launches = 0;
+    std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
+    std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
+};
+
+struct qpzk_batch {
+    qpzk_ctx* ctx = nullptr;
+    uint32_t log_n = 0, rate_bits = 0, cap_height = 0, num_cols = 0, salt_cols = 0, leaf_width = 0;
+    uint64_t num_leaves = 0;
+    uint32_t log_leaves = 0, num_levels = 0;  // levels[0] = leaf digests ... levels[num_levels-1] = cap
+    uint64_t* coeffs = nullptr;               // num_cols x n (null for a bare MerkleTree)
+    uint64_t* leaves = nullptr;
+    uint64_t* digests = nullptr;
+    bool own_leaves = true;
+};
+
+struct qpzk_challenger {
+    qpzk_ctx* ctx = nullptr;
+    ChallengerDev* dev = nullptr;
+    uint64_t* scratch = nullptr;  // device staging for observed elements / drawn challenges
+    uint32_t scratch_words = 0;
+};
+
+static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
+
+// ---------------------------------------------------------------------------------------------
+// device memory helpers (stream-ordered pool)
+// ---------------------------------------------------------------------------------------------
+static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
+    *p = nullptr;
+    if (!words) words = 1;
+    CK(cudaMallocAsync((void**)p, words * sizeof(uint64_t), ctx->stream));
+    return 0;
+}
+static void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words = 0) {
+    if (!p) return;
+    if (zero_words && ctx->zeroize) cudaMemsetAsync(p, 0, zero_words * sizeof(uint64_t), ctx->stream);
+    cudaFreeAsync(p, ctx->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// root-power tables (built once per size on the host, at most a few thousand elements)
+// ---------------------------------------------------------------------------------------------
+static int upload_words(qpzk_ctx* ctx, const std::vector<uint64_t>& h, uint64_t** d) {
+    CK(cudaMalloc((void**)d, h.size() * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static void fill_powers(uint64_t base, uint64_t hi_size, std::vector<uint64_t>& lo, std::vector<uint64_t>& hi) {
+    lo.resize(TW_LO_SIZE);
+    hi.resize(hi_size);
+    uint64_t v = 1;
+    for (uint32_t i = 0; i < TW_LO_SIZE; i++) { lo[i] = v; v = gl_mul_host(v, base); }
+    uint64_t step = v;  // base^TW_LO_SIZE
+    v = 1;
+    for (uint64_t i = 0; i < hi_size; i++) { hi[i] = v; v = gl_mul_host(v, step); }
+}
+
+static int get_pow_tables(qpzk_ctx* ctx, uint32_t log_size, bool inverse, PowTables* out) {
+    auto key = std::make_pair(log_size, inverse ? 1 : 0);
+    auto it = ctx->pow_tables.find(key);
+    if (it == ctx->pow_tables.end()) {
+        uint64_t w = gl_root_of_unity_host(log_size);
+        if (inverse) w = gl_inv_host(w);
+        PowTables t;
+        t.hi_size = log_size > TW_LO_BITS ? (1ull << (log_size - TW_LO_BITS)) : 1;
+        std::vector<uint64_t> lo, hi;
+        fill_powers(w, t.hi_size, lo, hi);
+        int rc;
+        if ((rc = upload_words(ctx, lo, &t.lo))) return rc;
+        if ((rc = upload_words(ctx, hi, &t.hi))) return rc;
+        it = ctx->pow_tables.emplace(key, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// coset j' (leaf block index) uses shift s = g * w_L^bitrev_r(j')
+static int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, CosetTables* out) {
+    auto key = std::make_pair(log_n, rate_bits);
+    auto it = ctx->coset_tables.find(key);
+    if (it == ctx->coset_tables.end()) {
+        uint32_t cosets = 1u << rate_bits;
+        CosetTables t;
+        t.hi_size = log_n > TW_LO_BITS ? (1ull << (log_n - TW_LO_BITS)) : 1;
+        uint64_t wL = gl_root_of_unity_host(log_n + rate_bits);
+        std::vector<uint64_t> lo_all, hi_all, lo, hi;
+        for (uint32_t jp = 0; jp < cosets; jp++) {
+            uint32_t j = 0;
+            for (uint32_t b = 0; b < rate_bits; b++) j |= ((jp >> b) & 1) << (rate_bits - 1 - b);
+            uint64_t s = gl_mul_host(GL_GENERATOR, gl_exp_host(wL, j));
+            fill_powers(s, t.hi_size, lo, hi);
+            lo_all.insert(lo_all.end(), lo.begin(), lo.end());
+            hi_all.insert(hi_all.end(), hi.begin(), hi.end());
+        }
+        int rc;
+        if ((rc = upload_words(ctx, lo_all, &t.lo))) return rc;
+        if ((rc = upload_words(ctx, hi_all, &t.hi))) return rc;
+        it = ctx->coset_tables.emplace(key, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* qpzk_last_error(void) { return g_err.c_str(); }
+extern "C" const char* qpzk_version(void) { return "qpzk-b200 0.1 (sm_100a)"; }
+
+static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
+    if (!out) return fail(QPZK_EINVAL, "out is null");
+    *out = nullptr;
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(QPZK_EINVAL, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(QPZK_ECUDA, "libqpzk is built for sm_100a only; device is older than Blackwell");
+    qpzk_ctx* ctx = new qpzk_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (own) {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+    }
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CK(upload_poseidon_constants());
+    for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev[i]));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int qpzk_ctx_create(int device, qpzk_ctx** out) {
+    GUARD_BEGIN return ctx_create_impl(device, nullptr, true, out); GUARD_END
+}
+extern "C" int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx** out) {
+    GUARD_BEGIN return ctx_create_impl(device, cuda_stream, false, out); GUARD_END
+}
+extern "C" void qpzk_ctx_destroy(qpzk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    for (auto& kv : ctx->coset_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
+    if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->zeroize = on != 0; return 0; }
+extern "C" int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->timing = on != 0; return 0; }
+extern "C" uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static void mark(qpzk_ctx* ctx, int i) {
+    if (ctx->timing) { cudaEventRecord(ctx->ev[i], ctx->stream); ctx->ev_valid[i] = true; }
+}
+extern "C" int qpzk_ctx_last_commit_timing(qpzk_ctx* ctx, float ms[4]) {
+    if (!ctx || !ms) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) {
+        ms[i] = 0;
+        if (ctx->ev_valid[i] && ctx->ev_valid[i + 1]) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// commit pipeline
+// ---------------------------------------------------------------------------------------------
+static void split_bits(uint32_t total, uint32_t max_bits, std::vector<uint32_t>& out) {
+    out.clear();
+    if (!total) return;
+    uint32_t k = (total + max_bits - 1) / max_bits;
+    uint32_t base = total / k, extra = total % k;
+    for (uint32_t i = 0; i < k; i++) out.push_back(base + (i < extra ? 1 : 0));
+}
+
+// values (natural order, column-major) -> coefficients (natural order, column-major)
+static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
+    if (!num_cols) return 0;
+    if (num_cols > 65535) return fail(QPZK_EINVAL, "num_cols > 65535");
+    PowTables inv;
+    int rc = get_pow_tables(ctx, log_n, true, &inv);
+    if (rc) return rc;
+    uint64_t n = 1ull << log_n;
+    uint64_t ninv = gl_inv_host(n % GL_P);
+    std::vector<uint32_t> passes;
+    if (log_n <= 12) passes.push_back(log_n); else split_bits(log_n, 10, passes);
+    if (passes.empty()) passes.push_back(0);
+    uint32_t b_lo = 0;
+    for (size_t i = 0; i < passes.size(); i++) {
+        NttPassArgs a{};
+        a.in = i == 0 ? values : coeffs;
+        a.out = coeffs;
+        a.in_stride = a.out_stride = n;
+        a.num_arrays = num_cols;
+        a.log_n = log_n; a.b_lo = b_lo; a.s = passes[i];
+        uint32_t room = i == 0 ? log_n - passes[i] : b_lo;
+        a.W = passes.size() == 1 ? 1 : (room >= 3 ? 8 : (1u << room));
+        a.mode = i == 0 ? NTT_INV_FIRST : NTT_INV_GENERIC;
+        a.num_cosets = 1;
+        a.tw_lo = inv.lo; a.tw_hi = inv.hi;
+        a.scale = i + 1 == passes.size() ? ninv : 1;
+        CK(launch_ntt_pass(a, ctx->stream));
+        ctx->launches++;
+        b_lo += passes[i];
+    }
+    return 0;
+}
+
+// coefficients -> leaf blocks [coset_begin, coset_begin + coset_count) of the LDE, row-major, leaf order
+static int run_lde(qpzk_ctx* ctx, const uint64_t* coeffs, uint64_t* leaves, uint32_t log_n, uint32_t num_cols,
+                   uint32_t leaf_width, uint32_t rate_bits, uint32_t coset_begin, uint32_t coset_count) {
+    if (!num_cols) return 0;
+    PowTables fwd;
+    CosetTables cs;
+    int rc = get_pow_tables(ctx, log_n, false, &fwd);
+    if (rc) return rc;
+    if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
+    uint64_t n = 1ull << log_n;
+    if ((uint64_t)num_cols * coset_count > 65535) return fail(QPZK_EINVAL, "num_cols * cosets > 65535");
+    // rows per block of the last pass: as many as fit ~72 KB of shared memory with all columns resident
+    uint32_t s_last = 0;
+    while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 9216) s_last++;
+    uint32_t rem = log_n - s_last;
+    const uint64_t* cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
+    const uint64_t* cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
+
+    uint64_t* inter = nullptr;
+    LdeLastArgs la{};
+    la.leaves = leaves; la.log_n = log_n; la.s = s_last; la.num_cols = num_cols; la.leaf_width = leaf_width;
+    la.num_cosets = coset_count; la.tw_lo = fwd.lo; la.tw_hi = fwd.hi; la.cs_lo = cs_lo; la.cs_hi = cs_hi;
+    la.cs_hi_size = cs.hi_size; la.in_stride = n;
+    if (rem == 0) {
+        la.in = coeffs; la.from_coeffs = 1;
+    } else {
+        if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols * n))) return rc;
+        std::vector<uint32_t> passes;
+        split_bits(rem, 10, passes);
+        uint32_t b_hi = log_n;
+        for (size_t i = 0; i < passes.size(); i++) {
+            NttPassArgs a{};
+            a.log_n = log_n; a.s = passes[i]; a.b_lo = b_hi - passes[i];
+            a.W = a.b_lo >= 3 ? 8 : (1u << a.b_lo);
+            a.in_stride = a.out_stride = n;
+            a.tw_lo = fwd.lo; a.tw_hi = fwd.hi; a.scale = 1;
+            if (i == 0) {
+                a.mode = NTT_FWD_COSET_FIRST; a.in = coeffs; a.out = inter; a.num_arrays = num_cols;
+                a.num_cosets = coset_count; a.cs_lo = cs_lo; a.cs_hi = cs_hi; a.cs_hi_size = cs.hi_size;
+            } else {
+                a.mode = NTT_FWD_GENERIC; a.in = inter; a.out = inter; a.num_arrays = (uint64_t)num_cols * coset_count;
+                a.num_cosets = 1;
+            }
+            cudaError_t e = launch_ntt_pass(a, ctx->stream);
+            if (e != cudaSuccess) { dev_free(ctx, inter); CK(e); }
+            ctx->launches++;
+            b_hi = a.b_lo;
+        }
+        la.in = inter; la.from_coeffs = 0;
+    }
+    cudaError_t e = launch_lde_last(la, ctx->stream);
+    ctx->launches++;
+    dev_free(ctx, inter, (uint64_t)coset_count * num_cols * n);
+    CK(e);
+    return 0;
+}
+
+static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
+    uint64_t words = 8 * b->num_leaves;  // all levels fit in 8N words
+    int rc = dev_alloc(ctx, &b->digests, words);
+    if (rc) return rc;
+    CK(launch_hash_rows(b->leaves, b->num_leaves, b->leaf_width, b->leaf_width, b->digests, ctx->stream));
+    ctx->launches++;
+    mark(ctx, 3);
+    CK(launch_merkle_levels(b->digests, b->num_levels, b->num_leaves, ctx->stream));
+    for (uint32_t l = 1; l < b->num_levels; l++) {
+        ctx->launches++;
+        if ((b->num_leaves >> l) <= TOP_LEVEL_NODES) break;
+    }
+    mark(ctx, 4);
+    return 0;
+}
+
+static void batch_release(qpzk_batch* b) {
+    if (!b) return;
+    qpzk_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    uint64_t n = 1ull << b->log_n;
+    dev_free(ctx, b->coeffs, (uint64_t)b->num_cols * n);
+    if (b->own_leaves) dev_free(ctx, b->leaves, b->num_leaves * b->leaf_width);
+    dev_free(ctx, b->digests);
+    delete b;
+}
+
+static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values, uint32_t log_n, uint32_t num_cols,
+                       uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin,
+                       uint32_t coset_count, bool keep_coeffs_copy, qpzk_batch** out) {
+    if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
+    *out = nullptr;
+    if (!cols_dev && num_cols) return fail(QPZK_EINVAL, "cols is null");
+    if (log_n > 26 || rate_bits > 8) return fail(QPZK_EINVAL, "log_n > 26 or rate_bits > 8");
+    uint32_t cosets = 1u << rate_bits;
+    if (!coset_count || (coset_count & (coset_count - 1)) || coset_begin % coset_count || coset_begin + coset_count > cosets)
+        return fail(QPZK_EINVAL, "bad coset range");
+    uint32_t lost = rate_bits - ilog2(coset_count);  // tree levels above this slice
+    uint32_t log_L = log_n + rate_bits;
+    if (cap_height > log_L) return fail(QPZK_EINVAL, "cap_height exceeds log2(number of leaves)");
+    if (cap_height < lost) return fail(QPZK_EINVAL, "cap_height too small for this coset split");
+    if (salt_dev && coset_count != cosets) return fail(QPZK_EINVAL, "salt is not supported with a coset split");
+    CK(cudaSetDevice(ctx->device));
+
+    qpzk_batch* b = new qpzk_batch();
+    b->ctx = ctx; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height - lost;
+    b->num_cols = num_cols; b->salt_cols = salt_dev ? QPZK_SALT_SIZE : 0; b->leaf_width = num_cols + b->salt_cols;
+    uint64_t n = 1ull << log_n;
+    b->num_leaves = n * coset_count;
+    b->log_leaves = log_n + ilog2(coset_count);
+    b->num_levels = b->log_leaves - b->cap_height + 1;
+    int rc;
+    for (int i = 0; i < 5; i++) ctx->ev_valid[i] = false;
+    mark(ctx, 0);
+    if (from_values || keep_coeffs_copy) {
+        if ((rc = dev_alloc(ctx, &b->coeffs, (uint64_t)num_cols * n))) { batch_release(b); return rc; }
+    }
+    const uint64_t* coeffs = b->coeffs;
+    if (from_values) {
+        if ((rc = run_intt(ctx, cols_dev, b->coeffs, log_n, num_cols))) { batch_release(b); return rc; }
+    } else if (keep_coeffs_copy) {
+        cudaError_t e = cudaMemcpyAsync(b->coeffs, cols_dev, (uint64_t)num_cols * n * sizeof(uint64_t),
+                                        cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { batch_release(b); CK(e); }
+    } else {
+        coeffs = cols_dev;
+    }
+    mark(ctx, 1);
+    if ((rc = dev_alloc(ctx, &b->leaves, b->num_leaves * b->leaf_width))) { batch_release(b); return rc; }
+    if ((rc = run_lde(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count))) {
+        batch_release(b); return rc;
+    }
+    if (salt_dev) {
+        cudaError_t e = launch_salt_scatter(salt_dev, b->leaves, log_L, num_cols, b->leaf_width, b->salt_cols, ctx->stream);
+        ctx->launches++;
+        if (e != cudaSuccess) { batch_release(b); CK(e); }
+    }
+    mark(ctx, 2);
+    if ((rc = build_tree(ctx, b))) { batch_release(b); return rc; }
+    *out = b;
+    return 0;
+}
+
+// stage a host matrix on the device, run fn, release the staging buffer
+template <typename F>
+static int with_staged(qpzk_ctx* ctx, const uint64_t* host, uint64_t words, const uint64_t* host2, uint64_t words2, F fn) {
+    uint64_t *d = nullptr, *d2 = nullptr;
+    int rc;
+    CK(cudaSetDevice(ctx->device));
+    if (host && words) {
+        if ((rc = dev_alloc(ctx, &d, words))) return rc;
+        CK(cudaMemcpyAsync(d, host, words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (host2 && words2) {
+        if ((rc = dev_alloc(ctx, &d2, words2))) { dev_free(ctx, d); return rc; }
+        CK(cudaMemcpyAsync(d2, host2, words2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = fn(d, d2);
+    dev_free(ctx, d, words);
+    dev_free(ctx, d2, words2);
+    return rc;
+}
+
+extern "C" int qpzk_commit_from_values_dev(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
+    GUARD_BEGIN return commit_impl(ctx, cols, true, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
+}
+extern "C" int qpzk_commit_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
+    GUARD_BEGIN return commit_impl(ctx, cols, false, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
+}
+extern "C" int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint32_t num_cols,
+                                                  uint32_t rate_bits, uint32_t cap_height, uint32_t coset_begin,
+                                                  uint32_t coset_count, qpzk_batch** out) {
+    GUARD_BEGIN return commit_impl(ctx, coeffs, false, log_n, num_cols, rate_bits, cap_height, nullptr, coset_begin, coset_count, false, out); GUARD_END
+}
+extern "C" int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
+    GUARD_BEGIN
+    if (!ctx || !values || !coeffs) return fail(QPZK_EINVAL, "null argument");
+    if (log_n > 26) return fail(QPZK_EINVAL, "log_n > 26");
+    CK(cudaSetDevice(ctx->device));
+    return run_intt(ctx, values, coeffs, log_n, num_cols);
+    GUARD_END
+}
+
+static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, uint32_t log_n, uint32_t num_cols,
+                       uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
+    if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
+    if (log_n > 26 || rate_bits > 8) return fail(QPZK_EINVAL, "log_n > 26 or rate_bits > 8");
+    if (!cols && num_cols) return fail(QPZK_EINVAL, "cols is null");
+    uint64_t n = 1ull << log_n;
+    uint64_t salt_words = salt ? (uint64_t)QPZK_SALT_SIZE * (n << rate_bits) : 0;
+    return with_staged(ctx, cols, (uint64_t)num_cols * n, salt, salt_words, [&](uint64_t* d, uint64_t* d2) {
+        return commit_impl(ctx, d, from_values, log_n, num_cols, rate_bits, cap_height, d2, 0, 1u << rate_bits, true, out);
+    });
+}
+extern "C" int qpzk_commit_from_values(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                                       uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
+    GUARD_BEGIN return commit_host(ctx, cols, true, log_n, num_cols, rate_bits, cap_height, salt, out); GUARD_END
+}
+extern "C" int qpzk_commit_from_coeffs(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
+                                       uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
+    GUARD_BEGIN return commit_host(ctx, cols, false, log_n, num_cols, rate_bits, cap_height, salt, out); GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// MerkleTree::new
+// ---------------------------------------------------------------------------------------------
+static int merkle_impl(qpzk_ctx* ctx, uint64_t* leaves_dev_owned, const uint64_t* leaves_dev_borrowed, uint64_t num_leaves,
+                       uint32_t leaf_len, uint32_t cap_height, qpzk_batch** out) {
+    qpzk_batch* b = new qpzk_batch();
+    b->ctx = ctx; b->cap_height = cap_height; b->leaf_width = leaf_len; b->num_cols = leaf_len;
+    b->num_leaves = num_leaves; b->log_leaves = ilog2(num_leaves); b->num_levels = b->log_leaves - cap_height + 1;
+    b->leaves = leaves_dev_owned ? leaves_dev_owned : const_cast<uint64_t*>(leaves_dev_borrowed);
+    b->own_leaves = leaves_dev_owned != nullptr;
+    b->num_cols = 0;  // no polynomials behind a bare tree
+    for (int i = 0; i < 5; i++) ctx->ev_valid[i] = false;
+    mark(ctx, 2);
+    int rc = build_tree(ctx, b);
+    if (rc) { batch_release(b); return rc; }
+    *out = b;
+    return 0;
+}
+
+static int merkle_check(qpzk_ctx* ctx, const void* leaves, uint64_t num_leaves, uint32_t cap_height, qpzk_batch** out) {
+    if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
+    *out = nullptr;
+    if (!num_leaves || (num_leaves & (num_leaves - 1))) return fail(QPZK_EINVAL, "num_leaves must be a power of two");
+    if (num_leaves > (1ull << 34)) return fail(QPZK_EINVAL, "too many leaves");
+    if (cap_height > ilog2(num_leaves)) return fail(QPZK_EINVAL, "cap_height exceeds log2(number of leaves)");
+    if (!leaves) return fail(QPZK_EINVAL, "leaves is null");
+    return 0;
+}
+
+extern "C" int qpzk_merkle_new_dev(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,
+                                   uint32_t cap_height, qpzk_batch** out) {
+    GUARD_BEGIN
+    int rc = merkle_check(ctx, leaves, num_leaves, cap_height, out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t* copy;
+    if ((rc = dev_alloc(ctx, &copy, num_leaves * leaf_len))) return rc;
+    CK(cudaMemcpyAsync(copy, leaves, num_leaves * leaf_len * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return merkle_impl(ctx, copy, nullptr, num_leaves, leaf_len, cap_height, out);
+    GUARD_END
+}
+extern "C" int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,
+                               uint32_t cap_height, qpzk_batch** out) {
+    GUARD_BEGIN
+    int rc = merkle_check(ctx, leaves, num_leaves, cap_height, out);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t* copy;
+    if ((rc = dev_alloc(ctx, &copy, num_leaves * leaf_len))) return rc;
+    CK(cudaMemcpyAsync(copy, leaves, num_leaves * leaf_len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    return merkle_impl(ctx, copy, nullptr, num_leaves, leaf_len, cap_height, out);
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch accessors
+// ---------------------------------------------------------------------------------------------
+extern "C" void qpzk_batch_free(qpzk_batch* b) { batch_release(b); }
+extern "C" uint64_t qpzk_batch_num_leaves(const qpzk_batch* b) { return b ? b->num_leaves : 0; }
+extern "C" uint32_t qpzk_batch_leaf_len(const qpzk_batch* b) { return b ? b->leaf_width : 0; }
+extern "C" uint32_t qpzk_batch_cap_len(const qpzk_batch* b) { return b ? 1u << b->cap_height : 0; }
+extern "C" const uint64_t* qpzk_batch_leaves_dev(const qpzk_batch* b) { return b ? b->leaves : nullptr; }
+extern "C" const uint64_t* qpzk_batch_coeffs_dev(const qpzk_batch* b) { return b ? b->coeffs : nullptr; }
+
+static int d2h(const qpzk_batch* b, uint64_t* dst, const uint64_t* src, uint64_t words) {
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaMemcpyAsync(dst, src, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->ctx->stream));
+    CK(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+extern "C" int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out) {
+    GUARD_BEGIN
+    if (!b || !out) return fail(QPZK_EINVAL, "null argument");
+    return d2h(b, out, b->digests + digest_level_off(b->num_leaves, b->num_levels - 1), 4ull << b->cap_height);
+    GUARD_END
+}
+extern "C" int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out) {
+    GUARD_BEGIN
+    if (!b || !out) return fail(QPZK_EINVAL, "null argument");
+    if (!b->coeffs) return fail(QPZK_EINVAL, "batch holds no polynomials");
+    return d2h(b, out, b->coeffs, (uint64_t)b->num_cols << b->log_n);
+    GUARD_END
+}
+extern "C" int qpzk_batch_rows(const qpzk_batch* b, uint64_t first_row, uint64_t num_rows, uint64_t* out) {
+    GUARD_BEGIN
+    if (!b || !out) return fail(QPZK_EINVAL, "null argument");
+    if (first_row + num_rows > b->num_leaves) return fail(QPZK_EINVAL, "row range out of bounds");
+    return d2h(b, out, b->leaves + first_row * b->leaf_width, num_rows * b->leaf_width);
+    GUARD_END
+}
+extern "C" int qpzk_batch_digests(const qpzk_batch* b, uint32_t level, uint64_t* out) {
+    GUARD_BEGIN
+    if (!b || !out) return fail(QPZK_EINVAL, "null argument");
+    if (level >= b->num_levels) return fail(QPZK_EINVAL, "level above the cap");
+    return d2h(b, out, b->digests + digest_level_off(b->num_leaves, level), 4 * (b->num_leaves >> level));
+    GUARD_END
+}
+
+extern "C" int qpzk_batch_open(const qpzk_batch* b, const uint64_t* idx, uint32_t k, uint64_t* rows, uint64_t* siblings) {
+    GUARD_BEGIN
+    if (!b || !idx || !rows || !siblings) return fail(QPZK_EINVAL, "null argument");
+    qpzk_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < k; i++) if (idx[i] >= b->num_leaves) return fail(QPZK_EINVAL, "leaf index out of bounds");
+    uint32_t ns = b->log_leaves - b->cap_height;
+    uint64_t per = b->leaf_width + 4ull * ns;
+    uint64_t *d_idx, *d_out;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_idx, k))) return rc;
+    if ((rc = dev_alloc(ctx, &d_out, per * k))) { dev_free(ctx, d_idx); return rc; }
+    CK(cudaMemcpyAsync(d_idx, idx, k * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    FriGatherArgs g{};
+    g.trees[0] = FriTreeDesc{b->leaves, b->digests, b->leaf_width, b->log_leaves, b->cap_height, 0};
+    g.num_trees = 1; g.num_oracles = 1; g.indices = d_idx; g.proof = d_out; g.query_base = 0; g.query_words = per;
+    CK(launch_fri_gather(g, k, ctx->stream));
+    ctx->launches++;
+    std::vector<uint64_t> h(per * k);
+    CK(cudaMemcpyAsync(h.data(), d_out, per * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < k; i++) {
+        memcpy(rows + (uint64_t)i * b->leaf_width, h.data() + i * per, b->leaf_width * sizeof(uint64_t));
+        memcpy(siblings + (uint64_t)i * 4 * ns, h.data() + i * per + b->leaf_width, 4ull * ns * sizeof(uint64_t));
+    }
+    dev_free(ctx, d_idx); dev_free(ctx, d_out);
+    return 0;
+    GUARD_END
+}
+
+extern "C" int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t point[2], uint64_t* out) {
+    GUARD_BEGIN
+    if (!b || !point || !out) return fail(QPZK_EINVAL, "null argument");
+    if (!b->coeffs) return fail(QPZK_EINVAL, "batch holds no polynomials");
+    if (point[0] >= GL_P || point[1] >= GL_P) return fail(QPZK_EINVAL, "point is not canonical");
+    qpzk_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    uint64_t* d;
+    int rc = dev_alloc(ctx, &d, 2ull * b->num_cols);
+    if (rc) return rc;
+    CK(launch_eval_ext(b->coeffs, 1ull << b->log_n, b->log_n, b->num_cols, point, d, ctx->stream));
+    ctx->launches++;
+    rc = d2h(b, out, d, 2ull * b->num_cols);
+    dev_free(ctx, d);
+    return rc;
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// Challenger
+// ---------------------------------------------------------------------------------------------
+extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {
+    GUARD_BEGIN
+    if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    qpzk_challenger* ch = new qpzk_challenger();
+    ch->ctx = ctx;
+    ch->scratch_words = 4096;
+    CK(cudaMalloc((void**)&ch->dev, sizeof(ChallengerDev)));
+    CK(cudaMalloc((void**)&ch->scratch, ch->scratch_words * sizeof(uint64_t)));
+    CK(cudaMemsetAsync(ch->dev, 0, sizeof(ChallengerDev), ctx->stream));
+    *out = ch;
+    return 0;
+    GUARD_END
+}
+extern "C" void qpzk_challenger_free(qpzk_challenger* ch) {
+    if (!ch) return;
+    cudaSetDevice(ch->ctx->device);
+    cudaStreamSynchronize(ch->ctx->stream);
+    cudaFree(ch->dev); cudaFree(ch->scratch);
+    delete ch;
+}
+extern "C" int qpzk_challenger_observe(qpzk_challenger* ch, const uint64_t* elems, uint32_t n) {
+    GUARD_BEGIN
+    if (!ch || (!elems && n)) return fail(QPZK_EINVAL, "null argument");
+    qpzk_ctx* ctx = ch->ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < n; i++) if (elems[i] >= GL_P) return fail(QPZK_EINVAL, "observed element is not canonical");
+    for (uint32_t off = 0; off < n; off += ch->scratch_words) {
+        uint32_t m = n - off < ch->scratch_words ? n - off : ch->scratch_words;
+        CK(cudaMemcpyAsync(ch->scratch, elems + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(launch_challenger_observe(ch->dev, ch->scratch, m, ctx->stream));
+        ctx->launches++;
+        CK(cudaStreamSynchronize(ctx->stream));  // scratch and the (pageable) source are reused
+    }
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_challenger_observe_cap(qpzk_challenger* ch, const qpzk_batch* b) {
+    GUARD_BEGIN
+    if (!ch || !b) return fail(QPZK_EINVAL, "null argument");
+    if (ch->ctx != b->ctx) return fail(QPZK_EINVAL, "challenger and batch belong to different contexts");
+    CK(cudaSetDevice(ch->ctx->device));
+    CK(launch_challenger_observe(ch->dev, b->digests + digest_level_off(b->num_leaves, b->num_levels - 1),
+                                 4u << b->cap_height, ch->ctx->stream));
+    ch->ctx->launches++;
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_challenger_get(qpzk_challenger* ch, uint64_t* out, uint32_t n) {
+    GUARD_BEGIN
+    if (!ch || (!out && n)) return fail(QPZK_EINVAL, "null argument");
+    if (n > ch->scratch_words) return fail(QPZK_EINVAL, "too many challenges in one call");
+    qpzk_ctx* ctx = ch->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_challenger_get(ch->dev, ch->scratch, n, ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ch->scratch, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+    GUARD_END
+}
+static_assert(sizeof(qpzk_challenger_state) == sizeof(ChallengerDev), "challenger state layouts must match");
+extern "C" int qpzk_challenger_export(qpzk_challenger* ch, qpzk_challenger_state* out) {
+    GUARD_BEGIN
+    if (!ch || !out) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ch->ctx->device));
+    CK(cudaMemcpyAsync(out, ch->dev, sizeof(ChallengerDev), cudaMemcpyDeviceToHost, ch->ctx->stream));
+    CK(cudaStreamSynchronize(ch->ctx->stream));
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_challenger_import(qpzk_challenger* ch, const qpzk_challenger_state* in) {
+    GUARD_BEGIN
+    if (!ch || !in) return fail(QPZK_EINVAL, "null argument");
+    if (in->input_len >= 8 || in->output_len > 8) return fail(QPZK_EINVAL, "bad challenger buffer lengths");
+    CK(cudaSetDevice(ch->ctx->device));
+    CK(cudaMemcpyAsync(ch->dev, in, sizeof(ChallengerDev), cudaMemcpyHostToDevice, ch->ctx->stream));
+    CK(cudaStreamSynchronize(ch->ctx->stream));
+    return 0;
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// FRI
+// ---------------------------------------------------------------------------------------------
+extern "C" int qpzk_fri_params_constant_arity(qpzk_fri_params* p, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
+                                              uint32_t pow_bits, uint32_t num_queries, uint32_t arity_bits,
+                                              uint32_t final_poly_bits) {
+    if (!p) return fail(QPZK_EINVAL, "null argument");
+    if (arity_bits < 1 || arity_bits > 4) return fail(QPZK_EINVAL, "arity_bits must be in 1..4");
+    memset(p, 0, sizeof *p);
+    p->rate_bits = rate_bits; p->cap_height = cap_height; p->proof_of_work_bits = pow_bits; p->num_query_rounds = num_queries;
+    uint32_t d = log_n;
+    while (d > final_poly_bits && d + rate_bits - arity_bits >= cap_height && p->num_rounds < QPZK_MAX_FRI_ROUNDS) {
+        p->arity_bits[p->num_rounds++] = arity_bits;
+        d -= arity_bits;
+    }
+    return 0;
+}
+
+extern "C" size_t qpzk_fri_proof_words(const qpzk_fri_params* p, uint32_t log_n, uint32_t num_oracles, const uint32_t* leaf_lens) {
+    uint32_t log_L = log_n + p->rate_bits;
+    size_t w = (size_t)p->num_rounds * ((size_t)4 << p->cap_height);
+    size_t per_q = 0;
+    for (uint32_t o = 0; o < num_oracles; o++) per_q += leaf_lens[o] + 4 * (size_t)(log_L - p->cap_height);
+    uint32_t lg = log_L, deg = log_n;
+    for (uint32_t r = 0; r < p->num_rounds; r++) {
+        lg -= p->arity_bits[r]; deg -= p->arity_bits[r];
+        per_q += ((size_t)2 << p->arity_bits[r]) + 4 * (size_t)(lg - p->cap_height);
+    }
+    return w + per_q * p->num_query_rounds + ((size_t)2 << deg) + 1;
+}
+
+struct DevBufs {  // frees everything it holds on scope exit
+    qpzk_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit DevBufs(qpzk_ctx* c) : ctx(c) {}
+    ~DevBufs() { for (void* p : ptrs) dev_free(ctx, p); }
+    int alloc(uint64_t** p, uint64_t words) { int rc = dev_alloc(ctx, p, words); if (!rc) ptrs.push_back(*p); return rc; }
+};
+
+extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
+                              const qpzk_fri_instance* inst, const qpzk_fri_params* p, qpzk_challenger* ch,
+                              uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out) {
+    GUARD_BEGIN
+    if (!ctx || !oracles || !inst || !p || !ch || !proof_out) return fail(QPZK_EINVAL, "null argument");
+    if (!num_oracles || num_oracles > MAX_ORACLES) return fail(QPZK_EINVAL, "num_oracles must be in 1..8");
+    if (!inst->num_batches || inst->num_batches > MAX_FRI_BATCHES) return fail(QPZK_EINVAL, "num_batches must be in 1..8");
+    if (p->num_rounds > MAX_FRI_ROUNDS) return fail(QPZK_EINVAL, "too many FRI rounds");
+    if (ch->ctx != ctx) return fail(QPZK_EINVAL, "challenger belongs to another context");
+    const uint32_t log_n = oracles[0]->log_n, rate_bits = p->rate_bits, log_L = log_n + rate_bits;
+    for (uint32_t o = 0; o < num_oracles; o++) {
+        const qpzk_batch* b = oracles[o];
+        if (!b || b->ctx != ctx) return fail(QPZK_EINVAL, "oracle belongs to another context");
+        if (!b->coeffs || b->log_n != log_n || b->rate_bits != rate_bits || b->num_leaves != (1ull << log_L))
+            return fail(QPZK_EINVAL, "oracles must be full polynomial batches of equal degree and rate");
+        if (b->cap_height != p->cap_height) return fail(QPZK_EINVAL, "oracle cap_height differs from fri params");
+    }
+    uint32_t total_arity = 0;
+    for (uint32_t r = 0; r < p->num_rounds; r++) {
+        if (p->arity_bits[r] < 1 || p->arity_bits[r] > 4) return fail(QPZK_EINVAL, "arity_bits must be in 1..4");
+        total_arity += p->arity_bits[r];
+        if (total_arity > log_n) return fail(QPZK_EINVAL, "reduction arities exceed the degree");
+        if (log_L - total_arity < p->cap_height) return fail(QPZK_EINVAL, "cap_height exceeds a FRI layer's tree height");
+    }
+    if (pow_witness_in != QPZK_POW_SEARCH && pow_witness_in >= GL_P) return fail(QPZK_EINVAL, "pow witness is not canonical");
+    if (p->proof_of_work_bits > 40) return fail(QPZK_EINVAL, "proof_of_work_bits too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    // ---- instance on the device
+    uint32_t total_polys = 0, max_k = 0;
+    FriCombineArgs ca{};
+    for (uint32_t b = 0; b < inst->num_batches; b++) {
+        ca.batch_off[b] = total_polys;
+        total_polys += inst->batch_sizes[b];
+        if (inst->batch_sizes[b] > max_k) max_k = inst->batch_sizes[b];
+        ca.points[2 * b] = inst->points[2 * b]; ca.points[2 * b + 1] = inst->points[2 * b + 1];
+        if (ca.points[2 * b] >= GL_P || ca.points[2 * b + 1] >= GL_P) return fail(QPZK_EINVAL, "opening point is not canonical");
+    }
+    ca.batch_off[inst->num_batches] = total_polys;
+    std::vector<bool> used(inst->num_batches * num_oracles, false);
+    {
+        uint32_t k = 0;
+        for (uint32_t b = 0; b < inst->num_batches; b++)
+            for (uint32_t j = 0; j < inst->batch_sizes[b]; j++, k++) {
+                uint32_t o = inst->poly_oracle[k];
+                if (o >= num_oracles || inst->poly_index[k] >= oracles[o]->num_cols) return fail(QPZK_EINVAL, "polynomial reference out of range");
+                used[b * num_oracles + o] = true;
+            }
+    }
+    DevBufs bufs(ctx);
+    int rc;
+    uint64_t *d_refs, *d_alpha, *d_apow, *d_evals, *d_reduced, *d_open, *d_found, *d_proof;
+    if ((rc = bufs.alloc(&d_refs, total_polys + 1))) return rc;  // two u32 arrays packed
+    uint32_t* d_po = reinterpret_cast<uint32_t*>(d_refs);
+    uint32_t* d_pi = d_po + total_polys;
+    CK(cudaMemcpyAsync(d_po, inst->poly_oracle, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pi, inst->poly_index, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if ((rc = bufs.alloc(&d_alpha, 8))) return rc;             // alpha, then beta per round reuses +2
+    if ((rc = bufs.alloc(&d_apow, 2ull * (max_k + 1)))) return rc;
+    uint64_t eval_words = 0;
+    for (uint32_t b = 0; b < inst->num_batches; b++)
+        for (uint32_t o = 0; o < num_oracles; o++) {
+            ca.eval_off[b * num_oracles + o] = (uint32_t)eval_words;
+            if (used[b * num_oracles + o]) eval_words += oracles[o]->num_cols;
+        }
+    if ((rc = bufs.alloc(&d_evals, 2 * eval_words))) return rc;
+    if ((rc = bufs.alloc(&d_reduced, 2ull * inst->num_batches))) return rc;
+    if ((rc = bufs.alloc(&d_open, 2ull * total_polys))) return rc;
+    if ((rc = bufs.alloc(&d_found, 4 + p->num_query_rounds))) return rc;  // [0]=found, [1]=witness, [2]=status, [4..]=indices
+
+    // ---- alpha and its powers; openings of every referenced oracle at every batch point
+    CK(launch_challenger_get(ch->dev, d_alpha, 2, st)); ctx->launches++;
+    CK(launch_alpha_powers(d_alpha, d_apow, max_k + 1, st)); ctx->launches++;
+    for (uint32_t b = 0; b < inst->num_batches; b++)
+        for (uint32_t o = 0; o < num_oracles; o++)
+            if (used[b * num_oracles + o]) {
+                CK(launch_eval_ext(oracles[o]->coeffs, 1ull << log_n, log_n, oracles[o]->num_cols, &ca.points[2 * b],
+                                   d_evals + 2ull * ca.eval_off[b * num_oracles + o], st));
+                ctx->launches++;
+            }
+
+    // ---- batch-opening polynomial, evaluated on the LDE domain in leaf order
+    PowTables fwd_n, inv_L;
+    CosetTables cs;
+    if ((rc = get_pow_tables(ctx, log_n, false, &fwd_n))) return rc;
+    if ((rc = get_pow_tables(ctx, log_L, true, &inv_L))) return rc;
+    if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
+    const uint64_t L = 1ull << log_L;
+    std::vector<uint64_t*> layer(p->num_rounds + 1);
+    if ((rc = bufs.alloc(&layer[0], 2 * L))) return rc;
+    ca.log_n = log_n; ca.rate_bits = rate_bits; ca.num_batches = inst->num_batches; ca.num_oracles = num_oracles;
+    for (uint32_t o = 0; o < num_oracles; o++) { ca.leaves[o] = oracles[o]->leaves; ca.leaf_width[o] = oracles[o]->leaf_width; }
+    ca.poly_oracle = d_po; ca.poly_index = d_pi; ca.apow = d_apow; ca.evals = d_evals; ca.reduced = d_reduced;
+    ca.openings_out = d_open; ca.values = layer[0]; ca.tw_lo = fwd_n.lo; ca.tw_hi = fwd_n.hi; ca.cs_lo = cs.lo;
+    CK(launch_fri_combine(ca, st)); ctx->launches += 2;
+
+    // ---- proof buffer layout
+    std::vector<uint32_t> leaf_lens(num_oracles);
+    for (uint32_t o = 0; o < num_oracles; o++) leaf_lens[o] = oracles[o]->leaf_width;
+    const size_t proof_words = qpzk_fri_proof_words(p, log_n, num_oracles, leaf_lens.data());
+    const size_t cap_words = (size_t)4 << p->cap_height;
+    const size_t final_len = (size_t)1 << (log_n - total_arity);
+    const size_t query_base = p->num_rounds * cap_words;
+    const size_t query_words = p->num_query_rounds ? (proof_words - 1 - 2 * final_len - query_base) / p->num_query_rounds : 0;
+    if ((rc = bufs.alloc(&d_proof, proof_words))) return rc;
+
+    // ---- commit phase
+    std::vector<uint64_t*> round_digests(p->num_rounds);
+    uint32_t lg = log_L;
+    uint64_t shift = GL_GENERATOR;
+    uint64_t* d_beta = d_alpha + 2;
+    for (uint32_t r = 0; r < p->num_rounds; r++) {
+        const uint32_t ab = p->arity_bits[r];
+        const uint64_t rows = 1ull << (lg - ab);
+        if ((rc = bufs.alloc(&round_digests[r], 8 * rows))) return rc;
+        CK(launch_hash_rows(layer[r], rows, 2u << ab, 2u << ab, round_digests[r], st)); ctx->launches++;
+        const uint32_t levels = (lg - ab) - p->cap_height + 1;
+        CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += levels > 1 ? 1 : 0;
+        const uint64_t* cap = round_digests[r] + digest_level_off(rows, levels - 1);
+        CK(cudaMemcpyAsync(d_proof + r * cap_words, cap, cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        CK(launch_challenger_observe(ch->dev, cap, (uint32_t)cap_words, st)); ctx->launches++;
+        CK(launch_challenger_get(ch->dev, d_beta, 2, st)); ctx->launches++;
+        if ((rc = bufs.alloc(&layer[r + 1], 2 * rows))) return rc;
+        FriFoldArgs fa{};
+        fa.in = layer[r]; fa.out = layer[r + 1]; fa.lg = lg; fa.log_L = log_L; fa.beta = d_beta;
+        fa.shift_inv = gl_inv_host(shift);
+        fa.arity_inv = gl_inv_host(1ull << ab);
+        uint64_t wa_inv = gl_inv_host(gl_root_of_unity_host(ab));
+        for (uint32_t j = 0; j < 8; j++) fa.itw[j] = gl_exp_host(wa_inv, j);
+        fa.itw_lo = inv_L.lo; fa.itw_hi = inv_L.hi;
+        CK(launch_fri_fold(fa, ab, st)); ctx->launches++;
+        shift = gl_exp_host(shift, 1ull << ab);
+        lg -= ab;
+    }
+    // ---- final polynomial: coefficients of the last layer, truncated; observed by the challenger
+    uint64_t* d_final = d_proof + proof_words - 1 - 2 * final_len;
+    {
+        FriFinalArgs fa{};
+        fa.in = layer[p->num_rounds]; fa.out = d_final; fa.lg = lg; fa.log_L = log_L; fa.rate_bits = rate_bits;
+        fa.shift_inv = gl_inv_host(shift); fa.len_inv = gl_inv_host(1ull << lg);
+        fa.itw_lo = inv_L.lo; fa.itw_hi = inv_L.hi;
+        cudaError_t e = launch_fri_final_poly(fa, st);
+        if (e == cudaErrorInvalidValue) return fail(QPZK_EINVAL, "final FRI layer too large (reduce more rounds)");
+        CK(e); ctx->launches++;
+        CK(launch_challenger_observe(ch->dev, d_final, (uint32_t)(2 * final_len), st)); ctx->launches++;
+    }
+    // ---- proof of work, query indices
+    unsigned long long* d_foundp = reinterpret_cast<unsigned long long*>(d_found);
+    uint64_t* d_indices = d_found + 4;
+    CK(launch_pow(ch->dev, p->proof_of_work_bits, pow_witness_in, p->num_query_rounds, L, d_foundp,
+                  d_proof + proof_words - 1, d_indices, reinterpret_cast<uint32_t*>(d_found + 2), ctx->num_sms, st));
+    ctx->launches += pow_witness_in == QPZK_POW_SEARCH ? 2 : 1;
+    // ---- query phase
+    FriGatherArgs g{};
+    for (uint32_t o = 0; o < num_oracles; o++)
+        g.trees[o] = FriTreeDesc{oracles[o]->leaves, oracles[o]->digests, oracles[o]->leaf_width, log_L, p->cap_height, 0};
+    lg = log_L;
+    for (uint32_t r = 0; r < p->num_rounds; r++) {
+        lg -= p->arity_bits[r];
+        g.trees[num_oracles + r] = FriTreeDesc{layer[r], round_digests[r], 2u << p->arity_bits[r], lg, p->cap_height, p->arity_bits[r]};
+    }
+    g.num_trees = num_oracles + p->num_rounds; g.num_oracles = num_oracles; g.indices = d_indices; g.proof = d_proof;
+    g.query_base = query_base; g.query_words = query_words;
+    CK(launch_fri_gather(g, p->num_query_rounds, st)); ctx->launches++;
+
+    uint32_t status[2] = {0, 0};
+    CK(cudaMemcpyAsync(proof_out, d_proof, proof_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (openings_out) CK(cudaMemcpyAsync(openings_out, d_open, 2ull * total_polys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d_found + 2, sizeof status, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!status[0]) return fail(QPZK_EPOW, "proof-of-work witness does not reach the required leading zeros");
+    return 0;
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// microbenchmarks (roofline denominators)
+// ---------------------------------------------------------------------------------------------
+extern "C" int qpzk_bench_imad(qpzk_ctx* ctx, uint32_t iters, double* imad_per_sec) {
+    GUARD_BEGIN
+    if (!ctx || !imad_per_sec) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    float ms = 0; double ops = 0;
+    CK(run_imad_bench(iters, ctx->num_sms, ctx->stream, &ms, &ops));
+    ctx->launches += 2;
+    *imad_per_sec = ops / (ms * 1e-3);
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_bench_poseidon(qpzk_ctx* ctx, uint32_t perms_per_thread, double* perms_per_sec) {
+    GUARD_BEGIN
+    if (!ctx || !perms_per_sec) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    float ms = 0; double total = 0;
+    CK(run_poseidon_bench(perms_per_thread, ctx->num_sms, ctx->stream, &ms, &total));
+    ctx->launches += 2;
+    *perms_per_sec = total / (ms * 1e-3);
+    return 0;
+    GUARD_END
+}

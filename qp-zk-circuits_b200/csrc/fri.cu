@@ -1,0 +1,255 @@
+// FRI kernels: polynomial openings at an extension point, the batch-opening combine evaluated
+// pointwise on the committed LDE leaves, value-domain folding, final-polynomial interpolation and the
+// query-phase gather.
+//
+// Replaces qp-plonky2 =1.5.5 `PolynomialBatch::prove_openings`, `fri_proof` / `fri_committed_trees` /
+// `fri_prover_query_rounds` and `OpeningSet::new`'s polynomial evaluations (SURVEY.md 8a rows a11, a12,
+// a14, a15; Appendix A.7/A.8); reference call sites: `prove()` at wormhole/prover/src/lib.rs:171-175,
+// wormhole/aggregator/src/private_batch/prover/lib.rs:326-330,
+// wormhole/aggregator/src/public_batch/prover/lib.rs:301-305; FRI parameters at
+// wormhole/circuit/src/profile.rs:168-174.
+//
+// Upstream works on COEFFICIENTS (reduce_polys_base, divide_by_linear, reduce_with_powers on chunks,
+// coset_fft per round).  Field elements are canonical, so any algebraically equal computation gives
+// identical bits; this file computes the same objects in the VALUE domain, where every step is an
+// independent per-point (or per-chunk) kernel over data that is already resident and already in leaf
+// (bit-reversed) order:
+//   final_values[p] = sum_b alpha^(k_{b+1}+...) * (sum_j alpha^j f_bj(x_p) - sum_j alpha^j f_bj(z_b)) / (x_p - z_b)
+//   fold:  16 consecutive values = one coset {x * w16^u};  size-16 inverse DFT gives a_t = x^t P_t(x^16),
+//          folded value = sum_t a_t (beta/x)^t, and lands at the bit-reversed position of the next layer.
+#include "internal.cuh"
+#include "goldilocks.cuh"
+#include "ntt_local.cuh"
+
+namespace qpzk {
+
+__device__ __forceinline__ ext2 ext_shfl_xor(ext2 v, int m) {
+    ext2 r;
+    r.a = __shfl_xor_sync(0xffffffffu, v.a, m);
+    r.b = __shfl_xor_sync(0xffffffffu, v.b, m);
+    return r;
+}
+
+// out[c] = poly_c(z) for every column; coefficients column-major, natural order.  One block per column;
+// thread t runs Horner in z^T over coefficients t, t+T, ... (coalesced), then the block sums z^t * partial_t.
+__global__ void __launch_bounds__(EVAL_THREADS)
+eval_ext_kernel(const uint64_t* __restrict__ coeffs, uint64_t col_stride, uint32_t log_n, ext2 z,
+                uint64_t* __restrict__ out) {
+    __shared__ ext2 red[EVAL_THREADS];
+    const uint64_t n = 1ull << log_n;
+    const uint64_t* c = coeffs + (uint64_t)blockIdx.x * col_stride;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    ext2 zT = ext_exp(z, T);
+    ext2 acc = ext_make(0, 0);
+    if (t < n) {
+        uint64_t last = t + ((n - 1 - t) / T) * T;
+        for (int64_t i = (int64_t)last; i >= (int64_t)t; i -= T) {
+            acc = ext_mul(acc, zT);
+            acc.a = gl_add(acc.a, c[i]);
+        }
+        acc = ext_mul(acc, ext_exp(z, t));
+    }
+    red[t] = acc;
+    __syncthreads();
+    for (uint32_t h = T >> 1; h > 0; h >>= 1) {
+        if (t < h) red[t] = ext_add(red[t], red[t + h]);
+        __syncthreads();
+    }
+    if (t == 0) { out[2 * blockIdx.x] = red[0].a; out[2 * blockIdx.x + 1] = red[0].b; }
+}
+
+// apow[j] = alpha^j for j in [0, count)
+__global__ void alpha_powers_kernel(const uint64_t* __restrict__ alpha, uint64_t* __restrict__ apow, uint32_t count) {
+    if (threadIdx.x || blockIdx.x) return;
+    ext2 a = ext_make(alpha[0], alpha[1]);
+    ext2 p = ext_make(1, 0);
+    for (uint32_t j = 0; j < count; j++) {
+        apow[2 * j] = p.a; apow[2 * j + 1] = p.b;
+        p = ext_mul(p, a);
+    }
+}
+
+// reduced[b] = sum_j alpha^j * opening_bj  with opening_bj = evals[b][oracle_j][index_j]
+__global__ void reduce_openings_kernel(FriCombineArgs a) {
+    uint32_t b = blockIdx.x;
+    if (threadIdx.x) return;
+    ext2 acc = ext_make(0, 0);
+    uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
+    for (uint32_t j = 0; j < k; j++) {
+        uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
+        const uint64_t* ev = a.evals + 2 * ((uint64_t)a.eval_off[b * a.num_oracles + o] + idx);
+        ext2 ap = ext_make(a.apow[2 * j], a.apow[2 * j + 1]);
+        acc = ext_add(acc, ext_mul(ap, ext_make(ev[0], ev[1])));
+        // also record the opening itself in instance order (the caller may want OpeningSet values)
+        a.openings_out[2 * (off + j)] = ev[0];
+        a.openings_out[2 * (off + j) + 1] = ev[1];
+    }
+    a.reduced[2 * b] = acc.a; a.reduced[2 * b + 1] = acc.b;
+}
+
+// One warp per LDE point p (leaf order).  x_p = s_j' * w_n^bitrev(r) for p = j' * n + r.
+__global__ void __launch_bounds__(COMBINE_THREADS) fri_combine_kernel(FriCombineArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n = 1ull << a.log_n;
+    if (p >= (n << a.rate_bits)) return;
+    const uint32_t jp = (uint32_t)(p >> a.log_n);
+    const uint64_t r = p & (n - 1);
+    const uint64_t m = a.log_n ? (__brevll(r) >> (64 - a.log_n)) : 0;
+    const uint64_t x = gl_mul(a.cs_lo[(size_t)jp * TW_LO_SIZE + 1], tw_get(a.tw_lo, a.tw_hi, m));
+    ext2 sum = ext_make(0, 0);
+    for (uint32_t b = 0; b < a.num_batches; b++) {
+        uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
+        ext2 acc = ext_make(0, 0);
+        for (uint32_t j = lane; j < k; j += 32) {
+            uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
+            uint64_t v = a.leaves[o][p * a.leaf_width[o] + idx];
+            acc = ext_add(acc, ext_scale(ext_make(a.apow[2 * j], a.apow[2 * j + 1]), v));
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) acc = ext_add(acc, ext_shfl_xor(acc, sft));
+        ext2 numer = ext_sub(acc, ext_make(a.reduced[2 * b], a.reduced[2 * b + 1]));
+        ext2 denom = ext_make(gl_sub(x, a.points[2 * b]), gl_neg(a.points[2 * b + 1]));
+        ext2 q = ext_mul(numer, ext_inv(denom));
+        sum = ext_add(ext_mul(sum, ext_make(a.apow[2 * k], a.apow[2 * k + 1])), q);
+    }
+    if (lane == 0) { a.values[2 * p] = sum.a; a.values[2 * p + 1] = sum.b; }
+}
+
+// Fold one layer in the value domain.  in: 2^lg ext values in bit-reversed order on the coset
+// shift * <w_{2^lg}>;  out: 2^(lg-AB) values, bit-reversed order, on the coset shift^(2^AB) * <w_{2^(lg-AB)}>.
+template <int AB>
+__global__ void __launch_bounds__(128) fri_fold_kernel(FriFoldArgs a) {
+    constexpr int A = 1 << AB;
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lgo = a.lg - AB;
+    if (c >> lgo) return;
+    ext2 v[A];
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.in + 2 * (c << AB));
+#pragma unroll
+    for (int k = 0; k < A; k++) { ulonglong2 t = src[k]; v[k] = ext_make(t.x, t.y); }
+    // inverse DFT, decimation in time: memory order is bit-reversed u, output natural t
+#pragma unroll
+    for (int lh = 0; lh < AB; lh++) {
+        const int h = 1 << lh;
+#pragma unroll
+        for (int t = 0; t < A / 2; t++) {
+            const int j = t & (h - 1), e0 = ((t >> lh) << (lh + 1)) + j, e1 = e0 + h;
+            ext2 y = v[e1];
+            if (j) y = ext_scale(y, a.itw[j << (AB - 1 - lh)]);
+            ext2 x0 = v[e0];
+            v[e0] = ext_add(x0, y);
+            v[e1] = ext_sub(x0, y);
+        }
+    }
+    // x_c^-1 = shift^-1 * w_{2^lg}^(-m),  m = bitrev_{lg-AB}(c);  table holds powers of w_L^-1
+    const uint64_t m = lgo ? (__brevll(c) >> (64 - lgo)) : 0;
+    const uint64_t xinv = gl_mul(a.shift_inv, tw_get(a.itw_lo, a.itw_hi, m << (a.log_L - a.lg)));
+    ext2 beta = ext_make(a.beta[0], a.beta[1]);
+    ext2 gam = ext_scale(beta, xinv);
+    ext2 acc = v[A - 1];
+#pragma unroll
+    for (int t = A - 2; t >= 0; t--) acc = ext_add(ext_mul(acc, gam), v[t]);
+    acc = ext_scale(acc, a.arity_inv);
+    a.out[2 * c] = acc.a; a.out[2 * c + 1] = acc.b;
+}
+
+// Coefficients of the last layer: values (bit-reversed) on shift * <w_len>  ->  natural coefficients,
+// truncated to len >> rate_bits.  Single block; the ext vector is a 2-wide tile for the shared transform.
+__global__ void __launch_bounds__(NTT_THREADS) fri_final_poly_kernel(FriFinalArgs a) {
+    extern __shared__ uint64_t smem[];
+    const uint32_t len = 1u << a.lg;
+    uint64_t* sm = smem;
+    uint64_t* ltw = smem + 2 * (size_t)len;
+    for (uint32_t j = threadIdx.x; j < (len >> 1); j += blockDim.x)
+        ltw[j] = tw_get(a.itw_lo, a.itw_hi, (uint64_t)j << (a.log_L - a.lg));
+    for (uint32_t i = threadIdx.x; i < 2 * len; i += blockDim.x) sm[i] = a.in[i];
+    __syncthreads();
+    local_ntt<true>(sm, ltw, a.lg, 2);
+    const uint32_t keep = len >> a.rate_bits;
+    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
+        uint64_t f = gl_mul(a.len_inv, gl_exp(a.shift_inv, i));
+        a.out[2 * i] = gl_mul(sm[2 * i], f);
+        a.out[2 * i + 1] = gl_mul(sm[2 * i + 1], f);
+    }
+}
+
+// Query phase: one block per query copies leaf rows and Merkle paths into the flat proof buffer.
+__global__ void __launch_bounds__(128) fri_query_gather_kernel(FriGatherArgs a) {
+    const uint32_t q = blockIdx.x;
+    uint64_t x = a.indices[q];
+    uint64_t* out = a.proof + a.query_base + (uint64_t)q * a.query_words;
+    for (uint32_t t = 0; t < a.num_trees; t++) {
+        const FriTreeDesc& d = a.trees[t];
+        if (t >= a.num_oracles) x >>= d.arity_bits;  // FRI round trees are indexed by the coset index
+        const uint64_t* row = d.leaves + x * d.leaf_len;
+        for (uint32_t i = threadIdx.x; i < d.leaf_len; i += blockDim.x) out[i] = row[i];
+        out += d.leaf_len;
+        const uint32_t ns = d.log_leaves - d.cap_height;
+        const uint64_t N = 1ull << d.log_leaves;
+        for (uint32_t i = threadIdx.x; i < 4 * ns; i += blockDim.x) {
+            uint32_t l = i >> 2;
+            uint64_t node = (x >> l) ^ 1;
+            out[i] = d.digests[digest_level_off(N, l) + 4 * node + (i & 3)];
+        }
+        out += 4 * ns;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_eval_ext(const uint64_t* coeffs, uint64_t col_stride, uint32_t log_n, uint32_t num_cols,
+                            const uint64_t z[2], uint64_t* out_dev, cudaStream_t st) {
+    if (!num_cols) return cudaSuccess;
+    ext2 zz; zz.a = z[0]; zz.b = z[1];
+    eval_ext_kernel<<<num_cols, EVAL_THREADS, 0, st>>>(coeffs, col_stride, log_n, zz, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, uint32_t count, cudaStream_t st) {
+    alpha_powers_kernel<<<1, 32, 0, st>>>(alpha_dev, apow_dev, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st) {
+    reduce_openings_kernel<<<a.num_batches, 32, 0, st>>>(a);
+    uint64_t L = 1ull << (a.log_n + a.rate_bits);
+    uint64_t blocks = (L * 32 + COMBINE_THREADS - 1) / COMBINE_THREADS;
+    fri_combine_kernel<<<(unsigned)blocks, COMBINE_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fri_fold(const FriFoldArgs& a, uint32_t arity_bits, cudaStream_t st) {
+    uint64_t chunks = 1ull << (a.lg - arity_bits);
+    unsigned blocks = (unsigned)((chunks + 127) / 128);
+    switch (arity_bits) {
+        case 1: fri_fold_kernel<1><<<blocks, 128, 0, st>>>(a); break;
+        case 2: fri_fold_kernel<2><<<blocks, 128, 0, st>>>(a); break;
+        case 3: fri_fold_kernel<3><<<blocks, 128, 0, st>>>(a); break;
+        case 4: fri_fold_kernel<4><<<blocks, 128, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st) {
+    uint32_t len = 1u << a.lg;
+    size_t smem = (2 * (size_t)len + len / 2 + 1) * sizeof(uint64_t);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)fri_final_poly_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fri_final_poly_kernel<<<1, NTT_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fri_gather(const FriGatherArgs& a, uint32_t num_queries, cudaStream_t st) {
+    if (!num_queries) return cudaSuccess;
+    fri_query_gather_kernel<<<num_queries, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace qpzk

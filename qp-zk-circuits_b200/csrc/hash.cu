@@ -1,0 +1,244 @@
+// Poseidon hashing kernels: Merkle leaf sponge straight from the row-major LDE buffer, 2-to-1
+// compression levels down to the cap, the device-resident Fiat-Shamir challenger, and the FRI
+// proof-of-work grinder.
+//
+// Replaces qp-plonky2 =1.5.5 `MerkleTree::new` (fill_digests_buf), `PoseidonHash::{hash_no_pad,
+// hash_or_noop,two_to_one}`, `Challenger` and `fri_proof_of_work` (SURVEY.md 8a rows a7, a8, a10,
+// a13; Appendix A.4-A.7).  Reached in the reference only through `prove()`
+// (wormhole/prover/src/lib.rs:171-175) and `CircuitBuilder::build` (wormhole/circuit/src/circuit.rs:206-216).
+#include "internal.cuh"
+#include "poseidon.cuh"
+#include "poseidon_rc.cuh"
+
+namespace qpzk {
+
+// ---------------------------------------------------------------------------------------------
+// constants upload (once per device)
+// ---------------------------------------------------------------------------------------------
+cudaError_t upload_poseidon_constants() {
+    static uint64_t split[2 * 372];
+    for (int i = 0; i < 372; i++) {
+        uint64_t c = i < 360 ? QPZK_POSEIDON_RC_HOST[i] : 0;
+        split[i] = c & 0xFFFFFFFFu;
+        split[372 + i] = c >> 32;
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_rc_split, split, sizeof split);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_rc_first, QPZK_POSEIDON_RC_HOST, 12 * sizeof(uint64_t));
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaf digests: digest[row] = hash_or_noop(leaves[row, 0..leaf_len))
+// One thread per row; overwrite-mode sponge, rate 8.  The next chunk is loaded before the
+// permutation of the current one so the (strided, L1-served) loads hide under ~20k integer ops.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HASH_THREADS)
+hash_rows_kernel(const uint64_t* __restrict__ leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
+                 uint64_t* __restrict__ digests) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    const uint64_t* p = leaves + row * row_stride;
+    uint64_t* d = digests + 4 * row;
+    if (leaf_len <= 4) {  // hash_or_noop: short rows are copied, zero-padded
+#pragma unroll
+        for (uint32_t i = 0; i < 4; i++) d[i] = i < leaf_len ? p[i] : 0;
+        return;
+    }
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    uint32_t full = leaf_len / 8, tail = leaf_len % 8;
+    uint64_t nxt[8];
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) nxt[i] = __ldg(p + i);
+    }
+    for (uint32_t c = 0; c < full; c++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = nxt[i];
+        if (c + 1 < full) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) nxt[i] = __ldg(p + 8 * (c + 1) + i);
+        }
+        poseidon_permute(s);
+    }
+    if (tail) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((uint32_t)i < tail) s[i] = __ldg(p + 8 * full + i);
+        poseidon_permute(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = gl_canon(s[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one Merkle level: parent[i] = two_to_one(child[2i], child[2i+1])
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void compress_pair(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent,
+                                              uint64_t i) {
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + 8 * i);
+    ulonglong2 v0 = c[0], v1 = c[1], v2 = c[2], v3 = c[3];
+    uint64_t s[12] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y, 0, 0, 0, 0};
+    poseidon_permute(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(parent + 4 * i);
+    o[0] = make_ulonglong2(gl_canon(s[0]), gl_canon(s[1]));
+    o[1] = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
+}
+
+__global__ void __launch_bounds__(HASH_THREADS)
+merkle_level_kernel(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, uint64_t num_parents) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < num_parents) compress_pair(child, parent, i);
+}
+
+// The top of the tree (few nodes per level) in ONE single-block launch: levels are separated by a
+// block barrier instead of a kernel boundary.  Level l lives at digest_level_off(num_leaves, l).
+__global__ void __launch_bounds__(TOP_THREADS)
+merkle_top_kernel(uint64_t* __restrict__ digests, uint32_t first_level, uint32_t last_level, uint64_t num_leaves) {
+    for (uint32_t l = first_level; l <= last_level; l++) {
+        uint64_t parents = num_leaves >> l;
+        const uint64_t* child = digests + digest_level_off(num_leaves, l - 1);
+        uint64_t* parent = digests + digest_level_off(num_leaves, l);
+        for (uint64_t i = threadIdx.x; i < parents; i += blockDim.x) compress_pair(child, parent, i);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Challenger (duplex sponge, overwrite mode; pop challenges from the back of the output buffer)
+// ---------------------------------------------------------------------------------------------
+__device__ void ch_duplex(ChallengerDev* c) {
+    uint64_t s[12];
+    for (uint32_t i = 0; i < c->in_len; i++) c->state[i] = c->in[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = c->state[i];
+    c->in_len = 0;
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 12; i++) c->state[i] = gl_canon(s[i]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) c->out[i] = c->state[i];
+    c->out_len = 8;
+}
+
+__device__ void ch_observe(ChallengerDev* c, uint64_t x) {
+    c->out_len = 0;
+    c->in[c->in_len++] = x;
+    if (c->in_len == 8) ch_duplex(c);
+}
+
+__device__ uint64_t ch_get(ChallengerDev* c) {
+    if (c->in_len > 0 || c->out_len == 0) ch_duplex(c);
+    return c->out[--c->out_len];
+}
+
+__global__ void challenger_observe_kernel(ChallengerDev* c, const uint64_t* __restrict__ elems, uint32_t n) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (uint32_t i = 0; i < n; i++) ch_observe(c, elems[i]);
+}
+
+__global__ void challenger_get_kernel(ChallengerDev* c, uint64_t* __restrict__ out, uint32_t n) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (uint32_t i = 0; i < n; i++) out[i] = ch_get(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fri_proof_of_work: find the MINIMUM witness w such that, after observing w, the next challenge
+// (state[7] of the duplex) has >= pow_bits leading zeros.  Upstream uses rayon find_any (any valid
+// witness); the minimum is a valid choice and makes the result deterministic.
+// Threads poll `*found`; nobody waits on anybody, so there is no inter-block dependency.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HASH_THREADS)
+pow_grind_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, unsigned long long* found) {
+    uint64_t base[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) base[i] = c->state[i];
+    uint32_t pos = c->in_len;  // < 8 by the challenger invariant
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if ((uint32_t)i < pos) base[i] = c->in[i];
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t cand = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; cand < GL_P; cand += stride) {
+        if (cand >= *(volatile unsigned long long*)found) break;
+        uint64_t s[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = base[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((uint32_t)i == pos) s[i] = cand;
+        poseidon_permute(s);
+        uint64_t resp = gl_canon(s[7]);
+        if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) {
+            atomicMin(found, (unsigned long long)cand);
+            break;
+        }
+    }
+}
+
+// observe the witness (either the ground one or a caller-supplied one), draw the PoW response,
+// then draw the query indices.  status[0] = 1 if the response has enough leading zeros.
+__global__ void pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found,
+                                              uint64_t forced_witness, uint32_t pow_bits, uint32_t num_queries,
+                                              uint64_t lde_size, uint64_t* __restrict__ witness_out,
+                                              uint64_t* __restrict__ indices, uint32_t* status) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t w = forced_witness == ~0ULL ? (uint64_t)*found : forced_witness;
+    ch_observe(c, w);
+    uint64_t resp = ch_get(c);
+    status[0] = (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) ? 1u : 0u;
+    *witness_out = w;
+    for (uint32_t q = 0; q < num_queries; q++) indices[q] = ch_get(c) % lde_size;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
+                             uint64_t* digests, cudaStream_t st) {
+    if (num_rows == 0) return cudaSuccess;
+    uint64_t blocks = (num_rows + HASH_THREADS - 1) / HASH_THREADS;
+    hash_rows_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(leaves, num_rows, leaf_len, row_stride, digests);
+    return cudaGetLastError();
+}
+
+// digests: level 0 already filled.  Builds levels 1..num_levels-1.
+cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st) {
+    uint32_t l = 1;
+    for (; l < num_levels; l++) {
+        uint64_t parents = num_leaves >> l;
+        if (parents <= TOP_LEVEL_NODES) break;
+        uint64_t blocks = (parents + HASH_THREADS - 1) / HASH_THREADS;
+        merkle_level_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(
+            digests + digest_level_off(num_leaves, l - 1), digests + digest_level_off(num_leaves, l), parents);
+    }
+    if (l < num_levels) merkle_top_kernel<<<1, TOP_THREADS, 0, st>>>(digests, l, num_levels - 1, num_leaves);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    challenger_observe_kernel<<<1, 32, 0, st>>>(c, elems_dev, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    challenger_get_kernel<<<1, 32, 0, st>>>(c, out_dev, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
+                       uint64_t lde_size, unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices,
+                       uint32_t* status, int num_sms, cudaStream_t st) {
+    if (forced_witness == ~0ULL) {
+        cudaError_t e = cudaMemsetAsync(found_dev, 0xFF, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        pow_grind_kernel<<<num_sms * 4, HASH_THREADS, 0, st>>>(c, pow_bits, found_dev);
+    }
+    pow_finish_and_indices_kernel<<<1, 32, 0, st>>>(c, found_dev, forced_witness, pow_bits, num_queries, lde_size,
+                                                    witness_out, indices, status);
+    return cudaGetLastError();
+}
+
+}  // namespace qpzk

@@ -1,0 +1,149 @@
+// Internal declarations shared by the translation units of libqpzk.so (not part of the C ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace qpzk {
+
+constexpr int HASH_THREADS = 128;          // threads per block for one-thread-per-permutation kernels
+constexpr int TOP_THREADS = 256;           // single-block kernel for the top of a Merkle tree
+constexpr uint64_t TOP_LEVEL_NODES = 256;  // levels with <= this many parents go to the single-block kernel
+
+// Digest buffer of a tree with N leaves: level 0 (leaf digests, 4N words) first, then level 1 (2N words), ...
+// Word offset of level l:  8N - (8N >> l).
+__host__ __device__ __forceinline__ uint64_t digest_level_off(uint64_t num_leaves, uint32_t l) {
+    return 8 * num_leaves - ((8 * num_leaves) >> l);
+}
+
+// Device-resident Fiat-Shamir challenger; same field order as qpzk_challenger_state in include/qpzk.h.
+struct ChallengerDev {
+    uint64_t state[12];
+    uint64_t in[8];
+    uint64_t out[8];
+    uint32_t in_len;
+    uint32_t out_len;
+};
+
+// ---- ntt.cu ----
+constexpr int NTT_THREADS = 256;
+constexpr uint32_t TW_LO_BITS = 10;             // two-level power tables: w^idx = lo[idx & 1023] * hi[idx >> 10]
+constexpr uint32_t TW_LO_SIZE = 1u << TW_LO_BITS;
+
+enum NttMode : uint32_t {
+    NTT_INV_FIRST = 0,        // DIT, position bits [0, s); gathers the natural-order input at bit-reversed addresses
+    NTT_INV_GENERIC = 1,      // DIT, position bits [b_lo, b_lo+s), pre-twiddle
+    NTT_FWD_COSET_FIRST = 2,  // DIF, top bits [b_lo, log_n); scales by the coset powers on load; one output per coset
+    NTT_FWD_GENERIC = 3,      // DIF, position bits [b_lo, b_lo+s), post-twiddle
+};
+
+struct NttPassArgs {
+    const uint64_t* in;
+    uint64_t* out;
+    uint64_t in_stride, out_stride;  // words between consecutive arrays
+    uint64_t num_arrays;             // grid.y
+    uint32_t log_n, b_lo, s, W;
+    uint32_t mode, num_cosets;
+    const uint64_t *tw_lo, *tw_hi;   // powers of w_n (forward) or w_n^-1 (inverse)
+    const uint64_t *cs_lo, *cs_hi;   // per-coset powers of s_j = g * w_L^bitrev(j)
+    uint64_t cs_hi_size;
+    uint64_t scale;                  // multiplied into every output (1/n on the last inverse pass), 1 = none
+};
+
+struct LdeLastArgs {
+    const uint64_t* in;   // from_coeffs ? coefficients [C][n] : intermediate [coset][C][n]
+    uint64_t in_stride;
+    uint64_t* leaves;     // [2^rate_bits * n][leaf_width]
+    uint32_t log_n, s, num_cols, leaf_width, num_cosets, from_coeffs;
+    const uint64_t *tw_lo, *tw_hi, *cs_lo, *cs_hi;
+    uint64_t cs_hi_size;
+};
+
+cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st);
+cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st);
+cudaError_t launch_bitrev_copy(const uint64_t* in, uint64_t* out, uint32_t log_n, uint64_t num_arrays,
+                               uint64_t in_stride, uint64_t out_stride, cudaStream_t st);
+cudaError_t launch_salt_scatter(const uint64_t* salt, uint64_t* leaves, uint32_t log_L, uint32_t num_cols,
+                                uint32_t leaf_width, uint32_t salt_cols, cudaStream_t st);
+
+// ---- hash.cu ----
+cudaError_t upload_poseidon_constants();
+cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
+                             uint64_t* digests, cudaStream_t st);
+cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st);
+cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
+cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);
+cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
+                       uint64_t lde_size, unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices,
+                       uint32_t* status, int num_sms, cudaStream_t st);
+
+// ---- fri.cu ----
+constexpr int EVAL_THREADS = 256;
+constexpr int COMBINE_THREADS = 256;
+constexpr uint32_t MAX_ORACLES = 8;
+constexpr uint32_t MAX_FRI_ROUNDS = 16;
+constexpr uint32_t MAX_FRI_BATCHES = 8;
+
+struct FriCombineArgs {
+    uint32_t log_n, rate_bits, num_batches, num_oracles;
+    const uint64_t* leaves[MAX_ORACLES];
+    uint32_t leaf_width[MAX_ORACLES];
+    uint32_t batch_off[MAX_FRI_BATCHES + 1];  // prefix sums of batch sizes
+    uint32_t eval_off[MAX_FRI_BATCHES * MAX_ORACLES];  // ext offset of evals[b][o] inside `evals`
+    uint64_t points[2 * MAX_FRI_BATCHES];
+    const uint32_t *poly_oracle, *poly_index;  // device
+    const uint64_t* apow;      // device: alpha^j, ext
+    const uint64_t* evals;     // device: per (batch, oracle) evaluations of every column at the batch point
+    uint64_t* reduced;         // device: 2 * num_batches
+    uint64_t* openings_out;    // device: 2 * total polys, instance order
+    uint64_t* values;          // device: 2 * L, leaf order
+    const uint64_t *tw_lo, *tw_hi;  // powers of w_n
+    const uint64_t* cs_lo;          // per-coset powers (entry 1 = the coset shift itself)
+};
+
+struct FriFoldArgs {
+    const uint64_t* in;
+    uint64_t* out;
+    uint32_t lg, log_L;
+    const uint64_t* beta;          // device, ext
+    uint64_t shift_inv, arity_inv;
+    uint64_t itw[8];               // w_arity^-j
+    const uint64_t *itw_lo, *itw_hi;  // powers of w_L^-1
+};
+
+struct FriFinalArgs {
+    const uint64_t* in;
+    uint64_t* out;
+    uint32_t lg, log_L, rate_bits;
+    uint64_t shift_inv, len_inv;
+    const uint64_t *itw_lo, *itw_hi;
+};
+
+struct FriTreeDesc {
+    const uint64_t* leaves;
+    const uint64_t* digests;
+    uint32_t leaf_len, log_leaves, cap_height, arity_bits;
+};
+
+struct FriGatherArgs {
+    FriTreeDesc trees[MAX_ORACLES + MAX_FRI_ROUNDS];
+    uint32_t num_trees, num_oracles;
+    const uint64_t* indices;  // device
+    uint64_t* proof;          // device
+    uint64_t query_base, query_words;
+};
+
+cudaError_t launch_eval_ext(const uint64_t* coeffs, uint64_t col_stride, uint32_t log_n, uint32_t num_cols,
+                            const uint64_t z[2], uint64_t* out_dev, cudaStream_t st);
+cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, uint32_t count, cudaStream_t st);
+cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st);
+cudaError_t launch_fri_fold(const FriFoldArgs& a, uint32_t arity_bits, cudaStream_t st);
+cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st);
+cudaError_t launch_fri_gather(const FriGatherArgs& a, uint32_t num_queries, cudaStream_t st);
+
+}  // namespace qpzk
+
+namespace qpzk {
+// ---- bench.cu ----
+cudaError_t run_imad_bench(uint32_t iters, int num_sms, cudaStream_t st, float* ms, double* ops);
+cudaError_t run_poseidon_bench(uint32_t perms, int num_sms, cudaStream_t st, float* ms, double* total);
+}  // namespace qpzk

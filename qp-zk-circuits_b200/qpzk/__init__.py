@@ -1,0 +1,440 @@
+"""Host-side mirror of the plonky2 commitment surface over libqpzk.so (ctypes on the C ABI of include/qpzk.h).
+
+The reference's host language is Rust (no cargo/rustc in this image), so this module plays the role of the
+`-sys` + safe wrapper crate that a `[patch.crates-io]` fork of qp-plonky2 =1.5.5 would contain (see
+INTEGRATION.md).  Names, argument meaning and error behaviour follow the upstream API the reference reaches
+through `prove()` (reference wormhole/prover/src/lib.rs:171-175):
+
+    PolynomialBatch.from_values(values, rate_bits, blinding_salt, cap_height)
+    PolynomialBatch.from_coeffs(polynomials, rate_bits, blinding_salt, cap_height)
+    PolynomialBatch.prove_openings(instance, oracles, challenger, fri_params)
+    MerkleTree.new(leaves, cap_height) / .cap / .prove(leaf_index)
+    Challenger.observe_elements / observe_cap / get_n_challenges
+
+There is no CPU fallback: importing works anywhere (so symbol checks run without a GPU), but creating a
+Context fails loudly when the library or a Blackwell device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libqpzk.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "qpzk.h")
+
+P = 0xFFFFFFFF00000001
+GENERATOR = 14293326489335486720
+POW_SEARCH = 0xFFFFFFFFFFFFFFFF
+SALT_SIZE = 4
+MAX_FRI_ROUNDS = 16
+U64P = C.POINTER(C.c_uint64)
+U32P = C.POINTER(C.c_uint32)
+
+
+class QpzkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("qpzk error %d: %s" % (code, msg))
+        self.code = code
+
+
+class FriParams(C.Structure):
+    _fields_ = [("rate_bits", C.c_uint32), ("cap_height", C.c_uint32), ("proof_of_work_bits", C.c_uint32),
+                ("num_query_rounds", C.c_uint32), ("num_rounds", C.c_uint32),
+                ("arity_bits", C.c_uint32 * MAX_FRI_ROUNDS)]
+
+    @property
+    def reduction_arity_bits(self):
+        return list(self.arity_bits)[:self.num_rounds]
+
+
+class _FriInstance(C.Structure):
+    _fields_ = [("num_batches", C.c_uint32), ("points", U64P), ("batch_sizes", U32P),
+                ("poly_oracle", U32P), ("poly_index", U32P)]
+
+
+class ChallengerState(C.Structure):
+    _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8),
+                ("output_buffer", C.c_uint64 * 8), ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libqpzk.so and declare every prototype of include/qpzk.h.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpzkError(-2, "libqpzk.so not built (run `make -C qp-zk-circuits_b200` or __graft_entry__.build()); "
+                            "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    sig = {
+        "qpzk_last_error": (C.c_char_p, []),
+        "qpzk_version": (C.c_char_p, []),
+        "qpzk_ctx_create": (i, [i, C.POINTER(vp)]),
+        "qpzk_ctx_create_on_stream": (i, [i, vp, C.POINTER(vp)]),
+        "qpzk_ctx_destroy": (None, [vp]),
+        "qpzk_ctx_synchronize": (i, [vp]),
+        "qpzk_ctx_set_zeroize": (i, [vp, i]),
+        "qpzk_ctx_set_timing": (i, [vp, i]),
+        "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
+        "qpzk_ctx_launch_count": (u64, [vp]),
+        "qpzk_commit_from_values": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
+        "qpzk_commit_from_coeffs": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
+        "qpzk_commit_from_values_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
+        "qpzk_commit_from_coeffs_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
+        "qpzk_commit_cosets_from_coeffs_dev": (i, [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(vp)]),
+        "qpzk_intt_columns_dev": (i, [vp, vp, vp, u32, u32]),
+        "qpzk_merkle_new": (i, [vp, vp, u64, u32, u32, C.POINTER(vp)]),
+        "qpzk_merkle_new_dev": (i, [vp, vp, u64, u32, u32, C.POINTER(vp)]),
+        "qpzk_batch_free": (None, [vp]),
+        "qpzk_batch_num_leaves": (u64, [vp]),
+        "qpzk_batch_leaf_len": (u32, [vp]),
+        "qpzk_batch_cap_len": (u32, [vp]),
+        "qpzk_batch_cap": (i, [vp, vp]),
+        "qpzk_batch_coeffs": (i, [vp, vp]),
+        "qpzk_batch_rows": (i, [vp, u64, u64, vp]),
+        "qpzk_batch_digests": (i, [vp, u32, vp]),
+        "qpzk_batch_open": (i, [vp, vp, u32, vp, vp]),
+        "qpzk_batch_eval_ext": (i, [vp, vp, vp]),
+        "qpzk_batch_leaves_dev": (vp, [vp]),
+        "qpzk_batch_coeffs_dev": (vp, [vp]),
+        "qpzk_challenger_create": (i, [vp, C.POINTER(vp)]),
+        "qpzk_challenger_free": (None, [vp]),
+        "qpzk_challenger_observe": (i, [vp, vp, u32]),
+        "qpzk_challenger_observe_cap": (i, [vp, vp]),
+        "qpzk_challenger_get": (i, [vp, vp, u32]),
+        "qpzk_challenger_export": (i, [vp, C.POINTER(ChallengerState)]),
+        "qpzk_challenger_import": (i, [vp, C.POINTER(ChallengerState)]),
+        "qpzk_fri_params_constant_arity": (i, [C.POINTER(FriParams), u32, u32, u32, u32, u32, u32, u32]),
+        "qpzk_fri_proof_words": (C.c_size_t, [C.POINTER(FriParams), u32, u32, U32P]),
+        "qpzk_fri_prove": (i, [vp, C.POINTER(vp), u32, C.POINTER(_FriInstance), C.POINTER(FriParams), vp, u64, vp, vp]),
+        "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
+        "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)  # AttributeError here = header/library mismatch
+        f.restype, f.argtypes = res, args
+    L._qpzk_symbols = sorted(sig)
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise QpzkError(rc, load_library().qpzk_last_error().decode())
+
+
+def _host(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + one CUDA stream (qpzk_ctx).  `stream` may be a raw cudaStream_t (int), e.g.
+    torch.cuda.current_stream().cuda_stream, so that torch events on that stream time the kernels."""
+
+    def __init__(self, device=0, stream=None):
+        L = load_library()
+        h = C.c_void_p()
+        if stream is None:
+            _check(L.qpzk_ctx_create(device, C.byref(h)))
+        else:
+            _check(L.qpzk_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
+        self.h, self.device, self.L = h, device, L
+
+    def synchronize(self):
+        _check(self.L.qpzk_ctx_synchronize(self.h))
+
+    def set_zeroize(self, on):
+        _check(self.L.qpzk_ctx_set_zeroize(self.h, int(on)))
+
+    def set_timing(self, on):
+        _check(self.L.qpzk_ctx_set_timing(self.h, int(on)))
+
+    def last_commit_timing(self):
+        ms = (C.c_float * 4)()
+        _check(self.L.qpzk_ctx_last_commit_timing(self.h, ms))
+        return dict(zip(("intt_ms", "lde_ms", "leaf_hash_ms", "merkle_levels_ms"), [float(x) for x in ms]))
+
+    def launch_count(self):
+        return int(self.L.qpzk_ctx_launch_count(self.h))
+
+    def bench_imad(self, iters=4096):
+        v = C.c_double()
+        _check(self.L.qpzk_bench_imad(self.h, iters, C.byref(v)))
+        return v.value
+
+    def bench_poseidon(self, perms=64):
+        v = C.c_double()
+        _check(self.L.qpzk_bench_poseidon(self.h, perms, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.L.qpzk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MerkleTree:
+    """MerkleTree<F, PoseidonHash>: `.cap`, `.prove(i)`, `.get(i)`."""
+
+    def __init__(self, ctx, handle, owner=None):
+        self.ctx, self.h, self._owner = ctx, handle, owner
+        L = ctx.L
+        self.num_leaves = int(L.qpzk_batch_num_leaves(handle))
+        self.leaf_len = int(L.qpzk_batch_leaf_len(handle))
+        self.cap_len = int(L.qpzk_batch_cap_len(handle))
+        self.cap_height = self.cap_len.bit_length() - 1
+
+    @classmethod
+    def new(cls, ctx, leaves, cap_height):
+        """leaves: (num_leaves, leaf_len) uint64, row-major."""
+        a = np.ascontiguousarray(leaves, dtype=np.uint64)
+        if a.ndim != 2:
+            raise QpzkError(-1, "leaves must be a 2-D array")
+        h = C.c_void_p()
+        _check(ctx.L.qpzk_merkle_new(ctx.h, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], cap_height, C.byref(h)))
+        t = cls(ctx, h)
+        t._free = True
+        return t
+
+    @property
+    def cap(self):
+        out = np.zeros((self.cap_len, 4), np.uint64)
+        _check(self.ctx.L.qpzk_batch_cap(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def digests(self, level=0):
+        out = np.zeros((self.num_leaves >> level, 4), np.uint64)
+        _check(self.ctx.L.qpzk_batch_digests(self.h, level, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get(self, i):
+        return self.rows(i, 1)[0]
+
+    def rows(self, first, count):
+        out = np.zeros((count, self.leaf_len), np.uint64)
+        _check(self.ctx.L.qpzk_batch_rows(self.h, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def open(self, indices):
+        """(rows, siblings) for several leaves: MerkleTree::prove + the leaf data."""
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        ns = (self.num_leaves.bit_length() - 1) - self.cap_height
+        rows = np.zeros((idx.size, self.leaf_len), np.uint64)
+        sib = np.zeros((idx.size, ns, 4), np.uint64)
+        _check(self.ctx.L.qpzk_batch_open(self.h, idx.ctypes.data_as(C.c_void_p), idx.size,
+                                          rows.ctypes.data_as(C.c_void_p), sib.ctypes.data_as(C.c_void_p)))
+        return rows, sib
+
+    def prove(self, leaf_index):
+        return self.open([leaf_index])[1][0]
+
+    def free(self):
+        if getattr(self, "_free", False) and self.h:
+            self.ctx.L.qpzk_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PolynomialBatch:
+    """PolynomialBatch<F, C, D>: coefficients + salted LDE leaves + Merkle tree, all device resident."""
+
+    def __init__(self, ctx, handle, log_n, num_cols, rate_bits, cap_height, salted):
+        self.ctx, self.h = ctx, handle
+        self.degree_log, self.num_cols, self.rate_bits, self.cap_height = log_n, num_cols, rate_bits, cap_height
+        self.blinding = salted
+        self.merkle_tree = MerkleTree(ctx, handle, owner=self)
+        self.leaf_len = self.merkle_tree.leaf_len
+
+    @classmethod
+    def _commit(cls, ctx, fn, cols, rate_bits, salt, cap_height):
+        a = np.ascontiguousarray(cols, dtype=np.uint64)
+        if a.ndim != 2:
+            raise QpzkError(-1, "expected a (num_polys, n) array")
+        num_cols, n = a.shape
+        if n == 0 or n & (n - 1):
+            raise QpzkError(-1, "polynomial length must be a power of two")
+        log_n = n.bit_length() - 1
+        sp = None
+        if salt is not None:
+            s = np.ascontiguousarray(salt, dtype=np.uint64)
+            if s.shape != (SALT_SIZE, n << rate_bits):
+                raise QpzkError(-1, "salt must have shape (4, n << rate_bits)")
+            sp = s.ctypes.data_as(C.c_void_p)
+        h = C.c_void_p()
+        _check(fn(ctx.h, a.ctypes.data_as(C.c_void_p), log_n, num_cols, rate_bits, cap_height, sp, C.byref(h)))
+        return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, salt is not None)
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, blinding_salt, cap_height):
+        return cls._commit(ctx, ctx.L.qpzk_commit_from_values, values, rate_bits, blinding_salt, cap_height)
+
+    @classmethod
+    def from_coeffs(cls, ctx, polynomials, rate_bits, blinding_salt, cap_height):
+        return cls._commit(ctx, ctx.L.qpzk_commit_from_coeffs, polynomials, rate_bits, blinding_salt, cap_height)
+
+    @classmethod
+    def from_device(cls, ctx, dev_ptr, log_n, num_cols, rate_bits, cap_height, values=True, salt_ptr=None):
+        """Inputs already resident in HBM (dev_ptr = raw device address, e.g. tensor.data_ptr())."""
+        fn = ctx.L.qpzk_commit_from_values_dev if values else ctx.L.qpzk_commit_from_coeffs_dev
+        h = C.c_void_p()
+        _check(fn(ctx.h, C.c_void_p(dev_ptr), log_n, num_cols, rate_bits, cap_height,
+                  C.c_void_p(salt_ptr) if salt_ptr else None, C.byref(h)))
+        return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, salt_ptr is not None)
+
+    @classmethod
+    def cosets_from_coeffs_device(cls, ctx, dev_ptr, log_n, num_cols, rate_bits, cap_height, coset_begin, coset_count):
+        h = C.c_void_p()
+        _check(ctx.L.qpzk_commit_cosets_from_coeffs_dev(ctx.h, C.c_void_p(dev_ptr), log_n, num_cols, rate_bits,
+                                                        cap_height, coset_begin, coset_count, C.byref(h)))
+        return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, False)
+
+    @property
+    def polynomials(self):
+        out = np.zeros((self.num_cols, 1 << self.degree_log), np.uint64)
+        _check(self.ctx.L.qpzk_batch_coeffs(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @property
+    def cap(self):
+        return self.merkle_tree.cap
+
+    def get_lde_values(self, index, step=1):
+        """Upstream get_lde_values(index, step): the row of LDE point index*step, without the salt."""
+        log_L = self.degree_log + self.rate_bits
+        i = index * step
+        r = int(format(i, "0%db" % log_L)[::-1], 2) if log_L else 0
+        return self.merkle_tree.get(r)[:self.num_cols]
+
+    def eval_ext(self, point):
+        pt, pp = _host(point)
+        out = np.zeros((self.num_cols, 2), np.uint64)
+        _check(self.ctx.L.qpzk_batch_eval_ext(self.h, pp, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @staticmethod
+    def prove_openings(instance, oracles, challenger, fri_params, pow_witness=None, return_openings=False):
+        """PolynomialBatch::prove_openings -> flat FriProof (layout in include/qpzk.h)."""
+        ctx = oracles[0].ctx
+        L = ctx.L
+        arr = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
+        lens = np.array([o.leaf_len for o in oracles], np.uint32)
+        words = L.qpzk_fri_proof_words(C.byref(fri_params), oracles[0].degree_log, len(oracles),
+                                       lens.ctypes.data_as(U32P))
+        proof = np.zeros(words, np.uint64)
+        openings = np.zeros((int(instance.sizes.sum()), 2), np.uint64)
+        w = POW_SEARCH if pow_witness is None else pow_witness
+        _check(L.qpzk_fri_prove(ctx.h, arr, len(oracles), C.byref(instance.c), C.byref(fri_params), challenger.h, w,
+                                proof.ctypes.data_as(C.c_void_p), openings.ctypes.data_as(C.c_void_p)))
+        return (proof, openings) if return_openings else proof
+
+    def free(self):
+        if self.h:
+            self.ctx.L.qpzk_batch_free(self.h)
+            self.h = None
+            self.merkle_tree.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class FriInstanceInfo:
+    """batches = [(point (2 words), [(oracle_index, polynomial_index), ...]), ...]"""
+
+    def __init__(self, batches):
+        self.points = np.array([w for pt, _ in batches for w in pt], np.uint64)
+        self.sizes = np.array([len(ps) for _, ps in batches], np.uint32)
+        self.po = np.array([o for _, ps in batches for o, _ in ps], np.uint32)
+        self.pi = np.array([i for _, ps in batches for _, i in ps], np.uint32)
+        self.c = _FriInstance(len(batches), self.points.ctypes.data_as(U64P), self.sizes.ctypes.data_as(U32P),
+                              self.po.ctypes.data_as(U32P), self.pi.ctypes.data_as(U32P))
+
+
+def fri_params(log_n, rate_bits=3, cap_height=4, proof_of_work_bits=16, num_query_rounds=28, arity_bits=4,
+               final_poly_bits=5):
+    """FriConfig + ConstantArityBits(4, 5) as used by the reference (wormhole/circuit/src/profile.rs:168-174)."""
+    p = FriParams()
+    _check(load_library().qpzk_fri_params_constant_arity(C.byref(p), log_n, rate_bits, cap_height, proof_of_work_bits,
+                                                         num_query_rounds, arity_bits, final_poly_bits))
+    return p
+
+
+class Challenger:
+    """Challenger<F, PoseidonHash>; the sponge lives on the device so that caps never travel to the host."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(ctx.L.qpzk_challenger_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def observe_elements(self, elems):
+        a, p = _host(np.asarray(elems, dtype=np.uint64).reshape(-1))
+        _check(self.ctx.L.qpzk_challenger_observe(self.h, p, a.size))
+
+    observe_element = lambda self, x: self.observe_elements([x])
+    observe_hash = observe_elements
+    observe_extension_elements = observe_elements
+
+    def observe_cap(self, cap_or_batch):
+        if isinstance(cap_or_batch, (PolynomialBatch, MerkleTree)):
+            _check(self.ctx.L.qpzk_challenger_observe_cap(self.h, cap_or_batch.h))
+        else:
+            self.observe_elements(cap_or_batch)
+
+    def get_n_challenges(self, n):
+        out = np.zeros(n, np.uint64)
+        _check(self.ctx.L.qpzk_challenger_get(self.h, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def get_challenge(self):
+        return int(self.get_n_challenges(1)[0])
+
+    def get_extension_challenge(self):
+        return self.get_n_challenges(2)
+
+    def export_state(self):
+        s = ChallengerState()
+        _check(self.ctx.L.qpzk_challenger_export(self.h, C.byref(s)))
+        return (list(s.sponge_state), list(s.input_buffer)[:s.input_len], list(s.output_buffer)[:s.output_len])
+
+    def import_state(self, sponge_state, input_buffer=(), output_buffer=()):
+        s = ChallengerState()
+        for k, v in enumerate(sponge_state):
+            s.sponge_state[k] = v
+        for k, v in enumerate(input_buffer):
+            s.input_buffer[k] = v
+        for k, v in enumerate(output_buffer):
+            s.output_buffer[k] = v
+        s.input_len, s.output_len = len(input_buffer), len(output_buffer)
+        _check(self.ctx.L.qpzk_challenger_import(self.h, C.byref(s)))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.qpzk_challenger_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
