@@ -58,6 +58,9 @@ struct qpzk_ctx {
     cudaEvent_t ev[5] = {};
     bool ev_valid[5] = {};
     uint64_t launches = 0;
+    // The context stays alive until qpzk_ctx_destroy has been called AND every batch / challenger created
+    // from it has been freed, whatever order a binding's finalizers run in.
+    int refs = 1;
     std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
     std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
 };
@@ -204,8 +207,8 @@ extern "C" int qpzk_ctx_create(int device, qpzk_ctx** out) {
 extern "C" int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx** out) {
     GUARD_BEGIN return ctx_create_impl(device, cuda_stream, false, out); GUARD_END
 }
-extern "C" void qpzk_ctx_destroy(qpzk_ctx* ctx) {
-    if (!ctx) return;
+static void ctx_unref(qpzk_ctx* ctx) {
+    if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
@@ -213,6 +216,9 @@ extern "C" void qpzk_ctx_destroy(qpzk_ctx* ctx) {
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+extern "C" void qpzk_ctx_destroy(qpzk_ctx* ctx) {
+    if (ctx) ctx_unref(ctx);
 }
 extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
     if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
@@ -362,6 +368,7 @@ static void batch_release(qpzk_batch* b) {
     if (b->own_leaves) dev_free(ctx, b->leaves, b->num_leaves * b->leaf_width);
     dev_free(ctx, b->digests);
     delete b;
+    ctx_unref(ctx);
 }
 
 static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values, uint32_t log_n, uint32_t num_cols,
@@ -382,6 +389,7 @@ static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values
     CK(cudaSetDevice(ctx->device));
 
     qpzk_batch* b = new qpzk_batch();
+    ctx->refs++;
     b->ctx = ctx; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height - lost;
     b->num_cols = num_cols; b->salt_cols = salt_dev ? QPZK_SALT_SIZE : 0; b->leaf_width = num_cols + b->salt_cols;
     uint64_t n = 1ull << log_n;
@@ -488,6 +496,7 @@ extern "C" int qpzk_commit_from_coeffs(qpzk_ctx* ctx, const uint64_t* cols, uint
 static int merkle_impl(qpzk_ctx* ctx, uint64_t* leaves_dev_owned, const uint64_t* leaves_dev_borrowed, uint64_t num_leaves,
                        uint32_t leaf_len, uint32_t cap_height, qpzk_batch** out) {
     qpzk_batch* b = new qpzk_batch();
+    ctx->refs++;
     b->ctx = ctx; b->cap_height = cap_height; b->leaf_width = leaf_len; b->num_cols = leaf_len;
     b->num_leaves = num_leaves; b->log_leaves = ilog2(num_leaves); b->num_levels = b->log_leaves - cap_height + 1;
     b->leaves = leaves_dev_owned ? leaves_dev_owned : const_cast<uint64_t*>(leaves_dev_borrowed);
@@ -637,6 +646,7 @@ extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     CK(cudaSetDevice(ctx->device));
     qpzk_challenger* ch = new qpzk_challenger();
+    ctx->refs++;
     ch->ctx = ctx;
     ch->scratch_words = 4096;
     CK(cudaMalloc((void**)&ch->dev, sizeof(ChallengerDev)));
@@ -651,7 +661,9 @@ extern "C" void qpzk_challenger_free(qpzk_challenger* ch) {
     cudaSetDevice(ch->ctx->device);
     cudaStreamSynchronize(ch->ctx->stream);
     cudaFree(ch->dev); cudaFree(ch->scratch);
+    qpzk_ctx* ctx = ch->ctx;
     delete ch;
+    ctx_unref(ctx);
 }
 extern "C" int qpzk_challenger_observe(qpzk_challenger* ch, const uint64_t* elems, uint32_t n) {
     GUARD_BEGIN
@@ -900,13 +912,11 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         CK(e); ctx->launches++;
         CK(launch_challenger_observe(ch->dev, d_final, (uint32_t)(2 * final_len), st)); ctx->launches++;
     }
-    // ---- proof of work, query indices
+    // ---- proof of work, query indices, query phase.  The grinder tests windows of candidates in
+    // increasing order; a window without a hit (probability e^-4 per window) is followed by the next one.
     unsigned long long* d_foundp = reinterpret_cast<unsigned long long*>(d_found);
     uint64_t* d_indices = d_found + 4;
-    CK(launch_pow(ch->dev, p->proof_of_work_bits, pow_witness_in, p->num_query_rounds, L, d_foundp,
-                  d_proof + proof_words - 1, d_indices, reinterpret_cast<uint32_t*>(d_found + 2), ctx->num_sms, st));
-    ctx->launches += pow_witness_in == QPZK_POW_SEARCH ? 2 : 1;
-    // ---- query phase
+    uint32_t* d_status = reinterpret_cast<uint32_t*>(d_found + 2);
     FriGatherArgs g{};
     for (uint32_t o = 0; o < num_oracles; o++)
         g.trees[o] = FriTreeDesc{oracles[o]->leaves, oracles[o]->digests, oracles[o]->leaf_width, log_L, p->cap_height, 0};
@@ -915,15 +925,22 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         lg -= p->arity_bits[r];
         g.trees[num_oracles + r] = FriTreeDesc{layer[r], round_digests[r], 2u << p->arity_bits[r], lg, p->cap_height, p->arity_bits[r]};
     }
-    g.num_trees = num_oracles + p->num_rounds; g.num_oracles = num_oracles; g.indices = d_indices; g.proof = d_proof;
-    g.query_base = query_base; g.query_words = query_words;
-    CK(launch_fri_gather(g, p->num_query_rounds, st)); ctx->launches++;
-
+    g.num_trees = num_oracles + p->num_rounds; g.num_oracles = num_oracles; g.indices = d_indices; g.status = d_status;
+    g.proof = d_proof; g.query_base = query_base; g.query_words = query_words;
+    const uint64_t window = 1ull << (p->proof_of_work_bits + 2 < 14 ? 14 : p->proof_of_work_bits + 2);
     uint32_t status[2] = {0, 0};
-    CK(cudaMemcpyAsync(proof_out, d_proof, proof_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    if (openings_out) CK(cudaMemcpyAsync(openings_out, d_open, 2ull * total_polys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, d_found + 2, sizeof status, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    for (uint64_t base = 0;; base += window) {
+        CK(launch_pow(ch->dev, p->proof_of_work_bits, pow_witness_in, p->num_query_rounds, L, base, window, d_foundp,
+                      d_proof + proof_words - 1, d_indices, d_status, st));
+        ctx->launches += pow_witness_in == QPZK_POW_SEARCH ? 2 : 1;
+        CK(launch_fri_gather(g, p->num_query_rounds, st)); ctx->launches++;
+        CK(cudaMemcpyAsync(proof_out, d_proof, proof_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (openings_out) CK(cudaMemcpyAsync(openings_out, d_open, 2ull * total_polys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status, d_status, sizeof status, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (status[0] != 2) break;
+        if (base + window >= GL_P - window) return fail(QPZK_EPOW, "proof of work failed: no witness in the field");
+    }
     if (!status[0]) return fail(QPZK_EPOW, "proof-of-work witness does not reach the required leading zeros");
     return 0;
     GUARD_END

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(NTT_THREADS) fri_final_poly_kernel(FriFinalArg
 // Query phase: one block per query copies leaf rows and Merkle paths into the flat proof buffer.
 __global__ void __launch_bounds__(128) fri_query_gather_kernel(FriGatherArgs a) {
     const uint32_t q = blockIdx.x;
+    if (a.status && a.status[0] != 1) return;  // no valid PoW witness yet: the indices are not defined
     uint64_t x = a.indices[q];
     uint64_t* out = a.proof + a.query_base + (uint64_t)q * a.query_words;
     for (uint32_t t = 0; t < a.num_trees; t++) {

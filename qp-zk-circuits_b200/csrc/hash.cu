@@ -147,43 +147,43 @@ __global__ void challenger_get_kernel(ChallengerDev* c, uint64_t* __restrict__ o
 // fri_proof_of_work: find the MINIMUM witness w such that, after observing w, the next challenge
 // (state[7] of the duplex) has >= pow_bits leading zeros.  Upstream uses rayon find_any (any valid
 // witness); the minimum is a valid choice and makes the result deterministic.
-// Threads poll `*found`; nobody waits on anybody, so there is no inter-block dependency.
+// One launch tests the window [base, base+count): one candidate per thread, atomicMin of the hits.
+// Windows are tried in increasing order, so the first window with a hit contains the global minimum.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HASH_THREADS)
-pow_grind_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, unsigned long long* found) {
-    uint64_t base[12];
+pow_grind_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, uint64_t base, uint64_t count,
+                 unsigned long long* found) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t cand = base + i;
+    if (cand >= GL_P) return;
+    uint64_t s[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) base[i] = c->state[i];
+    for (int k = 0; k < 12; k++) s[k] = c->state[k];
     uint32_t pos = c->in_len;  // < 8 by the challenger invariant
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if ((uint32_t)i < pos) base[i] = c->in[i];
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t cand = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; cand < GL_P; cand += stride) {
-        if (cand >= *(volatile unsigned long long*)found) break;
-        uint64_t s[12];
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = base[i];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if ((uint32_t)i == pos) s[i] = cand;
-        poseidon_permute(s);
-        uint64_t resp = gl_canon(s[7]);
-        if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) {
-            atomicMin(found, (unsigned long long)cand);
-            break;
-        }
+    for (int k = 0; k < 8; k++) {
+        if ((uint32_t)k < pos) s[k] = c->in[k];
+        if ((uint32_t)k == pos) s[k] = cand;
     }
+    poseidon_permute(s);
+    uint64_t resp = gl_canon(s[7]);
+    if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) atomicMin(found, (unsigned long long)cand);
 }
 
-// observe the witness (either the ground one or a caller-supplied one), draw the PoW response,
-// then draw the query indices.  status[0] = 1 if the response has enough leading zeros.
+// Observe the witness (the ground one or a caller-supplied one), draw the PoW response, then draw the
+// query indices.  status[0]: 1 = ok, 0 = witness does not reach the difficulty, 2 = no hit in this window
+// (challenger untouched; the host launches the next window).
 __global__ void pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found,
                                               uint64_t forced_witness, uint32_t pow_bits, uint32_t num_queries,
                                               uint64_t lde_size, uint64_t* __restrict__ witness_out,
                                               uint64_t* __restrict__ indices, uint32_t* status) {
     if (threadIdx.x || blockIdx.x) return;
-    uint64_t w = forced_witness == ~0ULL ? (uint64_t)*found : forced_witness;
+    uint64_t w = forced_witness;
+    if (forced_witness == ~0ULL) {
+        w = (uint64_t)*found;
+        if (w == ~0ULL) { status[0] = 2; return; }
+    }
     ch_observe(c, w);
     uint64_t resp = ch_get(c);
     status[0] = (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) ? 1u : 0u;
@@ -229,12 +229,14 @@ cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t 
 }
 
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
-                       uint64_t lde_size, unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices,
-                       uint32_t* status, int num_sms, cudaStream_t st) {
+                       uint64_t lde_size, uint64_t window_base, uint64_t window_count,
+                       unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices, uint32_t* status,
+                       cudaStream_t st) {
     if (forced_witness == ~0ULL) {
         cudaError_t e = cudaMemsetAsync(found_dev, 0xFF, sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        pow_grind_kernel<<<num_sms * 4, HASH_THREADS, 0, st>>>(c, pow_bits, found_dev);
+        uint64_t blocks = (window_count + HASH_THREADS - 1) / HASH_THREADS;
+        pow_grind_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(c, pow_bits, window_base, window_count, found_dev);
     }
     pow_finish_and_indices_kernel<<<1, 32, 0, st>>>(c, found_dev, forced_witness, pow_bits, num_queries, lde_size,
                                                     witness_out, indices, status);

@@ -73,8 +73,9 @@ cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
-                       uint64_t lde_size, unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices,
-                       uint32_t* status, int num_sms, cudaStream_t st);
+                       uint64_t lde_size, uint64_t window_base, uint64_t window_count,
+                       unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices, uint32_t* status,
+                       cudaStream_t st);
 
 // ---- fri.cu ----
 constexpr int EVAL_THREADS = 256;
@@ -128,6 +129,7 @@ struct FriGatherArgs {
     FriTreeDesc trees[MAX_ORACLES + MAX_FRI_ROUNDS];
     uint32_t num_trees, num_oracles;
     const uint64_t* indices;  // device
+    const uint32_t* status;   // device, may be null; the kernel does nothing unless status[0] == 1
     uint64_t* proof;          // device
     uint64_t query_base, query_words;
 };

@@ -1,0 +1,65 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/qpzk.h declares, its pure
+host functions agree with the oracle, and the product fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def _declared_symbols(header):
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qpzk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(qpzk):
+    lib = qpzk.load_library()
+    declared = _declared_symbols(qpzk.HEADER_PATH)
+    assert len(declared) >= 40
+    raw = C.CDLL(qpzk.LIB_PATH)
+    missing = [s for s in declared if not hasattr(raw, s)]
+    assert not missing, missing
+    # and the Python mirror binds exactly the declared set
+    assert sorted(lib._qpzk_symbols) == declared
+
+
+def test_version_string(qpzk):
+    assert b"sm_100a" in qpzk.load_library().qpzk_version()
+
+
+def test_fri_params_and_proof_size_match_oracle(qpzk, orc):
+    for log_n in (5, 6, 10, 13, 15, 16, 20):
+        for fpb in (2, 5):
+            g = qpzk.fri_params(log_n, 3, 4, 16, 28, 4, fpb)
+            o = orc.fri_params(log_n, 3, 4, 16, 28, 4, fpb)
+            assert g.reduction_arity_bits == list(o.arity_bits)[:o.num_rounds]
+            lens = np.array([85, 135, 24, 20], np.uint32)
+            words = qpzk.load_library().qpzk_fri_proof_words(C.byref(g), log_n, 4, lens.ctypes.data_as(qpzk.U32P))
+            assert words == orc.fri_proof_words(o, log_n, lens)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.fri_params(10, arity_bits=5)
+
+
+def test_challenger_state_layout_matches_header(qpzk, orc):
+    assert C.sizeof(qpzk.ChallengerState) == C.sizeof(orc.ChallengerState) == 12 * 8 + 8 * 8 + 8 * 8 + 8
+
+
+def test_no_cpu_fallback_without_gpu(qpzk):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; the failure path is for GPU-less hosts")
+    with pytest.raises(qpzk.QpzkError) as e:
+        qpzk.Context(0)
+    assert e.value.code in (-1, -2)
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "qp-zk-circuits_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "orc_" not in text and "import oracle" not in text, f

@@ -1,0 +1,269 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs -- bit-exact, since everything on this path is integer arithmetic."""
+import numpy as np
+import pytest
+
+from conftest import P, splitmix_columns
+
+pytestmark = pytest.mark.gpu
+
+
+def brev(x, bits):
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+# ---- MerkleTree::new -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nl,ll,h", [(1, 5, 0), (1, 3, 0), (2, 9, 1), (8, 3, 0), (8, 4, 3), (16, 7, 2), (64, 8, 4),
+                                     (512, 135, 4), (1024, 32, 4), (4096, 20, 0), (2048, 143, 8), (256, 1, 2)])
+def test_merkle_tree_matches_oracle(ctx, qpzk, orc, nl, ll, h):
+    rng = np.random.default_rng(nl * 1000 + ll)
+    leaves = rng.integers(0, P, size=(nl, ll), dtype=np.uint64)
+    t = qpzk.MerkleTree.new(ctx, leaves, h)
+    o = orc.MerkleTree(leaves, h)
+    assert (t.cap == o.cap()).all()
+    assert (t.digests(0) == np.stack([orc.hash_or_noop(l) for l in leaves[:64]]))[:64].all() if nl >= 64 else True
+    idx = sorted({0, nl - 1, nl // 3, nl // 2})
+    rows, sib = t.open(idx)
+    for k, i in enumerate(idx):
+        assert (rows[k] == leaves[i]).all()
+        assert (sib[k] == o.prove(i)).all()
+        assert orc.merkle_verify(rows[k], i, t.cap, sib[k])
+
+
+def test_merkle_edge_values(ctx, qpzk, orc):
+    # all-zero and all-(p-1) leaves exercise the reduction corner cases of the permutation
+    for v in (0, P - 1, 0xFFFFFFFF, 0xFFFFFFFF00000000):
+        leaves = np.full((16, 12), v, np.uint64)
+        assert (qpzk.MerkleTree.new(ctx, leaves, 1).cap == orc.MerkleTree(leaves, 1).cap()).all()
+
+
+def test_merkle_errors(ctx, qpzk):
+    rng = np.random.default_rng(0)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.MerkleTree.new(ctx, rng.integers(0, P, size=(8, 3), dtype=np.uint64), 4)   # cap_height > log2(leaves)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.MerkleTree.new(ctx, rng.integers(0, P, size=(6, 3), dtype=np.uint64), 0)   # not a power of two
+
+
+# ---- PolynomialBatch::from_values / from_coeffs -----------------------------------------------------------------
+@pytest.mark.parametrize("log_n,C_", [(0, 3), (1, 2), (2, 1), (3, 5), (5, 9), (6, 135), (8, 135), (10, 20), (11, 3),
+                                      (12, 16), (13, 135), (13, 85), (14, 7), (15, 4), (16, 5), (17, 2)])
+def test_commit_from_values_matches_oracle(ctx, qpzk, orc, log_n, C_):
+    cols = splitmix_columns(0x51575A4B00000000 + log_n, C_, 1 << log_n)
+    h = min(4, log_n + 3)
+    b = qpzk.PolynomialBatch.from_values(ctx, cols, 3, None, h)
+    o = orc.PolynomialBatch.from_values(cols, 3, h)
+    assert (b.polynomials == o.coeffs()).all()
+    assert (b.merkle_tree.rows(0, 1 << (log_n + 3)) == o.leaves()).all()
+    assert (b.cap == o.cap()).all()
+    b2 = qpzk.PolynomialBatch.from_coeffs(ctx, o.coeffs(), 3, None, h)
+    assert (b2.cap == o.cap()).all()
+    L = 1 << (log_n + 3)
+    i = (3 * L) // 7
+    assert (b.get_lde_values(i) == o.leaves()[brev(i, log_n + 3)]).all()
+
+
+@pytest.mark.parametrize("rate_bits,h", [(0, 0), (1, 1), (2, 3), (4, 5), (3, 0), (3, 8)])
+def test_commit_other_rates_and_caps(ctx, qpzk, orc, rate_bits, h):
+    cols = splitmix_columns(42 + rate_bits, 6, 1 << 7)
+    b = qpzk.PolynomialBatch.from_values(ctx, cols, rate_bits, None, h)
+    o = orc.PolynomialBatch.from_values(cols, rate_bits, h)
+    assert (b.cap == o.cap()).all()
+    assert (b.merkle_tree.rows(0, 1 << (7 + rate_bits)) == o.leaves()).all()
+
+
+def test_commit_with_salt(ctx, qpzk, orc):
+    rng = np.random.default_rng(21)
+    log_n, C_ = 7, 10
+    cols = splitmix_columns(5, C_, 1 << log_n)
+    salt = rng.integers(0, P, size=(4, 1 << (log_n + 3)), dtype=np.uint64)
+    b = qpzk.PolynomialBatch.from_values(ctx, cols, 3, salt, 4)
+    o = orc.PolynomialBatch.from_values(cols, 3, 4, salt)
+    assert b.leaf_len == C_ + 4
+    assert (b.merkle_tree.rows(0, 1 << (log_n + 3)) == o.leaves()).all()
+    assert (b.cap == o.cap()).all()
+
+
+def test_commit_edge_values(ctx, qpzk, orc):
+    n = 64
+    cols = np.stack([np.zeros(n, np.uint64), np.full(n, P - 1, np.uint64), np.arange(n, dtype=np.uint64),
+                     np.full(n, 0xFFFFFFFF00000000, np.uint64), np.full(n, 0xFFFFFFFF, np.uint64)])
+    b = qpzk.PolynomialBatch.from_values(ctx, cols, 3, None, 4)
+    o = orc.PolynomialBatch.from_values(cols, 3, 4)
+    assert (b.polynomials == o.coeffs()).all() and (b.cap == o.cap()).all()
+
+
+def test_commit_errors(ctx, qpzk):
+    cols = splitmix_columns(1, 2, 8)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.from_values(ctx, cols, 3, None, 7)       # cap_height > log2(8*8)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.from_values(ctx, cols[:, :6], 3, None, 1)  # length not a power of two
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.from_values(ctx, cols, 3, np.zeros((4, 8), np.uint64), 1)  # wrong salt shape
+
+
+def test_linearity_of_the_lde(ctx, qpzk):
+    # size-independent property: LDE(a + b) = LDE(a) + LDE(b) (mod p), checked on rows
+    log_n = 12
+    a = splitmix_columns(7, 4, 1 << log_n)
+    b = splitmix_columns(8, 4, 1 << log_n)
+    s = ((a.astype(object) + b.astype(object)) % P).astype(np.uint64)
+    ra = qpzk.PolynomialBatch.from_values(ctx, a, 3, None, 4).merkle_tree.rows(100, 50).astype(object)
+    rb = qpzk.PolynomialBatch.from_values(ctx, b, 3, None, 4).merkle_tree.rows(100, 50).astype(object)
+    rs = qpzk.PolynomialBatch.from_values(ctx, s, 3, None, 4).merkle_tree.rows(100, 50).astype(object)
+    assert ((ra + rb) % P == rs).all()
+
+
+def test_coset_split_equals_full_commit(ctx, qpzk, orc):
+    """leaf block j is one Merkle subtree; per-coset commits reproduce slices of the full cap."""
+    import torch
+    log_n, C_ = 9, 11
+    cols = splitmix_columns(99, C_, 1 << log_n)
+    full = qpzk.PolynomialBatch.from_values(ctx, cols, 3, None, 4)
+    coeffs = torch.from_numpy(full.polynomials.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    cap = full.cap
+    for count in (1, 2, 4, 8):
+        got = []
+        for begin in range(0, 8, count):
+            part = qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeffs.data_ptr(), log_n, C_, 3, 4, begin, count)
+            got.append(part.cap)
+            n = 1 << log_n
+            assert (part.merkle_tree.rows(0, 16) == full.merkle_tree.rows(begin * n, 16)).all()
+        assert (np.concatenate(got) == cap).all()
+
+
+# ---- openings, challenger ------------------------------------------------------------------------------------------
+def test_eval_ext_matches_oracle(ctx, qpzk, orc):
+    for log_n, C_ in [(0, 2), (3, 4), (7, 33), (10, 135), (13, 20)]:
+        cols = splitmix_columns(log_n + 300, C_, 1 << log_n)
+        b = qpzk.PolynomialBatch.from_values(ctx, cols, 3, None, min(4, log_n + 3))
+        o = orc.PolynomialBatch.from_values(cols, 3, min(4, log_n + 3))
+        for z in ([3, 5], [P - 1, 0], [0, 0], [12345678901234567, 98765432109876543]):
+            assert (b.eval_ext(z) == o.eval_ext(z)).all()
+
+
+def test_challenger_matches_oracle(ctx, qpzk, orc):
+    g, o = qpzk.Challenger(ctx), orc.Challenger()
+    rng = np.random.default_rng(1)
+    for n_obs, n_get in [(3, 2), (8, 1), (13, 9), (0, 3), (1, 1), (64, 4)]:
+        x = rng.integers(0, P, size=n_obs, dtype=np.uint64)
+        g.observe_elements(x); o.observe(x)
+        assert (g.get_n_challenges(n_get) == o.get(n_get)).all()
+        assert g.export_state() == o.export()
+    st = g.export_state()
+    g2 = qpzk.Challenger(ctx)
+    g2.import_state(*st)
+    assert g2.get_challenge() == int(o.get(1)[0])
+    with pytest.raises(qpzk.QpzkError):
+        g.observe_elements([P])  # non-canonical input is rejected at the boundary
+
+
+# ---- FRI -----------------------------------------------------------------------------------------------------------
+def _setup(ctx, qpzk, orc, log_n, Cs, salted=()):
+    n = 1 << log_n
+    rng = np.random.default_rng(5 + log_n)
+    gb, ob = [], []
+    for i, c in enumerate(Cs):
+        cols = splitmix_columns(77 + i + log_n, c, n)
+        salt = rng.integers(0, P, size=(4, n << 3), dtype=np.uint64) if i in salted else None
+        if i == len(Cs) - 1:  # the quotient oracle enters as coefficients (from_coeffs)
+            gb.append(qpzk.PolynomialBatch.from_coeffs(ctx, cols, 3, salt, 4))
+            ob.append(orc.PolynomialBatch.from_coeffs(cols, 3, 4, salt))
+        else:
+            gb.append(qpzk.PolynomialBatch.from_values(ctx, cols, 3, salt, 4))
+            ob.append(orc.PolynomialBatch.from_values(cols, 3, 4, salt))
+    gch, och = qpzk.Challenger(ctx), orc.Challenger()
+    digest = np.arange(4, dtype=np.uint64) + 11  # stands for circuit_digest / public_inputs_hash
+    gch.observe_hash(digest); och.observe(digest)
+    for g, o in zip(gb, ob):
+        gch.observe_cap(g); och.observe(o.cap())
+    zg, zo = gch.get_extension_challenge(), och.get(2)
+    assert (zg == zo).all()
+    wn = orc.lib().orc_gl_root_of_unity(log_n)
+    gz = [orc.lib().orc_gl_mul(int(zo[0]), wn), orc.lib().orc_gl_mul(int(zo[1]), wn)]
+    allp = [(o, i) for o in range(len(Cs)) for i in range(Cs[o])]
+    nxt = [(2, i) for i in range(min(2, Cs[2]))]
+    batches = [([int(zo[0]), int(zo[1])], allp), (gz, nxt)]
+    op = np.concatenate([np.concatenate([ob[o].eval_ext(zo) for o in range(len(Cs))]),
+                         np.stack([ob[o].eval_ext(gz)[i] for o, i in nxt])])
+    gch.observe_extension_elements(op); och.observe(op)
+    return gb, ob, gch, och, qpzk.FriInstanceInfo(batches), orc.Instance(batches), op
+
+
+@pytest.mark.parametrize("log_n,Cs,pow_bits,nq,fpb,salted", [
+    (6, [5, 9, 3, 2], 8, 5, 2, ()),
+    (5, [3, 4, 2, 2], 4, 3, 5, ()),           # no reduction rounds at all
+    (8, [4, 6, 3, 2], 10, 7, 3, (1, 2, 3)),   # salted (blinding) oracles
+    (10, [8, 13, 4, 4], 16, 28, 5, ()),
+    (13, [85, 135, 20, 16], 16, 28, 5, ()),   # leaf-circuit shape, reference FRI parameters
+])
+def test_fri_proof_matches_oracle_and_verifies(ctx, qpzk, orc, log_n, Cs, pow_bits, nq, fpb, salted):
+    gb, ob, gch, och, gi, oi, op = _setup(ctx, qpzk, orc, log_n, Cs, salted)
+    gp = qpzk.fri_params(log_n, 3, 4, pow_bits, nq, 4, fpb)
+    opar = orc.fri_params(log_n, 3, 4, pow_bits, nq, 4, fpb)
+    ochv = och.clone()
+    gproof, gopen = qpzk.PolynomialBatch.prove_openings(gi, gb, gch, gp, return_openings=True)
+    oproof = orc.fri_prove(ob, oi, opar, och)   # coefficient-domain prover (upstream's algorithm)
+    assert (gopen == op).all()
+    assert (gproof == oproof).all()            # caps, query rounds, final poly, minimum PoW witness: bit-exact
+    assert gch.export_state() == och.export()  # transcript left in the same state
+    lens, caps = [b.leaf_len for b in gb], [b.cap for b in gb]
+    assert orc.fri_verify(log_n, lens, caps, oi, op, opar, ochv, gproof) == 0
+
+
+def test_fri_caller_supplied_pow_witness(ctx, qpzk, orc):
+    gb, ob, gch, och, gi, oi, op = _setup(ctx, qpzk, orc, 6, [5, 9, 3, 2])
+    gp = qpzk.fri_params(6, 3, 4, 8, 4, 4, 2)
+    st = gch.export_state()
+    proof = qpzk.PolynomialBatch.prove_openings(gi, gb, gch, gp)
+    w = int(proof[-1])
+    g2 = qpzk.Challenger(ctx); g2.import_state(*st)
+    assert (qpzk.PolynomialBatch.prove_openings(gi, gb, g2, gp, pow_witness=w) == proof).all()
+    if w > 0:  # the ground witness is the minimum: nothing below it is accepted
+        g3 = qpzk.Challenger(ctx); g3.import_state(*st)
+        with pytest.raises(qpzk.QpzkError) as e:
+            qpzk.PolynomialBatch.prove_openings(gi, gb, g3, gp, pow_witness=w - 1)
+        assert e.value.code == -4
+
+
+def test_fri_argument_errors(ctx, qpzk, orc):
+    gb, ob, gch, och, gi, oi, op = _setup(ctx, qpzk, orc, 6, [5, 9, 3, 2])
+    gp = qpzk.fri_params(6, 3, 4, 8, 4, 4, 2)
+    bad = qpzk.FriInstanceInfo([([1, 2], [(0, 99)])])
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.prove_openings(bad, gb, gch, gp)
+    bad = qpzk.FriInstanceInfo([([P, 2], [(0, 0)])])
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.prove_openings(bad, gb, gch, gp)
+
+
+# ---- BASELINE.json full-size shape through size-independent properties ---------------------------------------------
+def test_full_size_commit_properties(ctx, qpzk, orc):
+    """2^18 x 135 (config 3 of BASELINE.json is 2^16..2^22; the oracle needs minutes beyond 2^16, so the larger
+    sizes are checked through properties): sampled LDE rows equal direct polynomial evaluation of the returned
+    coefficients, sampled Merkle paths verify against the cap with the oracle hasher, first coset equals the
+    oracle's LDE restricted to that coset."""
+    import torch
+    log_n, C_ = 18, 135
+    n, log_L = 1 << log_n, log_n + 3
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randint(0, 2**62, (C_, n), generator=g, device="cuda", dtype=torch.int64)  # < p, canonical
+    torch.cuda.synchronize()
+    b = qpzk.PolynomialBatch.from_device(ctx, x.data_ptr(), log_n, C_, 3, 4, values=True)
+    cap = b.cap
+    cols = x[:3].cpu().numpy().view(np.uint64)
+    idx = [0, 1, n - 1, n, 5 * n + 12345, (1 << log_L) - 1, 777777]
+    rows, sib = b.merkle_tree.open(idx)
+    wl = orc.lib().orc_gl_root_of_unity(log_L)
+    for k, j in enumerate(idx):
+        assert orc.merkle_verify(rows[k], j, cap, sib[k])
+        pt = orc.GENERATOR * pow(wl, brev(j, log_L), P) % P
+        for c in range(3):  # Horner on the oracle's coefficients of the same column
+            co = orc.fft(cols[c], inverse=True)
+            acc = 0
+            for v in co[::-1]:
+                acc = (acc * pt + int(v)) % P
+            assert acc == int(rows[k][c])
+    assert (b.polynomials[:3] == np.stack([orc.fft(cols[c], inverse=True) for c in range(3)])).all()

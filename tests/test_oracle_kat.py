@@ -1,0 +1,199 @@
+"""CPU tests: pin the oracle against every known-answer vector available for this path.
+
+The reference tree holds no golden LDE / Merkle / FRI vectors; what exists is pinned here:
+the three upstream Poseidon-12 permutation KATs, the round-constant self-checks, the Goldilocks generator
+facts and the reference-side constants that fix the configuration
+(p at wormhole/inputs/src/lib.rs:23; FRI parameters at wormhole/circuit/src/profile.rs:168-174).
+"""
+import numpy as np
+import pytest
+
+import gen_poseidon_constants as gen
+
+P = 0xFFFFFFFF00000001
+
+
+def test_round_constants_self_checks():
+    rc = gen.round_constants()
+    gen.self_check(rc)
+    assert len(rc) == 360 and all(c < P for c in rc)
+
+
+def test_permutation_kats_python_twin():
+    rc = gen.round_constants()
+    fast = gen.derive_fast_partial(rc)
+    for inp, want in gen.KATS:
+        want = [int(w, 16) for w in want.split()]
+        assert gen.poseidon_naive(inp, rc) == want
+        assert gen.poseidon_fast(inp, rc, fast) == want
+
+
+def test_permutation_kats_c_oracle(orc):
+    for inp, want in gen.KATS:
+        want = [int(w, 16) for w in want.split()]
+        assert [int(x) for x in orc.poseidon(inp)] == want
+        assert [int(x) for x in orc.poseidon(inp, naive=True)] == want
+
+
+def test_naive_equals_sparse_random(orc):
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        x = rng.integers(0, P, size=12, dtype=np.uint64)
+        assert (orc.poseidon(x) == orc.poseidon(x, naive=True)).all()
+
+
+def test_goldilocks_generators(orc):
+    L = orc.lib()
+    g, w = 14293326489335486720, 7277203076849721926
+    assert L.orc_gl_exp(g, (P - 1) >> 32) == w
+    assert L.orc_gl_exp(w, 1 << 31) == P - 1 and L.orc_gl_exp(w, 1 << 32) == 1
+    for q in (2, 3, 5, 17, 257, 65537):  # g is a generator: non-trivial at every prime factor of p-1
+        assert L.orc_gl_exp(g, (P - 1) // q) != 1
+    assert L.orc_gl_exp(7, (P - 1) // 2) == P - 1  # 7 is a non-residue => X^2 - 7 irreducible
+    for k in range(0, 33):
+        assert L.orc_gl_root_of_unity(k) == pow(w, 1 << (32 - k), P)
+
+
+def test_field_mul_against_bigint(orc):
+    rng = np.random.default_rng(5)
+    L = orc.lib()
+    edge = [0, 1, 2, P - 1, P - 2, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFF00000000, 1 << 63]
+    vals = edge + [int(x) for x in rng.integers(0, P, size=64, dtype=np.uint64)]
+    for a in vals:
+        for b in vals[:24]:
+            assert L.orc_gl_mul(a, b) == a * b % P
+    for a in vals[1:20]:
+        assert L.orc_gl_mul(a, L.orc_gl_inv(a)) == 1
+
+
+def test_fft_against_definition(orc):
+    rng = np.random.default_rng(2)
+    for log_n in (0, 1, 3, 5):
+        n = 1 << log_n
+        a = rng.integers(0, P, size=n, dtype=np.uint64)
+        w = orc.lib().orc_gl_root_of_unity(log_n)
+        want = [sum(int(a[j]) * pow(w, i * j, P) for j in range(n)) % P for i in range(n)]
+        assert [int(x) for x in orc.fft(a)] == want
+        assert (orc.fft(orc.fft(a), inverse=True) == a).all()
+        shift = orc.GENERATOR
+        want = [sum(int(a[j]) * pow(shift * pow(w, i, P) % P, j, P) for j in range(n)) % P for i in range(n)]
+        assert [int(x) for x in orc.coset_fft(a)] == want
+
+
+def test_hashing_rules(orc):
+    # hash_or_noop: <= 4 elements are copied and zero padded; longer inputs go through the sponge
+    assert list(orc.hash_or_noop([5, 6])) == [5, 6, 0, 0]
+    assert list(orc.hash_or_noop([1, 2, 3, 4])) == [1, 2, 3, 4]
+    x = np.arange(1, 6, dtype=np.uint64)
+    st = np.zeros(12, np.uint64); st[:5] = x
+    assert (orc.hash_or_noop(x) == orc.poseidon(st)[:4]).all()
+    # overwrite mode: second chunk overwrites state[0..len) only, no padding
+    x = np.arange(1, 12, dtype=np.uint64)
+    st = np.zeros(12, np.uint64); st[:8] = x[:8]
+    st = orc.poseidon(st); st[:3] = x[8:]
+    assert (orc.hash_no_pad(x) == orc.poseidon(st)[:4]).all()
+    l, r = np.arange(4, dtype=np.uint64), np.arange(4, 8, dtype=np.uint64)
+    st = np.zeros(12, np.uint64); st[:4] = l; st[4:8] = r
+    assert (orc.two_to_one(l, r) == orc.poseidon(st)[:4]).all()
+
+
+def test_merkle_tree(orc):
+    rng = np.random.default_rng(3)
+    for nl, ll, h in [(1, 5, 0), (8, 3, 0), (8, 4, 3), (16, 7, 2), (64, 135, 4)]:
+        leaves = rng.integers(0, P, size=(nl, ll), dtype=np.uint64)
+        t = orc.MerkleTree(leaves, h)
+        cap = t.cap()
+        assert cap.shape == (1 << h, 4)
+        if h == nl.bit_length() - 1:  # cap == leaf digests
+            assert all((cap[i] == orc.hash_or_noop(leaves[i])).all() for i in range(nl))
+        for i in range(nl):
+            assert orc.merkle_verify(leaves[i], i, cap, t.prove(i))
+        if nl > 1:
+            assert not orc.merkle_verify(leaves[0], 1, cap, t.prove(0))
+    with pytest.raises(ValueError):
+        orc.MerkleTree(rng.integers(0, P, size=(8, 3), dtype=np.uint64), 4)  # cap_height > log2(leaves)
+
+
+def test_challenger_duplex(orc):
+    c = orc.Challenger()
+    c.observe([1, 2, 3])
+    st = np.zeros(12, np.uint64); st[:3] = [1, 2, 3]
+    out = orc.poseidon(st)
+    got = c.get(3)
+    assert list(got) == [int(out[7]), int(out[6]), int(out[5])]  # popped from the back of state[0..8]
+    c.observe([9])  # observing clears the output buffer
+    st = out.copy(); st[0] = 9
+    assert int(c.get(1)[0]) == int(orc.poseidon(st)[7])
+    c2 = orc.Challenger(); c2.observe(np.arange(8))  # a full rate block triggers the duplex immediately
+    st = np.zeros(12, np.uint64); st[:8] = np.arange(8)
+    assert list(c2.export()[0]) == [int(x) for x in orc.poseidon(st)]
+
+
+def test_fri_reduction_strategy(orc):
+    # ConstantArityBits(4, 5) with rate_bits 3, cap_height 4 (reference wormhole/circuit/src/profile.rs:168-174)
+    for d, want in [(13, [4, 4]), (15, [4, 4, 4]), (16, [4, 4, 4]), (5, []), (12, [4, 4]), (20, [4, 4, 4, 4])]:
+        p = orc.fri_params(d)
+        assert list(p.arity_bits)[:p.num_rounds] == want
+
+
+def _instance(orc, bs, Cs, log_n, ch):
+    zeta = ch.get(2)
+    wn = orc.lib().orc_gl_root_of_unity(log_n)
+    gz = [orc.lib().orc_gl_mul(int(zeta[0]), wn), orc.lib().orc_gl_mul(int(zeta[1]), wn)]
+    allp = [(o, i) for o in range(len(Cs)) for i in range(Cs[o])]
+    nxt = [(2, 0), (2, 1)]
+    batches = [([int(zeta[0]), int(zeta[1])], allp), (gz, nxt)]
+    op = np.concatenate([np.concatenate([bs[o].eval_ext(zeta) for o in range(len(Cs))]),
+                         np.stack([bs[o].eval_ext(gz)[i] for o, i in nxt])])
+    return orc.Instance(batches), op
+
+
+@pytest.mark.parametrize("log_n,pow_bits,final_bits,salted", [(6, 8, 2, False), (5, 4, 5, False), (8, 6, 3, True)])
+def test_fri_prove_verify_roundtrip(orc, log_n, pow_bits, final_bits, salted):
+    rng = np.random.default_rng(log_n)
+    Cs = [5, 9, 3, 2]
+    n = 1 << log_n
+    salt = lambda: rng.integers(0, P, size=(4, n << 3), dtype=np.uint64) if salted else None
+    bs = [orc.PolynomialBatch.from_values(rng.integers(0, P, size=(c, n), dtype=np.uint64), 3, 4, salt()) for c in Cs]
+    ch = orc.Challenger()
+    for b in bs:
+        ch.observe(b.cap())
+    inst, op = _instance(orc, bs, Cs, log_n, ch)
+    ch.observe(op)
+    params = orc.fri_params(log_n, pow_bits=pow_bits, num_queries=6, final_poly_bits=final_bits)
+    chv = ch.clone()
+    proof = orc.fri_prove(bs, inst, params, ch)
+    lens, caps = [b.leaf_len for b in bs], [b.cap() for b in bs]
+    assert orc.fri_verify(log_n, lens, caps, inst, op, params, chv, proof) == 0
+    assert chv.export() == ch.export()  # prover and verifier leave the transcript in the same state
+    # minimum-witness policy: no smaller witness satisfies the difficulty
+    for pos in (0, proof.size // 2, proof.size - 2, proof.size - 1):
+        bad = proof.copy(); bad[pos] ^= np.uint64(1)
+        c3 = orc.Challenger()
+        for b in bs:
+            c3.observe(b.cap())
+        c3.get(2); c3.observe(op)
+        assert orc.fri_verify(log_n, lens, caps, inst, op, params, c3, bad) != 0
+    op_bad = op.copy(); op_bad[3, 0] ^= np.uint64(1)
+    c4 = orc.Challenger()
+    for b in bs:
+        c4.observe(b.cap())
+    c4.get(2); c4.observe(op)
+    assert orc.fri_verify(log_n, lens, caps, inst, op_bad, params, c4, proof) != 0
+
+
+def test_lde_is_polynomial_evaluation(orc):
+    rng = np.random.default_rng(9)
+    log_n, C_ = 4, 3
+    n, L = 1 << log_n, 1 << (log_n + 3)
+    cols = rng.integers(0, P, size=(C_, n), dtype=np.uint64)
+    b = orc.PolynomialBatch.from_values(cols, 3, 2)
+    co, lv = b.coeffs(), b.leaves()
+    wn, wl = orc.lib().orc_gl_root_of_unity(log_n), orc.lib().orc_gl_root_of_unity(log_n + 3)
+    br = lambda x, bits: int(format(x, "0%db" % bits)[::-1], 2)
+    for c in range(C_):
+        for i in range(n):  # coefficients interpolate the values on the subgroup
+            assert sum(int(co[c][k]) * pow(wn, i * k, P) for k in range(n)) % P == int(cols[c][i])
+        for j in range(L):  # leaf row j holds P(g * w_L^bitrev(j))
+            x = orc.GENERATOR * pow(wl, br(j, log_n + 3), P) % P
+            assert sum(int(co[c][k]) * pow(x, k, P) for k in range(n)) % P == int(lv[j][c])
