@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""bench.py -- LDE + Poseidon-Merkle commit throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 22] [--impl ours|reference]
+
+A step = ONE `PolynomialBatch::from_values` of the raw-commit shape of BASELINE.json config 3:
+2^log_n trace rows x 135 Goldilocks columns, rate_bits 3, cap_height 4, no blinding, uniform random canonical
+inputs (synthetic).  Default log_n = 22, the largest size of the sweep; it fits one GPU.
+
+  value     whole-job commit throughput, algorithmic GB/s:
+            bytes_alg = 8*C*n*(1+2^rate_bits) + 32*(2*(2^rate_bits*n - 2^cap_height) + 2^cap_height)
+            divided by the device time of the step, inputs already resident in HBM.
+  e2e       the same metric through the host-buffer C-ABI call qpzk_commit_from_values (pinned host input,
+            host->device copy and the device->host read of the cap inside the timed region).
+  N > 1     strong scaling of the SAME commitment: columns are split for the iNTT, the coefficient
+            matrix is all-gathered over NCCL, each rank extends and hashes 2^rate_bits/N cosets (whole Merkle
+            subtrees), and the cap slices are all-gathered.  Time = max over ranks.
+  roofline  the dominant kernel (Poseidon leaf hashing) against the measured HBM peak, as the contract asks; the
+            LDE stage (HBM-bound by design) and the integer pipe (what actually bounds Poseidon) are reported
+            beside it as roofline_lde / int_pipe.
+  --impl reference   the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on a bounded
+            sample (2^16 x 135) of the same workload.  The Rust reference itself cannot be built here (no cargo,
+            un-vendored qp-plonky2), see DESIGN.md.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "qp-zk-circuits_b200"))
+
+NUM_COLS, RATE_BITS, CAP_HEIGHT = 135, 3, 4
+METRIC, UNIT = "lde_merkle_commit_throughput", "GB/s"
+P = 0xFFFFFFFF00000001
+
+
+def bytes_alg(log_n, num_cols=NUM_COLS, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
+    n, B, H = 1 << log_n, 1 << rate_bits, 1 << cap_height
+    return 8 * num_cols * n * (1 + B) + 32 * (2 * (B * n - H) + H)
+
+
+def perms(log_n, num_cols=NUM_COLS, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
+    L = (1 << log_n) << rate_bits
+    return L * ((num_cols + 7) // 8) + (L - (1 << cap_height))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_commit_sample(log_n_sample=16, repeats=1):
+    """The CPU restatement (oracle, OpenMP) on a bounded sample of the workload; returns (GB/s, cores, seconds)."""
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    rng = np.random.default_rng(16)
+    cols = rng.integers(0, P, size=(NUM_COLS, 1 << log_n_sample), dtype=np.uint64)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        b = orc.PolynomialBatch.from_values(cols, RATE_BITS, CAP_HEIGHT)
+        dt = time.perf_counter() - t0
+        del b
+        best = dt if best is None else min(best, dt)
+    return bytes_alg(log_n_sample) / best / 1e9, orc.num_threads(), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    sample = 16
+    rng = np.random.default_rng(16)
+    cols = rng.integers(0, P, size=(NUM_COLS, 1 << sample), dtype=np.uint64)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        b = orc.PolynomialBatch.from_values(cols, RATE_BITS, CAP_HEIGHT)
+        dt = time.perf_counter() - t0
+        del b
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    v = bytes_alg(sample) / (ms * 1e-3) / 1e9
+    desc = "one from_values of 2^%d x %d (rate_bits 3, cap_height 4) per step" % (sample, NUM_COLS)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks)", "data": "synthetic",
+        "config": {"workload": "raw commit 2^%d x %d, rate_bits 3, cap_height 4 (bounded CPU sample of config 3)" % (sample, NUM_COLS)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": desc,
+                         "note": "restated CPU baseline (oracle/, C + OpenMP) -- not the reference binary: no cargo/rustc here"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log-n", type=int, default=22)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import qpzk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    B = 1 << RATE_BITS
+    if world > B or B % world:
+        raise SystemExit("the coset split supports 1, 2, 4 or 8 ranks")
+
+    log_n, C_ = args.log_n, NUM_COLS
+    n = 1 << log_n
+    stream = torch.cuda.current_stream()
+    ctx = qpzk.Context(local_rank, stream=stream.cuda_stream)
+    ctx.set_timing(True)
+
+    # ---- synthetic input: this rank's column slice, canonical uniform values, resident in HBM
+    q = (C_ + world - 1) // world                      # columns per rank (last rank is zero padded)
+    c0, c1 = rank * q, min((rank + 1) * q, C_)
+    gen = torch.Generator(device=dev).manual_seed(0x5157 + log_n)
+    full = torch.randint(0, 2**63 - 1, (C_, n), generator=gen, device=dev, dtype=torch.int64)  # < 2^63 < p: canonical
+    mine = torch.zeros((q, n), dtype=torch.int64, device=dev)
+    mine[: c1 - c0] = full[c0:c1]
+    del full
+    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev)
+    coeff_all = torch.empty((world * q, n), dtype=torch.int64, device=dev) if world > 1 else None
+    cosets_per = B // world
+    cap_all = torch.empty((world, (1 << CAP_HEIGHT) // world * 4), dtype=torch.int64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    stage = {"intt_ms": 0.0, "lde_ms": 0.0, "leaf_hash_ms": 0.0, "merkle_levels_ms": 0.0, "allgather_ms": 0.0}
+
+    def step(record):
+        if world == 1:
+            b = qpzk.PolynomialBatch.from_device(ctx, mine.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT, values=True)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine.data_ptr(), coeff_mine.data_ptr(), log_n, q))
+            e0.record()
+            dist.all_gather_into_tensor(coeff_all, coeff_mine)
+            e1.record()
+            b = qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
+                                                               rank * cosets_per, cosets_per)
+        if record:
+            t = ctx.last_commit_timing()   # synchronises the stream
+            for k in ("intt_ms", "lde_ms", "leaf_hash_ms", "merkle_levels_ms"):
+                stage[k] += t[k]
+            if world > 1:
+                stage["allgather_ms"] += e0.elapsed_time(e1)
+        return b
+
+    def finish(b):
+        cap = torch.from_numpy(b.cap.view(np.int64).reshape(-1))  # tiny D2H read of this rank's cap slice
+        if world > 1:
+            dist.all_gather_into_tensor(cap_all, cap.to(dev).reshape(1, -1))
+        b.free()
+
+    # ---- device-resident timing: W warm-up, then exactly K steps between barriers + synchronize
+    for _ in range(args.warmup):
+        finish(step(False))
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        finish(step(False))
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    # per-stage durations from a separate pass (stage events synchronise the stream, so they stay out of the timed loop)
+    for _ in range(args.steps):
+        finish(step(True))
+    for k in stage:
+        stage[k] /= args.steps
+    t_ms = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = bytes_alg(log_n) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host input, H2D inside, cap D2H inside)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((c1 - c0 if world > 1 else C_, n), dtype=torch.int64).pin_memory()
+        host.copy_(mine[: host.shape[0]])
+        torch.cuda.synchronize()
+        hnp = host.numpy().view(np.uint64)
+
+        def e2e_step():
+            if world == 1:
+                bb = qpzk.PolynomialBatch.from_values(ctx, hnp, RATE_BITS, None, CAP_HEIGHT)
+                cap = bb.cap
+                bb.free()
+                return cap
+            mine[: host.shape[0]].copy_(host, non_blocking=True)
+            bb = step(False)
+            finish(bb)
+
+        for _ in range(2):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ms = 1e3 * float(dt.item()) / args.steps
+        e2e = {"value": bytes_alg(log_n) / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(host.numel() * 8), "d2h_bytes_per_step": int((1 << CAP_HEIGHT) // world * 32)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines
+    hbm_peak, peak_src = measured_peaks()
+    L = n << RATE_BITS
+    rows_here = L // world
+    leaf_bytes = rows_here * C_ * 8 + rows_here * 32                    # read each leaf row once, write its digest
+    leaf_gbs = leaf_bytes / (stage["leaf_hash_ms"] * 1e-3) / 1e9 if stage["leaf_hash_ms"] else None
+    lde_bytes = 8 * C_ * n * (1 + B) / world                            # read the trace once, write the LDE once
+    lde_ms = stage["intt_ms"] + stage["lde_ms"]
+    lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9 if lde_ms else None
+    imad_peak = ctx.bench_imad(8192)
+    perm_rate_kernel = rows_here * ((C_ + 7) // 8) / (stage["leaf_hash_ms"] * 1e-3) if stage["leaf_hash_ms"] else None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks)", "data": "synthetic",
+        "config": {"workload": "raw commit (BASELINE config 3): 2^%d rows x %d cols, rate_bits %d, cap_height %d, "
+                               "Poseidon-12 Merkle, blinding off" % (log_n, C_, RATE_BITS, CAP_HEIGHT),
+                   "l2": "inputs (%.2f GB per rank) and the LDE are larger than the 126 MB L2; no flush needed" % (mine.numel() * 8 / 1e9),
+                   "parallelism": "coset split x%d (iNTT column split + NCCL all-gather of coefficients)" % world if world > 1 else "single GPU",
+                   "bytes_alg": bytes_alg(log_n), "permutations": perms(log_n)},
+        "stages_ms": stage,
+        "roofline": {"kernel": "hash_rows_kernel (Poseidon leaf sponge, %d permutations per row)" % ((C_ + 7) // 8),
+                     "bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": None, "peak_source": peak_src + " (of measured)",
+                     "note": "integer-pipe bound, not HBM bound: see int_pipe; HBM fraction reported because the contract asks for it"},
+        "roofline_lde": {"kernels": "ntt_pass_kernel + lde_last_kernel", "bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": lde_gbs / hbm_peak if lde_gbs else None, "bytes": lde_bytes},
+        "roofline_commit": {"bound": "hbm", "achieved": value, "peak": hbm_peak * world, "unit": "GB/s",
+                            "frac": value / (hbm_peak * world)},
+        "int_pipe": {"imad_wide_per_s_measured": imad_peak, "poseidon_perms_per_s_in_kernel": perm_rate_kernel,
+                     "poseidon_perms_per_s_microbench": ctx.bench_poseidon(32)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        v, cores, secs = cpu_commit_sample(16)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": "one from_values of 2^16 x %d (same shape, smallest size of the sweep), %.1f s" % (C_, secs),
+                               "note": "restated CPU baseline (oracle/, C + OpenMP) -- not the reference binary"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,8 @@ def test_merkle_tree_matches_oracle(ctx, qpzk, orc, nl, ll, h):
     t = qpzk.MerkleTree.new(ctx, leaves, h)
     o = orc.MerkleTree(leaves, h)
     assert (t.cap == o.cap()).all()
-    assert (t.digests(0) == np.stack([orc.hash_or_noop(l) for l in leaves[:64]]))[:64].all() if nl >= 64 else True
+    k = min(nl, 64)
+    assert (t.digests(0)[:k] == np.stack([orc.hash_or_noop(l) for l in leaves[:k]])).all()
     idx = sorted({0, nl - 1, nl // 3, nl // 2})
     rows, sib = t.open(idx)
     for k, i in enumerate(idx):
