@@ -2,6 +2,7 @@
 // bench.py reports next to the HBM roofline ("IMAD_peak is measured by a microbenchmark").
 #include "../../include/qpzk.h"
 #include "internal.cuh"
+#include "poseidon_rc.cuh"
 #include "poseidon.cuh"
 
 namespace qpzk {

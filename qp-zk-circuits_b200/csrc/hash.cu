@@ -7,8 +7,8 @@
 // a13; Appendix A.4-A.7).  Reached in the reference only through `prove()`
 // (wormhole/prover/src/lib.rs:171-175) and `CircuitBuilder::build` (wormhole/circuit/src/circuit.rs:206-216).
 #include "internal.cuh"
-#include "poseidon.cuh"
 #include "poseidon_rc.cuh"
+#include "poseidon.cuh"
 
 namespace qpzk {
 
@@ -17,14 +17,27 @@ namespace qpzk {
 // ---------------------------------------------------------------------------------------------
 cudaError_t upload_poseidon_constants() {
     static uint64_t split[2 * 372];
-    for (int i = 0; i < 372; i++) {
-        uint64_t c = i < 360 ? QPZK_POSEIDON_RC_HOST[i] : 0;
-        split[i] = c & 0xFFFFFFFFu;
-        split[372 + i] = c >> 32;
-    }
+    for (int row = 0; row < 31; row++)
+        for (int i = 0; i < 12; i++) {
+            uint64_t c = (row >= 1 && row < 30) ? QPZK_POSEIDON_RC_HOST[12 * row + i] : 0;
+            if (SPARSE_ROUNDS > 0 && row == 4 + LITERAL_PARTIAL) c = i == 0 ? QPZK_POSEIDON_DEV_K[0] : 0;
+            split[12 * row + i] = c & 0xFFFFFFFFu;
+            split[372 + 12 * row + i] = c >> 32;
+        }
     cudaError_t e = cudaMemcpyToSymbol(c_rc_split, split, sizeof split);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_rc_first, QPZK_POSEIDON_RC_HOST, 12 * sizeof(uint64_t));
+    e = cudaMemcpyToSymbol(c_rc_first, QPZK_POSEIDON_RC_HOST, 12 * sizeof(uint64_t));
+    if (e != cudaSuccess) return e;
+    const uint32_t pow2[2] = {16, 2};
+    if ((e = cudaMemcpyToSymbol(c_mds_pow2, pow2, sizeof pow2)) != cudaSuccess) return e;
+    if (SPARSE_ROUNDS > 0) {
+        if ((e = cudaMemcpyToSymbol(c_sp_k, QPZK_POSEIDON_DEV_K, SPARSE_ROUNDS * sizeof(uint64_t))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_sp_init, QPZK_POSEIDON_DEV_INIT, 121 * sizeof(uint64_t))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_sp_w, QPZK_POSEIDON_DEV_W, 11 * SPARSE_ROUNDS * sizeof(uint64_t))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_sp_vhat, QPZK_POSEIDON_DEV_VHAT, 11 * SPARSE_ROUNDS * sizeof(uint64_t))) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbol(c_sp_v26, QPZK_POSEIDON_DEV_V26, 12 * sizeof(uint64_t))) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------

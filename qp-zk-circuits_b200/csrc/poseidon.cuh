@@ -4,72 +4,259 @@
 // a8/a9, Appendix A.3/A.4): width 12, rate 8, x^7, 4 full + 22 partial + 4 full rounds,
 // MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...).
 //
-// B200 mapping.  The linear layer uses the literal small-constant MDS in every round: each output
-// lane is two chains of twelve IMAD.WIDE.U32 (32-bit half x immediate + 64-bit accumulator), which
-// is cheaper on the SM's integer pipes than the CPU-oriented sparse partial-round form (full-width
-// field multiplies).  The next round's constants are pre-split into 32-bit halves and seed those
-// accumulators, so adding round constants costs no instructions.  Rounds are a real loop (not
-// unrolled) to stay inside the instruction cache.
+// B200 mapping (measured: IMAD.WIDE issues at half the 32-bit IMAD rate, and the ALU and FMA pipes of
+// an SM sub-partition run side by side):
+//  * field multiply = 4 IMAD.WIDE + an add-with-carry chain written in PTX (~14 IADD3): products are
+//    assembled and reduced (2^64 = 2^32-1, 2^96 = -1) without any compare/select.
+//  * the linear layer of FULL rounds is the literal small-constant MDS: per output lane two chains of
+//    twelve IMAD.WIDE.U32 (32-bit half x immediate + 64-bit accumulator); the next round's constants
+//    are pre-split into 32-bit halves and seed the accumulators, so adding them costs nothing.
+//  * PARTIAL rounds are split: the first 22-m stay literal (FMA-pipe heavy), the last m use the sparse
+//    factorisation (ALU-pipe heavy: 22 full-width multiplies, one 160-bit dot-product accumulator).  Mixing
+//    the two forms balances the two pipes; m = QPZK_SPARSE_ROUNDS is set by the constants generator.
+//  * rounds are real loops (not unrolled) so the body stays inside the instruction cache.
 #pragma once
 #include "goldilocks.cuh"
 
 namespace qpzk {
 
-// RC split into zero-extended 32-bit halves: [0..360) low halves, [360..720) high halves,
-// followed by 12+12 zeros used as the "next round" constants of the last round.
+constexpr int SPARSE_ROUNDS = QPZK_SPARSE_ROUNDS;
+constexpr int LITERAL_PARTIAL = 22 - SPARSE_ROUNDS;
+
+// Row `next` of this table = constants folded into the MDS layer that precedes round `next`:
+// [0..372) zero-extended low halves, [372..744) high halves (31 rows of 12; row 30 is all zero).
 __constant__ uint64_t c_rc_split[2 * 372];
-__constant__ uint64_t c_rc_first[12];  // round-0 constants, added to the input state directly
+__constant__ uint64_t c_rc_first[12];                  // round-0 constants, added to the input directly
+// The two power-of-two MDS entries (16 and 2) are read from constant memory: as immediates ptxas rewrites
+// `mad.wide x, 16, acc` into a shift + 64-bit add sequence (4 ALU instructions instead of one IMAD.WIDE).
+__constant__ uint32_t c_mds_pow2[2];
+__constant__ uint64_t c_sp_k[SPARSE_ROUNDS + 1];       // lane-0 scalar of sparse round i (entry 0 is folded into the table)
+__constant__ uint64_t c_sp_init[121];
+__constant__ uint64_t c_sp_w[11 * SPARSE_ROUNDS + 1];
+__constant__ uint64_t c_sp_vhat[11 * SPARSE_ROUNDS + 1];
+__constant__ uint64_t c_sp_v26[12];                    // POST + RC[26], added after the sparse segment
+
+// ---- 128-bit product / reduction in PTX ---------------------------------------------------------
+struct u128w { uint32_t w0, w1, w2, w3; };
+
+__device__ __forceinline__ u128w mul_wide_w(uint64_t a, uint64_t b) {
+    u128w r;
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    asm("{\n\t.reg .u64 p00,p01,p10,p11;\n\t.reg .u32 x1,y0,y1,z0,z1,v0,v1;\n\t"
+        "mul.wide.u32 p00,%4,%6;\n\tmul.wide.u32 p01,%4,%7;\n\tmul.wide.u32 p10,%5,%6;\n\tmul.wide.u32 p11,%5,%7;\n\t"
+        "mov.b64 {%0,x1},p00;\n\tmov.b64 {y0,y1},p01;\n\tmov.b64 {z0,z1},p10;\n\tmov.b64 {v0,v1},p11;\n\t"
+        "add.cc.u32 %1,x1,y0;\n\taddc.cc.u32 %2,y1,v0;\n\taddc.u32 %3,v1,0;\n\t"
+        "add.cc.u32 %1,%1,z0;\n\taddc.cc.u32 %2,%2,z1;\n\taddc.u32 %3,%3,0;\n\t}"
+        : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return r;
+}
+
+__device__ __forceinline__ u128w sqr_wide_w(uint64_t a) {
+    u128w r;
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    asm("{\n\t.reg .u64 p00,pm,p11;\n\t.reg .u32 x1,y0,y1,v0,v1;\n\t"
+        "mul.wide.u32 p00,%4,%4;\n\tmul.wide.u32 pm,%4,%5;\n\tmul.wide.u32 p11,%5,%5;\n\t"
+        "mov.b64 {%0,x1},p00;\n\tmov.b64 {y0,y1},pm;\n\tmov.b64 {v0,v1},p11;\n\t"
+        "add.cc.u32 %1,x1,y0;\n\taddc.cc.u32 %2,y1,v0;\n\taddc.u32 %3,v1,0;\n\t"
+        "add.cc.u32 %1,%1,y0;\n\taddc.cc.u32 %2,%2,y1;\n\taddc.u32 %3,%3,0;\n\t}"
+        : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "r"(a0), "r"(a1));
+    return r;
+}
+
+// (w3:w2:w1:w0) mod p as an arbitrary u64 representative:  lo - w3 + w2*(2^32-1), with the borrow of the
+// subtraction and the carry of the addition folded into one correction of (carry - borrow) * (2^32-1).
+__device__ __forceinline__ uint64_t reduce_w(u128w x) {
+    uint32_t s0, s1;
+    asm("{\n\t.reg .u32 t0,t1,brw,u0,u1,k,m0,m1;\n\t"
+        "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 brw,0,0;\n\t"
+        "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
+        "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 k,brw,0;\n\t"
+        "sub.u32 m0,0,k;\n\tshr.s32 m1,k,31;\n\t"
+        "add.cc.u32 %0,t0,m0;\n\taddc.u32 %1,t1,m1;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(x.w0), "r"(x.w1), "r"(x.w2), "r"(x.w3));
+    return ((uint64_t)s1 << 32) | s0;
+}
+
+__device__ __forceinline__ uint64_t mulp(uint64_t a, uint64_t b) { return reduce_w(mul_wide_w(a, b)); }
+__device__ __forceinline__ uint64_t sqrp(uint64_t a) { return reduce_w(sqr_wide_w(a)); }
+
+// s + a*b  (mod p), s and the product arbitrary representatives: s is added into the 128-bit product
+// (cannot overflow 128 bits) before the single reduction.
+__device__ __forceinline__ uint64_t mul_addp(uint64_t a, uint64_t b, uint64_t s) {
+    u128w r = mul_wide_w(a, b);
+    uint32_t s0 = (uint32_t)s, s1 = (uint32_t)(s >> 32);
+    asm("add.cc.u32 %0,%0,%4;\n\taddc.cc.u32 %1,%1,%5;\n\taddc.cc.u32 %2,%2,0;\n\taddc.u32 %3,%3,0;"
+        : "+r"(r.w0), "+r"(r.w1), "+r"(r.w2), "+r"(r.w3) : "r"(s0), "r"(s1));
+    return reduce_w(r);
+}
+
+// x + k with k canonical (< p): one conditional +EPS is enough
+__device__ __forceinline__ uint64_t add_canon_p(uint64_t x, uint64_t k) {
+    uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), k0 = (uint32_t)k, k1 = (uint32_t)(k >> 32), s0, s1;
+    asm("{\n\t.reg .u32 c,m;\n\t"
+        "add.cc.u32 %0,%2,%4;\n\taddc.cc.u32 %1,%3,%5;\n\taddc.u32 c,0,0;\n\t"
+        "sub.u32 m,0,c;\n\t"
+        "add.cc.u32 %0,%0,m;\n\taddc.u32 %1,%1,0;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(x0), "r"(x1), "r"(k0), "r"(k1));
+    return ((uint64_t)s1 << 32) | s0;
+}
+
+// 160-bit accumulator for dot products of full-width operands
+struct acc160 { uint32_t a0, a1, a2, a3, a4; };
+
+__device__ __forceinline__ void mac160(acc160& acc, uint64_t a, uint64_t b) {
+    u128w r = mul_wide_w(a, b);
+    asm("add.cc.u32 %0,%0,%5;\n\taddc.cc.u32 %1,%1,%6;\n\taddc.cc.u32 %2,%2,%7;\n\taddc.cc.u32 %3,%3,%8;\n\taddc.u32 %4,%4,0;"
+        : "+r"(acc.a0), "+r"(acc.a1), "+r"(acc.a2), "+r"(acc.a3), "+r"(acc.a4)
+        : "r"(r.w0), "r"(r.w1), "r"(r.w2), "r"(r.w3));
+}
+
+// acc mod p;  a4 * 2^128 = -a4 * 2^32 (mod p), a4 < 2^5
+__device__ __forceinline__ uint64_t reduce160(const acc160& acc) {
+    u128w x; x.w0 = acc.a0; x.w1 = acc.a1; x.w2 = acc.a2; x.w3 = acc.a3;
+    uint64_t r = reduce_w(x);
+    uint64_t sub = (uint64_t)acc.a4 << 32;
+    uint64_t d = r - sub;
+    if (r < sub) d -= GL_EPS;  // borrowed 2^64 = EPS (mod p); d >= 2^64 - 2^37 here, no second borrow
+    return d;
+}
+
+// ---- round pieces ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t sbox7_nc(uint64_t x) {
+    uint64_t x2 = sqrp(x);
+    uint64_t x4 = sqrp(x2);
+    uint64_t x3 = mulp(x, x2);
+    return mulp(x3, x4);
+}
+
+// acc += x * C  as one IMAD.WIDE.U32 with an immediate multiplier (written in PTX so that the compiler does
+// not strength-reduce the small constants into shift/add sequences on the busier ALU pipe).
+template <uint32_t C>
+__device__ __forceinline__ void macw(uint64_t& acc, uint32_t x) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(x), "n"(C));
+}
 
 // MDS output lane from 32-bit half sums:  value = lo + 2^32 * hi  with lo, hi < 2^43.
 __device__ __forceinline__ uint64_t mds_combine(uint64_t lo, uint64_t hi) {
     uint32_t h1 = (uint32_t)(hi >> 32), h0 = (uint32_t)hi;
-    uint64_t t = lo + (uint64_t)h1 * 0xFFFFFFFFu;  // h1 * 2^64 = h1 * EPS (mod p); no overflow
-    uint64_t u = (uint64_t)h0 << 32;
-    uint64_t r = t + u;
-    if (r < u) r += GL_EPS;                         // wrapped value is < 2^43, cannot wrap again
-    return r;
+    uint64_t t = lo;
+    macw<0xFFFFFFFFu>(t, h1);                       // h1 * 2^64 = h1 * EPS (mod p); no overflow
+    uint32_t t0 = (uint32_t)t, t1 = (uint32_t)(t >> 32), s0, s1;
+    asm("{\n\t.reg .u32 c,m;\n\t"
+        "add.cc.u32 %1,%3,%4;\n\taddc.u32 c,0,0;\n\t"   // t + (h0 << 32): only the high word changes
+        "sub.u32 m,0,c;\n\t"
+        "add.cc.u32 %0,%2,m;\n\taddc.u32 %1,%1,0;\n\t}"  // + EPS on wrap; wrapped value < 2^43, cannot wrap again
+        : "=r"(s0), "=r"(s1) : "r"(t0), "r"(t1), "r"(h0));
+    return ((uint64_t)s1 << 32) | s0;
 }
 
-__device__ __forceinline__ uint64_t sbox7_nc(uint64_t x) {
-    uint64_t x2 = gl_sqr_nc(x);
-    uint64_t x4 = gl_sqr_nc(x2);
-    uint64_t x3 = gl_mul_nc(x, x2);
-    return gl_mul_nc(x3, x4);
-}
+template <int R, int I>
+struct MdsRow {
+    static __device__ __forceinline__ void run(uint64_t& lo, uint64_t& hi, const uint32_t (&l)[12], const uint32_t (&h)[12]) {
+        constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+        constexpr uint32_t c = CIRC[I] + ((R == 0 && I == 0) ? 8u : 0u);  // + DIAG
+        if (c == 16 || c == 2) {
+            const uint32_t cr = c_mds_pow2[c == 16 ? 0 : 1];
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(lo) : "r"(l[(I + R) % 12]), "r"(cr));
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(hi) : "r"(h[(I + R) % 12]), "r"(cr));
+        } else {
+            macw<c>(lo, l[(I + R) % 12]);
+            macw<c>(hi, h[(I + R) % 12]);
+        }
+        MdsRow<R, I + 1>::run(lo, hi, l, h);
+    }
+};
+template <int R>
+struct MdsRow<R, 12> {
+    static __device__ __forceinline__ void run(uint64_t&, uint64_t&, const uint32_t (&)[12], const uint32_t (&)[12]) {}
+};
 
-// s <- MDS * s + RC[next_round]   (constants folded into the accumulators)
-__device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next_round) {
-    constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+template <int R>
+struct MdsLayer {
+    static __device__ __forceinline__ void run(uint64_t (&s)[12], const uint32_t (&l)[12], const uint32_t (&h)[12],
+                                               const uint64_t* rc_lo, const uint64_t* rc_hi) {
+        uint64_t lo = rc_lo[R], hi = rc_hi[R];
+        MdsRow<R, 0>::run(lo, hi, l, h);
+        s[R] = mds_combine(lo, hi);
+        MdsLayer<R + 1>::run(s, l, h, rc_lo, rc_hi);
+    }
+};
+template <>
+struct MdsLayer<12> {
+    static __device__ __forceinline__ void run(uint64_t (&)[12], const uint32_t (&)[12], const uint32_t (&)[12],
+                                               const uint64_t*, const uint64_t*) {}
+};
+
+// s <- MDS * s + table row `next`
+__device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
     uint32_t l[12], h[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) { l[i] = (uint32_t)s[i]; h[i] = (uint32_t)(s[i] >> 32); }
-    const uint64_t* rc_lo = c_rc_split + 12 * next_round;
-    const uint64_t* rc_hi = c_rc_split + 372 + 12 * next_round;
+    MdsLayer<0>::run(s, l, h, c_rc_split + 12 * next, c_rc_split + 372 + 12 * next);
+}
+
+// The sparse segment: lanes 1..11 <- INIT * lanes 1..11, then SPARSE_ROUNDS rounds of
+//   x0 <- (x0 + K[i])^7;  s0' = 25*x0 + <VHAT[i], s[1..]>;  s[1+j] += W[i][j]*x0;   and finally s += V26.
+__device__ __forceinline__ void sparse_segment(uint64_t (&s)[12]) {
+    {
+        uint64_t t[11];
+#pragma unroll 1
+        for (int i = 0; i < 11; i++) {
+            acc160 acc = {0, 0, 0, 0, 0};
 #pragma unroll
-    for (int r = 0; r < 12; r++) {
-        uint64_t lo = rc_lo[r], hi = rc_hi[r];
+            for (int j = 0; j < 11; j++) mac160(acc, c_sp_init[11 * i + j], s[1 + j]);
+            uint64_t v = reduce160(acc);
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-            uint32_t c = CIRC[i] + ((r == 0 && i == 0) ? 8u : 0u);  // + DIAG
-            lo += (uint64_t)l[(i + r) % 12] * c;
-            hi += (uint64_t)h[(i + r) % 12] * c;
+            for (int k = 0; k < 11; k++) if (k == i) t[k] = v;
         }
-        s[r] = mds_combine(lo, hi);
+#pragma unroll
+        for (int j = 0; j < 11; j++) s[1 + j] = t[j];
     }
+#pragma unroll 1
+    for (int i = 0; i < SPARSE_ROUNDS; i++) {
+        uint64_t x0 = s[0];
+        if (i > 0) x0 = add_canon_p(x0, c_sp_k[i]);  // K[0] came in through the table row
+        x0 = sbox7_nc(x0);
+        acc160 acc = {0, 0, 0, 0, 0};
+        mac160(acc, 25, x0);
+        const uint64_t* vh = c_sp_vhat + 11 * i;
+        const uint64_t* w = c_sp_w + 11 * i;
+#pragma unroll
+        for (int j = 0; j < 11; j++) mac160(acc, vh[j], s[1 + j]);
+#pragma unroll
+        for (int j = 0; j < 11; j++) s[1 + j] = mul_addp(w[j], x0, s[1 + j]);
+        s[0] = reduce160(acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = add_canon_p(s[i], c_sp_v26[i]);
 }
 
 // In/out: arbitrary u64 representatives (inputs from memory are canonical; outputs may be >= p).
+// ONE round loop shares a single copy of the S-box and MDS code between all full and literal partial rounds;
+// the 12 S-boxes of a full round run as 3 passes over 4 lanes with a register rotation in between.  This keeps
+// the whole permutation well inside the instruction cache (instruction-fetch stalls were the top stall reason
+// of the straight-line version, profiles/r1_poseidon_notes.md).
 __device__ __forceinline__ void poseidon_permute(uint64_t (&s)[12]) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_nc(s[i], c_rc_first[i]);
+    for (int i = 0; i < 12; i++) s[i] = add_canon_p(s[i], c_rc_first[i]);
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
-        s[0] = sbox7_nc(s[0]);
-        if (r < 4 || r >= 26) {
-#pragma unroll
-            for (int i = 1; i < 12; i++) s[i] = sbox7_nc(s[i]);
+        if (SPARSE_ROUNDS > 0 && r == 4 + LITERAL_PARTIAL) {
+            sparse_segment(s);
+            r = 26;
         }
-        mds_layer_rc(s, r + 1);  // round 30 "constants" are zeros
+        if (r < 4 || r >= 26) {
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                uint64_t a = sbox7_nc(s[0]), b = sbox7_nc(s[1]), c = sbox7_nc(s[2]), d = sbox7_nc(s[3]);
+#pragma unroll
+                for (int i = 0; i < 8; i++) s[i] = s[i + 4];  // rotate by 4 lanes; three passes restore the order
+                s[8] = a; s[9] = b; s[10] = c; s[11] = d;
+            }
+        } else {
+            s[0] = sbox7_nc(s[0]);
+        }
+        mds_layer_rc(s, r + 1);  // row 30 is zero
     }
 }
 

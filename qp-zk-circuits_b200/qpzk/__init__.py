@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libqpzk.so")
+LIB_PATH = os.environ.get("QPZK_LIB") or os.path.join(os.path.dirname(_HERE), "libqpzk.so")
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "qpzk.h")
 
 P = 0xFFFFFFFF00000001

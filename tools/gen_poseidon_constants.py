@@ -145,7 +145,7 @@ def poseidon_naive(state, rc):
     return s
 
 
-def derive_fast_partial(rc):
+def derive_fast_partial(rc, m_sparse=N_PARTIAL):
     """Sparse re-factoring of the 22 partial rounds (Poseidon paper, App. B), derived here from
     the MDS matrix and round constants alone; algebraically identical to the naive rounds.
 
@@ -155,18 +155,20 @@ def derive_fast_partial(rc):
                      x <- x + POST   (folded into the constants of full round 26)
     """
     m = mds_matrix()
+    first = N_PARTIAL - m_sparse   # partial rounds [0, first) stay in the literal form
     # 1. push lane>=1 constants forward so that only lane 0 receives a scalar per round
     ks, delta = [], [0] * 12
-    for r in range(N_PARTIAL):
+    for r in range(first, N_PARTIAL):
         c = rc[12 * (4 + r):12 * (4 + r) + 12]
         ks.append((c[0] + delta[0]) % P)
         u = matvec(m, [0] + [(delta[i] + c[i]) % P for i in range(1, 12)])
         delta = u
     post = delta
     # 2. sparse factorisation, last round first:  T = [[t00, v],[w, B]] = [[t00, v*B^-1],[w, I]] * diag(1, B)
-    w_l, vhat_l = [None] * N_PARTIAL, [None] * N_PARTIAL
+    w_l, vhat_l = [None] * m_sparse, [None] * m_sparse
     t = m
-    for r in reversed(range(N_PARTIAL)):
+    init = [[1 if i == j else 0 for j in range(11)] for i in range(11)]
+    for r in reversed(range(m_sparse)):
         b = [row[1:] for row in t[1:]]
         binv = matinv(b)
         v = [t[0][1:]]
@@ -187,8 +189,12 @@ def poseidon_fast(state, rc, fast):
         s = [(x + c) % P for x, c in zip(s, rc[12 * r:12 * r + 12])]
         s = [pow(x, 7, P) for x in s]
         s = matvec(m, s)
+    for r in range(4, 4 + N_PARTIAL - len(ks)):   # literal partial rounds
+        s = [(x + c) % P for x, c in zip(s, rc[12 * r:12 * r + 12])]
+        s[0] = pow(s[0], 7, P)
+        s = matvec(m, s)
     s = [s[0]] + matvec(init, s[1:])
-    for r in range(N_PARTIAL):
+    for r in range(len(ks)):
         x0 = pow((s[0] + ks[r]) % P, 7, P)
         d = (25 * x0 + sum(a * b for a, b in zip(vhat_l[r], s[1:]))) % P
         s = [d] + [(s[1 + i] + w_l[r][i] * x0) % P for i in range(11)]
@@ -213,6 +219,8 @@ def check_permutation(rc, fast):
         want = [int(w, 16) for w in want.split()]
         assert poseidon_naive(inp, rc) == want, "naive KAT mismatch"
         assert poseidon_fast(inp, rc, fast) == want, "fast KAT mismatch"
+        for m_sparse in (0, 1, 7, 11, 21):
+            assert poseidon_fast(inp, rc, derive_fast_partial(rc, m_sparse)) == want, "split KAT mismatch"
     rnd = random.Random(7)
     for _ in range(8):
         x = [rnd.randrange(P) for _ in range(12)]
@@ -233,7 +241,26 @@ def emit_fast(f, prefix, fast, qual):
     arr("PARTIAL_POST", post, "[12]")
 
 
-def emit(path, rc, guard, decl, fast=None, prefix="", qual="static const uint64_t"):
+def emit_device_split(f, rc, m_sparse):
+    """Tables for the CUDA permutation: the first 22-m partial rounds literal, the last m sparse."""
+    ks, init, w_l, vhat_l, post = derive_fast_partial(rc, m_sparse)
+    f.write("// Device permutation schedule: %d literal + %d sparse partial rounds.\n" % (N_PARTIAL - m_sparse, m_sparse))
+    f.write("#define QPZK_SPARSE_ROUNDS %d\n" % m_sparse)
+    def arr(name, vals, n):
+        f.write("static const uint64_t QPZK_POSEIDON_DEV_%s[%d] = {\n" % (name, max(n, 1)))
+        vals = list(vals) or [0]
+        for i in range(0, len(vals), 4):
+            f.write("  " + ", ".join("0x%016xULL" % v for v in vals[i:i + 4]) + ",\n")
+        f.write("};\n")
+    arr("K", ks, m_sparse)
+    arr("INIT", [x for row in init for x in row], 121)
+    arr("W", [x for row in w_l for x in row], 11 * m_sparse)
+    arr("VHAT", [x for row in vhat_l for x in row], 11 * m_sparse)
+    # constants added to the state after the sparse segment: POST + RC[round 26]
+    arr("V26", [(a + b) % P for a, b in zip(post, rc[12 * 26:12 * 26 + 12])], 12)
+
+
+def emit(path, rc, guard, decl, fast=None, prefix="", qual="static const uint64_t", device_split=None):
     lines = [
         "// GENERATED by tools/gen_poseidon_constants.py -- do not edit.",
         "// Poseidon-12 (Goldilocks) round constants: ChaCha8Rng::seed_from_u64(0), 360 x gen_range(0..p)",
@@ -249,6 +276,8 @@ def emit(path, rc, guard, decl, fast=None, prefix="", qual="static const uint64_
         if fast is not None:
             f.write("// Sparse partial-round factorisation (derive_fast_partial in the generator).\n")
             emit_fast(f, prefix, fast, qual)
+        if device_split is not None:
+            emit_device_split(f, rc, device_split)
         f.write("#endif\n")
 
 
@@ -261,5 +290,6 @@ if __name__ == "__main__":
     emit(os.path.join(root, "oracle", "poseidon_rc.h"), rc, "ORACLE_POSEIDON_RC_H",
          "static const uint64_t POSEIDON_RC", fast, "POSEIDON_")
     emit(os.path.join(root, "qp-zk-circuits_b200", "csrc", "poseidon_rc.cuh"), rc, "QPZK_POSEIDON_RC_CUH",
-         "static const uint64_t QPZK_POSEIDON_RC_HOST", fast, "QPZK_POSEIDON_")
+         "static const uint64_t QPZK_POSEIDON_RC_HOST", None, "QPZK_POSEIDON_",
+         device_split=int(os.environ.get("QPZK_SPARSE_ROUNDS", "22")))
     print("ok: 360 constants, self-checks pass; naive and sparse forms match the 3 permutation KATs")
