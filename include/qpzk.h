@@ -15,7 +15,7 @@
  *    thread-local message.  No C++ exception or abort crosses this boundary.
  *  - field elements are canonical Goldilocks values (< p = 2^64 - 2^32 + 1), little-endian uint64_t;
  *    extension elements are two consecutive words [a0, a1] (a0 + a1*X, X^2 = 7).
- *    Non-canonical inputs are rejected by the *_checked variants only; outputs are always canonical.
+ *    Outputs are always canonical; opening points, observed elements and PoW witnesses are checked at the boundary.
  *  - host pointers are owned by the caller and only read/written during the call; device memory is
  *    owned by the library behind opaque handles.  Functions suffixed _dev take DEVICE pointers.
  *  - one qpzk_ctx = one device + one CUDA stream; a context must not be used from two threads at

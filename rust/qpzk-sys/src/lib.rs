@@ -1,0 +1,71 @@
+//! Raw bindings to `include/qpzk.h`.  One item per C entry point; see the header for the contract
+//! (return 0 = OK, negative = error, message via `qpzk_last_error()`; no panic crosses the boundary).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)] pub struct qpzk_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }
+#[repr(C)] pub struct qpzk_challenger { _p: [u8; 0] }
+
+pub const QPZK_POW_SEARCH: u64 = u64::MAX;
+pub const QPZK_MAX_FRI_ROUNDS: usize = 16;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct qpzk_challenger_state {
+    pub sponge_state: [u64; 12],
+    pub input_buffer: [u64; 8],
+    pub output_buffer: [u64; 8],
+    pub input_len: u32,
+    pub output_len: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct qpzk_fri_params {
+    pub rate_bits: u32,
+    pub cap_height: u32,
+    pub proof_of_work_bits: u32,
+    pub num_query_rounds: u32,
+    pub num_rounds: u32,
+    pub arity_bits: [u32; QPZK_MAX_FRI_ROUNDS],
+}
+
+#[repr(C)]
+pub struct qpzk_fri_instance {
+    pub num_batches: u32,
+    pub points: *const u64,
+    pub batch_sizes: *const u32,
+    pub poly_oracle: *const u32,
+    pub poly_index: *const u32,
+}
+
+extern "C" {
+    pub fn qpzk_last_error() -> *const c_char;
+    pub fn qpzk_ctx_create(device: c_int, out: *mut *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_ctx_create_on_stream(device: c_int, stream: *mut c_void, out: *mut *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_ctx_destroy(ctx: *mut qpzk_ctx);
+    pub fn qpzk_ctx_synchronize(ctx: *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_commit_from_values(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
+                                   cap_height: u32, salt: *const u64, out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_commit_from_coeffs(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
+                                   cap_height: u32, salt: *const u64, out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_merkle_new(ctx: *mut qpzk_ctx, leaves: *const u64, num_leaves: u64, leaf_len: u32, cap_height: u32,
+                           out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_batch_free(b: *mut qpzk_batch);
+    pub fn qpzk_batch_cap_len(b: *const qpzk_batch) -> u32;
+    pub fn qpzk_batch_cap(b: *const qpzk_batch, out: *mut u64) -> c_int;
+    pub fn qpzk_batch_coeffs(b: *const qpzk_batch, out: *mut u64) -> c_int;
+    pub fn qpzk_batch_rows(b: *const qpzk_batch, first_row: u64, num_rows: u64, out: *mut u64) -> c_int;
+    pub fn qpzk_batch_open(b: *const qpzk_batch, idx: *const u64, k: u32, rows: *mut u64, siblings: *mut u64) -> c_int;
+    pub fn qpzk_batch_eval_ext(b: *const qpzk_batch, point: *const u64, out: *mut u64) -> c_int;
+    pub fn qpzk_challenger_create(ctx: *mut qpzk_ctx, out: *mut *mut qpzk_challenger) -> c_int;
+    pub fn qpzk_challenger_free(ch: *mut qpzk_challenger);
+    pub fn qpzk_challenger_import(ch: *mut qpzk_challenger, state: *const qpzk_challenger_state) -> c_int;
+    pub fn qpzk_challenger_export(ch: *mut qpzk_challenger, state: *mut qpzk_challenger_state) -> c_int;
+    pub fn qpzk_fri_proof_words(p: *const qpzk_fri_params, log_n: u32, num_oracles: u32, leaf_lens: *const u32) -> usize;
+    pub fn qpzk_fri_prove(ctx: *mut qpzk_ctx, oracles: *const *const qpzk_batch, num_oracles: u32,
+                          instance: *const qpzk_fri_instance, params: *const qpzk_fri_params,
+                          ch: *mut qpzk_challenger, pow_witness_in: u64, proof_out: *mut u64,
+                          openings_out: *mut u64) -> c_int;
+}
