@@ -253,6 +253,15 @@ static void split_bits(uint32_t total, uint32_t max_bits, std::vector<uint32_t>&
     for (uint32_t i = 0; i < k; i++) out.push_back(base + (i < extra ? 1 : 0));
 }
 
+// Tile width of a strided pass: at least 8 words (64 B segments), and wide enough that a block works on about
+// 4096 elements (a 2^6 x 8 tile keeps only a quarter of the 256 threads busy in the butterfly phase).
+static uint32_t tile_width(uint32_t s, uint32_t room_bits) {
+    uint32_t lw = 3;
+    while (s + lw < 12) lw++;
+    if (lw > room_bits) lw = room_bits;
+    return 1u << lw;
+}
+
 // values (natural order, column-major) -> coefficients (natural order, column-major)
 static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
     if (!num_cols) return 0;
@@ -273,8 +282,8 @@ static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uin
         a.in_stride = a.out_stride = n;
         a.num_arrays = num_cols;
         a.log_n = log_n; a.b_lo = b_lo; a.s = passes[i];
-        uint32_t room = i == 0 ? log_n - passes[i] : b_lo;
-        a.W = passes.size() == 1 ? 1 : (room >= 3 ? 8 : (1u << room));
+        uint32_t room = i == 0 ? log_n - passes[i] : b_lo;   // bits available for the tile width
+        a.W = passes.size() == 1 ? 1 : tile_width(passes[i], room);
         a.mode = i == 0 ? NTT_INV_FIRST : NTT_INV_GENERIC;
         a.num_cosets = 1;
         a.tw_lo = inv.lo; a.tw_hi = inv.hi;
@@ -297,9 +306,9 @@ static int run_lde(qpzk_ctx* ctx, const uint64_t* coeffs, uint64_t* leaves, uint
     if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
     uint64_t n = 1ull << log_n;
     if ((uint64_t)num_cols * coset_count > 65535) return fail(QPZK_EINVAL, "num_cols * cosets > 65535");
-    // rows per block of the last pass: as many as fit ~72 KB of shared memory with all columns resident
+    // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
     uint32_t s_last = 0;
-    while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 9216) s_last++;
+    while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
     uint32_t rem = log_n - s_last;
     const uint64_t* cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
     const uint64_t* cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
@@ -319,7 +328,7 @@ static int run_lde(qpzk_ctx* ctx, const uint64_t* coeffs, uint64_t* leaves, uint
         for (size_t i = 0; i < passes.size(); i++) {
             NttPassArgs a{};
             a.log_n = log_n; a.s = passes[i]; a.b_lo = b_hi - passes[i];
-            a.W = a.b_lo >= 3 ? 8 : (1u << a.b_lo);
+            a.W = tile_width(a.s, a.b_lo);
             a.in_stride = a.out_stride = n;
             a.tw_lo = fwd.lo; a.tw_hi = fwd.hi; a.scale = 1;
             if (i == 0) {

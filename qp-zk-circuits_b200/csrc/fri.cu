@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NTT_THREADS) fri_final_poly_kernel(FriFinalArg
         ltw[j] = tw_get(a.itw_lo, a.itw_hi, (uint64_t)j << (a.log_L - a.lg));
     for (uint32_t i = threadIdx.x; i < 2 * len; i += blockDim.x) sm[i] = a.in[i];
     __syncthreads();
-    local_ntt<true>(sm, ltw, a.lg, 2);
+    local_ntt<true>(sm, ltw, a.lg, 2, true, TileMap{2u, 1u, 0u});
     const uint32_t keep = len >> a.rate_bits;
     for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
         uint64_t f = gl_mul(a.len_inv, gl_exp(a.shift_inv, i));

@@ -84,7 +84,96 @@ __device__ __forceinline__ uint64_t gl_sqr_nc(uint64_t a) {
     gl_sqr_wide(a, lo, hi);
     return gl_reduce128_nc(lo, hi);
 }
-__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_canon(gl_mul_nc(a, b)); }
+__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b);
+
+// ---- 128-bit product / reduction in PTX ---------------------------------------------------------
+struct u128w { uint32_t w0, w1, w2, w3; };
+
+__device__ __forceinline__ u128w mul_wide_w(uint64_t a, uint64_t b) {
+    u128w r;
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    asm("{\n\t.reg .u64 p00,p01,p10,p11;\n\t.reg .u32 x1,y0,y1,z0,z1,v0,v1;\n\t"
+        "mul.wide.u32 p00,%4,%6;\n\tmul.wide.u32 p01,%4,%7;\n\tmul.wide.u32 p10,%5,%6;\n\tmul.wide.u32 p11,%5,%7;\n\t"
+        "mov.b64 {%0,x1},p00;\n\tmov.b64 {y0,y1},p01;\n\tmov.b64 {z0,z1},p10;\n\tmov.b64 {v0,v1},p11;\n\t"
+        "add.cc.u32 %1,x1,y0;\n\taddc.cc.u32 %2,y1,v0;\n\taddc.u32 %3,v1,0;\n\t"
+        "add.cc.u32 %1,%1,z0;\n\taddc.cc.u32 %2,%2,z1;\n\taddc.u32 %3,%3,0;\n\t}"
+        : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return r;
+}
+
+__device__ __forceinline__ u128w sqr_wide_w(uint64_t a) {
+    u128w r;
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    asm("{\n\t.reg .u64 p00,pm,p11;\n\t.reg .u32 x1,y0,y1,v0,v1;\n\t"
+        "mul.wide.u32 p00,%4,%4;\n\tmul.wide.u32 pm,%4,%5;\n\tmul.wide.u32 p11,%5,%5;\n\t"
+        "mov.b64 {%0,x1},p00;\n\tmov.b64 {y0,y1},pm;\n\tmov.b64 {v0,v1},p11;\n\t"
+        "add.cc.u32 %1,x1,y0;\n\taddc.cc.u32 %2,y1,v0;\n\taddc.u32 %3,v1,0;\n\t"
+        "add.cc.u32 %1,%1,y0;\n\taddc.cc.u32 %2,%2,y1;\n\taddc.u32 %3,%3,0;\n\t}"
+        : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "r"(a0), "r"(a1));
+    return r;
+}
+
+// (w3:w2:w1:w0) mod p as an arbitrary u64 representative:  lo - w3 + w2*(2^32-1), with the borrow of the
+// subtraction and the carry of the addition folded into one correction of (carry - borrow) * (2^32-1).
+__device__ __forceinline__ uint64_t reduce_w(u128w x) {
+    uint32_t s0, s1;
+    asm("{\n\t.reg .u32 t0,t1,brw,u0,u1,k,m0,m1;\n\t"
+        "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 brw,0,0;\n\t"
+        "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
+        "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 k,brw,0;\n\t"
+        "sub.u32 m0,0,k;\n\tshr.s32 m1,k,31;\n\t"
+        "add.cc.u32 %0,t0,m0;\n\taddc.u32 %1,t1,m1;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(x.w0), "r"(x.w1), "r"(x.w2), "r"(x.w3));
+    return ((uint64_t)s1 << 32) | s0;
+}
+
+__device__ __forceinline__ uint64_t mulp(uint64_t a, uint64_t b) { return reduce_w(mul_wide_w(a, b)); }
+__device__ __forceinline__ uint64_t sqrp(uint64_t a) { return reduce_w(sqr_wide_w(a)); }
+
+// s + a*b  (mod p), s and the product arbitrary representatives: s is added into the 128-bit product
+// (cannot overflow 128 bits) before the single reduction.
+__device__ __forceinline__ uint64_t mul_addp(uint64_t a, uint64_t b, uint64_t s) {
+    u128w r = mul_wide_w(a, b);
+    uint32_t s0 = (uint32_t)s, s1 = (uint32_t)(s >> 32);
+    asm("add.cc.u32 %0,%0,%4;\n\taddc.cc.u32 %1,%1,%5;\n\taddc.cc.u32 %2,%2,0;\n\taddc.u32 %3,%3,0;"
+        : "+r"(r.w0), "+r"(r.w1), "+r"(r.w2), "+r"(r.w3) : "r"(s0), "r"(s1));
+    return reduce_w(r);
+}
+
+// x + k with k canonical (< p): one conditional +EPS is enough
+__device__ __forceinline__ uint64_t add_canon_p(uint64_t x, uint64_t k) {
+    uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), k0 = (uint32_t)k, k1 = (uint32_t)(k >> 32), s0, s1;
+    asm("{\n\t.reg .u32 c,m;\n\t"
+        "add.cc.u32 %0,%2,%4;\n\taddc.cc.u32 %1,%3,%5;\n\taddc.u32 c,0,0;\n\t"
+        "sub.u32 m,0,c;\n\t"
+        "add.cc.u32 %0,%0,m;\n\taddc.u32 %1,%1,0;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(x0), "r"(x1), "r"(k0), "r"(k1));
+    return ((uint64_t)s1 << 32) | s0;
+}
+
+// 160-bit accumulator for dot products of full-width operands
+struct acc160 { uint32_t a0, a1, a2, a3, a4; };
+
+__device__ __forceinline__ void mac160(acc160& acc, uint64_t a, uint64_t b) {
+    u128w r = mul_wide_w(a, b);
+    asm("add.cc.u32 %0,%0,%5;\n\taddc.cc.u32 %1,%1,%6;\n\taddc.cc.u32 %2,%2,%7;\n\taddc.cc.u32 %3,%3,%8;\n\taddc.u32 %4,%4,0;"
+        : "+r"(acc.a0), "+r"(acc.a1), "+r"(acc.a2), "+r"(acc.a3), "+r"(acc.a4)
+        : "r"(r.w0), "r"(r.w1), "r"(r.w2), "r"(r.w3));
+}
+
+// acc mod p;  a4 * 2^128 = -a4 * 2^32 (mod p), a4 < 2^5
+__device__ __forceinline__ uint64_t reduce160(const acc160& acc) {
+    u128w x; x.w0 = acc.a0; x.w1 = acc.a1; x.w2 = acc.a2; x.w3 = acc.a3;
+    uint64_t r = reduce_w(x);
+    uint64_t sub = (uint64_t)acc.a4 << 32;
+    uint64_t d = r - sub;
+    if (r < sub) d -= GL_EPS;  // borrowed 2^64 = EPS (mod p); d >= 2^64 - 2^37 here, no second borrow
+    return d;
+}
+
+// canonical product through the PTX path (used by the NTT / FRI kernels)
+__device__ __forceinline__ uint64_t gl_mulc(uint64_t a, uint64_t b) { return gl_canon(mulp(a, b)); }
+__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_mulc(a, b); }
 
 // host versions (table construction at context creation; never on the data path)
 inline uint64_t gl_mul_host(uint64_t a, uint64_t b) {

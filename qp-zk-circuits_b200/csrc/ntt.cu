@@ -27,9 +27,11 @@ namespace qpzk {
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
     extern __shared__ uint64_t smem[];
     const uint32_t s = a.s, W = a.W, S = 1u << s;
+    const TileMap map{W, 1u, W == 1 ? 1u : 0u};   // sm[e * W + w]; a single-column tile is padded
     uint64_t* sm = smem;
-    uint64_t* ltw = smem + (size_t)S * W;
+    uint64_t* ltw = smem + (W == 1 ? padded_len(S) : S * W);
     const uint32_t b_hi = a.b_lo + s;
+    const uint32_t lW = 31 - __clz(W);
 
     uint32_t tile = blockIdx.x, coset = 0;
     if (a.mode == NTT_FWD_COSET_FIRST) { coset = tile & (a.num_cosets - 1); tile /= a.num_cosets; }
@@ -45,55 +47,55 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
         // gather: slot (a_hi, w) <- in[a_hi * 2^(log_n - s) + q0 + w], placed at e = bitrev_s(a_hi)
         uint64_t q0 = (uint64_t)tile * W;
         for (uint32_t i = threadIdx.x; i < S * W; i += blockDim.x) {
-            uint32_t w = i % W, ah = i / W;
-            sm[brev(ah, s) * W + w] = in[((uint64_t)ah << (a.log_n - s)) + q0 + w];
+            uint32_t w = i & (W - 1), ah = i >> lW;
+            sm[map(brev(ah, s), w)] = in[((uint64_t)ah << (a.log_n - s)) + q0 + w];
         }
     } else {
-        uint64_t lowtiles = (1ull << a.b_lo) / W;
-        hi = tile / lowtiles;
-        low0 = (tile % lowtiles) * W;
+        uint32_t llow = a.b_lo - lW;  // log2(number of W-wide tiles across the low bits)
+        hi = tile >> llow;
+        low0 = (uint64_t)(tile & ((1u << llow) - 1)) << lW;
         uint64_t base = (hi << b_hi) + low0;
         for (uint32_t i = threadIdx.x; i < S * W; i += blockDim.x) {
-            uint32_t w = i % W, e = i / W;
+            uint32_t w = i & (W - 1), e = i >> lW;
             uint64_t p = base + ((uint64_t)e << a.b_lo) + w;
             uint64_t v = in[p];
             if (a.mode == NTT_FWD_COSET_FIRST) {  // c_p * s_j^p  (b_hi == log_n here, so p is the coefficient index)
                 const uint64_t* clo = a.cs_lo + (size_t)coset * TW_LO_SIZE;
                 const uint64_t* chi = a.cs_hi + (size_t)coset * a.cs_hi_size;
-                v = gl_mul(v, tw_get(clo, chi, p));
+                v = gl_mulc(v, tw_get(clo, chi, p));
             } else if (a.mode == NTT_INV_GENERIC && a.b_lo) {  // DIT pre-twiddle w_{2^b_hi}^(bitrev_s(e) * k1)
                 uint64_t k1 = low0 + w;
-                v = gl_mul(v, tw_get(a.tw_lo, a.tw_hi, ((uint64_t)brev(e, s) * k1) << (a.log_n - b_hi)));
+                v = gl_mulc(v, tw_get(a.tw_lo, a.tw_hi, ((uint64_t)brev(e, s) * k1) << (a.log_n - b_hi)));
             }
-            sm[e * W + w] = v;
+            sm[map(e, w)] = v;
         }
     }
     __syncthreads();
 
-    if (a.mode == NTT_INV_FIRST || a.mode == NTT_INV_GENERIC) local_ntt<true>(sm, ltw, s, W);
-    else local_ntt<false>(sm, ltw, s, W);
+    if (a.mode == NTT_INV_FIRST || a.mode == NTT_INV_GENERIC) local_ntt<true>(sm, ltw, s, W, true, map);
+    else local_ntt<false>(sm, ltw, s, W, true, map);
 
     uint64_t* out = a.out + (col + (uint64_t)coset * a.num_arrays) * a.out_stride;
     if (a.mode == NTT_INV_FIRST) {
         uint64_t q0 = (uint64_t)tile * W;
         for (uint32_t i = threadIdx.x; i < S * W; i += blockDim.x) {
-            uint32_t e = i % S, w = i / S;  // contiguous chunk per w
+            uint32_t e = i & (S - 1), w = i >> s;  // contiguous chunk per w
             uint64_t c = brev((uint32_t)(q0 + w), a.log_n - s);
-            uint64_t v = sm[e * W + w];
-            if (a.scale != 1) v = gl_mul(v, a.scale);
+            uint64_t v = sm[map(e, w)];
+            if (a.scale != 1) v = gl_mulc(v, a.scale);
             out[(c << s) + e] = v;
         }
     } else {
         uint64_t base = (hi << b_hi) + low0;
         for (uint32_t i = threadIdx.x; i < S * W; i += blockDim.x) {
-            uint32_t w = i % W, e = i / W;
-            uint64_t v = sm[e * W + w];
+            uint32_t w = i & (W - 1), e = i >> lW;
+            uint64_t v = sm[map(e, w)];
             if ((a.mode == NTT_FWD_COSET_FIRST || a.mode == NTT_FWD_GENERIC) && a.b_lo) {
                 // DIF post-twiddle w_{2^b_hi}^(k_local * p_low), k_local = bitrev_s(e)
                 uint64_t pl = low0 + w;
-                v = gl_mul(v, tw_get(a.tw_lo, a.tw_hi, ((uint64_t)brev(e, s) * pl) << (a.log_n - b_hi)));
+                v = gl_mulc(v, tw_get(a.tw_lo, a.tw_hi, ((uint64_t)brev(e, s) * pl) << (a.log_n - b_hi)));
             }
-            if (a.scale != 1) v = gl_mul(v, a.scale);
+            if (a.scale != 1) v = gl_mulc(v, a.scale);
             out[base + ((uint64_t)e << a.b_lo) + w] = v;
         }
     }
@@ -104,7 +106,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
 // store reads it with stride R+1, conflict-free).
 __global__ void __launch_bounds__(NTT_THREADS) lde_last_kernel(LdeLastArgs a) {
     extern __shared__ uint64_t smem[];
-    const uint32_t s = a.s, R = 1u << s, RP = R + 1, C = a.num_cols;
+    const uint32_t s = a.s, R = 1u << s, RP = padded_len(R) | 1u, C = a.num_cols;
+    const TileMap map{1u, RP, 1u};                 // sm[c * RP + pad(e)], RP odd: the row-major store is conflict free
     uint64_t* sm = smem;
     uint64_t* ltw = smem + (size_t)C * RP;
     const uint64_t n = 1ull << a.log_n;
@@ -118,38 +121,23 @@ __global__ void __launch_bounds__(NTT_THREADS) lde_last_kernel(LdeLastArgs a) {
     const uint64_t* clo = a.cs_lo + (size_t)coset * TW_LO_SIZE;
     const uint64_t* chi = a.cs_hi + (size_t)coset * a.cs_hi_size;
     for (uint32_t i = threadIdx.x; i < C * R; i += blockDim.x) {
-        uint32_t e = i % R, c = i / R;
+        uint32_t e = i & (R - 1), c = i >> s;
         uint64_t p = (q << s) + e;
         uint64_t v;
         if (a.from_coeffs) {  // single-pass LDE (log_n <= s): scale the coefficients here
-            v = gl_mul(a.in[(uint64_t)c * a.in_stride + p], tw_get(clo, chi, p));
+            v = gl_mulc(a.in[(uint64_t)c * a.in_stride + p], tw_get(clo, chi, p));
         } else {
             v = a.in[((uint64_t)coset * C + c) * a.in_stride + p];
         }
-        sm[c * RP + e] = v;
+        sm[map(e, c)] = v;
     }
     __syncthreads();
 
-    uint32_t nbf = C * (R >> 1);
-    for (int lh = (int)s - 1; lh >= 0; lh--) {
-        uint32_t h = 1u << lh;
-        for (uint32_t b = threadIdx.x; b < nbf; b += blockDim.x) {
-            uint32_t t = b % (R >> 1), c = b / (R >> 1);
-            uint32_t j = t & (h - 1), e0 = ((t >> lh) << (lh + 1)) + j, e1 = e0 + h;
-            uint64_t tw = ltw[j << (s - 1 - lh)];
-            uint64_t* col = sm + c * RP;
-            uint64_t x = col[e0], y = col[e1];
-            col[e0] = gl_add(x, y);
-            col[e1] = gl_mul(gl_sub(x, y), tw);
-        }
-        __syncthreads();
-    }
+    local_ntt<false>(sm, ltw, s, C, false, map);
 
     uint64_t* rows = a.leaves + ((uint64_t)coset * n + (q << s)) * a.leaf_width;
-    for (uint32_t i = threadIdx.x; i < C * R; i += blockDim.x) {
-        uint32_t c = i % C, e = i / C;
-        rows[(uint64_t)e * a.leaf_width + c] = sm[c * RP + e];
-    }
+    for (uint32_t e = threadIdx.x / 32; e < R; e += blockDim.x / 32)      // one warp per row: coalesced row stores
+        for (uint32_t c = threadIdx.x % 32; c < C; c += 32) rows[(uint64_t)e * a.leaf_width + c] = sm[map(e, c)];
 }
 
 // out[c][bitrev(i)] = in[c][i]  (natural <-> bit-reversed order of one column-major matrix)
@@ -183,7 +171,8 @@ cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st) {
     uint64_t n = 1ull << a.log_n;
     uint64_t tiles = n / ((1ull << a.s) * a.W);
     if (a.mode == NTT_FWD_COSET_FIRST) tiles *= a.num_cosets;
-    size_t smem = ((size_t)(1u << a.s) * a.W + (1u << a.s) / 2 + 1) * sizeof(uint64_t);
+    uint32_t S = 1u << a.s;
+    size_t smem = ((size_t)(a.W == 1 ? padded_len(S) : S * a.W) + S / 2 + 1) * sizeof(uint64_t);
     cudaError_t e = ensure_smem((const void*)ntt_pass_kernel, smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)tiles, (unsigned)a.num_arrays);
@@ -195,7 +184,7 @@ cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st) {
     uint64_t n = 1ull << a.log_n;
     uint64_t blocks = (n >> a.s) * a.num_cosets;
     uint32_t R = 1u << a.s;
-    size_t smem = ((size_t)a.num_cols * (R + 1) + R / 2 + 1) * sizeof(uint64_t);
+    size_t smem = ((size_t)a.num_cols * (padded_len(R) | 1u) + R / 2 + 1) * sizeof(uint64_t);
     cudaError_t e = ensure_smem((const void*)lde_last_kernel, smem);
     if (e != cudaSuccess) return e;
     lde_last_kernel<<<(unsigned)blocks, NTT_THREADS, smem, st>>>(a);
