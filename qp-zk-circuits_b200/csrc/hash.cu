@@ -17,19 +17,32 @@ namespace qpzk {
 // ---------------------------------------------------------------------------------------------
 cudaError_t upload_poseidon_constants() {
     static uint64_t split[2 * 372];
+    static uint32_t limb[31 * 36];
     for (int row = 0; row < 31; row++)
         for (int i = 0; i < 12; i++) {
             uint64_t c = (row >= 1 && row < 30) ? QPZK_POSEIDON_RC_HOST[12 * row + i] : 0;
             if (SPARSE_ROUNDS > 0 && row == 4 + LITERAL_PARTIAL) c = i == 0 ? QPZK_POSEIDON_DEV_K[0] : 0;
             split[12 * row + i] = c & 0xFFFFFFFFu;
             split[372 + 12 * row + i] = c >> 32;
+            limb[36 * row + i] = (uint32_t)c & 0x3FFFFFu;
+            limb[36 * row + 12 + i] = (uint32_t)(c >> 22) & 0x3FFFFFu;
+            limb[36 * row + 24 + i] = (uint32_t)(c >> 44);
         }
-    cudaError_t e = cudaMemcpyToSymbol(c_rc_split, split, sizeof split);
+    cudaError_t e;
+#if QPZK_MDS_FFT
+    (void)split;
+    e = cudaMemcpyToSymbol(c_rc_limb, limb, sizeof limb);
+#else
+    (void)limb;
+    e = cudaMemcpyToSymbol(c_rc_split, split, sizeof split);
+#endif
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_rc_first, QPZK_POSEIDON_RC_HOST, 12 * sizeof(uint64_t));
     if (e != cudaSuccess) return e;
+#if !QPZK_MDS_FFT
     const uint32_t pow2[2] = {16, 2};
     if ((e = cudaMemcpyToSymbol(c_mds_pow2, pow2, sizeof pow2)) != cudaSuccess) return e;
+#endif
     if (SPARSE_ROUNDS > 0) {
         if ((e = cudaMemcpyToSymbol(c_sp_k, QPZK_POSEIDON_DEV_K, SPARSE_ROUNDS * sizeof(uint64_t))) != cudaSuccess) return e;
         if ((e = cudaMemcpyToSymbol(c_sp_init, QPZK_POSEIDON_DEV_INIT, 121 * sizeof(uint64_t))) != cudaSuccess) return e;

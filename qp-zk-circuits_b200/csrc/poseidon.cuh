@@ -102,6 +102,81 @@ struct MdsLayer<12> {
                                                const uint64_t*, const uint64_t*) {}
 };
 
+#ifndef QPZK_MDS_FFT
+#define QPZK_MDS_FFT 1
+#endif
+
+#if QPZK_MDS_FFT
+// ---- add/shift-only MDS on 22/22/20-bit limbs ----------------------------------------------------------------
+// The circulant is a product in Z[x]/(x^12 - 1); a 4-point DFT over the three stride-3 subsequences splits it into
+// Z[x]/(x^3-1) x Z[i][x]/(x^3-i) x Z[x]/(x^3+1), where the transformed matrix is [16,32,16], [(2,1),(-4,-1),(16,-1)],
+// [-1,-8,2] (derivation and exhaustive self-check: tools/derive_mds_fft.py).  All arithmetic is wrapping 32-bit;
+// the true outputs are < 2^31, so nothing is lost.  ~70 IADD3/LEA/IMAD per limb instead of 144 IMAD.WIDE per
+// 32-bit half: the layer moves off the FMA-heavy pipe, the bottleneck of the literal form (profiles/r1_summary.md).
+// Row `next` of c_rc_limb = the next round's constants split into the same limbs, added in the output stage.
+__constant__ uint32_t c_rc_limb[31 * 36];
+
+__device__ __forceinline__ void mds_limb(const uint32_t (&e)[12], const uint32_t* __restrict__ rc, uint32_t (&y)[12]) {
+    uint32_t A[3], B[3], Cr[3], Ci[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        uint32_t t = e[j] + e[j + 6], u = e[j + 3] + e[j + 9];
+        A[j] = t + u; B[j] = t - u;
+        Cr[j] = e[j] - e[j + 6]; Ci[j] = e[j + 3] - e[j + 9];
+    }
+    const uint32_t T = A[0] + A[1] + A[2];
+    const uint32_t TA[3] = {T + A[2], T + A[0], T + A[1]};
+    const uint32_t P2[3] = {8u * B[2] - B[0] - 2u * B[1], 0u - 8u * B[0] - B[1] - 2u * B[2], 2u * B[0] - 8u * B[1] - B[2]};
+    const uint32_t r0 = Cr[0], r1 = Cr[1], r2 = Cr[2], i0 = Ci[0], i1 = Ci[1], i2 = Ci[2];
+    const uint32_t P1r[3] = {2u * r0 - i0 - 16u * i1 + r1 + 4u * i2 + r2,
+                             i0 - 4u * r0 + 2u * r1 - i1 + r2 - 16u * i2,
+                             16u * r0 + i0 - 4u * r1 + i1 + 2u * r2 - i2};
+    const uint32_t P1i[3] = {2u * i0 + r0 + 16u * r1 + i1 - 4u * r2 + i2,
+                             r1 - 4u * i0 - r0 + 2u * i1 + 16u * r2 + i2,
+                             16u * i0 - r0 - 4u * i1 - r1 + 2u * i2 + r2};
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const uint32_t U = 16u * TA[j] + P2[j], V = 16u * TA[j] - P2[j];
+        y[j] = U + P1r[j] + rc[j];
+        y[j + 3] = V + P1i[j] + rc[j + 3];
+        y[j + 6] = U - P1r[j] + rc[j + 6];
+        y[j + 9] = V - P1i[j] + rc[j + 9];
+    }
+    y[0] += 8u * e[0];
+}
+
+// y0 + 2^22 y1 + 2^44 y2 (each < 2^31) as an arbitrary u64 representative mod p
+__device__ __forceinline__ uint64_t limb_combine(uint32_t y0, uint32_t y1, uint32_t y2) {
+    uint64_t a = (uint64_t)y0 + ((uint64_t)y1 << 22);            // < 2^54
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), s0, s1;
+    // (w2:w1) = a1 + y2 * 2^12;  w2 * 2^64 = w2 * (2^32 - 1) (mod p), w2 < 2^12;  one +EPS if the sum wraps
+    asm("{\n\t.reg .u32 w1,w2,t0,t1,c,m;\n\t"
+        "add.cc.u32 w1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"
+        "sub.cc.u32 t0,0,w2;\n\tsubc.u32 t1,w2,0;\n\t"
+        "add.cc.u32 %0,%2,t0;\n\taddc.cc.u32 %1,w1,t1;\n\taddc.u32 c,0,0;\n\t"
+        "sub.u32 m,0,c;\n\t"
+        "add.cc.u32 %0,%0,m;\n\taddc.u32 %1,%1,0;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(y2 << 12), "r"(y2 >> 20));
+    return ((uint64_t)s1 << 32) | s0;
+}
+
+// s <- MDS * s + table row `next`
+__device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
+    const uint32_t* rc = c_rc_limb + 36 * next;
+    uint32_t e[12], y0[12], y1[12], y2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[i] = (uint32_t)s[i] & 0x3FFFFFu;
+    mds_limb(e, rc, y0);
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[i] = (uint32_t)(s[i] >> 22) & 0x3FFFFFu;
+    mds_limb(e, rc + 12, y1);
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[i] = (uint32_t)(s[i] >> 44);
+    mds_limb(e, rc + 24, y2);
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = limb_combine(y0[i], y1[i], y2[i]);
+}
+#else
 // s <- MDS * s + table row `next`
 __device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
     uint32_t l[12], h[12];
@@ -109,6 +184,8 @@ __device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
     for (int i = 0; i < 12; i++) { l[i] = (uint32_t)s[i]; h[i] = (uint32_t)(s[i] >> 32); }
     MdsLayer<0>::run(s, l, h, c_rc_split + 12 * next, c_rc_split + 372 + 12 * next);
 }
+
+#endif  // QPZK_MDS_FFT
 
 // The sparse segment: lanes 1..11 <- INIT * lanes 1..11, then SPARSE_ROUNDS rounds of
 //   x0 <- (x0 + K[i])^7;  s0' = 25*x0 + <VHAT[i], s[1..]>;  s[1+j] += W[i][j]*x0;   and finally s += V26.
