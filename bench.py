@@ -287,7 +287,11 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
+            ts = time.perf_counter()
             e2e_step()
+            if os.environ.get("QPZK_BENCH_DEBUG"):
+                torch.cuda.synchronize()
+                print("e2e step %.1f ms" % (1e3 * (time.perf_counter() - ts)), file=sys.stderr)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:

@@ -69,6 +69,12 @@ int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on);
 int qpzk_ctx_last_commit_timing(qpzk_ctx* ctx, float ms[4]);
 /* number of kernel launches issued through this context since creation */
 uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx);
+/* Device buffers released by qpzk_batch_free / at the end of a call stay in a per-context cache and are reused by
+ * the next request of the same shape (a prover commits the same shapes over and over, reference
+ * wormhole/prover/src/lib.rs:137-175), so a steady-state commit performs no device allocation.
+ * qpzk_ctx_trim returns the cached blocks to the driver; qpzk_ctx_cached_bytes reports their total size. */
+int qpzk_ctx_trim(qpzk_ctx* ctx);
+uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx);
 
 /* ---- PolynomialBatch::from_values / from_coeffs --------------------------------------------------
  * Replaces qp-plonky2 `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing,

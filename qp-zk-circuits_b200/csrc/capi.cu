@@ -61,6 +61,9 @@ struct qpzk_ctx {
     // The context stays alive until qpzk_ctx_destroy has been called AND every batch / challenger created
     // from it has been freed, whatever order a binding's finalizers run in.
     int refs = 1;
+    std::multimap<uint64_t, void*> cache;                              // free device blocks by size in bytes
+    std::map<void*, uint64_t> block_bytes;                             // every block this context allocated
+    uint64_t cached_bytes = 0;
     std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
     std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
 };
@@ -88,16 +91,50 @@ static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++;
 // ---------------------------------------------------------------------------------------------
 // device memory helpers (stream-ordered pool)
 // ---------------------------------------------------------------------------------------------
+// Every buffer of the data path comes from a per-context cache of device blocks: a freed block is kept (size
+// keyed) and handed to the next request of about the same size.  All work of a context is ordered on its one
+// stream, so reuse needs no event and no driver call; in steady state (the prover commits the same shapes over
+// and over) a commit performs no allocation at all.  cudaMalloc runs only while the cache warms up; when it fails,
+// the cache is released once and the request retried.  (cudaMallocAsync was measured to stall the host for
+// 0.1-3 s per commit when commits are issued back to back: its pool cannot reuse blocks whose frees are still
+// pending and keeps mapping new memory instead.)
+static void cache_trim(qpzk_ctx* ctx) {
+    if (ctx->cache.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->cache) { cudaFree(kv.second); ctx->block_bytes.erase(kv.second); }
+    ctx->cache.clear();
+    ctx->cached_bytes = 0;
+}
 static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
     *p = nullptr;
     if (!words) words = 1;
-    CK(cudaMallocAsync((void**)p, words * sizeof(uint64_t), ctx->stream));
+    uint64_t bytes = (words * sizeof(uint64_t) + 511) & ~511ull;
+    auto it = ctx->cache.lower_bound(bytes);
+    if (it != ctx->cache.end() && it->first <= bytes + bytes / 8) {
+        *p = (uint64_t*)it->second;
+        ctx->cached_bytes -= it->first;
+        ctx->cache.erase(it);
+        return 0;
+    }
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cache_trim(ctx);
+        e = cudaMalloc(&q, bytes);
+    }
+    CK(e);
+    ctx->block_bytes[q] = bytes;
+    *p = (uint64_t*)q;
     return 0;
 }
 static void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words = 0) {
     if (!p) return;
     if (zero_words && ctx->zeroize) cudaMemsetAsync(p, 0, zero_words * sizeof(uint64_t), ctx->stream);
-    cudaFreeAsync(p, ctx->stream);
+    auto it = ctx->block_bytes.find(p);
+    if (it == ctx->block_bytes.end()) { cudaFree(p); return; }  // not ours (cannot happen)
+    ctx->cache.emplace(it->second, p);
+    ctx->cached_bytes += it->second;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -191,10 +228,6 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     } else {
         ctx->stream = (cudaStream_t)stream;
     }
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     CK(upload_poseidon_constants());
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
@@ -211,6 +244,7 @@ static void ctx_unref(qpzk_ctx* ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->block_bytes) cudaFree(kv.first);   // cached blocks (every live handle has been freed by now)
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (auto& kv : ctx->coset_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -228,6 +262,13 @@ extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
 extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->zeroize = on != 0; return 0; }
 extern "C" int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->timing = on != 0; return 0; }
 extern "C" uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int qpzk_ctx_trim(qpzk_ctx* ctx) {
+    if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    cache_trim(ctx);
+    return 0;
+}
+extern "C" uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx) { return ctx ? ctx->cached_bytes : 0; }
 
 static void mark(qpzk_ctx* ctx, int i) {
     if (ctx->timing) { cudaEventRecord(ctx->ev[i], ctx->stream); ctx->ev_valid[i] = true; }

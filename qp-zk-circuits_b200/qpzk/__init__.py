@@ -82,6 +82,8 @@ def load_library():
         "qpzk_ctx_set_timing": (i, [vp, i]),
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
+        "qpzk_ctx_trim": (i, [vp]),
+        "qpzk_ctx_cached_bytes": (u64, [vp]),
         "qpzk_commit_from_values": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_coeffs": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_values_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
@@ -162,6 +164,13 @@ class Context:
 
     def launch_count(self):
         return int(self.L.qpzk_ctx_launch_count(self.h))
+
+    def trim(self):
+        """Return the cached device blocks to the driver."""
+        _check(self.L.qpzk_ctx_trim(self.h))
+
+    def cached_bytes(self):
+        return int(self.L.qpzk_ctx_cached_bytes(self.h))
 
     def bench_imad(self, iters=4096):
         v = C.c_double()

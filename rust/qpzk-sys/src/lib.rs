@@ -46,6 +46,8 @@ extern "C" {
     pub fn qpzk_ctx_create_on_stream(device: c_int, stream: *mut c_void, out: *mut *mut qpzk_ctx) -> c_int;
     pub fn qpzk_ctx_destroy(ctx: *mut qpzk_ctx);
     pub fn qpzk_ctx_synchronize(ctx: *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_ctx_trim(ctx: *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_ctx_cached_bytes(ctx: *const qpzk_ctx) -> u64;
     pub fn qpzk_commit_from_values(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
                                    cap_height: u32, salt: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_commit_from_coeffs(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
