@@ -107,6 +107,14 @@ int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev
 int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint64_t* coeffs_dev, uint32_t log_n,
                           uint32_t num_cols);
 
+/* ---- PoseidonPermutation::permute on `count` states of 12 words (host buffers) ---------------------
+ * Replaces qp-plonky2 `PoseidonPermutation::permute` / `Poseidon::poseidon`.  Inputs may be
+ * any u64 representatives of field elements; outputs are canonical. */
+int qpzk_poseidon_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint64_t* out);
+/* Self-test hook (tests only): out = MDS * state + round constants of round `next_round` (0 and 30: none),
+ * canonical.  Lets a test drive the carry paths of the limb-domain linear layer with chosen states. */
+int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint32_t next_round, uint64_t* out);
+
 /* ---- MerkleTree::new(leaves, cap_height) / .cap / .prove / .leaves -------------------------------
  * leaves: num_leaves x leaf_len words, row-major.  num_leaves must be a power of two, cap_height <= log2. */
 int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,

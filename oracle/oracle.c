@@ -55,6 +55,9 @@ static inline uint64_t sbox7(uint64_t x) {
     return gl_mul(x3, x4);
 }
 
+/* the 360 round constants, for tests that restate a single layer */
+void orc_poseidon_rc(uint64_t out[360]) { for (int i = 0; i < 360; i++) out[i] = POSEIDON_RC[i]; }
+
 /* out[r] = sum_i CIRC[i]*s[(i+r)%12] + DIAG[r]*s[r]; products are < 2^70 so a u128 accumulator is exact. */
 static inline void mds_layer(uint64_t s[12]) {
     uint64_t out[12];

@@ -24,6 +24,7 @@ uint64_t orc_gl_exp(uint64_t a, uint64_t e);
 uint64_t orc_gl_root_of_unity(unsigned log_n);
 
 /* ---- Poseidon-12 ---- */
+void orc_poseidon_rc(uint64_t out[360]);   /* round constants */
 void orc_poseidon_naive(uint64_t s[12]);  /* literal round structure */
 void orc_poseidon(uint64_t s[12]);        /* sparse partial rounds; identical function */
 void orc_hash_no_pad(const uint64_t* in, size_t n, uint64_t out[4]);

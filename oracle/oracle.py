@@ -55,7 +55,7 @@ def lib():
         L.orc_gl_inv.restype = C.c_uint64; L.orc_gl_inv.argtypes = [C.c_uint64]
         L.orc_gl_exp.restype = C.c_uint64; L.orc_gl_exp.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_gl_root_of_unity.restype = C.c_uint64; L.orc_gl_root_of_unity.argtypes = [C.c_uint]
-        for f in (L.orc_poseidon, L.orc_poseidon_naive):
+        for f in (L.orc_poseidon, L.orc_poseidon_naive, L.orc_poseidon_rc):
             f.restype = None; f.argtypes = [U64P]
         for f in (L.orc_hash_no_pad, L.orc_hash_or_noop):
             f.restype = None; f.argtypes = [U64P, C.c_size_t, U64P]
@@ -107,6 +107,12 @@ def _p32(a):
 
 def _u64(a):
     return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def round_constants():
+    out = np.zeros(360, np.uint64)
+    lib().orc_poseidon_rc(_p64(out))
+    return out
 
 
 def poseidon(state, naive=False):

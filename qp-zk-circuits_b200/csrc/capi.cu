@@ -689,6 +689,35 @@ extern "C" int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t point[2],
 }
 
 // ---------------------------------------------------------------------------------------------
+// PoseidonPermutation::permute (batch) and the linear-layer self-test hook
+// ---------------------------------------------------------------------------------------------
+static int permute_impl(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, int row, uint64_t* out) {
+    if (!ctx || (!states && count) || (!out && count)) return fail(QPZK_EINVAL, "null argument");
+    if (count > (1ull << 32)) return fail(QPZK_EINVAL, "too many states");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t *d_in, *d_out;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_in, 12 * count))) return rc;
+    if ((rc = dev_alloc(ctx, &d_out, 12 * count))) { dev_free(ctx, d_in); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_in, states, 12 * count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { e = launch_permute(d_in, count, row, d_out, ctx->stream); ctx->launches++; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 12 * count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d_in, 12 * count); dev_free(ctx, d_out, 12 * count);
+    CK(e);
+    return 0;
+}
+extern "C" int qpzk_poseidon_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint64_t* out) {
+    GUARD_BEGIN return permute_impl(ctx, states, count, -1, out); GUARD_END
+}
+extern "C" int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint32_t next_round, uint64_t* out) {
+    GUARD_BEGIN
+    if (next_round > 30) return fail(QPZK_EINVAL, "next_round must be in 0..30");
+    return permute_impl(ctx, states, count, (int)next_round, out);
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
 // Challenger
 // ---------------------------------------------------------------------------------------------
 extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {

@@ -147,7 +147,7 @@ __device__ __forceinline__ uint64_t add_canon_p(uint64_t x, uint64_t k) {
         "add.cc.u32 %0,%2,%4;\n\taddc.cc.u32 %1,%3,%5;\n\taddc.u32 c,0,0;\n\t"
         "sub.u32 m,0,c;\n\t"
         "add.cc.u32 %0,%0,m;\n\taddc.u32 %1,%1,0;\n\t}"
-        : "=r"(s0), "=r"(s1) : "r"(x0), "r"(x1), "r"(k0), "r"(k1));
+        : "=&r"(s0), "=&r"(s1) : "r"(x0), "r"(x1), "r"(k0), "r"(k1));
     return ((uint64_t)s1 << 32) | s0;
 }
 

@@ -24,9 +24,10 @@ cudaError_t upload_poseidon_constants() {
             if (SPARSE_ROUNDS > 0 && row == 4 + LITERAL_PARTIAL) c = i == 0 ? QPZK_POSEIDON_DEV_K[0] : 0;
             split[12 * row + i] = c & 0xFFFFFFFFu;
             split[372 + 12 * row + i] = c >> 32;
-            limb[36 * row + i] = (uint32_t)c & 0x3FFFFFu;
-            limb[36 * row + 12 + i] = (uint32_t)(c >> 22) & 0x3FFFFFu;
-            limb[36 * row + 24 + i] = (uint32_t)(c >> 44);
+            const uint64_t cl = c >= 4096 ? c - 4096 : c + (GL_P - 4096);  // limb_combine adds 4096 back
+            limb[36 * row + i] = (uint32_t)cl & 0x3FFFFFu;
+            limb[36 * row + 12 + i] = (uint32_t)(cl >> 22) & 0x3FFFFFu;
+            limb[36 * row + 24 + i] = (uint32_t)(cl >> 44);
         }
     cudaError_t e;
 #if QPZK_MDS_FFT
@@ -215,6 +216,29 @@ __global__ void pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned l
     status[0] = (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) ? 1u : 0u;
     *witness_out = w;
     for (uint32_t q = 0; q < num_queries; q++) indices[q] = ch_get(c) % lde_size;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PoseidonPermutation::permute on a batch of states (12 words each, any u64 representatives), and a self-test
+// hook that applies ONE linear layer (MDS + constants row `next`) so that tests can drive its carry paths with
+// chosen states (random inputs reach them with probability ~2^-20).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HASH_THREADS)
+permute_kernel(const uint64_t* __restrict__ in, uint64_t count, int mds_only_row, uint64_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+    if (mds_only_row >= 0) mds_layer_rc(s, mds_only_row); else poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[12 * i + k] = gl_canon(s[k]);
+}
+
+cudaError_t launch_permute(const uint64_t* in, uint64_t count, int mds_only_row, uint64_t* out, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    permute_kernel<<<(unsigned)((count + HASH_THREADS - 1) / HASH_THREADS), HASH_THREADS, 0, st>>>(in, count, mds_only_row, out);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -69,6 +69,7 @@ cudaError_t launch_salt_scatter(const uint64_t* salt, uint64_t* leaves, uint32_t
 cudaError_t upload_poseidon_constants();
 cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
                              uint64_t* digests, cudaStream_t st);
+cudaError_t launch_permute(const uint64_t* in, uint64_t count, int mds_only_row, uint64_t* out, cudaStream_t st);
 cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st);
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);

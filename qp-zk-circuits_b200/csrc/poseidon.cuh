@@ -61,7 +61,7 @@ __device__ __forceinline__ uint64_t mds_combine(uint64_t lo, uint64_t hi) {
         "add.cc.u32 %1,%3,%4;\n\taddc.u32 c,0,0;\n\t"   // t + (h0 << 32): only the high word changes
         "sub.u32 m,0,c;\n\t"
         "add.cc.u32 %0,%2,m;\n\taddc.u32 %1,%1,0;\n\t}"  // + EPS on wrap; wrapped value < 2^43, cannot wrap again
-        : "=r"(s0), "=r"(s1) : "r"(t0), "r"(t1), "r"(h0));
+        : "=&r"(s0), "=&r"(s1) : "r"(t0), "r"(t1), "r"(h0));
     return ((uint64_t)s1 << 32) | s0;
 }
 
@@ -105,6 +105,9 @@ struct MdsLayer<12> {
 #ifndef QPZK_MDS_FFT
 #define QPZK_MDS_FFT 1
 #endif
+#ifndef QPZK_SBOX_PASSES
+#define QPZK_SBOX_PASSES 3   // S-boxes of a full round: 3 passes over 4 lanes (smallest code), 2 over 6, or 1 over 12
+#endif
 
 #if QPZK_MDS_FFT
 // ---- add/shift-only MDS on 22/22/20-bit limbs ----------------------------------------------------------------
@@ -145,18 +148,23 @@ __device__ __forceinline__ void mds_limb(const uint32_t (&e)[12], const uint32_t
     y[0] += 8u * e[0];
 }
 
-// y0 + 2^22 y1 + 2^44 y2 (each < 2^31) as an arbitrary u64 representative mod p
+// y0 + 2^22 y1 + 2^44 y2 - 4096 (each y < 2^31) as an arbitrary u64 representative mod p; the table constants
+// carry the -4096 (c_rc_limb holds the limbs of c - 4096 mod p).  The top limb is pre-reduced in the limb domain:
+// y2 = h * 2^20 + l and h * 2^64 = h * 2^32 - h (mod p), so limb 1 takes h << 10 and limb 0 takes 4096 - h >= 0.
+// What remains can exceed 2^64 only through the carry of the last addition: one +EPS, which cannot wrap again.
 __device__ __forceinline__ uint64_t limb_combine(uint32_t y0, uint32_t y1, uint32_t y2) {
-    uint64_t a = (uint64_t)y0 + ((uint64_t)y1 << 22);            // < 2^54
-    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), s0, s1;
-    // (w2:w1) = a1 + y2 * 2^12;  w2 * 2^64 = w2 * (2^32 - 1) (mod p), w2 < 2^12;  one +EPS if the sum wraps
-    asm("{\n\t.reg .u32 w1,w2,t0,t1,c,m;\n\t"
-        "add.cc.u32 w1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"
-        "sub.cc.u32 t0,0,w2;\n\tsubc.u32 t1,w2,0;\n\t"
-        "add.cc.u32 %0,%2,t0;\n\taddc.cc.u32 %1,w1,t1;\n\taddc.u32 c,0,0;\n\t"
-        "sub.u32 m,0,c;\n\t"
-        "add.cc.u32 %0,%0,m;\n\taddc.u32 %1,%1,0;\n\t}"
-        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(y2 << 12), "r"(y2 >> 20));
+    const uint32_t h = y2 >> 20;
+    const uint32_t t0 = y0 + 4096u - h;
+    const uint32_t t1 = y1 + (h << 10);
+    const uint64_t a = (uint64_t)t0 + ((uint64_t)t1 << 22);           // < 2^54
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), l12 = y2 << 12, s0, s1;
+    // Only add-flavoured carry ops: ptxas keeps the raw adder carry in CC.CF (after sub.cc it is NOT-borrow), so
+    // chains that mix add.cc with subc do not compute what the PTX manual's prose suggests.
+    asm("{\n\t.reg .u32 k,m;\n\t"
+        "add.cc.u32 %1,%3,%4;\n\taddc.u32 k,0,0;\n\t"               // high word + l * 2^12;  k = carry
+        "sub.u32 m,0,k;\n\t"                                         // carry * (2^32 - 1) = (0 : m)
+        "add.cc.u32 %0,%2,m;\n\taddc.u32 %1,%1,0;\n\t}"
+        : "=&r"(s0), "=&r"(s1) : "r"(a0), "r"(a1), "r"(l12));
     return ((uint64_t)s1 << 32) | s0;
 }
 
@@ -238,6 +246,21 @@ __device__ __forceinline__ void poseidon_permute(uint64_t (&s)[12]) {
             r = 26;
         }
         if (r < 4 || r >= 26) {
+#if QPZK_SBOX_PASSES == 1
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = sbox7_nc(s[i]);
+#elif QPZK_SBOX_PASSES == 2
+#pragma unroll 1
+            for (int k = 0; k < 2; k++) {
+                uint64_t t[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) t[i] = sbox7_nc(s[i]);
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[i] = s[i + 6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[6 + i] = t[i];
+            }
+#else
 #pragma unroll 1
             for (int k = 0; k < 3; k++) {
                 uint64_t a = sbox7_nc(s[0]), b = sbox7_nc(s[1]), c = sbox7_nc(s[2]), d = sbox7_nc(s[3]);
@@ -245,6 +268,7 @@ __device__ __forceinline__ void poseidon_permute(uint64_t (&s)[12]) {
                 for (int i = 0; i < 8; i++) s[i] = s[i + 4];  // rotate by 4 lanes; three passes restore the order
                 s[8] = a; s[9] = b; s[10] = c; s[11] = d;
             }
+#endif
         } else {
             s[0] = sbox7_nc(s[0]);
         }

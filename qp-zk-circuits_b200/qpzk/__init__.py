@@ -83,6 +83,8 @@ def load_library():
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
         "qpzk_ctx_trim": (i, [vp]),
+        "qpzk_poseidon_permute": (i, [vp, vp, u64, vp]),
+        "qpzk_selftest_mds_layer": (i, [vp, vp, u64, u32, vp]),
         "qpzk_ctx_cached_bytes": (u64, [vp]),
         "qpzk_commit_from_values": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_coeffs": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
@@ -171,6 +173,18 @@ class Context:
 
     def cached_bytes(self):
         return int(self.L.qpzk_ctx_cached_bytes(self.h))
+
+    def poseidon_permute(self, states, mds_only_round=None):
+        """PoseidonPermutation::permute on an (N, 12) array; inputs may be non-canonical, outputs are canonical.
+        mds_only_round = r applies only the linear layer + constants of round r (self-test hook)."""
+        a = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 12)
+        out = np.zeros_like(a)
+        if mds_only_round is None:
+            _check(self.L.qpzk_poseidon_permute(self.h, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p)))
+        else:
+            _check(self.L.qpzk_selftest_mds_layer(self.h, a.ctypes.data_as(C.c_void_p), a.shape[0], mds_only_round,
+                                                  out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def bench_imad(self, iters=4096):
         v = C.c_double()

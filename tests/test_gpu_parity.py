@@ -12,6 +12,59 @@ def brev(x, bits):
     return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
 
 
+# ---- PoseidonPermutation::permute and its linear layer -----------------------------------------------------------
+MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+
+
+def test_poseidon_permute_matches_oracle_and_kats(ctx, orc):
+    rng = np.random.default_rng(5)
+    states = rng.integers(0, P, size=(300, 12), dtype=np.uint64)
+    states[0] = 0
+    states[1] = np.arange(12)
+    states[2] = P - 1
+    got = ctx.poseidon_permute(states)
+    want = np.stack([orc.poseidon(s) for s in states])
+    assert (got == want).all()
+    assert got[0][0] == 0x3c18a9786cb0b359 and got[1][0] == 0xd64e1e3efc5b8e9e and got[2][0] == 0xbe0085cfc57a8357
+    # non-canonical representatives (x and x + p name the same field element) must give the same permutation
+    nc = states[:64].copy()
+    small = nc < np.uint64(2**32 - 1)
+    nc[small] += np.uint64(P)
+    assert small.any() or True
+    edge = np.full((4, 12), 2**64 - 1, np.uint64)           # == 2^32 - 2 mod p
+    assert (ctx.poseidon_permute(edge) == np.stack([orc.poseidon(np.full(12, (2**64 - 1) % P, np.uint64))] * 4)).all()
+    assert (ctx.poseidon_permute(nc) == want[:64]).all()
+
+
+def test_mds_layer_carry_paths(ctx, orc):
+    """One linear layer (limb-domain MDS + next round's constants) on states chosen to hit every carry/wrap path:
+    all-ones words, values just below/above p and 2^64, single hot lanes, limb boundaries (2^22, 2^44)."""
+    rc = orc.round_constants()
+    rng = np.random.default_rng(9)
+    specials = [0, 1, P - 1, P, P + 1, 2**64 - 1, 2**64 - 2**32, 2**32 - 1, 2**32, 2**22 - 1, 2**22, 2**44 - 1, 2**44,
+                0xFFFFF00000000000, 0xFFFFFFFFFFC00000, 0x00000FFFFFFFFFFF, 0x8000000000000000]
+    states = [[v] * 12 for v in specials]
+    for lane in range(12):
+        for v in (2**64 - 1, P - 1):
+            st = [0] * 12
+            st[lane] = v
+            states.append(st)
+    for _ in range(400):
+        states.append([int(specials[i]) for i in rng.integers(0, len(specials), 12)])
+    for _ in range(400):
+        hi = rng.integers(0, 2**20, 12)
+        states.append([(2**64 - 1) - int(h) for h in hi])        # top limb all ones: sums that cross 2^64
+    arr = np.array(states, dtype=np.uint64)
+    for nxt in (0, 1, 4, 17, 29, 30):
+        got = ctx.poseidon_permute(arr, mds_only_round=nxt)
+        for st, g in zip(states, got):
+            for r in range(12):
+                v = sum(MDS_CIRC[i] * st[(i + r) % 12] for i in range(12)) + (8 * st[0] if r == 0 else 0)
+                if 1 <= nxt <= 29:
+                    v += int(rc[12 * nxt + r])
+                assert int(g[r]) == v % P, (nxt, st, r)
+
+
 # ---- MerkleTree::new -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nl,ll,h", [(1, 5, 0), (1, 3, 0), (2, 9, 1), (8, 3, 0), (8, 4, 3), (16, 7, 2), (64, 8, 4),
                                      (512, 135, 4), (1024, 32, 4), (4096, 20, 0), (2048, 143, 8), (256, 1, 2)])
