@@ -115,6 +115,49 @@ def cpu_commit_sample(log_n_sample=16, repeats=1):
     return bytes_alg(log_n_sample) / best / 1e9, orc.num_threads(), best
 
 
+def gpu_prove_synthetic(ctx, proofs=16):
+    """Leaf-shaped synthetic prove (BASELINE.json configs 1/2): 3 commits + openings + FRI per proof
+    through the host-buffer API, sequential on one context.  Returns (ms per proof, launches per proof)."""
+    import numpy as np
+    import qpzk
+    from qpzk import prover
+    shape = prover.LEAF_SHAPE
+    rng = np.random.default_rng(1)
+    cs = rng.integers(0, P, size=(shape["constants_sigmas"], 1 << shape["log_n"]), dtype=np.uint64)
+    circuit = prover.SyntheticCircuit(ctx, cs, shape)
+    inputs = [prover.synthetic_inputs(s, shape) for s in range(4)]
+    for i in range(3):
+        prover.prove_synthetic(circuit, **inputs[i % 4])
+    ctx.synchronize()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for i in range(proofs):
+        prover.prove_synthetic(circuit, **inputs[i % 4])
+    ctx.synchronize()
+    dt = (time.perf_counter() - t0) / proofs
+    return 1e3 * dt, (ctx.launch_count() - l0) // proofs
+
+
+def cpu_prove_synthetic(proofs=2):
+    """The same synthetic prove on the CPU restatement (all host cores); ms per proof."""
+    import numpy as np
+    from oracle import oracle as orc
+    orc.build()
+    sys.path.insert(0, os.path.join(ROOT, "qp-zk-circuits_b200"))
+    from qpzk import prover
+    shape = prover.LEAF_SHAPE
+    rng = np.random.default_rng(1)
+    cs = orc.PolynomialBatch.from_values(rng.integers(0, P, size=(shape["constants_sigmas"], 1 << shape["log_n"]), dtype=np.uint64), RATE_BITS, CAP_HEIGHT)
+    best = None
+    for s in range(proofs):
+        inp = prover.synthetic_inputs(s, shape)
+        t0 = time.perf_counter()
+        orc.prove_synthetic(cs, inp["wires"], inp["zs_partial_products"], inp["quotient_coeffs"], inp["public_inputs_hash"], shape["log_n"])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 1e3 * best, orc.num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,6 +188,8 @@ def run_reference(args):
                          "note": "restated CPU baseline (oracle/, C + OpenMP) -- not the reference binary: no cargo/rustc here"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "prove_synthetic": (lambda r: {"latency_ms": r[0], "proofs_per_s": 1e3 / r[0], "cores": r[1],
+                                       "what": "leaf-shaped synthetic prove (2^13; 135/20/16-column commits, openings, FRI) on the CPU restatement"})(cpu_prove_synthetic()),
     }))
 
 
@@ -157,6 +202,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prove", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -340,6 +386,17 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
+    if not args.no_prove:
+        ms, nl = gpu_prove_synthetic(ctx)
+        out["prove_synthetic"] = {"latency_ms": ms, "proofs_per_s": 1e3 / ms, "gpu_launches_per_proof": int(nl),
+                                  "what": "leaf-shaped synthetic prove (BASELINE configs 1/2 stand-in): 2^13 rows; commits of 135 / 20 / 16 "
+                                          "random columns, openings at zeta and g*zeta over 256 polynomials, FRI (rate 3, cap 4, 16 PoW bits, "
+                                          "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
+                                          "restatement (tests/test_gpu_parity.py); witness generation and quotient evaluation are not part of it"}
+        if not args.no_cpu_baseline:
+            cms, cores = cpu_prove_synthetic()
+            out["prove_synthetic"]["cpu_port_latency_ms"] = cms
+            out["prove_synthetic"]["cpu_cores"] = cores
     if not args.no_cpu_baseline:
         v, cores, secs = cpu_commit_sample(16)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

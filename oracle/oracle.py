@@ -321,3 +321,36 @@ def fri_verify(log_n, leaf_lens, caps, instance, openings, params, challenger, p
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---- the commitment / opening half of prove() on the CPU (mirror of qpzk/prover.py) ----------------
+def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient_coeffs, public_inputs_hash,
+                    log_n, num_zs=2, rate_bits=3, cap_height=4, pow_bits=16, num_queries=28, arity_bits=4,
+                    final_poly_bits=5):
+    """Same transcript and the same outputs as qpzk.prover.prove_synthetic, computed by the CPU restatement."""
+    ch = Challenger()
+    ch.observe(np.arange(4, dtype=np.uint64) + 11)
+    ch.observe(public_inputs_hash)
+    wires_b = PolynomialBatch.from_values(wires, rate_bits, cap_height)
+    ch.observe(wires_b.cap())
+    betas_gammas = ch.get(4)
+    zs_b = PolynomialBatch.from_values(zs_partial_products, rate_bits, cap_height)
+    ch.observe(zs_b.cap())
+    alphas = ch.get(2)
+    quot_b = PolynomialBatch.from_coeffs(quotient_coeffs, rate_bits, cap_height)
+    ch.observe(quot_b.cap())
+    zeta = ch.get(2)
+    g = lib().orc_gl_root_of_unity(log_n)
+    g_zeta = [lib().orc_gl_mul(int(zeta[0]), g), lib().orc_gl_mul(int(zeta[1]), g)]
+    oracles = [constants_sigmas_batch, wires_b, zs_b, quot_b]
+    all_polys = [(o, i) for o, b in enumerate(oracles) for i in range(b.num_cols)]
+    zs_next = [(2, i) for i in range(num_zs)]
+    inst = Instance([([int(zeta[0]), int(zeta[1])], all_polys), (g_zeta, zs_next)])
+    openings = np.concatenate([np.concatenate([b.eval_ext(zeta) for b in oracles]), zs_b.eval_ext(g_zeta)[:num_zs]])
+    ch.observe(openings)
+    params = fri_params(log_n, rate_bits, cap_height, pow_bits, num_queries, arity_bits, final_poly_bits)
+    verifier_ch = ch.clone()
+    proof = fri_prove(oracles, inst, params, ch)
+    return dict(caps=[wires_b.cap(), zs_b.cap(), quot_b.cap()], openings=openings, fri_proof=proof,
+                challenges=(betas_gammas, alphas, zeta), instance=inst, params=params, verifier_challenger=verifier_ch,
+                leaf_lens=[b.leaf_len for b in oracles], all_caps=[b.cap() for b in oracles])

@@ -1,0 +1,91 @@
+"""Leaf-shaped synthetic prove: the commitment / opening half of plonky2's `prove()` driven through the C ABI.
+
+`prove_with_partition_witness` (qp-plonky2 =1.5.5; reached from the reference at wormhole/prover/src/lib.rs:171-175)
+does, per proof (transcript in Appendix A.7):
+
+    wires        -> PolynomialBatch::from_values -> observe cap -> betas, gammas
+    zs + partial products -> from_values -> observe cap -> alphas
+    quotient chunks (coefficients) -> from_coeffs -> observe cap -> zeta
+    openings of all four oracles at zeta, of zs at g*zeta -> observe -> PolynomialBatch::prove_openings (FRI)
+
+Witness generation, the partial products and the quotient evaluation need the gate set of
+the un-vendored crate and are NOT part of this repo; here their outputs are stood in for by caller-supplied (random)
+columns of the right shapes, so the function exercises exactly the part of `prove()` this backend replaces and is
+labelled *synthetic* wherever it is reported.  The constants/sigmas oracle is committed once per circuit
+(`CircuitBuilder::build`, reference wormhole/circuit/src/circuit.rs:206-216), not per proof.
+
+Shapes of the leaf circuit: degree 2^13, 85 constants+sigmas, 135 wires, 20 zs/partial
+products, 16 quotient chunks; FRI rate_bits 3, cap_height 4, 16 PoW bits, 28 queries, arity 4, final poly <= 2^5
+(reference wormhole/circuit/src/profile.rs:168-174).
+"""
+import numpy as np
+
+from . import GENERATOR, P, Challenger, FriInstanceInfo, PolynomialBatch, fri_params  # noqa: F401
+
+LEAF_SHAPE = dict(log_n=13, constants_sigmas=85, wires=135, zs_partial_products=20, quotient=16, num_zs=2)
+RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, ARITY_BITS, FINAL_POLY_BITS = 3, 4, 16, 28, 4, 5
+
+
+def _root_of_unity(log_n):
+    w = 7277203076849721926  # order 2^32
+    for _ in range(32 - log_n):
+        w = w * w % P
+    return w
+
+
+class SyntheticCircuit:
+    """What `CircuitBuilder::build` leaves behind for the prover: the committed constants/sigmas oracle."""
+
+    def __init__(self, ctx, constants_sigmas, shape=LEAF_SHAPE):
+        self.ctx, self.shape = ctx, dict(shape)
+        self.log_n = shape["log_n"]
+        self.constants_sigmas = PolynomialBatch.from_values(ctx, constants_sigmas, RATE_BITS, None, CAP_HEIGHT)
+        self.circuit_digest = np.arange(4, dtype=np.uint64) + 11   # stands for the verifier-data digest
+        self.fri_params = fri_params(self.log_n, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, ARITY_BITS, FINAL_POLY_BITS)
+
+
+def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public_inputs_hash, pow_witness=None,
+                    keep_batches=False):
+    """One proof's worth of commitments + FRI.  Inputs are host arrays (values / coefficients, column-major).
+    Returns dict(caps=[wires, zs_pp, quotient], openings=(k, 2) array, fri_proof=flat words)."""
+    ctx, sh = circuit.ctx, circuit.shape
+    ch = Challenger(ctx)
+    ch.observe_hash(circuit.circuit_digest)
+    ch.observe_hash(public_inputs_hash)
+    wires_b = PolynomialBatch.from_values(ctx, wires, RATE_BITS, None, CAP_HEIGHT)
+    ch.observe_cap(wires_b)
+    betas_gammas = ch.get_n_challenges(4)                      # would feed the partial products (a16)
+    zs_b = PolynomialBatch.from_values(ctx, zs_partial_products, RATE_BITS, None, CAP_HEIGHT)
+    ch.observe_cap(zs_b)
+    alphas = ch.get_n_challenges(2)                            # would feed the quotient (a17)
+    quot_b = PolynomialBatch.from_coeffs(ctx, quotient_coeffs, RATE_BITS, None, CAP_HEIGHT)
+    ch.observe_cap(quot_b)
+    zeta = ch.get_extension_challenge()
+    g = _root_of_unity(circuit.log_n)
+    g_zeta = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
+    oracles = [circuit.constants_sigmas, wires_b, zs_b, quot_b]
+    all_polys = [(o, i) for o, b in enumerate(oracles) for i in range(b.num_cols)]
+    zs_next = [(2, i) for i in range(sh["num_zs"])]
+    inst = FriInstanceInfo([([int(zeta[0]), int(zeta[1])], all_polys), (g_zeta, zs_next)])
+    openings = np.concatenate([np.concatenate([b.eval_ext(zeta) for b in oracles]),
+                               zs_b.eval_ext(g_zeta)[:sh["num_zs"]]])
+    ch.observe_extension_elements(openings)
+    proof = PolynomialBatch.prove_openings(inst, oracles, ch, circuit.fri_params, pow_witness=pow_witness)
+    out = dict(caps=[wires_b.cap, zs_b.cap, quot_b.cap], openings=openings, fri_proof=proof,
+               challenges=(betas_gammas, alphas, zeta))
+    if keep_batches:
+        out["batches"] = (wires_b, zs_b, quot_b)
+    else:
+        for b in (wires_b, zs_b, quot_b):
+            b.free()
+    ch.free()
+    return out
+
+
+def synthetic_inputs(seed, shape=LEAF_SHAPE):
+    """Uniform canonical columns of the leaf shape (deterministic in `seed`)."""
+    rng = np.random.default_rng(seed)
+    n = 1 << shape["log_n"]
+    mk = lambda c: rng.integers(0, P, size=(c, n), dtype=np.uint64)
+    return dict(wires=mk(shape["wires"]), zs_partial_products=mk(shape["zs_partial_products"]),
+                quotient_coeffs=mk(shape["quotient"]), public_inputs_hash=rng.integers(0, P, size=4, dtype=np.uint64))

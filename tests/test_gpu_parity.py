@@ -321,3 +321,29 @@ def test_full_size_commit_properties(ctx, qpzk, orc):
                 acc = (acc * pt + int(v)) % P
             assert acc == int(rows[k][c])
     assert (b.polynomials[:3] == np.stack([orc.fft(cols[c], inverse=True) for c in range(3)])).all()
+
+
+# ---- the commitment / opening half of prove() (leaf-shaped synthetic prove, BASELINE.json configs 1/2) -------------
+@pytest.mark.parametrize("log_n", [8, 13])
+def test_prove_synthetic_matches_oracle_and_verifies(ctx, qpzk, orc, log_n):
+    from qpzk import prover
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n)
+    rng = np.random.default_rng(40 + log_n)
+    cs = rng.integers(0, P, size=(shape["constants_sigmas"], 1 << log_n), dtype=np.uint64)
+    circuit = prover.SyntheticCircuit(ctx, cs, shape)
+    inp = prover.synthetic_inputs(7, shape)
+    got = prover.prove_synthetic(circuit, **inp)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, inp["wires"], inp["zs_partial_products"], inp["quotient_coeffs"],
+                               inp["public_inputs_hash"], log_n)
+    for a, b in zip(got["caps"], want["caps"]):
+        assert (a == b).all()
+    assert (got["openings"] == want["openings"]).all()
+    assert (got["fri_proof"] == want["fri_proof"]).all()
+    rc = orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], want["openings"], want["params"],
+                        want["verifier_challenger"], got["fri_proof"])
+    assert rc == 0
+    # steady state: a second proof of the same shape allocates nothing new and frees everything it used
+    cached = ctx.cached_bytes()
+    prover.prove_synthetic(circuit, **prover.synthetic_inputs(8, shape))
+    assert ctx.cached_bytes() == cached

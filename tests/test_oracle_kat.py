@@ -197,3 +197,19 @@ def test_lde_is_polynomial_evaluation(orc):
         for j in range(L):  # leaf row j holds P(g * w_L^bitrev(j))
             x = orc.GENERATOR * pow(wl, br(j, log_n + 3), P) % P
             assert sum(int(co[c][k]) * pow(x, k, P) for k in range(n)) % P == int(lv[j][c])
+
+
+def test_oracle_prove_synthetic_is_accepted_by_the_oracle_verifier(orc):
+    """The CPU mirror of the commitment/opening half of prove() (used as the checker of qpzk.prover and as the CPU
+    baseline of bench.py's prove line) produces proofs its own verifier restatement accepts, and rejects tampering."""
+    log_n = 7
+    rng = np.random.default_rng(3)
+    mk = lambda c: rng.integers(0, orc.P, size=(c, 1 << log_n), dtype=np.uint64)
+    cs = orc.PolynomialBatch.from_values(mk(9), 3, 4)
+    out = orc.prove_synthetic(cs, mk(12), mk(4), mk(3), rng.integers(0, orc.P, size=4, dtype=np.uint64), log_n,
+                              pow_bits=6, num_queries=5)
+    args = (log_n, out["leaf_lens"], out["all_caps"], out["instance"], out["openings"], out["params"])
+    assert orc.fri_verify(*args, out["verifier_challenger"].clone(), out["fri_proof"]) == 0
+    bad = out["fri_proof"].copy()
+    bad[len(bad) // 2] ^= 1
+    assert orc.fri_verify(*args, out["verifier_challenger"].clone(), bad) != 0
