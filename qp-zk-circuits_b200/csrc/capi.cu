@@ -55,6 +55,8 @@ struct qpzk_ctx {
     int num_sms = 0;
     bool zeroize = true;
     bool timing = false;
+    cudaStream_t copy_stream = nullptr;   // H2D of host-buffer commits, overlapped with the per-column stages
+    cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[5] = {};
     bool ev_valid[5] = {};
     uint64_t launches = 0;
@@ -230,6 +232,8 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     }
     CK(upload_poseidon_constants());
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev[i]));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     *out = ctx;
     return 0;
 }
@@ -248,6 +252,8 @@ static void ctx_unref(qpzk_ctx* ctx) {
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (auto& kv : ctx->coset_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -336,35 +342,46 @@ static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uin
     return 0;
 }
 
-// coefficients -> leaf blocks [coset_begin, coset_begin + coset_count) of the LDE, row-major, leaf order
-static int run_lde(qpzk_ctx* ctx, const uint64_t* coeffs, uint64_t* leaves, uint32_t log_n, uint32_t num_cols,
-                   uint32_t leaf_width, uint32_t rate_bits, uint32_t coset_begin, uint32_t coset_count) {
-    if (!num_cols) return 0;
+// coefficients -> leaf blocks [coset_begin, coset_begin + coset_count) of the LDE, row-major, leaf order.
+// The strided passes work column by column, so they can run on a column range as soon as those columns are on the
+// device (the host-buffer commit overlaps them with the H2D copy of the next range); the last pass needs every
+// column of its rows and runs once.
+struct LdePlan {
+    qpzk_ctx* ctx = nullptr;
+    const uint64_t* coeffs = nullptr;
+    uint64_t* leaves = nullptr;
+    uint64_t* inter = nullptr;
+    uint32_t log_n = 0, num_cols = 0, leaf_width = 0, coset_count = 0, s_last = 0;
     PowTables fwd;
     CosetTables cs;
-    int rc = get_pow_tables(ctx, log_n, false, &fwd);
-    if (rc) return rc;
-    if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
-    uint64_t n = 1ull << log_n;
-    if ((uint64_t)num_cols * coset_count > 65535) return fail(QPZK_EINVAL, "num_cols * cosets > 65535");
-    // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
-    uint32_t s_last = 0;
-    while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
-    uint32_t rem = log_n - s_last;
-    const uint64_t* cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
-    const uint64_t* cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
+    const uint64_t *cs_lo = nullptr, *cs_hi = nullptr;
+    std::vector<uint32_t> passes;
 
-    uint64_t* inter = nullptr;
-    LdeLastArgs la{};
-    la.leaves = leaves; la.log_n = log_n; la.s = s_last; la.num_cols = num_cols; la.leaf_width = leaf_width;
-    la.num_cosets = coset_count; la.tw_lo = fwd.lo; la.tw_hi = fwd.hi; la.cs_lo = cs_lo; la.cs_hi = cs_hi;
-    la.cs_hi_size = cs.hi_size; la.in_stride = n;
-    if (rem == 0) {
-        la.in = coeffs; la.from_coeffs = 1;
-    } else {
-        if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols * n))) return rc;
-        std::vector<uint32_t> passes;
-        split_bits(rem, 10, passes);
+    int prepare(qpzk_ctx* c, const uint64_t* coeffs_, uint64_t* leaves_, uint32_t log_n_, uint32_t num_cols_,
+                uint32_t leaf_width_, uint32_t rate_bits, uint32_t coset_begin, uint32_t coset_count_) {
+        ctx = c; coeffs = coeffs_; leaves = leaves_; log_n = log_n_; num_cols = num_cols_; leaf_width = leaf_width_;
+        coset_count = coset_count_;
+        if (!num_cols) return 0;
+        int rc = get_pow_tables(ctx, log_n, false, &fwd);
+        if (rc) return rc;
+        if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
+        if (num_cols > 65535) return fail(QPZK_EINVAL, "num_cols > 65535");
+        // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
+        s_last = 0;
+        while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
+        cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
+        cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
+        passes.clear();
+        if (log_n > s_last) {
+            split_bits(log_n - s_last, 10, passes);
+            if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols << log_n))) return rc;
+        }
+        return 0;
+    }
+    // strided passes for columns [c0, c1)
+    int run_passes(uint32_t c0, uint32_t c1) {
+        if (passes.empty() || c1 <= c0) return 0;
+        const uint64_t n = 1ull << log_n;
         uint32_t b_hi = log_n;
         for (size_t i = 0; i < passes.size(); i++) {
             NttPassArgs a{};
@@ -372,26 +389,38 @@ static int run_lde(qpzk_ctx* ctx, const uint64_t* coeffs, uint64_t* leaves, uint
             a.W = tile_width(a.s, a.b_lo);
             a.in_stride = a.out_stride = n;
             a.tw_lo = fwd.lo; a.tw_hi = fwd.hi; a.scale = 1;
+            a.num_arrays = c1 - c0;
+            a.group_stride = (uint64_t)num_cols * n;
+            a.out = inter + (uint64_t)c0 * n;
             if (i == 0) {
-                a.mode = NTT_FWD_COSET_FIRST; a.in = coeffs; a.out = inter; a.num_arrays = num_cols;
+                a.mode = NTT_FWD_COSET_FIRST; a.in = coeffs + (uint64_t)c0 * n; a.num_groups = 1;
                 a.num_cosets = coset_count; a.cs_lo = cs_lo; a.cs_hi = cs_hi; a.cs_hi_size = cs.hi_size;
             } else {
-                a.mode = NTT_FWD_GENERIC; a.in = inter; a.out = inter; a.num_arrays = (uint64_t)num_cols * coset_count;
-                a.num_cosets = 1;
+                a.mode = NTT_FWD_GENERIC; a.in = a.out; a.num_groups = coset_count; a.num_cosets = 1;
             }
-            cudaError_t e = launch_ntt_pass(a, ctx->stream);
-            if (e != cudaSuccess) { dev_free(ctx, inter); CK(e); }
+            CK(launch_ntt_pass(a, ctx->stream));
             ctx->launches++;
             b_hi = a.b_lo;
         }
-        la.in = inter; la.from_coeffs = 0;
+        return 0;
     }
-    cudaError_t e = launch_lde_last(la, ctx->stream);
-    ctx->launches++;
-    dev_free(ctx, inter, (uint64_t)coset_count * num_cols * n);
-    CK(e);
-    return 0;
-}
+    int run_last() {
+        if (!num_cols) return 0;
+        LdeLastArgs la{};
+        la.leaves = leaves; la.log_n = log_n; la.s = s_last; la.num_cols = num_cols; la.leaf_width = leaf_width;
+        la.num_cosets = coset_count; la.tw_lo = fwd.lo; la.tw_hi = fwd.hi; la.cs_lo = cs_lo; la.cs_hi = cs_hi;
+        la.cs_hi_size = cs.hi_size; la.in_stride = 1ull << log_n;
+        la.in = passes.empty() ? coeffs : inter;
+        la.from_coeffs = passes.empty() ? 1 : 0;
+        CK(launch_lde_last(la, ctx->stream));
+        ctx->launches++;
+        return 0;
+    }
+    void release() {
+        if (inter) dev_free(ctx, inter, (uint64_t)coset_count * num_cols << log_n);
+        inter = nullptr;
+    }
+};
 
 static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
     uint64_t words = 8 * b->num_leaves;  // all levels fit in 8N words
@@ -421,12 +450,31 @@ static void batch_release(qpzk_batch* b) {
     ctx_unref(ctx);
 }
 
-static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values, uint32_t log_n, uint32_t num_cols,
+// Where the input columns come from.  Device-resident input: `dev` is set and fetch is a no-op.  Host input: the
+// columns are copied range by range on the context's copy stream and `fetch(c0, c1)` makes the context stream wait
+// for the range, so the per-column stages (iNTT, strided LDE passes) of one range overlap the copy of the next.
+struct ColumnSource {
+    const uint64_t* dev = nullptr;
+    const uint64_t* host = nullptr;
+    uint64_t* staging = nullptr;
+    uint32_t chunks = 1;
+};
+
+static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uint32_t c0, uint32_t c1) {
+    if (!src.host || c1 <= c0) return 0;
+    CK(cudaMemcpyAsync(src.staging + (uint64_t)c0 * n, src.host + (uint64_t)c0 * n, (uint64_t)(c1 - c0) * n * sizeof(uint64_t),
+                       cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    return 0;
+}
+
+static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin,
                        uint32_t coset_count, bool keep_coeffs_copy, qpzk_batch** out) {
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
-    if (!cols_dev && num_cols) return fail(QPZK_EINVAL, "cols is null");
+    if (!src.dev && !src.host && num_cols) return fail(QPZK_EINVAL, "cols is null");
     if (log_n > 26 || rate_bits > 8) return fail(QPZK_EINVAL, "log_n > 26 or rate_bits > 8");
     uint32_t cosets = 1u << rate_bits;
     if (!coset_count || (coset_count & (coset_count - 1)) || coset_begin % coset_count || coset_begin + coset_count > cosets)
@@ -449,24 +497,55 @@ static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values
     int rc;
     for (int i = 0; i < 5; i++) ctx->ev_valid[i] = false;
     mark(ctx, 0);
-    if (from_values || keep_coeffs_copy) {
+    const bool own_coeffs = from_values || keep_coeffs_copy || src.host;
+    if (own_coeffs) {
         if ((rc = dev_alloc(ctx, &b->coeffs, (uint64_t)num_cols * n))) { batch_release(b); return rc; }
     }
-    const uint64_t* coeffs = b->coeffs;
-    if (from_values) {
-        if ((rc = run_intt(ctx, cols_dev, b->coeffs, log_n, num_cols))) { batch_release(b); return rc; }
-    } else if (keep_coeffs_copy) {
-        cudaError_t e = cudaMemcpyAsync(b->coeffs, cols_dev, (uint64_t)num_cols * n * sizeof(uint64_t),
+    if (src.host) {
+        // from_coeffs copies straight into the batch's coefficient buffer; from_values needs a staging buffer
+        // (the first iNTT pass is out of place).  The copy stream must not overtake earlier users of the block.
+        if (from_values) {
+            if ((rc = dev_alloc(ctx, &src.staging, (uint64_t)num_cols * n))) { batch_release(b); return rc; }
+        } else {
+            src.staging = b->coeffs;
+        }
+        cudaError_t e = cudaEventRecord(ctx->copy_done, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0);
+        if (e != cudaSuccess) { if (from_values) dev_free(ctx, src.staging); batch_release(b); CK(e); }
+    }
+    const uint64_t* in_dev = src.host ? src.staging : src.dev;
+    const uint64_t* coeffs = own_coeffs ? b->coeffs : src.dev;
+    auto fail_out = [&](int code) {
+        if (src.host && from_values) dev_free(ctx, src.staging, (uint64_t)num_cols * n);
+        batch_release(b);
+        return code;
+    };
+    if (!from_values && keep_coeffs_copy && !src.host) {
+        cudaError_t e = cudaMemcpyAsync(b->coeffs, src.dev, (uint64_t)num_cols * n * sizeof(uint64_t),
                                         cudaMemcpyDeviceToDevice, ctx->stream);
         if (e != cudaSuccess) { batch_release(b); CK(e); }
-    } else {
-        coeffs = cols_dev;
     }
-    mark(ctx, 1);
-    if ((rc = dev_alloc(ctx, &b->leaves, b->num_leaves * b->leaf_width))) { batch_release(b); return rc; }
-    if ((rc = run_lde(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count))) {
-        batch_release(b); return rc;
+    if ((rc = dev_alloc(ctx, &b->leaves, b->num_leaves * b->leaf_width))) return fail_out(rc);
+    LdePlan lde;
+    if ((rc = lde.prepare(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count))) {
+        lde.release(); return fail_out(rc);
     }
+    const uint32_t chunks = src.host ? (src.chunks ? src.chunks : 1) : 1;
+    const uint32_t per = (num_cols + chunks - 1) / chunks;
+    for (uint32_t c0 = 0; c0 < num_cols; c0 += per) {
+        const uint32_t c1 = c0 + per < num_cols ? c0 + per : num_cols;
+        if ((rc = fetch_columns(ctx, src, n, c0, c1))) { lde.release(); return fail_out(rc); }
+        if (from_values && (rc = run_intt(ctx, in_dev + (uint64_t)c0 * n, b->coeffs + (uint64_t)c0 * n, log_n, c1 - c0))) {
+            lde.release(); return fail_out(rc);
+        }
+        if (c0 == 0) mark(ctx, 1);  // with one chunk: end of the iNTT stage (chunked runs interleave the stages)
+        if ((rc = lde.run_passes(c0, c1))) { lde.release(); return fail_out(rc); }
+    }
+    if (!num_cols) mark(ctx, 1);
+    rc = lde.run_last();
+    lde.release();
+    if (src.host && from_values) dev_free(ctx, src.staging, (uint64_t)num_cols * n);
+    if (rc) { batch_release(b); return rc; }
     if (salt_dev) {
         cudaError_t e = launch_salt_scatter(salt_dev, b->leaves, log_L, num_cols, b->leaf_width, b->salt_cols, ctx->stream);
         ctx->launches++;
@@ -478,38 +557,20 @@ static int commit_impl(qpzk_ctx* ctx, const uint64_t* cols_dev, bool from_values
     return 0;
 }
 
-// stage a host matrix on the device, run fn, release the staging buffer
-template <typename F>
-static int with_staged(qpzk_ctx* ctx, const uint64_t* host, uint64_t words, const uint64_t* host2, uint64_t words2, F fn) {
-    uint64_t *d = nullptr, *d2 = nullptr;
-    int rc;
-    CK(cudaSetDevice(ctx->device));
-    if (host && words) {
-        if ((rc = dev_alloc(ctx, &d, words))) return rc;
-        CK(cudaMemcpyAsync(d, host, words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (host2 && words2) {
-        if ((rc = dev_alloc(ctx, &d2, words2))) { dev_free(ctx, d); return rc; }
-        CK(cudaMemcpyAsync(d2, host2, words2 * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    rc = fn(d, d2);
-    dev_free(ctx, d, words);
-    dev_free(ctx, d2, words2);
-    return rc;
-}
+static ColumnSource dev_source(const uint64_t* p) { ColumnSource s; s.dev = p; return s; }
 
 extern "C" int qpzk_commit_from_values_dev(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
                                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
-    GUARD_BEGIN return commit_impl(ctx, cols, true, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
+    GUARD_BEGIN return commit_impl(ctx, dev_source(cols), true, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
 }
 extern "C" int qpzk_commit_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
                                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
-    GUARD_BEGIN return commit_impl(ctx, cols, false, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
+    GUARD_BEGIN return commit_impl(ctx, dev_source(cols), false, log_n, num_cols, rate_bits, cap_height, salt, 0, 1u << (rate_bits & 15), true, out); GUARD_END
 }
 extern "C" int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint32_t num_cols,
                                                   uint32_t rate_bits, uint32_t cap_height, uint32_t coset_begin,
                                                   uint32_t coset_count, qpzk_batch** out) {
-    GUARD_BEGIN return commit_impl(ctx, coeffs, false, log_n, num_cols, rate_bits, cap_height, nullptr, coset_begin, coset_count, false, out); GUARD_END
+    GUARD_BEGIN return commit_impl(ctx, dev_source(coeffs), false, log_n, num_cols, rate_bits, cap_height, nullptr, coset_begin, coset_count, false, out); GUARD_END
 }
 extern "C" int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
     GUARD_BEGIN
@@ -520,16 +581,33 @@ extern "C" int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values, uint
     GUARD_END
 }
 
+// Host-buffer commit: the input is copied in column ranges of >= 32 MB (at most 8) so that the copy of one range
+// overlaps the iNTT and the strided LDE passes of the previous one; small inputs go in one piece.
 static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     if (log_n > 26 || rate_bits > 8) return fail(QPZK_EINVAL, "log_n > 26 or rate_bits > 8");
     if (!cols && num_cols) return fail(QPZK_EINVAL, "cols is null");
+    CK(cudaSetDevice(ctx->device));
     uint64_t n = 1ull << log_n;
     uint64_t salt_words = salt ? (uint64_t)QPZK_SALT_SIZE * (n << rate_bits) : 0;
-    return with_staged(ctx, cols, (uint64_t)num_cols * n, salt, salt_words, [&](uint64_t* d, uint64_t* d2) {
-        return commit_impl(ctx, d, from_values, log_n, num_cols, rate_bits, cap_height, d2, 0, 1u << rate_bits, true, out);
-    });
+    uint64_t* d_salt = nullptr;
+    int rc;
+    if (salt_words) {
+        if ((rc = dev_alloc(ctx, &d_salt, salt_words))) return rc;
+        cudaError_t e = cudaMemcpyAsync(d_salt, salt, salt_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { dev_free(ctx, d_salt); CK(e); }
+    }
+    ColumnSource src;
+    src.host = cols;
+    uint64_t bytes = (uint64_t)num_cols * n * sizeof(uint64_t);
+    src.chunks = (uint32_t)(bytes >> 25);
+    if (src.chunks > 8) src.chunks = 8;
+    if (src.chunks < 1) src.chunks = 1;
+    if (!num_cols) { src.host = nullptr; src.dev = nullptr; }
+    rc = commit_impl(ctx, src, from_values, log_n, num_cols, rate_bits, cap_height, d_salt, 0, 1u << rate_bits, true, out);
+    dev_free(ctx, d_salt, salt_words);
+    return rc;
 }
 extern "C" int qpzk_commit_from_values(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
                                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {

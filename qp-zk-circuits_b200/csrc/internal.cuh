@@ -40,7 +40,9 @@ struct NttPassArgs {
     const uint64_t* in;
     uint64_t* out;
     uint64_t in_stride, out_stride;  // words between consecutive arrays
-    uint64_t num_arrays;             // grid.y
+    uint64_t num_arrays;             // grid.y: arrays per group
+    uint64_t num_groups;             // grid.z (FWD_GENERIC: one group per coset; 1 otherwise)
+    uint64_t group_stride;           // words between the same array of consecutive groups / cosets (in and out)
     uint32_t log_n, b_lo, s, W;
     uint32_t mode, num_cosets;
     const uint64_t *tw_lo, *tw_hi;   // powers of w_n (forward) or w_n^-1 (inverse)

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
     uint32_t tile = blockIdx.x, coset = 0;
     if (a.mode == NTT_FWD_COSET_FIRST) { coset = tile & (a.num_cosets - 1); tile /= a.num_cosets; }
     const uint64_t col = blockIdx.y;
-    const uint64_t* in = a.in + col * a.in_stride;
+    const uint64_t* in = a.in + col * a.in_stride + (uint64_t)blockIdx.z * a.group_stride;
 
     // local twiddles w_S^j = w_n^(j * n / S)
     for (uint32_t j = threadIdx.x; j < (S >> 1); j += blockDim.x)
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPassArgs a) {
     if (a.mode == NTT_INV_FIRST || a.mode == NTT_INV_GENERIC) local_ntt<true>(sm, ltw, s, W, true, map);
     else local_ntt<false>(sm, ltw, s, W, true, map);
 
-    uint64_t* out = a.out + (col + (uint64_t)coset * a.num_arrays) * a.out_stride;
+    uint64_t* out = a.out + col * a.out_stride + ((uint64_t)coset + blockIdx.z) * a.group_stride;
     if (a.mode == NTT_INV_FIRST) {
         uint64_t q0 = (uint64_t)tile * W;
         for (uint32_t i = threadIdx.x; i < S * W; i += blockDim.x) {
@@ -175,7 +175,7 @@ cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st) {
     size_t smem = ((size_t)(a.W == 1 ? padded_len(S) : S * a.W) + S / 2 + 1) * sizeof(uint64_t);
     cudaError_t e = ensure_smem((const void*)ntt_pass_kernel, smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)tiles, (unsigned)a.num_arrays);
+    dim3 grid((unsigned)tiles, (unsigned)a.num_arrays, (unsigned)(a.num_groups ? a.num_groups : 1));
     ntt_pass_kernel<<<grid, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
