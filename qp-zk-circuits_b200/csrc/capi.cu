@@ -7,6 +7,7 @@
 // prove_openings}`, `MerkleTree::new`, `fri_proof` (reference call sites
 // wormhole/prover/src/lib.rs:171-175 and the two aggregator provers).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -54,6 +55,7 @@ struct qpzk_ctx {
     bool own_stream = false;
     int num_sms = 0;
     bool zeroize = true;
+    bool legacy_ntt = false;   // QPZK_LEGACY_NTT=1: generic strided passes only (A/B testing of ntt_fwd.cu)
     bool timing = false;
     cudaStream_t copy_stream = nullptr;   // H2D of host-buffer commits, overlapped with the per-column stages
     cudaEvent_t copy_done = nullptr;
@@ -224,6 +226,7 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     qpzk_ctx* ctx = new qpzk_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    { const char* e = getenv("QPZK_LEGACY_NTT"); ctx->legacy_ntt = e && e[0] == '1'; }
     if (own) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
@@ -373,7 +376,9 @@ struct LdePlan {
         cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
         passes.clear();
         if (log_n > s_last) {
-            split_bits(log_n - s_last, 10, passes);
+            // 5..8-bit passes run on the register-resident kernel (ntt_fwd.cu); other splits on the generic one
+            const uint32_t rem = log_n - s_last;
+            split_bits(rem, (rem >= 10 || (rem >= 5 && rem <= 8)) && !ctx->legacy_ntt ? 8 : 10, passes);
             if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols << log_n))) return rc;
         }
         return 0;
@@ -398,7 +403,14 @@ struct LdePlan {
             } else {
                 a.mode = NTT_FWD_GENERIC; a.in = a.out; a.num_groups = coset_count; a.num_cosets = 1;
             }
-            CK(launch_ntt_pass(a, ctx->stream));
+            if (!ctx->legacy_ntt && ntt_fwd_supported(a)) {
+                const uint64_t tile_cosets = (n >> 12) * coset_count;
+                uint64_t cpb = tile_cosets * (c1 - c0) / 4096;
+                a.cols_per_block = (uint32_t)(cpb < 1 ? 1 : cpb > 32 ? 32 : cpb);
+                CK(launch_ntt_fwd(a, ctx->stream));
+            } else {
+                CK(launch_ntt_pass(a, ctx->stream));
+            }
             ctx->launches++;
             b_hi = a.b_lo;
         }

@@ -32,14 +32,35 @@ __device__ __forceinline__ uint64_t gl_add_nc(uint64_t a, uint64_t b) {
     }
     return s;
 }
-// canonical in -> canonical out
+// canonical in -> canonical out.  Device versions are carry chains without compares or selects (the NTT kernels are
+// bound by ALU instruction issue): a - b wraps exactly when a < b, and adding p back is subtracting 2^32 - 1 mod 2^64;
+// a + b is a - (p - b).  Only sub-flavoured carry ops are chained (see limb_combine in poseidon.cuh for why).
+__host__ __device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32), d0, d1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0,%2,%4;\n\tsubc.cc.u32 %1,%3,%5;\n\tsubc.u32 m,0,0;\n\t"   // m = borrow ? 0xffffffff : 0
+        "sub.cc.u32 %0,%0,m;\n\tsubc.u32 %1,%1,0;\n\t}"
+        : "=&r"(d0), "=&r"(d1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)d1 << 32) | d0;
+#else
+    return a >= b ? a - b : a + (GL_P - b);
+#endif
+}
 __host__ __device__ __forceinline__ uint64_t gl_add(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32), d0, d1;
+    asm("{\n\t.reg .u32 m,n0,n1;\n\t"
+        "sub.cc.u32 n0,1,%4;\n\tsubc.u32 n1,0xffffffff,%5;\n\t"                  // p - b  (= p for b = 0: still fine)
+        "sub.cc.u32 %0,%2,n0;\n\tsubc.cc.u32 %1,%3,n1;\n\tsubc.u32 m,0,0;\n\t"
+        "sub.cc.u32 %0,%0,m;\n\tsubc.u32 %1,%1,0;\n\t}"
+        : "=&r"(d0), "=&r"(d1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)d1 << 32) | d0;
+#else
     uint64_t s = a + b;
     if (s < a || s >= GL_P) s -= GL_P;
     return s;
-}
-__host__ __device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
-    return a >= b ? a - b : a + (GL_P - b);
+#endif
 }
 __host__ __device__ __forceinline__ uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
 

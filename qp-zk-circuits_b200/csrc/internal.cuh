@@ -49,6 +49,7 @@ struct NttPassArgs {
     const uint64_t *cs_lo, *cs_hi;   // per-coset powers of s_j = g * w_L^bitrev(j)
     uint64_t cs_hi_size;
     uint64_t scale;                  // multiplied into every output (1/n on the last inverse pass), 1 = none
+    uint32_t cols_per_block;         // ntt_fwd_kernel only: columns handled by one block (grid.y = ceil(num_arrays / it))
 };
 
 struct LdeLastArgs {
@@ -61,6 +62,8 @@ struct LdeLastArgs {
 };
 
 cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st);
+bool ntt_fwd_supported(const NttPassArgs& a);                          // ntt_fwd.cu: register-resident forward passes
+cudaError_t launch_ntt_fwd(const NttPassArgs& a, cudaStream_t st);
 cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st);
 cudaError_t launch_bitrev_copy(const uint64_t* in, uint64_t* out, uint32_t log_n, uint64_t num_arrays,
                                uint64_t in_stride, uint64_t out_stride, cudaStream_t st);

@@ -1,0 +1,184 @@
+// Strided passes of the coset low-degree extension, second generation: a 2^s-point transform (s = 5..8) over
+// position bits [b_lo, b_lo+s) done as TWO register-resident sub-transforms with a single shared-memory exchange,
+// and every position-dependent factor hoisted out of a loop over columns.
+//
+// Replaces the same upstream code as ntt.cu (`PolynomialCoeffs::{lde, coset_fft}` of qp-plonky2-field =1.5.5,
+// SURVEY.md 8a rows a2/a5) and computes, bit for bit, what ntt_pass_kernel computes in its FWD modes:
+//     out[hi, bitrev_s(f), low] = w_{2^b_hi}^(f*low) * sum_e x[hi, e, low] * w_S^(e*f),     S = 2^s,
+//     x = in * s_j^p  in the first pass (coset scaling),  p = e * 2^b_lo + low.
+//
+// Why it is faster (profiles/r1_summary.md: the old pass is bound by ALU instruction issue, ~430 instructions per
+// output element of a 7-bit pass, of which the butterflies are less than a third):
+//   * S = A*B.  With e = eg + B*k and f = f1 + A*f2:  w_S^(e f) = w_S^(eg f1) * w_B^(eg f2) * w_A^(k f1), so a thread
+//     first runs an A-point transform on A registers (inputs B apart: no exchange needed before it), multiplies by
+//     T[eg][f1], exchanges through shared memory once, and runs a B-point transform on B registers.  The twiddles
+//     inside the register transforms are roots of unity of order <= 16 = compile-time powers of two (2^12 has order
+//     16 in Goldilocks: w_2 = 2^96, w_4 = 2^48, w_8 = 2^24, w_16 = 2^12 are exactly plonky2's roots).
+//   * the coset scaling factors split as s^p = s^(B 2^b_lo k) * s^(eg 2^b_lo) * s^low: the first is the same for
+//     every thread (A values per coset), the second merges into T, the third merges into the output factor.  The
+//     output factors (one per output element of the tile) live in registers across the column loop, T and the
+//     A per-coset values in shared memory: per element and pass there remain 2-3 general multiplications instead
+//     of 5.5-7.5, and no table arithmetic at all inside the column loop.
+#include "internal.cuh"
+#include "goldilocks.cuh"
+#include "ntt_local.cuh"
+
+namespace qpzk {
+
+__host__ __device__ constexpr uint64_t pow2_mod_p(unsigned t) {   // 2^t mod p for t < 96, as a canonical constant
+    return t < 64 ? (1ull << t) : ((1ull << (t - 32)) - (1ull << (t - 64)));  // 2^64 = 2^32 - 1
+}
+
+// In-register decimation-in-frequency transform of 2^LOG values: natural order in, bit-reversed order out
+// (register r ends up holding frequency bitrev_LOG(r)).  Twiddle of the pair (k, k+half) is w_{2 half}^(k mod half)
+// = 2^((96/half) * (k mod half)).
+template <int LOG>
+__device__ __forceinline__ void dft_regs(uint64_t (&x)[1 << LOG]) {
+    constexpr int R = 1 << LOG;
+#pragma unroll
+    for (int t = 0; t < LOG; t++) {
+        const int half = R >> (t + 1);
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (k & half) continue;
+            const int j = k & (half - 1);
+            const uint64_t a = x[k], b = x[k + half];
+            x[k] = gl_add(a, b);
+            const uint64_t d = gl_sub(a, b);
+            x[k + half] = j == 0 ? d : gl_mulc(d, pow2_mod_p((96 / half) * j));
+        }
+    }
+}
+
+template <int BITS>
+__host__ __device__ constexpr uint32_t brev_c(uint32_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < BITS; i++) r |= ((x >> i) & 1u) << (BITS - 1 - i);
+    return r;
+}
+
+// Tile = 2^(SA+SB) positions of the pass x Wd = 4096 / 2^(SA+SB) consecutive low positions; 256 threads; every
+// thread handles 16 elements of each column in both phases.
+template <int SA, int SB>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
+    constexpr int S_LOG = SA + SB, A = 1 << SA, B = 1 << SB, S = 1 << S_LOG;
+    constexpr int LWD = 12 - S_LOG, WD = 1 << LWD, G = NTT_THREADS / WD;   // lanes along `low`, thread groups
+    constexpr int IT1 = B / G, IT2 = A / G;                                // items per thread in phase 1 / 2
+    static_assert(IT1 >= 1 && IT2 >= 1 && IT1 * A == 16 && IT2 * B == 16, "tile shape");
+    extern __shared__ uint64_t smem[];
+    uint64_t* buf = smem;                 // [f1][eg][w]
+    uint64_t* T = smem + S * WD;          // [eg][f1]
+    uint64_t* Ck = T + S;                 // [k]
+    const bool coset_first = a.mode == NTT_FWD_COSET_FIRST;
+    const uint32_t b_hi = a.b_lo + S_LOG;
+    const uint32_t w = threadIdx.x & (WD - 1), g = threadIdx.x >> LWD;
+
+    uint32_t tile = blockIdx.x, coset = 0;
+    if (coset_first) { coset = tile & (a.num_cosets - 1); tile /= a.num_cosets; }
+    const uint32_t llow = a.b_lo - LWD;
+    const uint64_t hi = tile >> llow;
+    const uint64_t low0 = (uint64_t)(tile & ((1u << llow) - 1)) << LWD;
+    const uint64_t base = (hi << b_hi) + low0;
+    const uint64_t* clo = a.cs_lo + (size_t)coset * TW_LO_SIZE;
+    const uint64_t* chi = a.cs_hi + (size_t)coset * a.cs_hi_size;
+
+    // ---- factors that do not depend on the column ----
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+        const uint32_t eg = i >> SA, f1 = i & (A - 1);
+        uint64_t t = tw_get(a.tw_lo, a.tw_hi, (uint64_t)(eg * f1) << (a.log_n - S_LOG));
+        if (coset_first) t = gl_mulc(t, tw_get(clo, chi, (uint64_t)eg << a.b_lo));
+        T[i] = t;
+    }
+    if (threadIdx.x < A) Ck[threadIdx.x] = coset_first ? tw_get(clo, chi, ((uint64_t)threadIdx.x << SB) << a.b_lo) : 1;
+    uint64_t O[IT2][B];   // output factor of (f1 = g + G*it, f2 = bitrev(r)) at this thread's low position
+    {
+        const uint64_t pl = low0 + w;
+        const uint64_t cw = coset_first ? tw_get(clo, chi, pl) : 1;
+#pragma unroll
+        for (int it = 0; it < IT2; it++) {
+            const uint32_t f1 = g + G * it;
+#pragma unroll
+            for (int r = 0; r < B; r++) {
+                const uint32_t f = f1 + A * brev_c<SB>(r);
+                uint64_t o = tw_get(a.tw_lo, a.tw_hi, ((uint64_t)f * pl) << (a.log_n - b_hi));
+                if (coset_first) o = gl_mulc(o, cw);
+                O[it][r] = o;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- columns ----
+    const uint32_t c_begin = blockIdx.y * a.cols_per_block;
+    const uint32_t c_end = min((uint32_t)a.num_arrays, c_begin + a.cols_per_block);
+    for (uint32_t col = c_begin; col < c_end; col++) {
+        const uint64_t* in = a.in + col * a.in_stride + (uint64_t)blockIdx.z * a.group_stride + base + w;
+        uint64_t* out = a.out + col * a.out_stride + ((uint64_t)coset + blockIdx.z) * a.group_stride + base + w;
+#pragma unroll
+        for (int it = 0; it < IT1; it++) {
+            const uint32_t eg = g + G * it;
+            uint64_t x[A];
+#pragma unroll
+            for (int k = 0; k < A; k++) x[k] = in[(uint64_t)(eg + B * k) << a.b_lo];
+            if (coset_first) {
+#pragma unroll
+                for (int k = 1; k < A; k++) x[k] = gl_mulc(x[k], Ck[k]);
+            }
+            dft_regs<SA>(x);
+#pragma unroll
+            for (int r = 0; r < A; r++) {
+                const uint32_t f1 = brev_c<SA>(r);
+                buf[(f1 * B + eg) * WD + w] = gl_mulc(x[r], T[eg * A + f1]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < IT2; it++) {
+            const uint32_t f1 = g + G * it;
+            uint64_t y[B];
+#pragma unroll
+            for (int j = 0; j < B; j++) y[j] = buf[(f1 * B + j) * WD + w];
+            dft_regs<SB>(y);
+            const uint32_t e0 = (__brev(f1) >> (32 - SA)) * B;   // slot of frequency f = f1 + A*f2 is bitrev_s(f)
+#pragma unroll
+            for (int r = 0; r < B; r++) out[(uint64_t)(e0 + r) << a.b_lo] = gl_mulc(y[r], O[it][r]);
+        }
+        __syncthreads();
+    }
+}
+
+bool ntt_fwd_supported(const NttPassArgs& a) {
+    if (a.mode != NTT_FWD_COSET_FIRST && a.mode != NTT_FWD_GENERIC) return false;
+    if (a.s < 5 || a.s > 8 || a.scale != 1) return false;
+    return a.b_lo >= 12 - a.s && a.log_n >= a.b_lo + a.s;
+}
+
+template <int SA, int SB>
+static cudaError_t launch_one(const NttPassArgs& a, dim3 grid, cudaStream_t st) {
+    constexpr int S = 1 << (SA + SB);
+    const size_t smem = ((size_t)4096 + S + (1 << SA)) * sizeof(uint64_t);
+    static bool attr_set = false;   // same value every time; a benign race at worst
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)ntt_fwd_kernel<SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ntt_fwd_kernel<SA, SB><<<grid, NTT_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_fwd(const NttPassArgs& a, cudaStream_t st) {
+    uint64_t tiles = (1ull << a.log_n) >> 12;
+    if (a.mode == NTT_FWD_COSET_FIRST) tiles *= a.num_cosets;
+    const uint32_t cpb = a.cols_per_block ? a.cols_per_block : 1;
+    dim3 grid((unsigned)tiles, (unsigned)((a.num_arrays + cpb - 1) / cpb), (unsigned)(a.num_groups ? a.num_groups : 1));
+    switch (a.s) {
+        case 5: return launch_one<3, 2>(a, grid, st);
+        case 6: return launch_one<3, 3>(a, grid, st);
+        case 7: return launch_one<4, 3>(a, grid, st);
+        case 8: return launch_one<4, 4>(a, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace qpzk
