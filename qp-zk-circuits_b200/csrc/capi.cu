@@ -372,13 +372,31 @@ struct LdePlan {
         // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
         s_last = 0;
         while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
+        // preferred: the 32-point in-register last pass (ntt_fwd.cu) whenever the polynomial is long enough
+        const bool fast = !ctx->legacy_ntt && log_n > 5 && (size_t)num_cols * 33 * 8 <= 160 * 1024;
+        if (fast) s_last = 5;
         cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
         cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
         passes.clear();
         if (log_n > s_last) {
-            // 5..8-bit passes run on the register-resident kernel (ntt_fwd.cu); other splits on the generic one
+            // 5..8-bit passes run on the register-resident kernel (ntt_fwd.cu), which needs b_lo >= 12 - s: the pass
+            // next to the last one takes 7 or 8 bits, the ones above it 5..8 each, and what does not fit this
+            // pattern (rem = 9, 10, 11 or < 7) starts with a short pass of the generic kernel.
             const uint32_t rem = log_n - s_last;
-            split_bits(rem, (rem >= 10 || (rem >= 5 && rem <= 8)) && !ctx->legacy_ntt ? 8 : 10, passes);
+            if (fast && rem >= 7) {
+                uint32_t top = 0, r = rem;
+                if (r >= 9 && r <= 11) { top = r - 8; r = 8; }             // generic 1..3 bits, then 8
+                std::vector<uint32_t> parts;
+                auto ok = [](uint32_t rest) { return rest == 0 || (rest >= 5 && rest != 9); };   // splittable into 5..8
+                const uint32_t last = (r >= 8 && ok(r - 8)) ? 8 : 7;
+                r -= last;
+                if (r) split_bits(r, 8, parts);
+                if (top) passes.push_back(top);
+                for (uint32_t x : parts) passes.push_back(x);
+                passes.push_back(last);
+            } else {
+                split_bits(rem, 10, passes);
+            }
             if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols << log_n))) return rc;
         }
         return 0;
@@ -424,7 +442,8 @@ struct LdePlan {
         la.cs_hi_size = cs.hi_size; la.in_stride = 1ull << log_n;
         la.in = passes.empty() ? coeffs : inter;
         la.from_coeffs = passes.empty() ? 1 : 0;
-        CK(launch_lde_last(la, ctx->stream));
+        if (!ctx->legacy_ntt && lde_last32_supported(la)) CK(launch_lde_last32(la, ctx->stream));
+        else CK(launch_lde_last(la, ctx->stream));
         ctx->launches++;
         return 0;
     }

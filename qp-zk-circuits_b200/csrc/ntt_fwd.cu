@@ -111,25 +111,39 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
     // ---- columns ----
     const uint32_t c_begin = blockIdx.y * a.cols_per_block;
     const uint32_t c_end = min((uint32_t)a.num_arrays, c_begin + a.cols_per_block);
+    // The inputs of the next column are requested right after the first phase has consumed the current ones, so the
+    // loads are in flight during the exchange and the second phase (one block per SM: nothing else would hide them).
+    const uint64_t in_off = (uint64_t)blockIdx.z * a.group_stride + base + w;
+    uint64_t x[IT1][A];
+    if (c_begin < c_end) {
+        const uint64_t* in = a.in + c_begin * a.in_stride + in_off;
+#pragma unroll
+        for (int it = 0; it < IT1; it++)
+#pragma unroll
+            for (int k = 0; k < A; k++) x[it][k] = in[(uint64_t)(g + G * it + B * k) << a.b_lo];
+    }
     for (uint32_t col = c_begin; col < c_end; col++) {
-        const uint64_t* in = a.in + col * a.in_stride + (uint64_t)blockIdx.z * a.group_stride + base + w;
         uint64_t* out = a.out + col * a.out_stride + ((uint64_t)coset + blockIdx.z) * a.group_stride + base + w;
 #pragma unroll
         for (int it = 0; it < IT1; it++) {
             const uint32_t eg = g + G * it;
-            uint64_t x[A];
-#pragma unroll
-            for (int k = 0; k < A; k++) x[k] = in[(uint64_t)(eg + B * k) << a.b_lo];
             if (coset_first) {
 #pragma unroll
-                for (int k = 1; k < A; k++) x[k] = gl_mulc(x[k], Ck[k]);
+                for (int k = 1; k < A; k++) x[it][k] = gl_mulc(x[it][k], Ck[k]);
             }
-            dft_regs<SA>(x);
+            dft_regs<SA>(x[it]);
 #pragma unroll
             for (int r = 0; r < A; r++) {
                 const uint32_t f1 = brev_c<SA>(r);
-                buf[(f1 * B + eg) * WD + w] = gl_mulc(x[r], T[eg * A + f1]);
+                buf[(f1 * B + eg) * WD + w] = gl_mulc(x[it][r], T[eg * A + f1]);
             }
+        }
+        if (col + 1 < c_end) {
+            const uint64_t* in = a.in + (col + 1) * a.in_stride + in_off;
+#pragma unroll
+            for (int it = 0; it < IT1; it++)
+#pragma unroll
+                for (int k = 0; k < A; k++) x[it][k] = in[(uint64_t)(g + G * it + B * k) << a.b_lo];
         }
         __syncthreads();
 #pragma unroll
@@ -145,6 +159,64 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
         }
         __syncthreads();
     }
+}
+
+// Last LDE pass, 32-point version: position bits [0, 5) of every column for CH chunks of 32 consecutive rows of one
+// coset.  A thread owns one (column, chunk): 32 registers, a full 32-point transform whose twiddles are powers of
+// two (w_32 = 2^6), no barrier inside the transform.  Shared memory is only the transposing buffer between the
+// column-major loads and the whole-row stores into the leaf matrix (row stride RP odd: both sides conflict free).
+__global__ void __launch_bounds__(LDE_LAST32_MAX_THREADS) lde_last32_kernel(LdeLastArgs a, uint32_t log_ch) {
+    extern __shared__ uint64_t smem[];
+    const uint32_t C = a.num_cols, CH = 1u << log_ch, R = 32u << log_ch, RP = R + 1;
+    const uint64_t n = 1ull << a.log_n;
+    const uint64_t blocks_per_coset = n >> (5 + log_ch);
+    const uint32_t coset = blockIdx.x / blocks_per_coset;
+    const uint64_t row0 = (blockIdx.x % blocks_per_coset) * R;
+
+    const uint64_t* in = a.in + (uint64_t)coset * C * a.in_stride + row0;
+#pragma unroll 8
+    for (uint32_t i = threadIdx.x; i < C * (R / 2); i += blockDim.x) {     // 16-byte loads, many in flight per thread
+        const uint32_t e = (i & (R / 2 - 1)) * 2, c = i >> (4 + log_ch);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(in + (uint64_t)c * a.in_stride + e);
+        smem[c * RP + e] = v.x;
+        smem[c * RP + e + 1] = v.y;
+    }
+    __syncthreads();
+    for (uint32_t item = threadIdx.x; item < C * CH; item += blockDim.x) {
+        const uint32_t c = item % C, ch = item / C;
+        uint64_t* col = smem + c * RP + ch * 32;
+        uint64_t x[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) x[k] = col[k];
+        dft_regs<5>(x);            // register r holds frequency bitrev_5(r): exactly the leaf order of the chunk
+#pragma unroll
+        for (int k = 0; k < 32; k++) col[k] = x[k];
+    }
+    __syncthreads();
+    uint64_t* rows = a.leaves + ((uint64_t)coset * n + row0) * a.leaf_width;
+    for (uint32_t e = threadIdx.x / 32; e < R; e += blockDim.x / 32)
+        for (uint32_t c = threadIdx.x % 32; c < C; c += 32) rows[(uint64_t)e * a.leaf_width + c] = smem[c * RP + e];
+}
+
+bool lde_last32_supported(const LdeLastArgs& a) {
+    return a.s == 5 && !a.from_coeffs && a.log_n >= 5 && a.num_cols >= 1 && (size_t)a.num_cols * 33 * 8 <= 160 * 1024;
+}
+
+cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st) {
+    // chunks per block: enough (column, chunk) items for ~256 threads, within ~96 KB of shared memory
+    uint32_t log_ch = 0;
+    while (log_ch < 5 && ((uint64_t)a.num_cols << log_ch) < 224 && a.log_n > 5 + log_ch &&
+           (size_t)a.num_cols * ((64u << log_ch) + 1) * 8 <= 96 * 1024) log_ch++;
+    const uint32_t items = a.num_cols << log_ch;
+    uint32_t threads = (items + 31) / 32 * 32;
+    if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
+    if (threads < 64) threads = 64;
+    const size_t smem = (size_t)a.num_cols * ((32u << log_ch) + 1) * sizeof(uint64_t);
+    cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t blocks = ((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets;
+    lde_last32_kernel<<<(unsigned)blocks, threads, smem, st>>>(a, log_ch);
+    return cudaGetLastError();
 }
 
 bool ntt_fwd_supported(const NttPassArgs& a) {
