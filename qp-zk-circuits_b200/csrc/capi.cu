@@ -442,7 +442,7 @@ struct LdePlan {
         la.cs_hi_size = cs.hi_size; la.in_stride = 1ull << log_n;
         la.in = passes.empty() ? coeffs : inter;
         la.from_coeffs = passes.empty() ? 1 : 0;
-        if (!ctx->legacy_ntt && lde_last32_supported(la)) CK(launch_lde_last32(la, ctx->stream));
+        if (!ctx->legacy_ntt && lde_last32_supported(la)) CK(launch_lde_last32(la, ctx->stream, ctx->num_sms));
         else CK(launch_lde_last(la, ctx->stream));
         ctx->launches++;
         return 0;

@@ -66,7 +66,7 @@ bool ntt_fwd_supported(const NttPassArgs& a);                          // ntt_fw
 cudaError_t launch_ntt_fwd(const NttPassArgs& a, cudaStream_t st);
 constexpr int LDE_LAST32_MAX_THREADS = 384;
 bool lde_last32_supported(const LdeLastArgs& a);                       // ntt_fwd.cu: 32-point in-register last pass
-cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st);
+cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms);
 cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st);
 cudaError_t launch_bitrev_copy(const uint64_t* in, uint64_t* out, uint32_t log_n, uint64_t num_arrays,
                                uint64_t in_stride, uint64_t out_stride, cudaStream_t st);

@@ -19,6 +19,8 @@
 //     output factors (one per output element of the tile) live in registers across the column loop, T and the
 //     A per-coset values in shared memory: per element and pass there remain 2-3 general multiplications instead
 //     of 5.5-7.5, and no table arithmetic at all inside the column loop.
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "goldilocks.cuh"
 #include "ntt_local.cuh"
@@ -198,11 +200,141 @@ __global__ void __launch_bounds__(LDE_LAST32_MAX_THREADS) lde_last32_kernel(LdeL
         for (uint32_t c = threadIdx.x % 32; c < C; c += 32) rows[(uint64_t)e * a.leaf_width + c] = smem[c * RP + e];
 }
 
+// ---- the same pass as a persistent, TMA-fed pipeline --------------------------------------------------------------
+// One block per SM walks over tiles.  A tile's input is C column segments of R*8 bytes: one warp requests them with
+// bulk asynchronous copies (cp.async.bulk, completion counted on an mbarrier) into one of two input buffers while the
+// block transforms the other; the transformed tile is written row-major into a third buffer, which for unsalted
+// leaves is exactly the tile's R*C*8 contiguous bytes of the leaf matrix, and leaves the SM as ONE bulk store.  Loads
+// of tile i+1, the 32-point transforms of tile i and the store of tile i-1 overlap; no thread issues a global
+// load or store instruction.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// blockDim = consumer threads (a multiple of 32) + one producer warp (the last one).
+__global__ void __launch_bounds__(LDE_LAST32_MAX_THREADS + 32)
+lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
+    extern __shared__ __align__(128) uint64_t smem[];
+    const uint32_t C = a.num_cols, CH = 1u << log_ch, R = 32u << log_ch, RP = R + 2;   // RP even: 16-byte aligned columns
+    const size_t in_words = (size_t)C * RP;                 // input buffer b starts at smem + b * in_words
+    uint64_t* out_buf = smem + 2 * in_words;                // [row][column]
+    uint64_t* bars = out_buf + (size_t)R * C;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 2);   // barrier b at +8*b
+    const uint64_t n = 1ull << a.log_n;
+    const uint32_t tiles_per_coset = (uint32_t)(n >> (5 + log_ch));
+    const uint32_t consumers = blockDim.x - 32;
+    const uint32_t lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(full0 + 8 * i) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= consumers) {
+        // ---- producer warp: C bulk copies of R*8 bytes per tile into the buffer the consumers have released ----
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const uint32_t b = it & 1;
+            if (it >= 2) mbar_wait(empty0 + 8 * b, ((it >> 1) - 1) & 1);
+            const uint32_t coset = tile / tiles_per_coset;
+            const uint64_t row0 = (uint64_t)(tile % tiles_per_coset) * R;
+            const uint64_t* src = a.in + (uint64_t)coset * C * a.in_stride + row0;
+            if (lane == 0) {
+                uint64_t st;
+                asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
+                             : "=l"(st) : "r"(full0 + 8 * b), "r"(C * R * 8u) : "memory");
+                (void)st;
+            }
+            __syncwarp();
+            for (uint32_t c = lane; c < C; c += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(smem + b * in_words + (size_t)c * RP)), "l"(src + (uint64_t)c * a.in_stride),
+                                "r"(R * 8u), "r"(full0 + 8 * b) : "memory");
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const uint32_t b = it & 1;
+        mbar_wait(full0 + 8 * b, (it >> 1) & 1);
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // out_buf is free again
+        asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
+        for (uint32_t item = threadIdx.x; item < C * CH; item += consumers) {
+            const uint32_t c = item % C, ch = item / C;
+            const uint64_t* col = smem + b * in_words + (size_t)c * RP + ch * 32;
+            uint64_t x[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) x[k] = col[k];
+            dft_regs<5>(x);
+            uint64_t* o = out_buf + (size_t)(ch * 32) * C + c;
+#pragma unroll
+            for (int k = 0; k < 32; k++) o[(size_t)k * C] = x[k];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+        asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
+        if (threadIdx.x == 0) {
+            uint64_t st;   // the input buffer may be refilled
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(empty0 + 8 * b) : "memory");
+            (void)st;
+            const uint32_t coset = tile / tiles_per_coset;
+            const uint64_t row0 = (uint64_t)(tile % tiles_per_coset) * R;
+            uint64_t* dst = a.leaves + ((uint64_t)coset * n + row0) * C;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(smem_u32(out_buf)), "r"(R * C * 8u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static bool lde_last32_tma_ok(const LdeLastArgs& a, uint32_t* log_ch_out, size_t* smem_out) {
+    if (a.leaf_width != a.num_cols) return false;          // salted leaves: rows are not contiguous
+    static const int first = [] { const char* e = getenv("QPZK_TMA_LOGCH"); return e ? atoi(e) : 1; }();
+    for (int log_ch = first; log_ch >= 0; log_ch--) {
+        if (a.log_n < 5u + log_ch) continue;
+        const size_t R = 32u << log_ch;
+        const size_t smem = (2 * (size_t)a.num_cols * (R + 2) + R * a.num_cols + 4) * sizeof(uint64_t);
+        if (smem > 220 * 1024) continue;
+        if ((R * a.num_cols * 8) % 16) continue;
+        *log_ch_out = log_ch; *smem_out = smem;
+        return true;
+    }
+    return false;
+}
+
 bool lde_last32_supported(const LdeLastArgs& a) {
     return a.s == 5 && !a.from_coeffs && a.log_n >= 5 && a.num_cols >= 1 && (size_t)a.num_cols * 33 * 8 <= 160 * 1024;
 }
 
-cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st) {
+cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms) {
+    {
+        uint32_t log_ch; size_t smem;
+        static const bool no_tma = [] { const char* e = getenv("QPZK_NO_TMA"); return e && e[0] == '1'; }();
+        const uint64_t tiles_min = (uint64_t)4 * num_sms;      // persistent pipeline only when every SM gets several tiles
+        if (!no_tma && lde_last32_tma_ok(a, &log_ch, &smem) &&
+            (((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets) >= tiles_min) {
+            const uint64_t tiles = ((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets;
+            const uint32_t items = a.num_cols << log_ch;
+            uint32_t threads = (items + 31) / 32 * 32;
+            if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
+            if (threads < 64) threads = 64;
+            cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            const uint64_t resident = (uint64_t)num_sms * (smem <= 110 * 1024 ? 2 : 1);   // two pipelines per SM when they fit
+            const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+            lde_last32_tma_kernel<<<grid, threads + 32, smem, st>>>(a, log_ch, (uint32_t)tiles);
+            return cudaGetLastError();
+        }
+    }
     // chunks per block: enough (column, chunk) items for ~256 threads, within ~96 KB of shared memory
     uint32_t log_ch = 0;
     while (log_ch < 5 && ((uint64_t)a.num_cols << log_ch) < 224 && a.log_n > 5 + log_ch &&
