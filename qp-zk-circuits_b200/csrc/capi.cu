@@ -833,12 +833,18 @@ extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {
     GUARD_BEGIN
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     CK(cudaSetDevice(ctx->device));
+    // state and staging come from the context's block cache: cudaMalloc / cudaFree synchronise the whole device and
+    // would serialise proofs that run concurrently on other contexts (one Challenger per proof)
+    uint64_t *dev = nullptr, *scratch = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &dev, (sizeof(ChallengerDev) + 7) / 8))) return rc;
+    if ((rc = dev_alloc(ctx, &scratch, 4096))) { dev_free(ctx, dev); return rc; }
     qpzk_challenger* ch = new qpzk_challenger();
     ctx->refs++;
     ch->ctx = ctx;
     ch->scratch_words = 4096;
-    CK(cudaMalloc((void**)&ch->dev, sizeof(ChallengerDev)));
-    CK(cudaMalloc((void**)&ch->scratch, ch->scratch_words * sizeof(uint64_t)));
+    ch->dev = reinterpret_cast<ChallengerDev*>(dev);
+    ch->scratch = scratch;
     CK(cudaMemsetAsync(ch->dev, 0, sizeof(ChallengerDev), ctx->stream));
     *out = ch;
     return 0;
@@ -847,9 +853,9 @@ extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {
 extern "C" void qpzk_challenger_free(qpzk_challenger* ch) {
     if (!ch) return;
     cudaSetDevice(ch->ctx->device);
-    cudaStreamSynchronize(ch->ctx->stream);
-    cudaFree(ch->dev); cudaFree(ch->scratch);
     qpzk_ctx* ctx = ch->ctx;
+    dev_free(ctx, ch->dev, (sizeof(ChallengerDev) + 7) / 8);   // stream ordered: later users of the block run after us
+    dev_free(ctx, ch->scratch);
     delete ch;
     ctx_unref(ctx);
 }

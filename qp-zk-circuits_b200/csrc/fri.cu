@@ -240,7 +240,7 @@ cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st) {
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute((const void*)fri_final_poly_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
         if (e != cudaSuccess) return e;
     }
     fri_final_poly_kernel<<<1, NTT_THREADS, smem, st>>>(a);

@@ -30,6 +30,12 @@ cudaError_t upload_poseidon_constants() {
             limb[36 * row + 24 + i] = (uint32_t)(cl >> 44);
         }
     cudaError_t e;
+    {
+        static uint64_t flat[372];
+        for (int row = 0; row < 31; row++)
+            for (int i = 0; i < 12; i++) flat[12 * row + i] = row < 30 ? QPZK_POSEIDON_RC_HOST[12 * row + i] : 0;
+        if ((e = cudaMemcpyToSymbol(d_rc_flat, flat, sizeof flat)) != cudaSuccess) return e;
+    }
 #if QPZK_MDS_FFT
     (void)split;
     e = cudaMemcpyToSymbol(c_rc_limb, limb, sizeof limb);
@@ -135,39 +141,59 @@ merkle_top_kernel(uint64_t* __restrict__ digests, uint32_t first_level, uint32_t
 // ---------------------------------------------------------------------------------------------
 // Challenger (duplex sponge, overwrite mode; pop challenges from the back of the output buffer)
 // ---------------------------------------------------------------------------------------------
-__device__ void ch_duplex(ChallengerDev* c) {
-    uint64_t s[12];
-    for (uint32_t i = 0; i < c->in_len; i++) c->state[i] = c->in[i];
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = c->state[i];
-    c->in_len = 0;
-    poseidon_permute(s);
-#pragma unroll
-    for (int i = 0; i < 12; i++) c->state[i] = gl_canon(s[i]);
-#pragma unroll
-    for (int i = 0; i < 8; i++) c->out[i] = c->state[i];
-    c->out_len = 8;
+// One warp runs the sponge: lane i < 12 keeps state word i in a register for the whole kernel, lane k < 8 keeps
+// pending input k, and every duplexing is one warp-wide permutation (poseidon_permute_warp).  Observing the ~260
+// opened values of a proof is 65 permutations in sequence; this is what sets the latency of that step.
+struct WarpChallenger {
+    uint64_t st, pend, outv;  // state word `lane`, pending input `lane`, output-buffer word `lane`
+    uint32_t in_len, out_len; // warp-uniform
+    int lane;
+    __device__ void load(const ChallengerDev* c) {
+        lane = threadIdx.x & 31;
+        st = lane < 12 ? c->state[lane] : 0;
+        pend = lane < 8 ? c->in[lane] : 0;
+        outv = lane < 8 ? c->out[lane] : 0;
+        in_len = c->in_len; out_len = c->out_len;
+    }
+    __device__ void store(ChallengerDev* c) const {
+        if (lane < 12) c->state[lane] = st;
+        if (lane < 8) { c->in[lane] = pend; c->out[lane] = outv; }
+        if (lane == 0) { c->in_len = in_len; c->out_len = out_len; }
+    }
+    __device__ void duplex() {
+        if ((uint32_t)lane < in_len) st = pend;
+        in_len = 0;
+        st = gl_canon(poseidon_permute_warp(st, lane));
+        outv = st;
+        out_len = 8;
+    }
+    __device__ void observe(uint64_t x) {   // x warp-uniform
+        out_len = 0;
+        if ((uint32_t)lane == in_len) pend = x;
+        if (++in_len == 8) duplex();
+    }
+    __device__ uint64_t get() {             // returns the challenge on every lane
+        if (in_len > 0 || out_len == 0) duplex();
+        --out_len;
+        return __shfl_sync(0xffffffffu, outv, out_len);
+    }
+};
+
+__global__ void __launch_bounds__(32) challenger_observe_kernel(ChallengerDev* c, const uint64_t* __restrict__ elems, uint32_t n) {
+    WarpChallenger w;
+    w.load(c);
+    for (uint32_t i = 0; i < n; i++) w.observe(elems[i]);
+    w.store(c);
 }
 
-__device__ void ch_observe(ChallengerDev* c, uint64_t x) {
-    c->out_len = 0;
-    c->in[c->in_len++] = x;
-    if (c->in_len == 8) ch_duplex(c);
-}
-
-__device__ uint64_t ch_get(ChallengerDev* c) {
-    if (c->in_len > 0 || c->out_len == 0) ch_duplex(c);
-    return c->out[--c->out_len];
-}
-
-__global__ void challenger_observe_kernel(ChallengerDev* c, const uint64_t* __restrict__ elems, uint32_t n) {
-    if (threadIdx.x || blockIdx.x) return;
-    for (uint32_t i = 0; i < n; i++) ch_observe(c, elems[i]);
-}
-
-__global__ void challenger_get_kernel(ChallengerDev* c, uint64_t* __restrict__ out, uint32_t n) {
-    if (threadIdx.x || blockIdx.x) return;
-    for (uint32_t i = 0; i < n; i++) out[i] = ch_get(c);
+__global__ void __launch_bounds__(32) challenger_get_kernel(ChallengerDev* c, uint64_t* __restrict__ out, uint32_t n) {
+    WarpChallenger w;
+    w.load(c);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t v = w.get();
+        if (w.lane == 0) out[i] = v;
+    }
+    w.store(c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,21 +227,28 @@ pow_grind_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, uint64_
 // Observe the witness (the ground one or a caller-supplied one), draw the PoW response, then draw the
 // query indices.  status[0]: 1 = ok, 0 = witness does not reach the difficulty, 2 = no hit in this window
 // (challenger untouched; the host launches the next window).
-__global__ void pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found,
-                                              uint64_t forced_witness, uint32_t pow_bits, uint32_t num_queries,
-                                              uint64_t lde_size, uint64_t* __restrict__ witness_out,
-                                              uint64_t* __restrict__ indices, uint32_t* status) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(32)
+pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found, uint64_t forced_witness,
+                              uint32_t pow_bits, uint32_t num_queries, uint64_t lde_size,
+                              uint64_t* __restrict__ witness_out, uint64_t* __restrict__ indices, uint32_t* status) {
     uint64_t w = forced_witness;
     if (forced_witness == ~0ULL) {
         w = (uint64_t)*found;
-        if (w == ~0ULL) { status[0] = 2; return; }
+        if (w == ~0ULL) { if (threadIdx.x == 0) status[0] = 2; return; }
     }
-    ch_observe(c, w);
-    uint64_t resp = ch_get(c);
-    status[0] = (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) ? 1u : 0u;
-    *witness_out = w;
-    for (uint32_t q = 0; q < num_queries; q++) indices[q] = ch_get(c) % lde_size;
+    WarpChallenger ch;
+    ch.load(c);
+    ch.observe(w);
+    const uint64_t resp = ch.get();
+    if (ch.lane == 0) {
+        status[0] = (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) ? 1u : 0u;
+        *witness_out = w;
+    }
+    for (uint32_t q = 0; q < num_queries; q++) {
+        const uint64_t v = ch.get();
+        if (ch.lane == 0) indices[q] = v % lde_size;
+    }
+    ch.store(c);
 }
 
 // ---------------------------------------------------------------------------------------------

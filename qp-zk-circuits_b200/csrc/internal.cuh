@@ -5,6 +5,10 @@
 
 namespace qpzk {
 
+// Opt-in dynamic shared memory limit of sm_100 (227 KB).  Kernels that may need more than 48 KB get THIS value set
+// before every launch: the attribute is process-wide per function, and setting a per-launch size from several host
+// threads races (one thread lowers it between another thread's set and launch); a constant is idempotent.
+constexpr int MAX_DYN_SMEM = 227 * 1024;
 constexpr int HASH_THREADS = 128;          // threads per block for one-thread-per-permutation kernels
 constexpr int TOP_THREADS = 256;           // single-block kernel for the top of a Merkle tree
 constexpr uint64_t TOP_LEVEL_NODES = 256;  // levels with <= this many parents go to the single-block kernel

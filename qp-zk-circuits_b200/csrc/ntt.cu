@@ -164,7 +164,8 @@ __global__ void salt_scatter_kernel(const uint64_t* __restrict__ salt, uint64_t*
 // ---------------------------------------------------------------------------------------------
 static cudaError_t ensure_smem(const void* fn, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (bytes > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
 cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st) {

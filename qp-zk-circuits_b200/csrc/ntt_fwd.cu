@@ -327,7 +327,7 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
             uint32_t threads = (items + 31) / 32 * 32;
             if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
             if (threads < 64) threads = 64;
-            cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
             if (e != cudaSuccess) return e;
             const uint64_t resident = (uint64_t)num_sms * (smem <= 110 * 1024 ? 2 : 1);   // two pipelines per SM when they fit
             const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
@@ -344,7 +344,7 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
     if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
     if (threads < 64) threads = 64;
     const size_t smem = (size_t)a.num_cols * ((32u << log_ch) + 1) * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     const uint64_t blocks = ((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets;
     lde_last32_kernel<<<(unsigned)blocks, threads, smem, st>>>(a, log_ch);
@@ -361,12 +361,7 @@ template <int SA, int SB>
 static cudaError_t launch_one(const NttPassArgs& a, dim3 grid, cudaStream_t st) {
     constexpr int S = 1 << (SA + SB);
     const size_t smem = ((size_t)4096 + S + (1 << SA)) * sizeof(uint64_t);
-    static bool attr_set = false;   // same value every time; a benign race at worst
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)ntt_fwd_kernel<SA, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+
     ntt_fwd_kernel<SA, SB><<<grid, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }

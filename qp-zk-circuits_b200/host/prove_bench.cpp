@@ -1,0 +1,178 @@
+// Native host-side driver of the C ABI (include/qpzk.h): the commitment / opening half of plonky2's `prove()` for
+// leaf-shaped synthetic witnesses, T host threads with one context (device + stream) each.
+//
+// This is the C++ stand-in for what a `[patch.crates-io]` fork of qp-plonky2 =1.5.5 does from Rust (INTEGRATION.md;
+// the reference toolchain is absent in this image): `prove_with_partition_witness` steps 2-9,
+// reached in the reference from wormhole/prover/src/lib.rs:171-175 and, one leaf proof per worker, from the
+// aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
+// exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
+//
+//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13]
+// prints one JSON line: proofs/s over all threads, mean latency per proof, and a checksum of every thread's first
+// proof (identical inputs must give identical proofs on every thread).
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/qpzk.h"
+
+static const uint64_t P = 0xFFFFFFFF00000001ULL;
+
+static uint64_t mulmod(uint64_t a, uint64_t b) { return (uint64_t)((unsigned __int128)a * b % P); }
+
+static uint64_t root_of_unity(unsigned log_n) {
+    uint64_t w = 7277203076849721926ULL;  // order 2^32
+    for (unsigned i = log_n; i < 32; i++) w = mulmod(w, w);
+    return w;
+}
+
+struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled below p
+    uint64_t s;
+    uint64_t next() {
+        for (;;) {
+            uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+            z ^= z >> 31;
+            if (z < P) return z;
+        }
+    }
+};
+
+static std::vector<uint64_t> random_columns(uint64_t seed, size_t cols, size_t n) {
+    SplitMix g{seed};
+    std::vector<uint64_t> v(cols * n);
+    for (auto& x : v) x = g.next();
+    return v;
+}
+
+#define QCHECK(call)                                                                          \
+    do {                                                                                      \
+        int rc_ = (call);                                                                     \
+        if (rc_ != 0) { fprintf(stderr, "%s -> %d: %s\n", #call, rc_, qpzk_last_error()); exit(2); } \
+    } while (0)
+
+struct Shape { unsigned log_n = 13, constants_sigmas = 85, wires = 135, zs_pp = 20, quotient = 16, num_zs = 2; };
+
+struct Worker {
+    int device;
+    Shape sh;
+    int proofs;
+    double seconds = 0;
+    uint64_t checksum = 0;
+    uint64_t launches = 0;
+
+    void run(std::atomic<int>* ready, std::atomic<bool>* go) {
+        const size_t n = (size_t)1 << sh.log_n;
+        qpzk_ctx* ctx;
+        QCHECK(qpzk_ctx_create(device, &ctx));
+        // what CircuitBuilder::build leaves behind: the committed constants/sigmas oracle
+        auto cs = random_columns(1, sh.constants_sigmas, n);
+        qpzk_batch* cs_b;
+        QCHECK(qpzk_commit_from_values(ctx, cs.data(), sh.log_n, sh.constants_sigmas, 3, 4, nullptr, &cs_b));
+        // four witnesses' worth of columns, reused round robin
+        std::vector<std::vector<uint64_t>> wires, zs, quot;
+        for (int s = 0; s < 4; s++) {
+            wires.push_back(random_columns(100 + s, sh.wires, n));
+            zs.push_back(random_columns(200 + s, sh.zs_pp, n));
+            quot.push_back(random_columns(300 + s, sh.quotient, n));
+        }
+        qpzk_fri_params fp;
+        QCHECK(qpzk_fri_params_constant_arity(&fp, sh.log_n, 3, 4, 16, 28, 4, 5));
+        const uint32_t leaf_lens[4] = {sh.constants_sigmas, sh.wires, sh.zs_pp, sh.quotient};
+        const size_t proof_words = qpzk_fri_proof_words(&fp, sh.log_n, 4, leaf_lens);
+        const uint32_t total = sh.constants_sigmas + sh.wires + sh.zs_pp + sh.quotient;
+        std::vector<uint32_t> po, pi;
+        for (uint32_t o = 0; o < 4; o++) for (uint32_t i = 0; i < leaf_lens[o]; i++) { po.push_back(o); pi.push_back(i); }
+        for (uint32_t i = 0; i < sh.num_zs; i++) { po.push_back(2); pi.push_back(i); }
+        const uint32_t sizes[2] = {total, sh.num_zs};
+        std::vector<uint64_t> proof(proof_words), openings(2 * (total + sh.num_zs));
+        const uint64_t digest[4] = {11, 12, 13, 14}, pih[4] = {21, 22, 23, 24};
+        const uint64_t g = root_of_unity(sh.log_n);
+
+        auto prove_one = [&](int s) {
+            qpzk_challenger* ch;
+            QCHECK(qpzk_challenger_create(ctx, &ch));
+            QCHECK(qpzk_challenger_observe(ch, digest, 4));
+            QCHECK(qpzk_challenger_observe(ch, pih, 4));
+            qpzk_batch *w_b, *z_b, *q_b;
+            uint64_t chal[4], zeta[2];
+            QCHECK(qpzk_commit_from_values(ctx, wires[s].data(), sh.log_n, sh.wires, 3, 4, nullptr, &w_b));
+            QCHECK(qpzk_challenger_observe_cap(ch, w_b));
+            QCHECK(qpzk_challenger_get(ch, chal, 4));   // betas, gammas (would feed the partial products)
+            QCHECK(qpzk_commit_from_values(ctx, zs[s].data(), sh.log_n, sh.zs_pp, 3, 4, nullptr, &z_b));
+            QCHECK(qpzk_challenger_observe_cap(ch, z_b));
+            QCHECK(qpzk_challenger_get(ch, chal, 2));   // alphas (would feed the quotient)
+            QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
+            QCHECK(qpzk_challenger_observe_cap(ch, q_b));
+            QCHECK(qpzk_challenger_get(ch, zeta, 2));
+            const uint64_t gz[2] = {mulmod(zeta[0], g), mulmod(zeta[1], g)};
+            const qpzk_batch* oracles[4] = {cs_b, w_b, z_b, q_b};
+            uint64_t* op = openings.data();
+            for (int o = 0; o < 4; o++) { QCHECK(qpzk_batch_eval_ext(oracles[o], zeta, op)); op += 2 * leaf_lens[o]; }
+            std::vector<uint64_t> znext(2 * sh.zs_pp);
+            QCHECK(qpzk_batch_eval_ext(z_b, gz, znext.data()));
+            memcpy(op, znext.data(), 2 * sh.num_zs * sizeof(uint64_t));
+            QCHECK(qpzk_challenger_observe(ch, openings.data(), (uint32_t)openings.size()));
+            const uint64_t points[4] = {zeta[0], zeta[1], gz[0], gz[1]};
+            qpzk_fri_instance inst{2, points, sizes, po.data(), pi.data()};
+            QCHECK(qpzk_fri_prove(ctx, oracles, 4, &inst, &fp, ch, QPZK_POW_SEARCH, proof.data(), nullptr));
+            qpzk_batch_free(w_b); qpzk_batch_free(z_b); qpzk_batch_free(q_b);
+            qpzk_challenger_free(ch);
+        };
+        prove_one(0); prove_one(1);   // warm-up: tables, block cache
+        for (uint64_t x : proof) checksum = (checksum ^ x) * 0x100000001B3ULL;
+        QCHECK(qpzk_ctx_synchronize(ctx));
+        ready->fetch_add(1);
+        while (!go->load()) std::this_thread::yield();
+        const uint64_t l0 = qpzk_ctx_launch_count(ctx);
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < proofs; i++) prove_one(i & 3);
+        QCHECK(qpzk_ctx_synchronize(ctx));
+        seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        launches = qpzk_ctx_launch_count(ctx) - l0;
+        qpzk_batch_free(cs_b);
+        qpzk_ctx_destroy(ctx);
+    }
+};
+
+int main(int argc, char** argv) {
+    int device = 0, threads = 1, proofs = 16;
+    Shape sh;
+    for (int i = 1; i + 1 < argc; i += 2) {
+        std::string k = argv[i];
+        int v = atoi(argv[i + 1]);
+        if (k == "--device") device = v;
+        else if (k == "--threads") threads = v;
+        else if (k == "--proofs") proofs = v;
+        else if (k == "--log-n") sh.log_n = (unsigned)v;
+        else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
+    }
+    std::vector<Worker> ws(threads);
+    std::vector<std::thread> th;
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    for (int t = 0; t < threads; t++) {
+        ws[t].device = device; ws[t].sh = sh; ws[t].proofs = proofs;
+        th.emplace_back([&, t] { ws[t].run(&ready, &go); });
+    }
+    while (ready.load() < threads) std::this_thread::yield();
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true);
+    for (auto& t : th) t.join();
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    double lat = 0;
+    bool same = true;
+    for (auto& w : ws) { lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum; }
+    printf("{\"threads\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+           "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\"}\n",
+           threads, proofs, sh.log_n, threads * proofs / wall, 1e3 * lat / threads,
+           (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum);
+    return same ? 0 : 3;
+}
