@@ -138,6 +138,20 @@ def gpu_prove_synthetic(ctx, proofs=16):
     return 1e3 * dt, (ctx.launch_count() - l0) // proofs
 
 
+def native_prove_bench(device, threads, proofs=32):
+    """The same synthetic prove driven from native code (qp-zk-circuits_b200/host/prove_bench.cpp: C++ threads on the
+    C ABI, one context per thread, pinned host buffers).  Returns the parsed JSON line or None."""
+    exe = os.path.join(ROOT, "qp-zk-circuits_b200", "prove_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs)],
+                           capture_output=True, text=True, timeout=300)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
 def cpu_prove_synthetic(proofs=2):
     """The same synthetic prove on the CPU restatement (all host cores); ms per proof."""
     import numpy as np
@@ -393,6 +407,12 @@ def main():
                                           "random columns, openings at zeta and g*zeta over 256 polynomials, FRI (rate 3, cap 4, 16 PoW bits, "
                                           "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
                                           "restatement (tests/test_gpu_parity.py); witness generation and quotient evaluation are not part of it"}
+        n1, n4 = native_prove_bench(local_rank, 1), native_prove_bench(local_rank, 4)
+        if n1 and n4:
+            out["prove_synthetic"]["native"] = {
+                "latency_ms_1_thread": n1["latency_ms"], "proofs_per_s_1_thread": n1["proofs_per_s"],
+                "proofs_per_s_4_threads": n4["proofs_per_s"], "gpu_launches_per_proof": n1["launches_per_proof"],
+                "what": "same proof from C++ host threads on the C ABI (host/prove_bench.cpp), one context per thread, pinned buffers"}
         if not args.no_cpu_baseline:
             cms, cores = cpu_prove_synthetic()
             out["prove_synthetic"]["cpu_port_latency_ms"] = cms

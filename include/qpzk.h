@@ -74,6 +74,11 @@ uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx);
  * wormhole/prover/src/lib.rs:137-175), so a steady-state commit performs no device allocation.
  * qpzk_ctx_trim returns the cached blocks to the driver; qpzk_ctx_cached_bytes reports their total size. */
 int qpzk_ctx_trim(qpzk_ctx* ctx);
+/* Page-locked host memory (cudaHostAlloc, portable): with pinned inputs the H2D copy of a host-buffer commit runs
+ * asynchronously on the context's copy stream, overlapped with the per-column stages; pageable memory works too but
+ * the driver stages it and blocks the calling thread.  NULL on failure. */
+void* qpzk_pinned_alloc(size_t bytes);
+void qpzk_pinned_free(void* p);
 uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx);
 
 /* ---- PolynomialBatch::from_values / from_coeffs --------------------------------------------------

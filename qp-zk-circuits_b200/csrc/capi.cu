@@ -271,6 +271,14 @@ extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
 extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->zeroize = on != 0; return 0; }
 extern "C" int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->timing = on != 0; return 0; }
 extern "C" uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+// Page-locked host buffers for callers that want the host<->device copies of the commit / proof calls to be truly
+// asynchronous (a pageable source is staged by the driver and blocks the calling thread).
+extern "C" void* qpzk_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void qpzk_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int qpzk_ctx_trim(qpzk_ctx* ctx) {
     if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
     CK(cudaSetDevice(ctx->device));
@@ -461,10 +469,7 @@ static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
     ctx->launches++;
     mark(ctx, 3);
     CK(launch_merkle_levels(b->digests, b->num_levels, b->num_leaves, ctx->stream));
-    for (uint32_t l = 1; l < b->num_levels; l++) {
-        ctx->launches++;
-        if ((b->num_leaves >> l) <= TOP_LEVEL_NODES) break;
-    }
+    ctx->launches += merkle_levels_launches(b->num_levels);
     mark(ctx, 4);
     return 0;
 }
@@ -1077,7 +1082,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         if ((rc = bufs.alloc(&round_digests[r], 8 * rows))) return rc;
         CK(launch_hash_rows(layer[r], rows, 2u << ab, 2u << ab, round_digests[r], st)); ctx->launches++;
         const uint32_t levels = (lg - ab) - p->cap_height + 1;
-        CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += levels > 1 ? 1 : 0;
+        CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += merkle_levels_launches(levels);
         const uint64_t* cap = round_digests[r] + digest_level_off(rows, levels - 1);
         CK(cudaMemcpyAsync(d_proof + r * cap_words, cap, cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         CK(launch_challenger_observe(ch->dev, cap, (uint32_t)cap_words, st)); ctx->launches++;

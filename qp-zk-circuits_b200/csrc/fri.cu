@@ -87,33 +87,56 @@ __global__ void reduce_openings_kernel(FriCombineArgs a) {
     a.reduced[2 * b] = acc.a; a.reduced[2 * b + 1] = acc.b;
 }
 
-// One warp per LDE point p (leaf order).  x_p = s_j' * w_n^bitrev(r) for p = j' * n + r.
+// One warp per 32 consecutive LDE points (leaf order).  x_p = s_j' * w_n^bitrev(r) for p = j' * n + r.
+// Phase 1: lane l inverts the denominators (x_p - z_b) of ITS point for every batch: 32 different inversions per
+// warp-instruction stream (the first version inverted the same denominator on all 32 lanes: ~5 k of the ~5.5 k
+// instructions a point cost).  Phase 2: point by point, the lanes share the sum over the opened polynomials and the
+// owning lane's inverses arrive by shuffle.
 __global__ void __launch_bounds__(COMBINE_THREADS) fri_combine_kernel(FriCombineArgs a) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n = 1ull << a.log_n;
-    if (p >= (n << a.rate_bits)) return;
-    const uint32_t jp = (uint32_t)(p >> a.log_n);
-    const uint64_t r = p & (n - 1);
-    const uint64_t m = a.log_n ? (__brevll(r) >> (64 - a.log_n)) : 0;
-    const uint64_t x = gl_mul(a.cs_lo[(size_t)jp * TW_LO_SIZE + 1], tw_get(a.tw_lo, a.tw_hi, m));
-    ext2 sum = ext_make(0, 0);
-    for (uint32_t b = 0; b < a.num_batches; b++) {
-        uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
-        ext2 acc = ext_make(0, 0);
-        for (uint32_t j = lane; j < k; j += 32) {
-            uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
-            uint64_t v = a.leaves[o][p * a.leaf_width[o] + idx];
-            acc = ext_add(acc, ext_scale(ext_make(a.apow[2 * j], a.apow[2 * j + 1]), v));
-        }
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n = 1ull << a.log_n, L = n << a.rate_bits;
+    const uint64_t p0 = warp << 5;
+    if (p0 >= L) return;
+    ext2 inv[MAX_FRI_BATCHES];
+    {
+        const uint64_t p = p0 + lane < L ? p0 + lane : L - 1;
+        const uint32_t jp = (uint32_t)(p >> a.log_n);
+        const uint64_t r = p & (n - 1);
+        const uint64_t m = a.log_n ? (__brevll(r) >> (64 - a.log_n)) : 0;
+        const uint64_t x = gl_mul(a.cs_lo[(size_t)jp * TW_LO_SIZE + 1], tw_get(a.tw_lo, a.tw_hi, m));
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) acc = ext_add(acc, ext_shfl_xor(acc, sft));
-        ext2 numer = ext_sub(acc, ext_make(a.reduced[2 * b], a.reduced[2 * b + 1]));
-        ext2 denom = ext_make(gl_sub(x, a.points[2 * b]), gl_neg(a.points[2 * b + 1]));
-        ext2 q = ext_mul(numer, ext_inv(denom));
-        sum = ext_add(ext_mul(sum, ext_make(a.apow[2 * k], a.apow[2 * k + 1])), q);
+        for (uint32_t b = 0; b < MAX_FRI_BATCHES; b++) {
+            inv[b] = ext_make(0, 0);
+            if (b < a.num_batches)
+                inv[b] = ext_inv(ext_make(gl_sub(x, a.points[2 * b]), gl_neg(a.points[2 * b + 1])));
+        }
     }
-    if (lane == 0) { a.values[2 * p] = sum.a; a.values[2 * p + 1] = sum.b; }
+    const uint32_t count = L - p0 < 32 ? (uint32_t)(L - p0) : 32u;
+    for (uint32_t pt = 0; pt < count; pt++) {
+        const uint64_t p = p0 + pt;
+        ext2 sum = ext_make(0, 0);
+#pragma unroll
+        for (uint32_t b = 0; b < MAX_FRI_BATCHES; b++) {
+            if (b >= a.num_batches) break;
+            uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
+            ext2 acc = ext_make(0, 0);
+            for (uint32_t j = lane; j < k; j += 32) {
+                uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
+                uint64_t v = a.leaves[o][p * a.leaf_width[o] + idx];
+                acc = ext_add(acc, ext_scale(ext_make(a.apow[2 * j], a.apow[2 * j + 1]), v));
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) acc = ext_add(acc, ext_shfl_xor(acc, sft));
+            ext2 numer = ext_sub(acc, ext_make(a.reduced[2 * b], a.reduced[2 * b + 1]));
+            ext2 dinv;
+            dinv.a = __shfl_sync(0xffffffffu, inv[b].a, pt);
+            dinv.b = __shfl_sync(0xffffffffu, inv[b].b, pt);
+            ext2 q = ext_mul(numer, dinv);
+            sum = ext_add(ext_mul(sum, ext_make(a.apow[2 * k], a.apow[2 * k + 1])), q);
+        }
+        if (lane == 0) { a.values[2 * p] = sum.a; a.values[2 * p + 1] = sum.b; }
+    }
 }
 
 // Fold one layer in the value domain.  in: 2^lg ext values in bit-reversed order on the coset
@@ -216,7 +239,7 @@ cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, u
 cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st) {
     reduce_openings_kernel<<<a.num_batches, 32, 0, st>>>(a);
     uint64_t L = 1ull << (a.log_n + a.rate_bits);
-    uint64_t blocks = (L * 32 + COMBINE_THREADS - 1) / COMBINE_THREADS;
+    uint64_t blocks = (L + COMBINE_THREADS - 1) / COMBINE_THREADS;   // one warp per 32 points
     fri_combine_kernel<<<(unsigned)blocks, COMBINE_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }

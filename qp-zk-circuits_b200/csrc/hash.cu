@@ -125,19 +125,6 @@ merkle_level_kernel(const uint64_t* __restrict__ child, uint64_t* __restrict__ p
     if (i < num_parents) compress_pair(child, parent, i);
 }
 
-// The top of the tree (few nodes per level) in ONE single-block launch: levels are separated by a
-// block barrier instead of a kernel boundary.  Level l lives at digest_level_off(num_leaves, l).
-__global__ void __launch_bounds__(TOP_THREADS)
-merkle_top_kernel(uint64_t* __restrict__ digests, uint32_t first_level, uint32_t last_level, uint64_t num_leaves) {
-    for (uint32_t l = first_level; l <= last_level; l++) {
-        uint64_t parents = num_leaves >> l;
-        const uint64_t* child = digests + digest_level_off(num_leaves, l - 1);
-        uint64_t* parent = digests + digest_level_off(num_leaves, l);
-        for (uint64_t i = threadIdx.x; i < parents; i += blockDim.x) compress_pair(child, parent, i);
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Challenger (duplex sponge, overwrite mode; pop challenges from the back of the output buffer)
 // ---------------------------------------------------------------------------------------------
@@ -252,6 +239,46 @@ pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Latency variants for small trees (a proof at 2^13 rows builds five trees of <= 2^16 leaves): one WARP per
+// permutation chain (poseidon_permute_warp).  A tree level or a short leaf sponge then takes the ~8 us of a
+// warp-wide permutation instead of the ~30 us of a one-thread permutation; used while the whole level fits the
+// GPU's resident warps at once (<= WARP_COOP_MAX chains), where the thread-per-chain kernels would leave the
+// machine idle anyway.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t WARP_COOP_MAX = 8192;
+constexpr int WARP_COOP_THREADS = 128;
+
+__global__ void __launch_bounds__(WARP_COOP_THREADS)
+merkle_level_warp_kernel(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, uint64_t num_parents) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= num_parents) return;
+    uint64_t st = lane < 8 ? child[8 * i + lane] : 0;
+    st = poseidon_permute_warp(st, lane);
+    if (lane < 4) parent[4 * i + lane] = gl_canon(st);
+}
+
+__global__ void __launch_bounds__(WARP_COOP_THREADS)
+hash_rows_warp_kernel(const uint64_t* __restrict__ leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
+                      uint64_t* __restrict__ digests) {
+    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= num_rows) return;
+    const uint64_t* p = leaves + row * row_stride;
+    uint64_t st = 0;
+    if (leaf_len <= 4) {   // hash_or_noop
+        if (lane < 4) digests[4 * row + lane] = (uint32_t)lane < leaf_len ? p[lane] : 0;
+        return;
+    }
+    for (uint32_t c = 0; c < leaf_len; c += 8) {
+        const uint32_t len = leaf_len - c < 8 ? leaf_len - c : 8;
+        if ((uint32_t)lane < len) st = p[c + lane];     // overwrite mode
+        st = poseidon_permute_warp(st, lane);
+    }
+    if (lane < 4) digests[4 * row + lane] = gl_canon(st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // PoseidonPermutation::permute on a batch of states (12 words each, any u64 representatives), and a self-test
 // hook that applies ONE linear layer (MDS + constants row `next`) so that tests can drive its carry paths with
 // chosen states (random inputs reach them with probability ~2^-20).
@@ -280,6 +307,11 @@ cudaError_t launch_permute(const uint64_t* in, uint64_t count, int mds_only_row,
 cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
                              uint64_t* digests, cudaStream_t st) {
     if (num_rows == 0) return cudaSuccess;
+    if (num_rows <= WARP_COOP_MAX) {
+        uint64_t blocks = (num_rows * 32 + WARP_COOP_THREADS - 1) / WARP_COOP_THREADS;
+        hash_rows_warp_kernel<<<(unsigned)blocks, WARP_COOP_THREADS, 0, st>>>(leaves, num_rows, leaf_len, row_stride, digests);
+        return cudaGetLastError();
+    }
     uint64_t blocks = (num_rows + HASH_THREADS - 1) / HASH_THREADS;
     hash_rows_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(leaves, num_rows, leaf_len, row_stride, digests);
     return cudaGetLastError();
@@ -287,17 +319,23 @@ cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t
 
 // digests: level 0 already filled.  Builds levels 1..num_levels-1.
 cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st) {
-    uint32_t l = 1;
-    for (; l < num_levels; l++) {
+    for (uint32_t l = 1; l < num_levels; l++) {
         uint64_t parents = num_leaves >> l;
-        if (parents <= TOP_LEVEL_NODES) break;
-        uint64_t blocks = (parents + HASH_THREADS - 1) / HASH_THREADS;
-        merkle_level_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(
-            digests + digest_level_off(num_leaves, l - 1), digests + digest_level_off(num_leaves, l), parents);
+        const uint64_t* child = digests + digest_level_off(num_leaves, l - 1);
+        uint64_t* parent = digests + digest_level_off(num_leaves, l);
+        if (parents <= WARP_COOP_MAX) {
+            uint64_t blocks = (parents * 32 + WARP_COOP_THREADS - 1) / WARP_COOP_THREADS;
+            merkle_level_warp_kernel<<<(unsigned)blocks, WARP_COOP_THREADS, 0, st>>>(child, parent, parents);
+        } else {
+            uint64_t blocks = (parents + HASH_THREADS - 1) / HASH_THREADS;
+            merkle_level_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(child, parent, parents);
+        }
     }
-    if (l < num_levels) merkle_top_kernel<<<1, TOP_THREADS, 0, st>>>(digests, l, num_levels - 1, num_leaves);
     return cudaGetLastError();
 }
+
+// number of kernel launches launch_merkle_levels issues (bookkeeping for qpzk_ctx_launch_count)
+uint32_t merkle_levels_launches(uint32_t num_levels) { return num_levels > 1 ? num_levels - 1 : 0; }
 
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;

@@ -10,8 +10,6 @@ namespace qpzk {
 // threads races (one thread lowers it between another thread's set and launch); a constant is idempotent.
 constexpr int MAX_DYN_SMEM = 227 * 1024;
 constexpr int HASH_THREADS = 128;          // threads per block for one-thread-per-permutation kernels
-constexpr int TOP_THREADS = 256;           // single-block kernel for the top of a Merkle tree
-constexpr uint64_t TOP_LEVEL_NODES = 256;  // levels with <= this many parents go to the single-block kernel
 
 // Digest buffer of a tree with N leaves: level 0 (leaf digests, 4N words) first, then level 1 (2N words), ...
 // Word offset of level l:  8N - (8N >> l).
@@ -83,6 +81,7 @@ cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t
                              uint64_t* digests, cudaStream_t st);
 cudaError_t launch_permute(const uint64_t* in, uint64_t count, int mds_only_row, uint64_t* out, cudaStream_t st);
 cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st);
+uint32_t merkle_levels_launches(uint32_t num_levels);
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,

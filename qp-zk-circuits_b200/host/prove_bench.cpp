@@ -7,7 +7,7 @@
 // aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
-//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13]
+//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13] [--pinned 1]
 // prints one JSON line: proofs/s over all threads, mean latency per proof, and a checksum of every thread's first
 // proof (identical inputs must give identical proofs on every thread).
 #include <atomic>
@@ -45,10 +45,28 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
     }
 };
 
-static std::vector<uint64_t> random_columns(uint64_t seed, size_t cols, size_t n) {
+static bool g_pinned = true;
+
+struct HostBuf {   // pinned (default) or pageable host buffer
+    uint64_t* p = nullptr;
+    size_t words = 0;
+    bool pinned = false;
+    HostBuf() = default;
+    explicit HostBuf(size_t w) : words(w), pinned(g_pinned) {
+        p = pinned ? (uint64_t*)qpzk_pinned_alloc(w * 8) : (uint64_t*)malloc(w * 8);
+        if (!p) { fprintf(stderr, "host allocation failed\n"); exit(2); }
+    }
+    HostBuf(HostBuf&& o) noexcept : p(o.p), words(o.words), pinned(o.pinned) { o.p = nullptr; }
+    HostBuf(const HostBuf&) = delete;
+    ~HostBuf() { if (p) { if (pinned) qpzk_pinned_free(p); else free(p); } }
+    uint64_t* data() { return p; }
+    size_t size() const { return words; }
+};
+
+static HostBuf random_columns(uint64_t seed, size_t cols, size_t n) {
     SplitMix g{seed};
-    std::vector<uint64_t> v(cols * n);
-    for (auto& x : v) x = g.next();
+    HostBuf v(cols * n);
+    for (size_t i = 0; i < v.size(); i++) v.p[i] = g.next();
     return v;
 }
 
@@ -77,7 +95,7 @@ struct Worker {
         qpzk_batch* cs_b;
         QCHECK(qpzk_commit_from_values(ctx, cs.data(), sh.log_n, sh.constants_sigmas, 3, 4, nullptr, &cs_b));
         // four witnesses' worth of columns, reused round robin
-        std::vector<std::vector<uint64_t>> wires, zs, quot;
+        std::vector<HostBuf> wires, zs, quot;
         for (int s = 0; s < 4; s++) {
             wires.push_back(random_columns(100 + s, sh.wires, n));
             zs.push_back(random_columns(200 + s, sh.zs_pp, n));
@@ -92,7 +110,7 @@ struct Worker {
         for (uint32_t o = 0; o < 4; o++) for (uint32_t i = 0; i < leaf_lens[o]; i++) { po.push_back(o); pi.push_back(i); }
         for (uint32_t i = 0; i < sh.num_zs; i++) { po.push_back(2); pi.push_back(i); }
         const uint32_t sizes[2] = {total, sh.num_zs};
-        std::vector<uint64_t> proof(proof_words), openings(2 * (total + sh.num_zs));
+        HostBuf proof(proof_words), openings(2 * (total + sh.num_zs)), znext(2 * sh.zs_pp);
         const uint64_t digest[4] = {11, 12, 13, 14}, pih[4] = {21, 22, 23, 24};
         const uint64_t g = root_of_unity(sh.log_n);
 
@@ -116,7 +134,6 @@ struct Worker {
             const qpzk_batch* oracles[4] = {cs_b, w_b, z_b, q_b};
             uint64_t* op = openings.data();
             for (int o = 0; o < 4; o++) { QCHECK(qpzk_batch_eval_ext(oracles[o], zeta, op)); op += 2 * leaf_lens[o]; }
-            std::vector<uint64_t> znext(2 * sh.zs_pp);
             QCHECK(qpzk_batch_eval_ext(z_b, gz, znext.data()));
             memcpy(op, znext.data(), 2 * sh.num_zs * sizeof(uint64_t));
             QCHECK(qpzk_challenger_observe(ch, openings.data(), (uint32_t)openings.size()));
@@ -127,7 +144,7 @@ struct Worker {
             qpzk_challenger_free(ch);
         };
         prove_one(0); prove_one(1);   // warm-up: tables, block cache
-        for (uint64_t x : proof) checksum = (checksum ^ x) * 0x100000001B3ULL;
+        for (size_t i = 0; i < proof.size(); i++) checksum = (checksum ^ proof.p[i]) * 0x100000001B3ULL;
         QCHECK(qpzk_ctx_synchronize(ctx));
         ready->fetch_add(1);
         while (!go->load()) std::this_thread::yield();
@@ -152,6 +169,7 @@ int main(int argc, char** argv) {
         else if (k == "--threads") threads = v;
         else if (k == "--proofs") proofs = v;
         else if (k == "--log-n") sh.log_n = (unsigned)v;
+        else if (k == "--pinned") g_pinned = v != 0;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);
@@ -166,10 +184,13 @@ int main(int argc, char** argv) {
     auto t0 = std::chrono::steady_clock::now();
     go.store(true);
     for (auto& t : th) t.join();
-    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    double lat = 0;
+    (void)t0;
+    double lat = 0, wall = 0;   // wall = the slowest thread's proving loop (threads start together; teardown excluded)
     bool same = true;
-    for (auto& w : ws) { lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum; }
+    for (auto& w : ws) {
+        lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum;
+        if (w.seconds > wall) wall = w.seconds;
+    }
     printf("{\"threads\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\"}\n",
            threads, proofs, sh.log_n, threads * proofs / wall, 1e3 * lat / threads,

@@ -83,6 +83,8 @@ def load_library():
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
         "qpzk_ctx_trim": (i, [vp]),
+        "qpzk_pinned_alloc": (vp, [C.c_size_t]),
+        "qpzk_pinned_free": (None, [vp]),
         "qpzk_poseidon_permute": (i, [vp, vp, u64, vp]),
         "qpzk_selftest_mds_layer": (i, [vp, vp, u64, u32, vp]),
         "qpzk_ctx_cached_bytes": (u64, [vp]),

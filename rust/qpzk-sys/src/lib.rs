@@ -47,6 +47,8 @@ extern "C" {
     pub fn qpzk_ctx_destroy(ctx: *mut qpzk_ctx);
     pub fn qpzk_ctx_synchronize(ctx: *mut qpzk_ctx) -> c_int;
     pub fn qpzk_ctx_trim(ctx: *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_pinned_alloc(bytes: usize) -> *mut c_void;
+    pub fn qpzk_pinned_free(p: *mut c_void);
     pub fn qpzk_poseidon_permute(ctx: *mut qpzk_ctx, states: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn qpzk_ctx_cached_bytes(ctx: *const qpzk_ctx) -> u64;
     pub fn qpzk_commit_from_values(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
