@@ -469,7 +469,7 @@ static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
     ctx->launches++;
     mark(ctx, 3);
     CK(launch_merkle_levels(b->digests, b->num_levels, b->num_leaves, ctx->stream));
-    ctx->launches += merkle_levels_launches(b->num_levels);
+    ctx->launches += merkle_levels_launches(b->num_levels, b->num_leaves);
     mark(ctx, 4);
     return 0;
 }
@@ -802,6 +802,41 @@ extern "C" int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t point[2],
     GUARD_END
 }
 
+extern "C" int qpzk_batches_eval_ext(qpzk_ctx* ctx, const qpzk_batch* const* batches, uint32_t num_batches,
+                                     const uint64_t point[2], uint64_t* out) {
+    GUARD_BEGIN
+    if (!ctx || !batches || !point || !out) return fail(QPZK_EINVAL, "null argument");
+    if (!num_batches || num_batches > MAX_EVAL_JOBS) return fail(QPZK_EINVAL, "num_batches must be in 1..64");
+    if (point[0] >= GL_P || point[1] >= GL_P) return fail(QPZK_EINVAL, "point is not canonical");
+    EvalMultiArgs ea{};
+    uint64_t total = 0;
+    for (uint32_t j = 0; j < num_batches; j++) {
+        const qpzk_batch* b = batches[j];
+        if (!b || b->ctx != ctx || !b->coeffs) return fail(QPZK_EINVAL, "batch holds no polynomials or belongs to another context");
+        if (b->log_n != batches[0]->log_n) return fail(QPZK_EINVAL, "batches must have the same degree");
+        total += b->num_cols;
+    }
+    CK(cudaSetDevice(ctx->device));
+    uint64_t* d;
+    int rc = dev_alloc(ctx, &d, 2 * total);
+    if (rc) return rc;
+    ea.num_jobs = num_batches; ea.log_n = batches[0]->log_n; ea.col_stride = 1ull << ea.log_n;
+    for (uint32_t j = 0; j < num_batches; j++) {
+        ea.coeffs[j] = batches[j]->coeffs;
+        ea.out[j] = d + 2ull * ea.col_begin[j];
+        ea.z[2 * j] = point[0]; ea.z[2 * j + 1] = point[1];
+        ea.col_begin[j + 1] = ea.col_begin[j] + batches[j]->num_cols;
+    }
+    cudaError_t e = launch_eval_ext_multi(ea, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 2 * total * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d);
+    CK(e);
+    return 0;
+    GUARD_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // PoseidonPermutation::permute (batch) and the linear-layer self-test hook
 // ---------------------------------------------------------------------------------------------
@@ -1038,13 +1073,21 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     // ---- alpha and its powers; openings of every referenced oracle at every batch point
     CK(launch_challenger_get(ch->dev, d_alpha, 2, st)); ctx->launches++;
     CK(launch_alpha_powers(d_alpha, d_apow, max_k + 1, st)); ctx->launches++;
-    for (uint32_t b = 0; b < inst->num_batches; b++)
-        for (uint32_t o = 0; o < num_oracles; o++)
-            if (used[b * num_oracles + o]) {
-                CK(launch_eval_ext(oracles[o]->coeffs, 1ull << log_n, log_n, oracles[o]->num_cols, &ca.points[2 * b],
-                                   d_evals + 2ull * ca.eval_off[b * num_oracles + o], st));
-                ctx->launches++;
-            }
+    {
+        EvalMultiArgs ea{};
+        ea.log_n = log_n; ea.col_stride = 1ull << log_n;
+        for (uint32_t b = 0; b < inst->num_batches; b++)
+            for (uint32_t o = 0; o < num_oracles; o++)
+                if (used[b * num_oracles + o]) {
+                    const uint32_t j = ea.num_jobs++;
+                    ea.coeffs[j] = oracles[o]->coeffs;
+                    ea.out[j] = d_evals + 2ull * ca.eval_off[b * num_oracles + o];
+                    ea.z[2 * j] = ca.points[2 * b]; ea.z[2 * j + 1] = ca.points[2 * b + 1];
+                    ea.col_begin[j + 1] = ea.col_begin[j] + oracles[o]->num_cols;
+                }
+        CK(launch_eval_ext_multi(ea, st));
+        ctx->launches++;
+    }
 
     // ---- batch-opening polynomial, evaluated on the LDE domain in leaf order
     PowTables fwd_n, inv_L;
@@ -1082,7 +1125,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         if ((rc = bufs.alloc(&round_digests[r], 8 * rows))) return rc;
         CK(launch_hash_rows(layer[r], rows, 2u << ab, 2u << ab, round_digests[r], st)); ctx->launches++;
         const uint32_t levels = (lg - ab) - p->cap_height + 1;
-        CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += merkle_levels_launches(levels);
+        CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += merkle_levels_launches(levels, rows);
         const uint64_t* cap = round_digests[r] + digest_level_off(rows, levels - 1);
         CK(cudaMemcpyAsync(d_proof + r * cap_words, cap, cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         CK(launch_challenger_observe(ch->dev, cap, (uint32_t)cap_words, st)); ctx->launches++;

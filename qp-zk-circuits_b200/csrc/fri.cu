@@ -58,33 +58,63 @@ eval_ext_kernel(const uint64_t* __restrict__ coeffs, uint64_t col_stride, uint32
     if (t == 0) { out[2 * blockIdx.x] = red[0].a; out[2 * blockIdx.x + 1] = red[0].b; }
 }
 
-// apow[j] = alpha^j for j in [0, count)
-__global__ void alpha_powers_kernel(const uint64_t* __restrict__ alpha, uint64_t* __restrict__ apow, uint32_t count) {
-    if (threadIdx.x || blockIdx.x) return;
-    ext2 a = ext_make(alpha[0], alpha[1]);
-    ext2 p = ext_make(1, 0);
-    for (uint32_t j = 0; j < count; j++) {
-        apow[2 * j] = p.a; apow[2 * j + 1] = p.b;
-        p = ext_mul(p, a);
+__global__ void __launch_bounds__(EVAL_THREADS) eval_ext_multi_kernel(EvalMultiArgs a) {
+    uint32_t job = 0;
+    while (job + 1 < a.num_jobs && blockIdx.x >= a.col_begin[job + 1]) job++;
+    const uint32_t col = blockIdx.x - a.col_begin[job];
+    __shared__ ext2 red[EVAL_THREADS];
+    const uint64_t n = 1ull << a.log_n;
+    const uint64_t* c = a.coeffs[job] + (uint64_t)col * a.col_stride;
+    const ext2 z = ext_make(a.z[2 * job], a.z[2 * job + 1]);
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    ext2 zT = ext_exp(z, T);
+    ext2 acc = ext_make(0, 0);
+    if (t < n) {
+        uint64_t last = t + ((n - 1 - t) / T) * T;
+        for (int64_t i = (int64_t)last; i >= (int64_t)t; i -= T) {
+            acc = ext_mul(acc, zT);
+            acc.a = gl_add(acc.a, c[i]);
+        }
+        acc = ext_mul(acc, ext_exp(z, t));
     }
+    red[t] = acc;
+    __syncthreads();
+    for (uint32_t h = T >> 1; h > 0; h >>= 1) {
+        if (t < h) red[t] = ext_add(red[t], red[t + h]);
+        __syncthreads();
+    }
+    if (t == 0) { a.out[job][2 * col] = red[0].a; a.out[job][2 * col + 1] = red[0].b; }
 }
 
-// reduced[b] = sum_j alpha^j * opening_bj  with opening_bj = evals[b][oracle_j][index_j]
-__global__ void reduce_openings_kernel(FriCombineArgs a) {
-    uint32_t b = blockIdx.x;
-    if (threadIdx.x) return;
+// apow[j] = alpha^j for j in [0, count): one thread per power (square-and-multiply, <= 2 log2(count) ext products)
+__global__ void alpha_powers_kernel(const uint64_t* __restrict__ alpha, uint64_t* __restrict__ apow, uint32_t count) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    ext2 p = ext_exp(ext_make(alpha[0], alpha[1]), j);
+    apow[2 * j] = p.a; apow[2 * j + 1] = p.b;
+}
+
+// reduced[b] = sum_j alpha^j * opening_bj  with opening_bj = evals[b][oracle_j][index_j]; one block per batch
+__global__ void __launch_bounds__(EVAL_THREADS) reduce_openings_kernel(FriCombineArgs a) {
+    __shared__ ext2 red[EVAL_THREADS];
+    const uint32_t b = blockIdx.x, t = threadIdx.x;
+    const uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
     ext2 acc = ext_make(0, 0);
-    uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
-    for (uint32_t j = 0; j < k; j++) {
+    for (uint32_t j = t; j < k; j += blockDim.x) {
         uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
         const uint64_t* ev = a.evals + 2 * ((uint64_t)a.eval_off[b * a.num_oracles + o] + idx);
-        ext2 ap = ext_make(a.apow[2 * j], a.apow[2 * j + 1]);
-        acc = ext_add(acc, ext_mul(ap, ext_make(ev[0], ev[1])));
+        acc = ext_add(acc, ext_mul(ext_make(a.apow[2 * j], a.apow[2 * j + 1]), ext_make(ev[0], ev[1])));
         // also record the opening itself in instance order (the caller may want OpeningSet values)
         a.openings_out[2 * (off + j)] = ev[0];
         a.openings_out[2 * (off + j) + 1] = ev[1];
     }
-    a.reduced[2 * b] = acc.a; a.reduced[2 * b + 1] = acc.b;
+    red[t] = acc;
+    __syncthreads();
+    for (uint32_t h = blockDim.x >> 1; h > 0; h >>= 1) {
+        if (t < h) red[t] = ext_add(red[t], red[t + h]);
+        __syncthreads();
+    }
+    if (t == 0) { a.reduced[2 * b] = red[0].a; a.reduced[2 * b + 1] = red[0].b; }
 }
 
 // One warp per 32 consecutive LDE points (leaf order).  x_p = s_j' * w_n^bitrev(r) for p = j' * n + r.
@@ -231,13 +261,20 @@ cudaError_t launch_eval_ext(const uint64_t* coeffs, uint64_t col_stride, uint32_
     return cudaGetLastError();
 }
 
+cudaError_t launch_eval_ext_multi(const EvalMultiArgs& a, cudaStream_t st) {
+    const uint32_t total = a.col_begin[a.num_jobs];
+    if (!total) return cudaSuccess;
+    eval_ext_multi_kernel<<<total, EVAL_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, uint32_t count, cudaStream_t st) {
-    alpha_powers_kernel<<<1, 32, 0, st>>>(alpha_dev, apow_dev, count);
+    alpha_powers_kernel<<<(count + 127) / 128, 128, 0, st>>>(alpha_dev, apow_dev, count);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st) {
-    reduce_openings_kernel<<<a.num_batches, 32, 0, st>>>(a);
+    reduce_openings_kernel<<<a.num_batches, EVAL_THREADS, 0, st>>>(a);
     uint64_t L = 1ull << (a.log_n + a.rate_bits);
     uint64_t blocks = (L + COMBINE_THREADS - 1) / COMBINE_THREADS;   // one warp per 32 points
     fri_combine_kernel<<<(unsigned)blocks, COMBINE_THREADS, 0, st>>>(a);
@@ -262,8 +299,8 @@ cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st) {
     size_t smem = (2 * (size_t)len + len / 2 + 1) * sizeof(uint64_t);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)fri_final_poly_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        static unsigned long long done = 0;
+        cudaError_t e = raise_smem_limit((const void*)fri_final_poly_kernel, &done);
         if (e != cudaSuccess) return e;
     }
     fri_final_poly_kernel<<<1, NTT_THREADS, smem, st>>>(a);

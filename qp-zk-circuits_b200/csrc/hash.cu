@@ -169,7 +169,11 @@ struct WarpChallenger {
 __global__ void __launch_bounds__(32) challenger_observe_kernel(ChallengerDev* c, const uint64_t* __restrict__ elems, uint32_t n) {
     WarpChallenger w;
     w.load(c);
-    for (uint32_t i = 0; i < n; i++) w.observe(elems[i]);
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {      // one coalesced load per 32 elements, then broadcast by shuffle
+        const uint64_t mine = i0 + w.lane < n ? elems[i0 + w.lane] : 0;
+        const uint32_t m = n - i0 < 32 ? n - i0 : 32;
+        for (uint32_t j = 0; j < m; j++) w.observe(__shfl_sync(0xffffffffu, mine, j));
+    }
     w.store(c);
 }
 
@@ -245,17 +249,31 @@ pow_finish_and_indices_kernel(ChallengerDev* c, const unsigned long long* found,
 // GPU's resident warps at once (<= WARP_COOP_MAX chains), where the thread-per-chain kernels would leave the
 // machine idle anyway.
 // ---------------------------------------------------------------------------------------------
-constexpr uint64_t WARP_COOP_MAX = 8192;
+constexpr uint64_t WARP_COOP_MAX = 4096;
 constexpr int WARP_COOP_THREADS = 128;
 
-__global__ void __launch_bounds__(WARP_COOP_THREADS)
-merkle_level_warp_kernel(const uint64_t* __restrict__ child, uint64_t* __restrict__ parent, uint64_t num_parents) {
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Up to six consecutive levels in one launch: a block of 32 warps owns 32 consecutive parents of level l0 (its
+// children are 64 digests of level l0-1), then 16 of level l0+1, ... -- a self-contained subtree, so the levels are
+// separated by a block barrier instead of a kernel boundary (a proof builds five trees; every saved launch is
+// ~10 us of dependent latency).
+constexpr int SUBTREE_THREADS = 1024;
+__global__ void __launch_bounds__(SUBTREE_THREADS)
+merkle_subtree_warp_kernel(uint64_t* __restrict__ digests, uint64_t num_leaves, uint32_t l0, uint32_t depth) {
+    const uint32_t warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    if (i >= num_parents) return;
-    uint64_t st = lane < 8 ? child[8 * i + lane] : 0;
-    st = poseidon_permute_warp(st, lane);
-    if (lane < 4) parent[4 * i + lane] = gl_canon(st);
+    for (uint32_t d = 0; d < depth; d++) {
+        const uint32_t l = l0 + d, per_block = 32u >> d;
+        const uint64_t parents = num_leaves >> l;
+        const uint64_t i = (uint64_t)blockIdx.x * per_block + warp;
+        if (warp < per_block && i < parents) {
+            const uint64_t* child = digests + digest_level_off(num_leaves, l - 1);
+            uint64_t* parent = digests + digest_level_off(num_leaves, l);
+            uint64_t st = lane < 8 ? child[8 * i + lane] : 0;
+            st = poseidon_permute_warp(st, lane);
+            if (lane < 4) parent[4 * i + lane] = gl_canon(st);
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(WARP_COOP_THREADS)
@@ -318,24 +336,40 @@ cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t
 }
 
 // digests: level 0 already filled.  Builds levels 1..num_levels-1.
-cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st) {
-    for (uint32_t l = 1; l < num_levels; l++) {
-        uint64_t parents = num_leaves >> l;
-        const uint64_t* child = digests + digest_level_off(num_leaves, l - 1);
-        uint64_t* parent = digests + digest_level_off(num_leaves, l);
-        if (parents <= WARP_COOP_MAX) {
-            uint64_t blocks = (parents * 32 + WARP_COOP_THREADS - 1) / WARP_COOP_THREADS;
-            merkle_level_warp_kernel<<<(unsigned)blocks, WARP_COOP_THREADS, 0, st>>>(child, parent, parents);
+// Plan shared by the launcher and the launch counter: thread-per-node levels while a level has more than
+// WARP_COOP_MAX parents, then subtree kernels of up to 6 levels each.
+static uint32_t merkle_plan(uint32_t num_levels, uint64_t num_leaves, uint64_t* digests, cudaStream_t st, bool launch) {
+    uint32_t launches = 0;
+    uint32_t l = 1;
+    while (l < num_levels) {
+        const uint64_t parents = num_leaves >> l;
+        if (parents > WARP_COOP_MAX) {
+            if (launch) {
+                uint64_t blocks = (parents + HASH_THREADS - 1) / HASH_THREADS;
+                merkle_level_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(
+                    digests + digest_level_off(num_leaves, l - 1), digests + digest_level_off(num_leaves, l), parents);
+            }
+            l++;
         } else {
-            uint64_t blocks = (parents + HASH_THREADS - 1) / HASH_THREADS;
-            merkle_level_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(child, parent, parents);
+            const uint32_t depth = num_levels - l < 6 ? num_levels - l : 6;
+            if (launch)
+                merkle_subtree_warp_kernel<<<(unsigned)((parents + 31) / 32), SUBTREE_THREADS, 0, st>>>(digests, num_leaves, l, depth);
+            l += depth;
         }
+        launches++;
     }
+    return launches;
+}
+
+cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st) {
+    merkle_plan(num_levels, num_leaves, digests, st, true);
     return cudaGetLastError();
 }
 
 // number of kernel launches launch_merkle_levels issues (bookkeeping for qpzk_ctx_launch_count)
-uint32_t merkle_levels_launches(uint32_t num_levels) { return num_levels > 1 ? num_levels - 1 : 0; }
+uint32_t merkle_levels_launches(uint32_t num_levels, uint64_t num_leaves) {
+    return merkle_plan(num_levels, num_leaves, nullptr, nullptr, false);
+}
 
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;

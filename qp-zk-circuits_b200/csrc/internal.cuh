@@ -9,6 +9,10 @@ namespace qpzk {
 // before every launch: the attribute is process-wide per function, and setting a per-launch size from several host
 // threads races (one thread lowers it between another thread's set and launch); a constant is idempotent.
 constexpr int MAX_DYN_SMEM = 227 * 1024;
+// Raise a kernel's dynamic shared memory limit to MAX_DYN_SMEM once per (kernel, device).  `done` is a per-kernel
+// bit mask of devices (callers pass a function-local static).  cudaFuncSetAttribute takes a device-wide lock; calling
+// it before every launch made concurrent provers on several host threads several times slower.
+cudaError_t raise_smem_limit(const void* fn, unsigned long long* done);
 constexpr int HASH_THREADS = 128;          // threads per block for one-thread-per-permutation kernels
 
 // Digest buffer of a tree with N leaves: level 0 (leaf digests, 4N words) first, then level 1 (2N words), ...
@@ -81,7 +85,7 @@ cudaError_t launch_hash_rows(const uint64_t* leaves, uint64_t num_rows, uint32_t
                              uint64_t* digests, cudaStream_t st);
 cudaError_t launch_permute(const uint64_t* in, uint64_t count, int mds_only_row, uint64_t* out, cudaStream_t st);
 cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_t num_leaves, cudaStream_t st);
-uint32_t merkle_levels_launches(uint32_t num_levels);
+uint32_t merkle_levels_launches(uint32_t num_levels, uint64_t num_leaves);
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
@@ -148,6 +152,18 @@ struct FriGatherArgs {
 
 cudaError_t launch_eval_ext(const uint64_t* coeffs, uint64_t col_stride, uint32_t log_n, uint32_t num_cols,
                             const uint64_t z[2], uint64_t* out_dev, cudaStream_t st);
+// several (coefficient matrix, point) jobs of the same degree in ONE launch (a proof evaluates four oracles at zeta
+// and one at g*zeta: five dependent-latency launches otherwise)
+constexpr uint32_t MAX_EVAL_JOBS = MAX_ORACLES * MAX_FRI_BATCHES;
+struct EvalMultiArgs {
+    uint32_t num_jobs, log_n;
+    uint64_t col_stride;
+    const uint64_t* coeffs[MAX_EVAL_JOBS];
+    uint64_t* out[MAX_EVAL_JOBS];
+    uint64_t z[2 * MAX_EVAL_JOBS];
+    uint32_t col_begin[MAX_EVAL_JOBS + 1];   // prefix sums of the jobs' column counts
+};
+cudaError_t launch_eval_ext_multi(const EvalMultiArgs& a, cudaStream_t st);
 cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, uint32_t count, cudaStream_t st);
 cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st);
 cudaError_t launch_fri_fold(const FriFoldArgs& a, uint32_t arity_bits, cudaStream_t st);

@@ -162,10 +162,21 @@ __global__ void salt_scatter_kernel(const uint64_t* __restrict__ salt, uint64_t*
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static cudaError_t ensure_smem(const void* fn, size_t bytes) {
+cudaError_t raise_smem_limit(const void* fn, unsigned long long* done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+    return e;
+}
+
+static cudaError_t ensure_smem(const void* fn, size_t bytes, unsigned long long* done) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     if (bytes > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    return raise_smem_limit(fn, done);
 }
 
 cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st) {
@@ -174,7 +185,8 @@ cudaError_t launch_ntt_pass(const NttPassArgs& a, cudaStream_t st) {
     if (a.mode == NTT_FWD_COSET_FIRST) tiles *= a.num_cosets;
     uint32_t S = 1u << a.s;
     size_t smem = ((size_t)(a.W == 1 ? padded_len(S) : S * a.W) + S / 2 + 1) * sizeof(uint64_t);
-    cudaError_t e = ensure_smem((const void*)ntt_pass_kernel, smem);
+    static unsigned long long done = 0;
+    cudaError_t e = ensure_smem((const void*)ntt_pass_kernel, smem, &done);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)tiles, (unsigned)a.num_arrays, (unsigned)(a.num_groups ? a.num_groups : 1));
     ntt_pass_kernel<<<grid, NTT_THREADS, smem, st>>>(a);
@@ -186,7 +198,8 @@ cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st) {
     uint64_t blocks = (n >> a.s) * a.num_cosets;
     uint32_t R = 1u << a.s;
     size_t smem = ((size_t)a.num_cols * (padded_len(R) | 1u) + R / 2 + 1) * sizeof(uint64_t);
-    cudaError_t e = ensure_smem((const void*)lde_last_kernel, smem);
+    static unsigned long long done = 0;
+    cudaError_t e = ensure_smem((const void*)lde_last_kernel, smem, &done);
     if (e != cudaSuccess) return e;
     lde_last_kernel<<<(unsigned)blocks, NTT_THREADS, smem, st>>>(a);
     return cudaGetLastError();

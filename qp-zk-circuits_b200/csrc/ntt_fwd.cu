@@ -327,7 +327,8 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
             uint32_t threads = (items + 31) / 32 * 32;
             if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
             if (threads < 64) threads = 64;
-            cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+            static unsigned long long done = 0;
+            cudaError_t e = raise_smem_limit((const void*)lde_last32_tma_kernel, &done);
             if (e != cudaSuccess) return e;
             const uint64_t resident = (uint64_t)num_sms * (smem <= 110 * 1024 ? 2 : 1);   // two pipelines per SM when they fit
             const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
@@ -344,7 +345,8 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
     if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
     if (threads < 64) threads = 64;
     const size_t smem = (size_t)a.num_cols * ((32u << log_ch) + 1) * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute((const void*)lde_last32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    static unsigned long long done32 = 0;
+    cudaError_t e = raise_smem_limit((const void*)lde_last32_kernel, &done32);
     if (e != cudaSuccess) return e;
     const uint64_t blocks = ((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets;
     lde_last32_kernel<<<(unsigned)blocks, threads, smem, st>>>(a, log_ch);

@@ -45,7 +45,7 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
     }
 };
 
-static bool g_pinned = true;
+static bool g_pinned = true, g_breakdown = false;
 
 struct HostBuf {   // pinned (default) or pageable host buffer
     uint64_t* p = nullptr;
@@ -114,7 +114,17 @@ struct Worker {
         const uint64_t digest[4] = {11, 12, 13, 14}, pih[4] = {21, 22, 23, 24};
         const uint64_t g = root_of_unity(sh.log_n);
 
+        double phase[8] = {0};
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto lap = [&](int k, std::chrono::steady_clock::time_point& t) {
+            if (!g_breakdown) return;
+            QCHECK(qpzk_ctx_synchronize(ctx));
+            auto t1 = now();
+            phase[k] += std::chrono::duration<double>(t1 - t).count();
+            t = t1;
+        };
         auto prove_one = [&](int s) {
+            auto tp = now();
             qpzk_challenger* ch;
             QCHECK(qpzk_challenger_create(ctx, &ch));
             QCHECK(qpzk_challenger_observe(ch, digest, 4));
@@ -124,24 +134,32 @@ struct Worker {
             QCHECK(qpzk_commit_from_values(ctx, wires[s].data(), sh.log_n, sh.wires, 3, 4, nullptr, &w_b));
             QCHECK(qpzk_challenger_observe_cap(ch, w_b));
             QCHECK(qpzk_challenger_get(ch, chal, 4));   // betas, gammas (would feed the partial products)
+            lap(0, tp);
             QCHECK(qpzk_commit_from_values(ctx, zs[s].data(), sh.log_n, sh.zs_pp, 3, 4, nullptr, &z_b));
             QCHECK(qpzk_challenger_observe_cap(ch, z_b));
             QCHECK(qpzk_challenger_get(ch, chal, 2));   // alphas (would feed the quotient)
+            lap(1, tp);
             QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
             QCHECK(qpzk_challenger_observe_cap(ch, q_b));
             QCHECK(qpzk_challenger_get(ch, zeta, 2));
+            lap(2, tp);
             const uint64_t gz[2] = {mulmod(zeta[0], g), mulmod(zeta[1], g)};
             const qpzk_batch* oracles[4] = {cs_b, w_b, z_b, q_b};
             uint64_t* op = openings.data();
-            for (int o = 0; o < 4; o++) { QCHECK(qpzk_batch_eval_ext(oracles[o], zeta, op)); op += 2 * leaf_lens[o]; }
+            QCHECK(qpzk_batches_eval_ext(ctx, oracles, 4, zeta, op));
+            op += 2 * total;
             QCHECK(qpzk_batch_eval_ext(z_b, gz, znext.data()));
             memcpy(op, znext.data(), 2 * sh.num_zs * sizeof(uint64_t));
+            lap(3, tp);
             QCHECK(qpzk_challenger_observe(ch, openings.data(), (uint32_t)openings.size()));
+            lap(4, tp);
             const uint64_t points[4] = {zeta[0], zeta[1], gz[0], gz[1]};
             qpzk_fri_instance inst{2, points, sizes, po.data(), pi.data()};
             QCHECK(qpzk_fri_prove(ctx, oracles, 4, &inst, &fp, ch, QPZK_POW_SEARCH, proof.data(), nullptr));
+            lap(5, tp);
             qpzk_batch_free(w_b); qpzk_batch_free(z_b); qpzk_batch_free(q_b);
             qpzk_challenger_free(ch);
+            lap(6, tp);
         };
         prove_one(0); prove_one(1);   // warm-up: tables, block cache
         for (size_t i = 0; i < proof.size(); i++) checksum = (checksum ^ proof.p[i]) * 0x100000001B3ULL;
@@ -154,6 +172,11 @@ struct Worker {
         QCHECK(qpzk_ctx_synchronize(ctx));
         seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         launches = qpzk_ctx_launch_count(ctx) - l0;
+        if (g_breakdown)
+            fprintf(stderr, "per proof (ms): wires commit+challenges %.3f | zs commit %.3f | quotient commit %.3f | openings %.3f | "
+                            "observe openings %.3f | fri_prove %.3f | free %.3f\n",
+                    1e3 * phase[0] / (proofs + 2), 1e3 * phase[1] / (proofs + 2), 1e3 * phase[2] / (proofs + 2), 1e3 * phase[3] / (proofs + 2),
+                    1e3 * phase[4] / (proofs + 2), 1e3 * phase[5] / (proofs + 2), 1e3 * phase[6] / (proofs + 2));
         qpzk_batch_free(cs_b);
         qpzk_ctx_destroy(ctx);
     }
@@ -170,6 +193,7 @@ int main(int argc, char** argv) {
         else if (k == "--proofs") proofs = v;
         else if (k == "--log-n") sh.log_n = (unsigned)v;
         else if (k == "--pinned") g_pinned = v != 0;
+        else if (k == "--breakdown") g_breakdown = v != 0;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);

@@ -83,6 +83,7 @@ def load_library():
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
         "qpzk_ctx_trim": (i, [vp]),
+        "qpzk_batches_eval_ext": (i, [vp, vp, u32, vp, vp]),
         "qpzk_pinned_alloc": (vp, [C.c_size_t]),
         "qpzk_pinned_free": (None, [vp]),
         "qpzk_poseidon_permute": (i, [vp, vp, u64, vp]),
@@ -351,6 +352,16 @@ class PolynomialBatch:
         pt, pp = _host(point)
         out = np.zeros((self.num_cols, 2), np.uint64)
         _check(self.ctx.L.qpzk_batch_eval_ext(self.h, pp, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @staticmethod
+    def eval_ext_many(batches, point):
+        """eval_ext of several batches of equal degree at one point: one launch, one copy; returns (sum cols, 2)."""
+        ctx = batches[0].ctx
+        pt, pp = _host(point)
+        arr = (C.c_void_p * len(batches))(*[b.h for b in batches])
+        out = np.zeros((sum(b.num_cols for b in batches), 2), np.uint64)
+        _check(ctx.L.qpzk_batches_eval_ext(ctx.h, arr, len(batches), pp, out.ctypes.data_as(C.c_void_p)))
         return out
 
     @staticmethod

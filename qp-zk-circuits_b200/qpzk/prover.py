@@ -67,8 +67,7 @@ def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public
     all_polys = [(o, i) for o, b in enumerate(oracles) for i in range(b.num_cols)]
     zs_next = [(2, i) for i in range(sh["num_zs"])]
     inst = FriInstanceInfo([([int(zeta[0]), int(zeta[1])], all_polys), (g_zeta, zs_next)])
-    openings = np.concatenate([np.concatenate([b.eval_ext(zeta) for b in oracles]),
-                               zs_b.eval_ext(g_zeta)[:sh["num_zs"]]])
+    openings = np.concatenate([PolynomialBatch.eval_ext_many(oracles, zeta), zs_b.eval_ext(g_zeta)[:sh["num_zs"]]])
     ch.observe_extension_elements(openings)
     proof = PolynomialBatch.prove_openings(inst, oracles, ch, circuit.fri_params, pow_witness=pow_witness)
     out = dict(caps=[wires_b.cap, zs_b.cap, quot_b.cap], openings=openings, fri_proof=proof,

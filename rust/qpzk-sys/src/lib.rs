@@ -47,6 +47,8 @@ extern "C" {
     pub fn qpzk_ctx_destroy(ctx: *mut qpzk_ctx);
     pub fn qpzk_ctx_synchronize(ctx: *mut qpzk_ctx) -> c_int;
     pub fn qpzk_ctx_trim(ctx: *mut qpzk_ctx) -> c_int;
+    pub fn qpzk_batches_eval_ext(ctx: *mut qpzk_ctx, batches: *const *const qpzk_batch, num_batches: u32, point: *const u64,
+                                 out: *mut u64) -> c_int;
     pub fn qpzk_pinned_alloc(bytes: usize) -> *mut c_void;
     pub fn qpzk_pinned_free(p: *mut c_void);
     pub fn qpzk_poseidon_permute(ctx: *mut qpzk_ctx, states: *const u64, count: u64, out: *mut u64) -> c_int;
