@@ -231,6 +231,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # Native multi-threaded prover runs FIRST, while this process holds no CUDA context: two processes with contexts
+    # on one GPU are time-sliced, which halves the child's throughput.  Every rank does it at once (N > 1: one
+    # prover per GPU = BASELINE configs 4/5, replicas without a data-path collective).
+    native = {}
+    if not args.no_prove:
+        tmax = max(1, min(4, (os.cpu_count() or 4) // world))
+        native[1] = native_prove_bench(local_rank, 1, 64)          # also warms the clocks
+        native[tmax] = native_prove_bench(local_rank, tmax, 64)
+        native["tmax"] = tmax
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -360,6 +369,14 @@ def main():
         e2e = {"value": bytes_alg(log_n) / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(host.numel() * 8), "d2h_bytes_per_step": int((1 << CAP_HEIGHT) // world * 32)}
 
+    # ---- independent proofs, one prover per GPU (BASELINE configs 4/5: replicas, no data-path collective) ----
+    native_all = None
+    if world > 1 and not args.no_prove:
+        r = native.get(native.get("tmax"))
+        v = torch.tensor([r["proofs_per_s"] if r else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(v)
+        native_all = float(v.item())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -407,11 +424,13 @@ def main():
                                           "random columns, openings at zeta and g*zeta over 256 polynomials, FRI (rate 3, cap 4, 16 PoW bits, "
                                           "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
                                           "restatement (tests/test_gpu_parity.py); witness generation and quotient evaluation are not part of it"}
-        n1, n4 = native_prove_bench(local_rank, 1), native_prove_bench(local_rank, 4)
+        if native_all is not None:
+            out["prove_synthetic"]["proofs_per_s_all_gpus"] = native_all   # min(4, cores/N) host threads per GPU, every rank at once
+        n1, n4 = native.get(1), native.get(native.get("tmax"))
         if n1 and n4:
             out["prove_synthetic"]["native"] = {
                 "latency_ms_1_thread": n1["latency_ms"], "proofs_per_s_1_thread": n1["proofs_per_s"],
-                "proofs_per_s_4_threads": n4["proofs_per_s"], "gpu_launches_per_proof": n1["launches_per_proof"],
+                "proofs_per_s_%d_threads" % native["tmax"]: n4["proofs_per_s"], "gpu_launches_per_proof": n1["launches_per_proof"],
                 "what": "same proof from C++ host threads on the C ABI (host/prove_bench.cpp), one context per thread, pinned buffers"}
         if not args.no_cpu_baseline:
             cms, cores = cpu_prove_synthetic()

@@ -198,10 +198,24 @@ def test_eval_ext_matches_oracle(ctx, qpzk, orc):
             assert (b.eval_ext(z) == o.eval_ext(z)).all()
 
 
+def test_eval_ext_many_matches_single_calls(ctx, qpzk, orc):
+    rng = np.random.default_rng(12)
+    batches = [qpzk.PolynomialBatch.from_values(ctx, rng.integers(0, P, size=(c, 256), dtype=np.uint64), 3, None, 4)
+               for c in (5, 1, 17)]
+    z = [int(x) for x in rng.integers(0, P, size=2, dtype=np.uint64)]
+    many = qpzk.PolynomialBatch.eval_ext_many(batches, z)
+    assert (many == np.concatenate([b.eval_ext(z) for b in batches])).all()
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.eval_ext_many(batches, [P, 0])          # point not canonical
+    other = qpzk.PolynomialBatch.from_values(ctx, rng.integers(0, P, size=(2, 128), dtype=np.uint64), 3, None, 4)
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.eval_ext_many([batches[0], other], z)   # different degrees
+
+
 def test_challenger_matches_oracle(ctx, qpzk, orc):
     g, o = qpzk.Challenger(ctx), orc.Challenger()
     rng = np.random.default_rng(1)
-    for n_obs, n_get in [(3, 2), (8, 1), (13, 9), (0, 3), (1, 1), (64, 4)]:
+    for n_obs, n_get in [(3, 2), (8, 1), (13, 9), (0, 3), (1, 1), (64, 4), (31, 1), (33, 8), (100, 5), (516, 2), (32, 17)]:
         x = rng.integers(0, P, size=n_obs, dtype=np.uint64)
         g.observe_elements(x); o.observe(x)
         assert (g.get_n_challenges(n_get) == o.get(n_get)).all()
