@@ -13,7 +13,10 @@ constexpr int MAX_DYN_SMEM = 227 * 1024;
 // bit mask of devices (callers pass a function-local static).  cudaFuncSetAttribute takes a device-wide lock; calling
 // it before every launch made concurrent provers on several host threads several times slower.
 cudaError_t raise_smem_limit(const void* fn, unsigned long long* done);
-constexpr int HASH_THREADS = 128;          // threads per block for one-thread-per-permutation kernels
+#ifndef QPZK_HASH_THREADS
+#define QPZK_HASH_THREADS 128
+#endif
+constexpr int HASH_THREADS = QPZK_HASH_THREADS;          // threads per block for one-thread-per-permutation kernels
 
 // Digest buffer of a tree with N leaves: level 0 (leaf digests, 4N words) first, then level 1 (2N words), ...
 // Word offset of level l:  8N - (8N >> l).
