@@ -162,6 +162,7 @@ struct Worker {
             lap(6, tp);
         };
         prove_one(0); prove_one(1);   // warm-up: tables, block cache
+        for (double& x : phase) x = 0;
         for (size_t i = 0; i < proof.size(); i++) checksum = (checksum ^ proof.p[i]) * 0x100000001B3ULL;
         QCHECK(qpzk_ctx_synchronize(ctx));
         ready->fetch_add(1);
@@ -175,8 +176,8 @@ struct Worker {
         if (g_breakdown)
             fprintf(stderr, "per proof (ms): wires commit+challenges %.3f | zs commit %.3f | quotient commit %.3f | openings %.3f | "
                             "observe openings %.3f | fri_prove %.3f | free %.3f\n",
-                    1e3 * phase[0] / (proofs + 2), 1e3 * phase[1] / (proofs + 2), 1e3 * phase[2] / (proofs + 2), 1e3 * phase[3] / (proofs + 2),
-                    1e3 * phase[4] / (proofs + 2), 1e3 * phase[5] / (proofs + 2), 1e3 * phase[6] / (proofs + 2));
+                    1e3 * phase[0] / proofs, 1e3 * phase[1] / proofs, 1e3 * phase[2] / proofs, 1e3 * phase[3] / proofs,
+                    1e3 * phase[4] / proofs, 1e3 * phase[5] / proofs, 1e3 * phase[6] / proofs);
         qpzk_batch_free(cs_b);
         qpzk_ctx_destroy(ctx);
     }
