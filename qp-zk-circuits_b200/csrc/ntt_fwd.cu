@@ -353,7 +353,61 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
     return cudaGetLastError();
 }
 
+// Short strided pass (1..4 bits): the whole 2^s-point transform of one low position fits one thread's registers, so
+// there is no exchange at all.  Used for the leftover top bits when the pass plan is not made of 5..8-bit passes
+// (n = 2^15, 2^16: 2 or 3 bits + 8 + 5).  256 consecutive low positions per block; same factor hoisting and column
+// loop as ntt_fwd_kernel.
+template <int S_LOG>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_small_kernel(NttPassArgs a) {
+    constexpr int A = 1 << S_LOG;
+    __shared__ uint64_t Ck[A];
+    const bool coset_first = a.mode == NTT_FWD_COSET_FIRST;
+    const uint32_t b_hi = a.b_lo + S_LOG;
+    uint32_t tile = blockIdx.x, coset = 0;
+    if (coset_first) { coset = tile & (a.num_cosets - 1); tile /= a.num_cosets; }
+    const uint32_t llow = a.b_lo - 8;
+    const uint64_t hi = tile >> llow;
+    const uint64_t low = ((uint64_t)(tile & ((1u << llow) - 1)) << 8) + threadIdx.x;
+    const uint64_t base = (hi << b_hi) + low;
+    const uint64_t* clo = a.cs_lo + (size_t)coset * TW_LO_SIZE;
+    const uint64_t* chi = a.cs_hi + (size_t)coset * a.cs_hi_size;
+    if (threadIdx.x < A) Ck[threadIdx.x] = coset_first ? tw_get(clo, chi, (uint64_t)threadIdx.x << a.b_lo) : 1;
+    uint64_t O[A];
+    {
+        const uint64_t cw = coset_first ? tw_get(clo, chi, low) : 1;
+#pragma unroll
+        for (int r = 0; r < A; r++) {
+            uint64_t o = tw_get(a.tw_lo, a.tw_hi, ((uint64_t)brev_c<S_LOG>(r) * low) << (a.log_n - b_hi));
+            if (coset_first) o = gl_mulc(o, cw);
+            O[r] = o;
+        }
+    }
+    __syncthreads();
+    const uint32_t c_begin = blockIdx.y * a.cols_per_block;
+    const uint32_t c_end = min((uint32_t)a.num_arrays, c_begin + a.cols_per_block);
+    const uint64_t in_off = (uint64_t)blockIdx.z * a.group_stride + base;
+    uint64_t x[A], y[A];
+    if (c_begin < c_end) {
+#pragma unroll
+        for (int k = 0; k < A; k++) x[k] = a.in[c_begin * a.in_stride + in_off + ((uint64_t)k << a.b_lo)];
+    }
+    for (uint32_t col = c_begin; col < c_end; col++) {
+#pragma unroll
+        for (int k = 0; k < A; k++) y[k] = (coset_first && k) ? gl_mulc(x[k], Ck[k]) : x[k];
+        if (col + 1 < c_end) {
+#pragma unroll
+            for (int k = 0; k < A; k++) x[k] = a.in[(col + 1) * a.in_stride + in_off + ((uint64_t)k << a.b_lo)];
+        }
+        dft_regs<S_LOG>(y);
+        uint64_t* out = a.out + col * a.out_stride + ((uint64_t)coset + blockIdx.z) * a.group_stride + base;
+#pragma unroll
+        for (int r = 0; r < A; r++) out[(uint64_t)r << a.b_lo] = gl_mulc(y[r], O[r]);   // slot of frequency bitrev(r) is r
+    }
+}
+
 bool ntt_fwd_supported(const NttPassArgs& a) {
+    if ((a.mode == NTT_FWD_COSET_FIRST || a.mode == NTT_FWD_GENERIC) && a.s >= 1 && a.s <= 4 && a.scale == 1 &&
+        a.b_lo >= 8 && a.log_n >= a.b_lo + a.s) return true;
     if (a.mode != NTT_FWD_COSET_FIRST && a.mode != NTT_FWD_GENERIC) return false;
     if (a.s < 5 || a.s > 8 || a.scale != 1) return false;
     return a.b_lo >= 12 - a.s && a.log_n >= a.b_lo + a.s;
@@ -369,6 +423,19 @@ static cudaError_t launch_one(const NttPassArgs& a, dim3 grid, cudaStream_t st) 
 }
 
 cudaError_t launch_ntt_fwd(const NttPassArgs& a, cudaStream_t st) {
+    if (a.s <= 4) {
+        uint64_t t = (1ull << a.log_n) >> (8 + a.s);
+        if (a.mode == NTT_FWD_COSET_FIRST) t *= a.num_cosets;
+        const uint32_t cpb = a.cols_per_block ? a.cols_per_block : 1;
+        dim3 grid((unsigned)t, (unsigned)((a.num_arrays + cpb - 1) / cpb), (unsigned)(a.num_groups ? a.num_groups : 1));
+        switch (a.s) {
+            case 1: ntt_fwd_small_kernel<1><<<grid, NTT_THREADS, 0, st>>>(a); break;
+            case 2: ntt_fwd_small_kernel<2><<<grid, NTT_THREADS, 0, st>>>(a); break;
+            case 3: ntt_fwd_small_kernel<3><<<grid, NTT_THREADS, 0, st>>>(a); break;
+            default: ntt_fwd_small_kernel<4><<<grid, NTT_THREADS, 0, st>>>(a); break;
+        }
+        return cudaGetLastError();
+    }
     uint64_t tiles = (1ull << a.log_n) >> 12;
     if (a.mode == NTT_FWD_COSET_FIRST) tiles *= a.num_cosets;
     const uint32_t cpb = a.cols_per_block ? a.cols_per_block : 1;
