@@ -50,6 +50,19 @@ def perms(log_n, num_cols=NUM_COLS, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
     return L * ((num_cols + 7) // 8) + (L - (1 << cap_height))
 
 
+def measured_traffic(log_n, world):
+    """DRAM bytes (read + write) of one hash_rows_kernel launch from the committed `ncu --set full` capture of the same
+    configuration (profiles/r1_traffic.json); None when that configuration was not captured."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            e = json.load(f)["per_log_n"][str(log_n)]
+        return e["dram_read_bytes"] + e["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -405,9 +418,12 @@ def main():
         "stages_ms": stage,
         "roofline": {"kernel": "hash_rows_kernel (Poseidon leaf sponge, %d permutations per row)" % ((C_ + 7) // 8),
                      "bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": None, "peak_source": peak_src + " (of measured)",
+                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": measured_traffic(log_n, world),
+                     "traffic_unit": "DRAM bytes read+written per launch (ncu --set full, profiles/r1_traffic.json)",
+                     "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src + " (of measured)",
+                     "pipes": "ncu: issue slots 73% busy, ALU pipe 80% of peak, FMA-heavy pipe ~79% (profiles/r1_summary.md C)",
                      "note": "integer-pipe bound, not HBM bound: see int_pipe; HBM fraction reported because the contract asks for it"},
-        "roofline_lde": {"kernels": "ntt_pass_kernel + lde_last_kernel", "bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak,
+        "roofline_lde": {"kernels": "ntt_pass_kernel (iNTT) + ntt_fwd_kernel x2 + lde_last32_tma_kernel", "bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": lde_gbs / hbm_peak if lde_gbs else None, "bytes": lde_bytes},
         "roofline_commit": {"bound": "hbm", "achieved": value, "peak": hbm_peak * world, "unit": "GB/s",
                             "frac": value / (hbm_peak * world)},

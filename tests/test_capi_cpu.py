@@ -63,3 +63,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in text and "orc_" not in text and "import oracle" not in text, f
+
+
+def test_native_driver_builds_and_fails_loudly_without_gpu(qpzk):
+    """host/prove_bench.cpp (the C++ caller of the C ABI) is built by `make`; on a GPU-less host it must exit with
+    the library's error, not fall back to anything."""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(qpzk.LIB_PATH), "prove_bench")
+    assert os.path.exists(exe), "run __graft_entry__.build() / make -C qp-zk-circuits_b200"
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; the failure path is for GPU-less hosts")
+    r = subprocess.run([exe, "--threads", "1", "--proofs", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "qpzk_ctx_create" in r.stderr
