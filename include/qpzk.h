@@ -211,6 +211,28 @@ int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num
                    const qpzk_fri_instance* instance, const qpzk_fri_params* params, qpzk_challenger* ch,
                    uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out);
 
+/* ---- permutation argument: all_wires_permutation_partial_products ----------------------------------
+ * Replaces qp-plonky2 `all_wires_permutation_partial_products` / `wires_permutation_partial_products_and_zs`
+ * (plonk/prover.rs; SURVEY.md 8a row a16, the step between the wires commitment and the zs/partial-products
+ * commitment of `prove()`, reference call site wormhole/prover/src/lib.rs:171-175).
+ *   wires, sigmas : num_routed x 2^log_n words, column-major: the routed wire values and the sigma polynomials'
+ *                   values on the subgroup (sigma_j(w^i) = k_j' * w^i' of the position wire (i, j) is copied to)
+ *   chunk         : quotient_degree_factor (8 for every reference circuit: max_quotient_degree_factor,
+ *                   common/src/circuit.rs:378-414); 1 <= ceil(num_routed / chunk) <= 32
+ *   betas, gammas : num_challenges (<= 8) canonical challenges each (host pointers in both variants)
+ *   out           : (num_challenges * ceil(num_routed / chunk)) x 2^log_n words, column-major, in the order of the
+ *                   committed zs_partial_products batch: Z of every challenge, then the partial products of
+ *                   challenge 0, of challenge 1, ...  (Z(1) = 1; the row for x holds Z(x) and the running products
+ *                   Z(x) * chunk_0 ... chunk_k for k < ceil(num_routed / chunk) - 1)
+ * The _dev variant takes device pointers for wires / sigmas / out (out may be passed straight to
+ * qpzk_commit_from_values_dev). */
+int qpzk_partial_products(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
+                          uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                          const uint64_t* gammas, uint64_t* out);
+int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires_dev, const uint64_t* sigmas_dev, uint32_t log_n,
+                              uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                              const uint64_t* gammas, uint64_t* out_dev);
+
 /* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------------- */
 /* IMAD.WIDE throughput: returns 32x32+64 multiply-adds per second measured over `iters` dependent-chain
  * iterations on every SM. */

@@ -371,6 +371,67 @@ void orc_batch_eval_ext(const orc_batch* b, const uint64_t point[2], uint64_t* o
 /* ------------------------------------------------------------------------------------------
  * Challenger
  * ------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------
+ * Partial products of the permutation argument ("next" tier; parity UNPINNED: no golden
+ * vector in the reference tree, restated from upstream plonky2 `plonk/prover.rs`
+ * `all_wires_permutation_partial_products` / `wires_permutation_partial_products_and_zs` and
+ * `plonk/permutation_argument.rs`/`util/partial_products.rs` [upstream-memory]):
+ *   per row i (x = w^i), per challenge (beta, gamma):
+ *     numerator_j = wire[i][j] + beta * (k_j * x) + gamma,  denominator_j = wire[i][j] + beta * sigma[i][j] + gamma,
+ *     k_j = g^j (get_unique_coset_shifts), quotient_j = numerator_j / denominator_j (batch inverse per row),
+ *     chunk products over `chunk` (= quotient_degree_factor = 8) consecutive quotients,
+ *     running products acc = Z(x) * q_0 * ... * q_k;  the last one is Z(g x), swapped with Z(x): the row holds
+ *     [pp_0 .. pp_{np-1}, Z(x)],  np = ceil(num_routed / chunk) - 1,  Z(w^0) = 1.
+ *   The committed batch is [Z of every challenge, then the partial products of challenge 0, 1, ...].
+ * wires, sigmas: num_routed x n column-major values.  out: (num_challenges * (np + 1)) x n column-major.
+ * ------------------------------------------------------------------------------------------ */
+int orc_partial_products(const uint64_t* wires, const uint64_t* sigmas, unsigned log_n, unsigned num_routed,
+                         unsigned chunk, unsigned num_challenges, const uint64_t* betas, const uint64_t* gammas,
+                         uint64_t* out) {
+    if (!chunk || !num_routed) return -1;
+    const size_t n = (size_t)1 << log_n;
+    const unsigned nchunks = (num_routed + chunk - 1) / chunk, np = nchunks - 1;
+    const uint64_t w = gl_root_of_unity(log_n);
+    uint64_t* k_is = (uint64_t*)malloc(num_routed * sizeof(uint64_t));
+    uint64_t* num = (uint64_t*)malloc(num_routed * sizeof(uint64_t));
+    uint64_t* den = (uint64_t*)malloc(num_routed * sizeof(uint64_t));
+    uint64_t* pre = (uint64_t*)malloc(num_routed * sizeof(uint64_t));
+    if (!k_is || !num || !den || !pre) { free(k_is); free(num); free(den); free(pre); return -3; }
+    k_is[0] = 1;
+    for (unsigned j = 1; j < num_routed; j++) k_is[j] = gl_mul(k_is[j - 1], GL_GENERATOR);
+    for (unsigned c = 0; c < num_challenges; c++) {
+        const uint64_t beta = betas[c], gamma = gammas[c];
+        uint64_t* z_col = out + (size_t)c * n;
+        uint64_t* pp_cols = out + ((size_t)num_challenges + (size_t)c * np) * n;
+        uint64_t z_x = 1, x = 1;
+        for (size_t i = 0; i < n; i++) {
+            for (unsigned j = 0; j < num_routed; j++) {
+                const uint64_t wv = wires[(size_t)j * n + i];
+                num[j] = gl_add(gl_add(wv, gl_mul(beta, gl_mul(k_is[j], x))), gamma);
+                den[j] = gl_add(gl_add(wv, gl_mul(beta, sigmas[(size_t)j * n + i])), gamma);
+            }
+            /* batch_multiplicative_inverse: prefix products, one inversion, back-substitution */
+            uint64_t acc = 1;
+            for (unsigned j = 0; j < num_routed; j++) { pre[j] = acc; acc = gl_mul(acc, den[j]); }
+            uint64_t inv = gl_inv(acc);
+            for (unsigned j = num_routed; j-- > 0;) { uint64_t d = den[j]; den[j] = gl_mul(inv, pre[j]); inv = gl_mul(inv, d); }
+            /* chunk products, running products, swap */
+            acc = z_x;
+            for (unsigned k = 0; k < nchunks; k++) {
+                uint64_t q = 1;
+                for (unsigned j = k * chunk; j < num_routed && j < (k + 1) * chunk; j++) q = gl_mul(q, gl_mul(num[j], den[j]));
+                acc = gl_mul(acc, q);
+                if (k < np) pp_cols[(size_t)k * n + i] = acc;
+            }
+            z_col[i] = z_x;     /* Z(x) stays in this row ... */
+            z_x = acc;          /* ... and Z(g x) moves on  */
+            x = gl_mul(x, w);
+        }
+    }
+    free(k_is); free(num); free(den); free(pre);
+    return 0;
+}
+
 void orc_challenger_init(orc_challenger* c) { memset(c, 0, sizeof *c); }
 
 static void duplexing(orc_challenger* c) {

@@ -25,6 +25,10 @@ uint64_t orc_gl_root_of_unity(unsigned log_n);
 
 /* ---- Poseidon-12 ---- */
 void orc_poseidon_rc(uint64_t out[360]);   /* round constants */
+/* partial products of the permutation argument (row a16, next tier, parity unpinned); see oracle.c */
+int orc_partial_products(const uint64_t* wires, const uint64_t* sigmas, unsigned log_n, unsigned num_routed,
+                         unsigned chunk, unsigned num_challenges, const uint64_t* betas, const uint64_t* gammas,
+                         uint64_t* out);
 void orc_poseidon_naive(uint64_t s[12]);  /* literal round structure */
 void orc_poseidon(uint64_t s[12]);        /* sparse partial rounds; identical function */
 void orc_hash_no_pad(const uint64_t* in, size_t n, uint64_t out[4]);

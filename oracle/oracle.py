@@ -57,6 +57,8 @@ def lib():
         L.orc_gl_root_of_unity.restype = C.c_uint64; L.orc_gl_root_of_unity.argtypes = [C.c_uint]
         for f in (L.orc_poseidon, L.orc_poseidon_naive, L.orc_poseidon_rc):
             f.restype = None; f.argtypes = [U64P]
+        L.orc_partial_products.restype = C.c_int
+        L.orc_partial_products.argtypes = [U64P, U64P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, U64P, U64P, U64P]
         for f in (L.orc_hash_no_pad, L.orc_hash_or_noop):
             f.restype = None; f.argtypes = [U64P, C.c_size_t, U64P]
         L.orc_two_to_one.restype = None; L.orc_two_to_one.argtypes = [U64P, U64P, U64P]
@@ -107,6 +109,20 @@ def _p32(a):
 
 def _u64(a):
     return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def partial_products(wires, sigmas, betas, gammas, chunk=8):
+    """all_wires_permutation_partial_products: wires, sigmas (num_routed, n) -> (len(betas) * ceil(R/chunk), n) in the
+    order of the committed batch: Z per challenge, then the partial products of challenge 0, 1, ..."""
+    w, sg = _u64(wires), _u64(sigmas)
+    R, n = w.shape
+    assert sg.shape == w.shape and n & (n - 1) == 0
+    b, g = _u64(betas), _u64(gammas)
+    nch = (R + chunk - 1) // chunk
+    out = np.zeros((b.size * nch, n), np.uint64)
+    rc = lib().orc_partial_products(_p64(w), _p64(sg), n.bit_length() - 1, R, chunk, b.size, _p64(b), _p64(g), _p64(out))
+    assert rc == 0
+    return out
 
 
 def round_constants():
@@ -326,14 +342,18 @@ def num_threads():
 # ---- the commitment / opening half of prove() on the CPU (mirror of qpzk/prover.py) ----------------
 def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient_coeffs, public_inputs_hash,
                     log_n, num_zs=2, rate_bits=3, cap_height=4, pow_bits=16, num_queries=28, arity_bits=4,
-                    final_poly_bits=5):
+                    final_poly_bits=5, sigmas=None, quotient_degree_factor=8):
     """Same transcript and the same outputs as qpzk.prover.prove_synthetic, computed by the CPU restatement."""
     ch = Challenger()
     ch.observe(np.arange(4, dtype=np.uint64) + 11)
     ch.observe(public_inputs_hash)
     wires_b = PolynomialBatch.from_values(wires, rate_bits, cap_height)
     ch.observe(wires_b.cap())
-    betas_gammas = ch.get(4)
+    betas_gammas = ch.get(2 * num_zs)
+    if zs_partial_products is None:
+        sg = _u64(sigmas)
+        zs_partial_products = partial_products(_u64(wires)[:sg.shape[0]], sg, betas_gammas[:num_zs],
+                                               betas_gammas[num_zs:], quotient_degree_factor)
     zs_b = PolynomialBatch.from_values(zs_partial_products, rate_bits, cap_height)
     ch.observe(zs_b.cap())
     alphas = ch.get(2)

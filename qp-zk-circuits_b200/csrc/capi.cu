@@ -1189,6 +1189,79 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// permutation argument: Z and partial products (perm.cu)
+// ---------------------------------------------------------------------------------------------
+static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, bool host, uint32_t log_n,
+                                 uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                                 const uint64_t* gammas, uint64_t* out) {
+    if (!ctx || !wires || !sigmas || !betas || !gammas || !out) return fail(QPZK_EINVAL, "null argument");
+    if (log_n > 28) return fail(QPZK_EINVAL, "log_n must be <= 28");
+    if (!num_routed || !chunk) return fail(QPZK_EINVAL, "num_routed and chunk must be positive");
+    const uint32_t nchunks = (num_routed + chunk - 1) / chunk;
+    if (nchunks > PP_MAX_CHUNKS) return fail(QPZK_EINVAL, "more than 32 chunks per row");
+    if (!num_challenges || num_challenges > 8) return fail(QPZK_EINVAL, "num_challenges must be in 1..8");
+    for (uint32_t c = 0; c < num_challenges; c++)
+        if (betas[c] >= GL_P || gammas[c] >= GL_P) return fail(QPZK_EINVAL, "challenge is not canonical");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n = 1ull << log_n, in_words = (uint64_t)num_routed * n, out_words = (uint64_t)num_challenges * nchunks * n;
+    PowTables tw;
+    int rc = get_pow_tables(ctx, log_n, false, &tw);
+    if (rc) return rc;
+    // small parameter block: betas | gammas | beta * k_j per challenge,  k_j = g^j (get_unique_coset_shifts)
+    std::vector<uint64_t> par(2 * num_challenges + (size_t)num_challenges * num_routed);
+    for (uint32_t c = 0; c < num_challenges; c++) {
+        par[c] = betas[c]; par[num_challenges + c] = gammas[c];
+        uint64_t k = 1;
+        for (uint32_t j = 0; j < num_routed; j++) {
+            par[2 * num_challenges + (size_t)c * num_routed + j] = gl_mul_host(betas[c], k);
+            k = gl_mul_host(k, GL_GENERATOR);
+        }
+    }
+    DevBufs bufs(ctx);
+    uint64_t *d_par, *d_chunk, *d_row, *d_w = nullptr, *d_s = nullptr, *d_out = nullptr;
+    if ((rc = bufs.alloc(&d_par, par.size()))) return rc;
+    if ((rc = bufs.alloc(&d_chunk, out_words))) return rc;
+    if ((rc = bufs.alloc(&d_row, (uint64_t)num_challenges * n))) return rc;
+    if (host) {
+        if ((rc = bufs.alloc(&d_w, in_words))) return rc;
+        if ((rc = bufs.alloc(&d_s, in_words))) return rc;
+        if ((rc = bufs.alloc(&d_out, out_words))) return rc;
+        CK(cudaMemcpyAsync(d_w, wires, in_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_s, sigmas, in_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    PartialProductsArgs a{};
+    a.wires = host ? d_w : wires; a.sigmas = host ? d_s : sigmas; a.col_stride = n;
+    a.log_n = log_n; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = nchunks; a.num_challenges = num_challenges;
+    a.betas = d_par; a.gammas = d_par + num_challenges; a.beta_k = d_par + 2 * num_challenges;
+    a.tw_lo = tw.lo; a.tw_hi = tw.hi;
+    a.chunkprod = d_chunk; a.rowprod = d_row; a.out = host ? d_out : out;
+    CK(launch_partial_products(a, ctx->stream));
+    ctx->launches += 3;
+    if (host) CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->zeroize) {   // everything here is a function of the (secret) wires
+        CK(cudaMemsetAsync(d_chunk, 0, out_words * sizeof(uint64_t), ctx->stream));
+        CK(cudaMemsetAsync(d_row, 0, (uint64_t)num_challenges * n * sizeof(uint64_t), ctx->stream));
+        if (host) {
+            CK(cudaMemsetAsync(d_w, 0, in_words * sizeof(uint64_t), ctx->stream));
+            CK(cudaMemsetAsync(d_out, 0, out_words * sizeof(uint64_t), ctx->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // `par` (pageable) and the caller's host buffers are released on return
+    return 0;
+}
+extern "C" int qpzk_partial_products(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
+                                     uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                                     const uint64_t* gammas, uint64_t* out) {
+    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, true, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+}
+extern "C" int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
+                                         uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                                         const uint64_t* gammas, uint64_t* out) {
+    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, false, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
 // microbenchmarks (roofline denominators)
 // ---------------------------------------------------------------------------------------------
 extern "C" int qpzk_bench_imad(qpzk_ctx* ctx, uint32_t iters, double* imad_per_sec) {

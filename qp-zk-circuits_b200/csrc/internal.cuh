@@ -173,6 +173,21 @@ cudaError_t launch_fri_fold(const FriFoldArgs& a, uint32_t arity_bits, cudaStrea
 cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st);
 cudaError_t launch_fri_gather(const FriGatherArgs& a, uint32_t num_queries, cudaStream_t st);
 
+// ---- perm.cu ----
+constexpr uint32_t PP_MAX_CHUNKS = 32;       // chunks per row: ceil(num_routed / chunk)
+struct PartialProductsArgs {
+    const uint64_t *wires, *sigmas;   // num_routed columns of n values, column-major
+    uint64_t col_stride;              // words between consecutive columns of wires / sigmas
+    uint32_t log_n, num_routed, chunk, nchunks, num_challenges;
+    const uint64_t *betas, *gammas;   // device, num_challenges each
+    const uint64_t* beta_k;           // device, [challenge][num_routed]: beta * g^j
+    const uint64_t *tw_lo, *tw_hi;    // powers of w_n
+    uint64_t* chunkprod;              // scratch: [challenge][chunk][row]
+    uint64_t* rowprod;                // scratch: [challenge][row]
+    uint64_t* out;                    // [Z of every challenge | partial products of challenge 0, 1, ...] x n
+};
+cudaError_t launch_partial_products(const PartialProductsArgs& a, cudaStream_t st);
+
 }  // namespace qpzk
 
 namespace qpzk {

@@ -119,6 +119,8 @@ def load_library():
         "qpzk_fri_params_constant_arity": (i, [C.POINTER(FriParams), u32, u32, u32, u32, u32, u32, u32]),
         "qpzk_fri_proof_words": (C.c_size_t, [C.POINTER(FriParams), u32, u32, U32P]),
         "qpzk_fri_prove": (i, [vp, C.POINTER(vp), u32, C.POINTER(_FriInstance), C.POINTER(FriParams), vp, u64, vp, vp]),
+        "qpzk_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
+        "qpzk_partial_products_dev": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -187,6 +189,24 @@ class Context:
         else:
             _check(self.L.qpzk_selftest_mds_layer(self.h, a.ctypes.data_as(C.c_void_p), a.shape[0], mds_only_round,
                                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def partial_products(self, wires, sigmas, betas, gammas, chunk=8):
+        """all_wires_permutation_partial_products (qp-plonky2 plonk/prover.rs): wires, sigmas (num_routed, n) values on
+        the subgroup -> (len(betas) * ceil(num_routed / chunk), n): Z of every challenge, then the partial products of
+        challenge 0, 1, ... -- the columns of the zs_partial_products commitment."""
+        w, wp = _host(wires)
+        sg, sp = _host(sigmas)
+        if w.ndim != 2 or sg.shape != w.shape or w.shape[1] & (w.shape[1] - 1) or not w.shape[1]:
+            raise QpzkError(-1, "wires and sigmas must be (num_routed, 2^k) arrays of the same shape")
+        b, bp = _host(betas)
+        g, gp = _host(gammas)
+        if b.ndim != 1 or b.shape != g.shape:
+            raise QpzkError(-1, "betas and gammas must have the same length")
+        R, n = w.shape
+        out = np.zeros((b.size * ((R + chunk - 1) // chunk), n), np.uint64)
+        _check(self.L.qpzk_partial_products(self.h, wp, sp, n.bit_length() - 1, R, chunk, b.size, bp, gp,
+                                            out.ctypes.data_as(C.c_void_p)))
         return out
 
     def bench_imad(self, iters=4096):

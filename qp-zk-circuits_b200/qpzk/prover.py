@@ -8,10 +8,12 @@ does, per proof (transcript in Appendix A.7):
     quotient chunks (coefficients) -> from_coeffs -> observe cap -> zeta
     openings of all four oracles at zeta, of zs at g*zeta -> observe -> PolynomialBatch::prove_openings (FRI)
 
-Witness generation, the partial products and the quotient evaluation need the gate set of
-the un-vendored crate and are NOT part of this repo; here their outputs are stood in for by caller-supplied (random)
-columns of the right shapes, so the function exercises exactly the part of `prove()` this backend replaces and is
-labelled *synthetic* wherever it is reported.  The constants/sigmas oracle is committed once per circuit
+Witness generation and the quotient evaluation need the gate set of the un-vendored crate and
+are NOT part of this repo; here their outputs are stood in for by caller-supplied (random) columns of the right shapes,
+so the function exercises exactly the part of `prove()` this backend replaces and is labelled *synthetic* wherever it
+is reported.  The partial products of the permutation argument (row a16) are gate independent: when the caller passes
+the sigma values (`sigmas`, num_routed x n) instead of ready-made zs/partial-product columns, they are computed on the
+device from the routed wires and the betas/gammas drawn from the transcript (`Context.partial_products`).  The constants/sigmas oracle is committed once per circuit
 (`CircuitBuilder::build`, reference wormhole/circuit/src/circuit.rs:206-216), not per proof.
 
 Shapes of the leaf circuit: degree 2^13, 85 constants+sigmas, 135 wires, 20 zs/partial
@@ -45,8 +47,11 @@ class SyntheticCircuit:
 
 
 def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public_inputs_hash, pow_witness=None,
-                    keep_batches=False):
+                    keep_batches=False, sigmas=None, quotient_degree_factor=8):
     """One proof's worth of commitments + FRI.  Inputs are host arrays (values / coefficients, column-major).
+    zs_partial_products may be None when `sigmas` (num_routed x n sigma values) is given: the columns are then
+    computed from wires[:num_routed] with the transcript's betas and gammas (upstream
+    `all_wires_permutation_partial_products`).
     Returns dict(caps=[wires, zs_pp, quotient], openings=(k, 2) array, fri_proof=flat words)."""
     ctx, sh = circuit.ctx, circuit.shape
     ch = Challenger(ctx)
@@ -54,7 +59,12 @@ def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public
     ch.observe_hash(public_inputs_hash)
     wires_b = PolynomialBatch.from_values(ctx, wires, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(wires_b)
-    betas_gammas = ch.get_n_challenges(4)                      # would feed the partial products (a16)
+    nz = sh["num_zs"]
+    betas_gammas = ch.get_n_challenges(2 * nz)                 # betas, then gammas (num_challenges each)
+    if zs_partial_products is None:
+        sg = np.asarray(sigmas, dtype=np.uint64)
+        zs_partial_products = ctx.partial_products(np.asarray(wires)[:sg.shape[0]], sg, betas_gammas[:nz],
+                                                   betas_gammas[nz:], quotient_degree_factor)
     zs_b = PolynomialBatch.from_values(ctx, zs_partial_products, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(zs_b)
     alphas = ch.get_n_challenges(2)                            # would feed the quotient (a17)

@@ -361,3 +361,83 @@ def test_prove_synthetic_matches_oracle_and_verifies(ctx, qpzk, orc, log_n):
     cached = ctx.cached_bytes()
     prover.prove_synthetic(circuit, **prover.synthetic_inputs(8, shape))
     assert ctx.cached_bytes() == cached
+
+
+# ---- permutation argument: all_wires_permutation_partial_products (row a16) ---------------------------------------
+@pytest.mark.parametrize("log_n,R,chunk,nch", [(13, 80, 8, 2), (15, 60, 8, 2), (6, 7, 8, 1), (0, 3, 2, 2), (1, 13, 5, 3),
+                                              (11, 135, 8, 2), (16, 80, 8, 2), (10, 256, 8, 1)])
+def test_partial_products_match_oracle(ctx, orc, log_n, R, chunk, nch):
+    rng = np.random.default_rng(1000 + log_n)
+    n = 1 << log_n
+    wires = rng.integers(0, P, size=(R, n), dtype=np.uint64)
+    sigmas = rng.integers(0, P, size=(R, n), dtype=np.uint64)
+    if n > 4:
+        wires[0, :4] = [0, P - 1, 1, P - 2]
+        sigmas[0, :4] = [P - 1, 0, P - 2, 1]
+    betas = rng.integers(0, P, size=nch, dtype=np.uint64)
+    gammas = rng.integers(0, P, size=nch, dtype=np.uint64)
+    got = ctx.partial_products(wires, sigmas, betas, gammas, chunk)
+    want = orc.partial_products(wires, sigmas, betas, gammas, chunk)
+    assert got.shape == want.shape == (nch * ((R + chunk - 1) // chunk), n)
+    assert (got == want).all()
+
+
+def test_partial_products_close_and_feed_the_commitment(ctx, orc, qpzk):
+    """Wires that satisfy a random copy-constraint system: Z(1) = 1 and the running product closes (the last row's
+    Z times its quotient product is 1, checked through the oracle's row quotients), and the output, committed with
+    from_values, gives the cap the oracle gets from its own partial products."""
+    from perm_util import root_of_unity, satisfied_permutation
+    log_n, R = 9, 24
+    wires, sigmas, _ = satisfied_permutation(log_n, R, seed=11)
+    betas = np.array([3, P - 5], np.uint64)
+    gammas = np.array([P - 1, 12345678901234567], np.uint64)
+    got = ctx.partial_products(wires, sigmas, betas, gammas, 8)
+    want = orc.partial_products(wires, sigmas, betas, gammas, 8)
+    assert (got == want).all() and (got[:2, 0] == 1).all()
+    n = 1 << log_n
+    for c in range(2):      # last row: Z(w^(n-1)) * prod of all quotients of that row == Z(w^n) == 1
+        num = den = 1
+        x = pow(root_of_unity(log_n), n - 1, P)
+        for j in range(R):
+            k = pow(14293326489335486720, j, P)
+            num = num * ((int(wires[j, n - 1]) + int(betas[c]) * k * x + int(gammas[c])) % P) % P
+            den = den * ((int(wires[j, n - 1]) + int(betas[c]) * int(sigmas[j, n - 1]) + int(gammas[c])) % P) % P
+        assert int(got[c, n - 1]) * num % P == den
+    gb = qpzk.PolynomialBatch.from_values(ctx, got, 3, None, 4)
+    ob = orc.PolynomialBatch.from_values(want, 3, 4)
+    assert (gb.cap == ob.cap()).all()
+
+
+def test_partial_products_rejects_bad_arguments(ctx, qpzk):
+    w = np.zeros((4, 8), np.uint64)
+    with pytest.raises(qpzk.QpzkError):
+        ctx.partial_products(w, w, [P], [0])                 # non-canonical challenge
+    with pytest.raises(qpzk.QpzkError):
+        ctx.partial_products(w, w[:, :4], [1], [0])          # shape mismatch
+    with pytest.raises(qpzk.QpzkError):
+        ctx.partial_products(np.zeros((300, 8), np.uint64), np.zeros((300, 8), np.uint64), [1], [0], chunk=8)  # 38 chunks
+
+
+def test_prove_synthetic_with_device_partial_products(ctx, qpzk, orc):
+    """Same transcript, but the zs / partial-product columns come from the routed wires and the sigma values through
+    the permutation-argument kernels, with the betas and gammas the transcript produced."""
+    from qpzk import prover
+    log_n, routed = 9, 80
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n)
+    rng = np.random.default_rng(77)
+    cs = rng.integers(0, P, size=(shape["constants_sigmas"], 1 << log_n), dtype=np.uint64)
+    circuit = prover.SyntheticCircuit(ctx, cs, shape)
+    inp = prover.synthetic_inputs(9, shape)
+    inp["zs_partial_products"] = None
+    sigmas = rng.integers(0, P, size=(routed, 1 << log_n), dtype=np.uint64)
+    got = prover.prove_synthetic(circuit, sigmas=sigmas, **inp)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, inp["wires"], None, inp["quotient_coeffs"], inp["public_inputs_hash"], log_n,
+                               sigmas=sigmas)
+    assert want["leaf_lens"][2] == 2 * ((routed + 7) // 8) == shape["zs_partial_products"]
+    for a, b in zip(got["caps"], want["caps"]):
+        assert (a == b).all()
+    assert (got["openings"] == want["openings"]).all()
+    assert (got["fri_proof"] == want["fri_proof"]).all()
+    assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], want["openings"], want["params"],
+                          want["verifier_challenger"], got["fri_proof"]) == 0

@@ -213,3 +213,68 @@ def test_oracle_prove_synthetic_is_accepted_by_the_oracle_verifier(orc):
     bad = out["fri_proof"].copy()
     bad[len(bad) // 2] ^= 1
     assert orc.fri_verify(*args, out["verifier_challenger"].clone(), bad) != 0
+
+
+# ---- permutation argument ------------------------------------------------------------------
+def _partial_products_bigint(wires, sigmas, betas, gammas, chunk):
+    """Literal big-integer restatement of upstream `wires_permutation_partial_products_and_zs` + the Z-first reorder
+    done in `prove()`: every quotient inverted on its own with pow(d, p-2, p)."""
+    from perm_util import P as PP, G, root_of_unity
+    R, n = wires.shape
+    w = root_of_unity(n.bit_length() - 1)
+    nch = (R + chunk - 1) // chunk
+    zs, pps = [], []
+    for beta, gamma in zip(betas, gammas):
+        z_x, x = 1, 1
+        z_col, pp_cols = [], [[] for _ in range(nch - 1)]
+        for i in range(n):
+            q = []
+            for j in range(R):
+                num = (int(wires[j, i]) + int(beta) * pow(G, j, PP) * x + int(gamma)) % PP
+                den = (int(wires[j, i]) + int(beta) * int(sigmas[j, i]) + int(gamma)) % PP
+                q.append(num * pow(den, PP - 2, PP) % PP)
+            acc = z_x
+            row = []
+            for k in range(nch):
+                for v in q[k * chunk:(k + 1) * chunk]:
+                    acc = acc * v % PP
+                row.append(acc)
+            z_col.append(z_x)
+            for k in range(nch - 1):
+                pp_cols[k].append(row[k])
+            z_x = row[-1]
+            x = x * w % PP
+        zs.append(z_col)
+        pps.extend(pp_cols)
+    return np.array(zs + pps, dtype=np.uint64), z_x
+
+
+@pytest.mark.parametrize("log_n,R,chunk", [(3, 10, 8), (4, 7, 8), (2, 13, 5), (0, 3, 2), (5, 16, 8)])
+def test_partial_products_against_bigint(orc, log_n, R, chunk):
+    rng = np.random.default_rng(100 + log_n)
+    n = 1 << log_n
+    wires = rng.integers(0, P, size=(R, n), dtype=np.uint64)
+    sigmas = rng.integers(0, P, size=(R, n), dtype=np.uint64)
+    betas = rng.integers(0, P, size=2, dtype=np.uint64)
+    gammas = rng.integers(0, P, size=2, dtype=np.uint64)
+    want, _ = _partial_products_bigint(wires, sigmas, betas, gammas, chunk)
+    got = orc.partial_products(wires, sigmas, betas, gammas, chunk)
+    assert got.shape == want.shape and (got == want).all()
+
+
+def test_partial_products_close_for_satisfied_copy_constraints(orc):
+    """The defining property: when the wires are constant on the cycles of sigma, Z returns to 1 after the last row,
+    i.e. Z(w^(n-1)) times the last row's quotient product is 1 -- and it does not when one wire is changed."""
+    from perm_util import satisfied_permutation
+    R, chunk, log_n = 20, 8, 5
+    wires, sigmas, _ = satisfied_permutation(log_n, R, seed=3)
+    betas = np.array([0x1234567890abcdef % P, 77], np.uint64)
+    gammas = np.array([0xfedcba0987654321 % P, 5], np.uint64)
+    _, z_end = _partial_products_bigint(wires, sigmas, betas, gammas, chunk)
+    assert z_end == 1
+    out = orc.partial_products(wires, sigmas, betas, gammas, chunk)
+    assert (out[0:2, 0] == 1).all()                       # Z(1) = 1 for both challenges
+    bad = wires.copy()
+    bad[3, 7] = (int(bad[3, 7]) + 1) % P
+    _, z_bad = _partial_products_bigint(bad, sigmas, betas, gammas, chunk)
+    assert z_bad != 1
