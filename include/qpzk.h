@@ -233,6 +233,35 @@ int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires_dev, const ui
                               uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                               const uint64_t* gammas, uint64_t* out_dev);
 
+/* ---- quotient polynomials: compute_quotient_polys for the permutation argument -----------------------
+ * Replaces the gate-independent part of qp-plonky2 `compute_quotient_polys` (plonk/prover.rs) and
+ * `eval_vanishing_poly_base_batch` (plonk/vanishing_poly.rs) -- SURVEY.md 8a row a17, the step between the
+ * zs/partial-products commitment and the quotient commitment of `prove()` (wormhole/prover/src/lib.rs:171-175).
+ * At every point x of the coset g<w_(n Q)> (Q = quotient_degree_factor, a power of two <= 2^rate_bits):
+ *     terms = [ L_0(x)(Z_c(x) - 1) for c ] ++ [ partial-product checks, challenge-major ] ++ [ gate terms ]
+ *     q_a(x) = (sum_t terms[t] alpha_a^t) / Z_H(x)
+ * followed by coset_ifft and the split into Q chunks of n coefficients per challenge.
+ *   constants_sigmas     : the circuit's constants/sigmas batch; sigma_j is column sigma_col0 + j
+ *   wires                : wires batch; the routed wires are columns [0, num_routed)
+ *   zs_partial_products  : the batch committed from qpzk_partial_products' output (same column order)
+ *   betas, gammas, alphas: num_challenges (<= 4) canonical challenges each (host)
+ *   gate_terms_dev       : NULL, or a DEVICE matrix [n*Q][num_gate_terms], row = leaf index (row j is the point with
+ *                          natural index bitrev(j)): the values upstream's evaluate_gate_constraints would produce.
+ *                          The gate set itself lives in the un-vendored crate and is not part of this library.
+ *   out                  : (num_challenges * Q) x 2^log_n coefficients, column-major: chunk k of challenge a is
+ *                          column a*Q + k -- the input of the quotient commitment (from_coeffs).
+ * qpzk_commit_quotient does the same and commits the chunks without leaving the device (rate_bits of the inputs). */
+int qpzk_quotient_polys(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                        const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                        uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                        const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
+                        uint32_t num_gate_terms, uint64_t* out);
+int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                         const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                         uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                         const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
+                         uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out);
+
 /* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------------- */
 /* IMAD.WIDE throughput: returns 32x32+64 multiply-adds per second measured over `iters` dependent-chain
  * iterations on every SM. */

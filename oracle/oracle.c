@@ -432,6 +432,93 @@ int orc_partial_products(const uint64_t* wires, const uint64_t* sigmas, unsigned
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Quotient polynomials, permutation argument + caller-supplied gate terms ("next" tier; parity
+ * UNPINNED).  Restated from upstream plonky2 `plonk/prover.rs: compute_quotient_polys`,
+ * `plonk/vanishing_poly.rs: eval_vanishing_poly_base_batch`, `util/partial_products.rs: check_partial_products`,
+ * `plonk/plonk_common.rs: ZeroPolyOnCoset, reduce_with_powers_multi` [upstream-memory], without lookups:
+ *   Q = quotient_degree_factor = 2^qbits, step = 2^(rate_bits - qbits), lde_size = n Q, next_step = Q
+ *   for i in 0..lde_size:  x = g w_{nQ}^i;  get_lde_values(i, step) = leaf row bitrev_{log L}(i step) of each batch
+ *     terms = [l_0(x) (z_x[c] - 1)]_c ++ [check_partial_products(...)]_c ++ gate terms
+ *     quotient_values[a][i] = reduce_with_powers(terms, alpha_a) * z_h_on_coset.eval_inverse(i)
+ *   per challenge: coset_ifft(shift g), then chunks of n coefficients.
+ * gate_terms: NULL or [nQ][num_gate_terms], row = leaf index (bitrev_{log nQ}(i)).
+ * out: (num_challenges Q) x n coefficients, column-major.
+ * ------------------------------------------------------------------------------------------ */
+int orc_quotient_polys(const orc_batch* cs, const orc_batch* wires, const orc_batch* zs, unsigned sigma_col0,
+                       unsigned num_routed, unsigned chunk, unsigned num_challenges, const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms,
+                       unsigned num_gate_terms, uint64_t* out) {
+    if (!chunk || (chunk & (chunk - 1)) || !num_routed || !num_challenges) return -1;
+    unsigned qbits = 0;
+    while ((1u << qbits) < chunk) qbits++;
+    const unsigned log_n = wires->log_n, rate_bits = wires->rate_bits, log_L = log_n + rate_bits, log_q = log_n + qbits;
+    if (qbits > rate_bits || cs->log_n != log_n || zs->log_n != log_n) return -1;
+    const size_t n = (size_t)1 << log_n, Lq = (size_t)1 << log_q, Q = (size_t)1 << qbits, step = (size_t)1 << (rate_bits - qbits);
+    const unsigned nchunks = (num_routed + chunk - 1) / chunk, np = nchunks - 1;
+    const size_t T = num_challenges + (size_t)num_challenges * nchunks + num_gate_terms;
+    uint64_t* k_is = (uint64_t*)malloc(num_routed * sizeof(uint64_t));
+    uint64_t* vals = (uint64_t*)malloc(num_challenges * Lq * sizeof(uint64_t));
+    uint64_t zh[256], zh_inv[256];
+    if (!k_is || !vals || Q > 256) { free(k_is); free(vals); return -3; }
+    k_is[0] = 1;
+    for (unsigned j = 1; j < num_routed; j++) k_is[j] = gl_mul(k_is[j - 1], GL_GENERATOR);
+    {
+        uint64_t g_pow_n = GL_GENERATOR;
+        for (unsigned b = 0; b < log_n; b++) g_pow_n = gl_mul(g_pow_n, g_pow_n);
+        const uint64_t wq = gl_root_of_unity(qbits);
+        uint64_t r = 1;
+        for (size_t k = 0; k < Q; k++) { zh[k] = gl_sub(gl_mul(g_pow_n, r), 1); zh_inv[k] = gl_inv(zh[k]); r = gl_mul(r, wq); }
+    }
+    const uint64_t w = gl_root_of_unity(log_q), n_f = (uint64_t)n % GL_P;
+#pragma omp parallel
+    {
+        uint64_t* terms = (uint64_t*)malloc(T * sizeof(uint64_t));
+#pragma omp for schedule(static)
+        for (size_t i = 0; i < Lq; i++) {
+            const uint64_t x = gl_mul(GL_GENERATOR, gl_exp(w, i));
+            const size_t row = bitrev(i * step, log_L), row_next = bitrev(((i + Q) % Lq) * step, log_L);
+            const uint64_t* lw = orc_merkle_leaf(wires->tree, row);
+            const uint64_t* ls = orc_merkle_leaf(cs->tree, row) + sigma_col0;
+            const uint64_t* lz = orc_merkle_leaf(zs->tree, row);
+            const uint64_t* lzn = orc_merkle_leaf(zs->tree, row_next);
+            const uint64_t l0 = gl_mul(zh[i % Q], gl_inv(gl_mul(n_f, gl_sub(x, 1))));
+            size_t t = 0;
+            for (unsigned c = 0; c < num_challenges; c++) terms[t++] = gl_mul(l0, gl_sub(lz[c], 1));
+            for (unsigned c = 0; c < num_challenges; c++) {
+                const uint64_t* pp = lz + num_challenges + (size_t)c * np;
+                for (unsigned k = 0; k < nchunks; k++) {
+                    uint64_t pn = 1, pd = 1;
+                    for (unsigned j = k * chunk; j < num_routed && j < (k + 1) * chunk; j++) {
+                        pn = gl_mul(pn, gl_add(gl_add(lw[j], gl_mul(betas[c], gl_mul(k_is[j], x))), gammas[c]));
+                        pd = gl_mul(pd, gl_add(gl_add(lw[j], gl_mul(betas[c], ls[j])), gammas[c]));
+                    }
+                    const uint64_t prev = k == 0 ? lz[c] : pp[k - 1], next = k == np ? lzn[c] : pp[k];
+                    terms[t++] = gl_sub(gl_mul(prev, pn), gl_mul(next, pd));
+                }
+            }
+            const size_t leaf_q = bitrev(i, log_q);
+            for (unsigned g = 0; g < num_gate_terms; g++) terms[t++] = gate_terms[leaf_q * num_gate_terms + g];
+            for (unsigned a = 0; a < num_challenges; a++) {
+                uint64_t acc = 0;                                 /* reduce_with_powers: Horner from the last term */
+                for (size_t u = T; u-- > 0;) acc = gl_add(gl_mul(acc, alphas[a]), terms[u]);
+                vals[a * Lq + i] = gl_mul(acc, zh_inv[i % Q]);
+            }
+        }
+        free(terms);
+    }
+    const uint64_t g_inv = gl_inv(GL_GENERATOR);
+    for (unsigned a = 0; a < num_challenges; a++) {                /* coset_ifft: ifft, then coefficient k *= g^-k */
+        uint64_t* v = vals + a * Lq;
+        orc_ifft(v, log_q);
+        uint64_t s = 1;
+        for (size_t k = 0; k < Lq; k++) { v[k] = gl_mul(v[k], s); s = gl_mul(s, g_inv); }
+    }
+    memcpy(out, vals, num_challenges * Lq * sizeof(uint64_t));   /* [a][Lq] contiguous = Q chunks of n per challenge */
+    free(k_is); free(vals);
+    return 0;
+}
+
 void orc_challenger_init(orc_challenger* c) { memset(c, 0, sizeof *c); }
 
 static void duplexing(orc_challenger* c) {

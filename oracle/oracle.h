@@ -64,6 +64,12 @@ size_t orc_batch_leaf_len(const orc_batch* b);
 /* evaluate every (unsalted) polynomial at an extension point; out = num_cols x 2 words */
 void orc_batch_eval_ext(const orc_batch* b, const uint64_t point[2], uint64_t* out);
 
+/* quotient polynomials of the permutation argument + caller-supplied gate terms (row a17, next tier, parity unpinned) */
+int orc_quotient_polys(const orc_batch* cs, const orc_batch* wires, const orc_batch* zs, unsigned sigma_col0,
+                       unsigned num_routed, unsigned chunk, unsigned num_challenges, const uint64_t* betas,
+                       const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms,
+                       unsigned num_gate_terms, uint64_t* out);
+
 /* ---- Challenger ---- */
 typedef struct {
     uint64_t state[12];

@@ -59,6 +59,9 @@ def lib():
             f.restype = None; f.argtypes = [U64P]
         L.orc_partial_products.restype = C.c_int
         L.orc_partial_products.argtypes = [U64P, U64P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, U64P, U64P, U64P]
+        L.orc_quotient_polys.restype = C.c_int
+        L.orc_quotient_polys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                                         U64P, U64P, U64P, U64P, C.c_uint, U64P]
         for f in (L.orc_hash_no_pad, L.orc_hash_or_noop):
             f.restype = None; f.argtypes = [U64P, C.c_size_t, U64P]
         L.orc_two_to_one.restype = None; L.orc_two_to_one.argtypes = [U64P, U64P, U64P]
@@ -122,6 +125,23 @@ def partial_products(wires, sigmas, betas, gammas, chunk=8):
     out = np.zeros((b.size * nch, n), np.uint64)
     rc = lib().orc_partial_products(_p64(w), _p64(sg), n.bit_length() - 1, R, chunk, b.size, _p64(b), _p64(g), _p64(out))
     assert rc == 0
+    return out
+
+
+def quotient_polys(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                   quotient_degree_factor=8, gate_terms=None):
+    """compute_quotient_polys for the permutation argument + optional gate terms ((n*Q, G) array, row = leaf index):
+    (len(alphas) * Q, n) quotient chunk coefficients."""
+    b, g, a = _u64(betas), _u64(gammas), _u64(alphas)
+    gt, G = None, 0
+    if gate_terms is not None:
+        gt = _u64(gate_terms)
+        G = gt.shape[1]
+    out = np.zeros((a.size * quotient_degree_factor, 1 << wires.log_n), np.uint64)
+    rc = lib().orc_quotient_polys(constants_sigmas.h, wires.h, zs_partial_products.h, sigma_col0, num_routed,
+                                  quotient_degree_factor, a.size, _p64(b), _p64(g), _p64(a),
+                                  _p64(gt) if gt is not None else None, G, _p64(out))
+    assert rc == 0, rc
     return out
 
 
@@ -342,7 +362,7 @@ def num_threads():
 # ---- the commitment / opening half of prove() on the CPU (mirror of qpzk/prover.py) ----------------
 def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient_coeffs, public_inputs_hash,
                     log_n, num_zs=2, rate_bits=3, cap_height=4, pow_bits=16, num_queries=28, arity_bits=4,
-                    final_poly_bits=5, sigmas=None, quotient_degree_factor=8):
+                    final_poly_bits=5, sigmas=None, quotient_degree_factor=8, sigma_col0=None):
     """Same transcript and the same outputs as qpzk.prover.prove_synthetic, computed by the CPU restatement."""
     ch = Challenger()
     ch.observe(np.arange(4, dtype=np.uint64) + 11)
@@ -356,7 +376,10 @@ def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient
                                                betas_gammas[num_zs:], quotient_degree_factor)
     zs_b = PolynomialBatch.from_values(zs_partial_products, rate_bits, cap_height)
     ch.observe(zs_b.cap())
-    alphas = ch.get(2)
+    alphas = ch.get(num_zs)
+    if quotient_coeffs is None:
+        quotient_coeffs = quotient_polys(constants_sigmas_batch, wires_b, zs_b, sigma_col0, _u64(sigmas).shape[0],
+                                         betas_gammas[:num_zs], betas_gammas[num_zs:], alphas, quotient_degree_factor)
     quot_b = PolynomialBatch.from_coeffs(quotient_coeffs, rate_bits, cap_height)
     ch.observe(quot_b.cap())
     zeta = ch.get(2)

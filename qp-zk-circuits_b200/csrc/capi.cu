@@ -70,6 +70,7 @@ struct qpzk_ctx {
     uint64_t cached_bytes = 0;
     std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
     std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
+    std::map<uint32_t, PowTables> unshift_tables;                       // log_size -> powers of g^-1 (coset_ifft)
 };
 
 struct qpzk_batch {
@@ -1259,6 +1260,159 @@ extern "C" int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires, c
                                          uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                                          const uint64_t* gammas, uint64_t* out) {
     GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, false, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// quotient polynomials of the permutation argument (+ caller-supplied gate terms) (quotient.cu)
+// ---------------------------------------------------------------------------------------------
+static int get_unshift_tables(qpzk_ctx* ctx, uint32_t log_size, PowTables* out) {
+    auto it = ctx->unshift_tables.find(log_size);
+    if (it == ctx->unshift_tables.end()) {
+        PowTables t;
+        t.hi_size = log_size > TW_LO_BITS ? (1ull << (log_size - TW_LO_BITS)) : 1;
+        std::vector<uint64_t> lo, hi;
+        fill_powers(gl_inv_host(GL_GENERATOR), t.hi_size, lo, hi);
+        int rc;
+        if ((rc = upload_words(ctx, lo, &t.lo))) return rc;
+        if ((rc = upload_words(ctx, hi, &t.hi))) return rc;
+        it = ctx->unshift_tables.emplace(log_size, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// Leaves *coeffs_out (device, (num_challenges << qbits) x n words = the quotient chunks, column-major) to the caller,
+// who releases it with dev_free.
+static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, const qpzk_batch* zs,
+                         uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
+                         const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
+                         const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out) {
+    *coeffs_out = nullptr;
+    if (!ctx || !cs || !wires || !zs || !betas || !gammas || !alphas) return fail(QPZK_EINVAL, "null argument");
+    if (cs->ctx != ctx || wires->ctx != ctx || zs->ctx != ctx) return fail(QPZK_EINVAL, "batch belongs to another context");
+    if (!num_challenges || num_challenges > QUOT_MAX_CHALLENGES) return fail(QPZK_EINVAL, "num_challenges must be in 1..4");
+    if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
+    const uint32_t qbits = ilog2(chunk), log_n = wires->log_n;
+    if (cs->log_n != log_n || zs->log_n != log_n || cs->rate_bits != wires->rate_bits || zs->rate_bits != wires->rate_bits)
+        return fail(QPZK_EINVAL, "the three batches must have the same degree and rate");
+    if (qbits > wires->rate_bits) return fail(QPZK_EINVAL, "quotient_degree_factor exceeds the blowup factor");
+    const uint64_t full = (1ull << log_n) << wires->rate_bits;
+    if (cs->num_leaves != full || wires->num_leaves != full || zs->num_leaves != full)
+        return fail(QPZK_EINVAL, "coset-split batches cannot feed the quotient");
+    if (!num_routed || num_routed > wires->num_cols || (uint64_t)sigma_col0 + num_routed > cs->num_cols)
+        return fail(QPZK_EINVAL, "routed wires / sigma columns out of range");
+    const uint32_t nchunks = (num_routed + chunk - 1) / chunk;
+    if (zs->num_cols < num_challenges * nchunks) return fail(QPZK_EINVAL, "zs/partial-products batch has too few columns");
+    if (num_gate_terms && !gate_terms_dev) return fail(QPZK_EINVAL, "gate_terms is null");
+    for (uint32_t c = 0; c < num_challenges; c++)
+        if (betas[c] >= GL_P || gammas[c] >= GL_P || alphas[c] >= GL_P) return fail(QPZK_EINVAL, "challenge is not canonical");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t log_q = log_n + qbits, Q = 1u << qbits;
+    const uint64_t n = 1ull << log_n, Lq = 1ull << log_q;
+    const uint32_t T = num_challenges + num_challenges * nchunks + num_gate_terms;
+    PowTables tw, un;
+    int rc;
+    if ((rc = get_pow_tables(ctx, log_q, false, &tw))) return rc;
+    if ((rc = get_unshift_tables(ctx, log_q, &un))) return rc;
+    // parameter block: betas | gammas | beta * k_j | alpha powers | Z_H on the coset and its inverses
+    std::vector<uint64_t> par;
+    par.insert(par.end(), betas, betas + num_challenges);
+    par.insert(par.end(), gammas, gammas + num_challenges);
+    for (uint32_t c = 0; c < num_challenges; c++) {
+        uint64_t k = 1;
+        for (uint32_t j = 0; j < num_routed; j++) { par.push_back(gl_mul_host(betas[c], k)); k = gl_mul_host(k, GL_GENERATOR); }
+    }
+    const size_t off_apow = par.size();
+    for (uint32_t c = 0; c < num_challenges; c++) {
+        uint64_t v = 1;
+        for (uint32_t t = 0; t < T; t++) { par.push_back(v); v = gl_mul_host(v, alphas[c]); }
+    }
+    const size_t off_zh = par.size();
+    {
+        const uint64_t g_pow_n = gl_exp_host(GL_GENERATOR, n), wq = gl_root_of_unity_host(qbits);
+        uint64_t r = 1;
+        for (uint32_t k = 0; k < Q; k++) {
+            const uint64_t v = gl_mul_host(g_pow_n, r);
+            par.push_back(v ? v - 1 : GL_P - 1);
+            r = gl_mul_host(r, wq);
+        }
+        for (uint32_t k = 0; k < Q; k++) par.push_back(gl_inv_host(par[off_zh + k]));
+    }
+    DevBufs bufs(ctx);
+    uint64_t *d_par, *d_vals, *d_coeffs;
+    if ((rc = bufs.alloc(&d_par, par.size()))) return rc;
+    if ((rc = bufs.alloc(&d_vals, (uint64_t)num_challenges * Lq))) return rc;
+    if ((rc = dev_alloc(ctx, &d_coeffs, (uint64_t)num_challenges * Lq))) return rc;
+    auto bail = [&](cudaError_t e, const char* what) {
+        dev_free(ctx, d_coeffs);
+        return fail(QPZK_ECUDA, std::string(what) + " failed: " + cudaGetErrorString(e));
+    };
+    cudaError_t e = cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+    QuotientArgs a{};
+    a.cs_leaves = cs->leaves; a.w_leaves = wires->leaves; a.z_leaves = zs->leaves;
+    a.cs_width = cs->leaf_width; a.w_width = wires->leaf_width; a.z_width = zs->leaf_width; a.sigma_col0 = sigma_col0;
+    a.log_n = log_n; a.qbits = qbits; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = nchunks;
+    a.num_challenges = num_challenges; a.num_gate_terms = num_gate_terms; a.num_terms = T;
+    a.gate_terms = gate_terms_dev;
+    a.betas = d_par; a.gammas = d_par + num_challenges; a.beta_k = d_par + 2 * num_challenges;
+    a.apow = d_par + off_apow; a.zh = d_par + off_zh;
+    a.n_field = n % GL_P;
+    a.tw_lo = tw.lo; a.tw_hi = tw.hi;
+    a.values = d_vals;
+    if ((e = launch_quotient_perm(a, ctx->stream)) != cudaSuccess) return bail(e, "quotient_perm_kernel");
+    ctx->launches++;
+    if ((rc = run_intt(ctx, d_vals, d_coeffs, log_q, num_challenges))) { dev_free(ctx, d_coeffs); return rc; }
+    if ((e = launch_coset_unshift(d_coeffs, log_q, num_challenges, un.lo, un.hi, ctx->stream)) != cudaSuccess)
+        return bail(e, "coset_unshift_kernel");
+    ctx->launches++;
+    if (ctx->zeroize) cudaMemsetAsync(d_vals, 0, (uint64_t)num_challenges * Lq * sizeof(uint64_t), ctx->stream);
+    // `par` is pageable host memory: the copy above was staged by the driver before cudaMemcpyAsync returned
+    *coeffs_out = d_coeffs;
+    *qbits_out = qbits;
+    return 0;
+}
+
+extern "C" int qpzk_quotient_polys(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                   const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                                   uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                                   const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
+                                   uint32_t num_gate_terms, uint64_t* out) {
+    GUARD_BEGIN
+    if (!out) return fail(QPZK_EINVAL, "null argument");
+    uint64_t* d;
+    uint32_t qbits;
+    int rc = quotient_impl(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
+                           num_challenges, betas, gammas, alphas, gate_terms_dev, num_gate_terms, &d, &qbits);
+    if (rc) return rc;
+    const uint64_t words = ((uint64_t)num_challenges << qbits) << wires->log_n;
+    cudaError_t e = cudaMemcpyAsync(out, d, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, d, words);
+    CK(e);
+    return 0;
+    GUARD_END
+}
+
+extern "C" int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                    const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                                    uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                                    const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
+                                    uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out) {
+    GUARD_BEGIN
+    if (!out) return fail(QPZK_EINVAL, "null argument");
+    *out = nullptr;
+    uint64_t* d;
+    uint32_t qbits;
+    int rc = quotient_impl(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
+                           num_challenges, betas, gammas, alphas, gate_terms_dev, num_gate_terms, &d, &qbits);
+    if (rc) return rc;
+    const uint32_t cols = num_challenges << qbits;
+    rc = commit_impl(ctx, dev_source(d), false, wires->log_n, cols, wires->rate_bits, cap_height, nullptr, 0,
+                     1u << wires->rate_bits, true, out);
+    dev_free(ctx, d, (uint64_t)cols << wires->log_n);
+    return rc;
+    GUARD_END
 }
 
 // ---------------------------------------------------------------------------------------------

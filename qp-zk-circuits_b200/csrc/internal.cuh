@@ -188,6 +188,25 @@ struct PartialProductsArgs {
 };
 cudaError_t launch_partial_products(const PartialProductsArgs& a, cudaStream_t st);
 
+// ---- quotient.cu ----
+constexpr uint32_t QUOT_MAX_CHALLENGES = 4;
+struct QuotientArgs {
+    const uint64_t *cs_leaves, *w_leaves, *z_leaves;   // leaf matrices of the three batches (row-major, leaf order)
+    uint32_t cs_width, w_width, z_width, sigma_col0;
+    uint32_t log_n, qbits, num_routed, chunk, nchunks, num_challenges, num_gate_terms, num_terms;
+    const uint64_t* gate_terms;        // [n << qbits][num_gate_terms], row = leaf index, or null
+    const uint64_t *betas, *gammas;    // device
+    const uint64_t* beta_k;            // device, [challenge][num_routed]: beta * g^j
+    const uint64_t* apow;              // device, [challenge][num_terms]: alpha^t
+    const uint64_t* zh;                // device, [2 << qbits]: Z_H on the coset, then its inverses
+    uint64_t n_field;                  // n as a field element
+    const uint64_t *tw_lo, *tw_hi;     // powers of w_{n << qbits}
+    uint64_t* values;                  // [challenge][n << qbits], natural order
+};
+cudaError_t launch_quotient_perm(const QuotientArgs& a, cudaStream_t st);
+cudaError_t launch_coset_unshift(uint64_t* coeffs, uint32_t log_len, uint32_t num_arrays, const uint64_t* lo,
+                                 const uint64_t* hi, cudaStream_t st);
+
 }  // namespace qpzk
 
 namespace qpzk {

@@ -121,6 +121,8 @@ def load_library():
         "qpzk_fri_prove": (i, [vp, C.POINTER(vp), u32, C.POINTER(_FriInstance), C.POINTER(FriParams), vp, u64, vp, vp]),
         "qpzk_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "qpzk_partial_products_dev": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
+        "qpzk_quotient_polys": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, vp]),
+        "qpzk_commit_quotient": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, u32, C.POINTER(vp)]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -350,6 +352,39 @@ class PolynomialBatch:
         _check(ctx.L.qpzk_commit_cosets_from_coeffs_dev(ctx.h, C.c_void_p(dev_ptr), log_n, num_cols, rate_bits,
                                                         cap_height, coset_begin, coset_count, C.byref(h)))
         return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, False)
+
+    @staticmethod
+    def _quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                       gate_terms_dev, num_gate_terms):
+        b, bp = _host(betas)
+        g, gp = _host(gammas)
+        al, ap = _host(alphas)
+        if not (b.ndim == g.ndim == al.ndim == 1 and b.size == g.size == al.size):
+            raise QpzkError(-1, "betas, gammas and alphas must have the same length")
+        keep = (b, g, al)
+        return keep, (wires.ctx.h, constants_sigmas.h, wires.h, zs_partial_products.h, sigma_col0, num_routed), \
+            (b.size, bp, gp, ap, C.c_void_p(gate_terms_dev) if gate_terms_dev else None, num_gate_terms)
+
+    @classmethod
+    def quotient_polys(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                       quotient_degree_factor=8, gate_terms_dev=None, num_gate_terms=0):
+        """compute_quotient_polys for the permutation argument (+ caller-supplied gate terms, a raw device address):
+        returns the (len(alphas) * quotient_degree_factor, n) quotient chunk coefficients."""
+        keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
+                                              betas, gammas, alphas, gate_terms_dev, num_gate_terms)
+        out = np.zeros((tail[0] * quotient_degree_factor, 1 << wires.degree_log), np.uint64)
+        _check(wires.ctx.L.qpzk_quotient_polys(*head, quotient_degree_factor, *tail, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @classmethod
+    def commit_quotient(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                        cap_height, quotient_degree_factor=8, gate_terms_dev=None, num_gate_terms=0):
+        """The same, committed (from_coeffs) without leaving the device."""
+        keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
+                                              betas, gammas, alphas, gate_terms_dev, num_gate_terms)
+        h = C.c_void_p()
+        _check(wires.ctx.L.qpzk_commit_quotient(*head, quotient_degree_factor, *tail, cap_height, C.byref(h)))
+        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, False)
 
     @property
     def polynomials(self):

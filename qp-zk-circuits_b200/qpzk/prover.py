@@ -11,9 +11,13 @@ does, per proof (transcript in Appendix A.7):
 Witness generation and the quotient evaluation need the gate set of the un-vendored crate and
 are NOT part of this repo; here their outputs are stood in for by caller-supplied (random) columns of the right shapes,
 so the function exercises exactly the part of `prove()` this backend replaces and is labelled *synthetic* wherever it
-is reported.  The partial products of the permutation argument (row a16) are gate independent: when the caller passes
-the sigma values (`sigmas`, num_routed x n) instead of ready-made zs/partial-product columns, they are computed on the
-device from the routed wires and the betas/gammas drawn from the transcript (`Context.partial_products`).  The constants/sigmas oracle is committed once per circuit
+is reported.  The permutation argument (rows a16/a17) is gate independent: when the caller passes the sigma values
+(`sigmas`, num_routed x n) instead of ready-made zs/partial-product columns, they are computed on the device from the
+routed wires and the betas/gammas drawn from the transcript (`Context.partial_products`); and when `quotient_coeffs`
+is None the quotient chunks are computed and committed on the device from the three committed batches and the alphas
+(`PolynomialBatch.commit_quotient`; the circuit's sigma columns are then `SyntheticCircuit.sigma_col0 ...`).  With both,
+and wires that satisfy the copy constraints, the result is a complete PLONK proof of a circuit without gates: the
+vanishing identity holds on the opened values (tests/perm_util.py: verify_gateless_openings).  The constants/sigmas oracle is committed once per circuit
 (`CircuitBuilder::build`, reference wormhole/circuit/src/circuit.rs:206-216), not per proof.
 
 Shapes of the leaf circuit: degree 2^13, 85 constants+sigmas, 135 wires, 20 zs/partial
@@ -38,8 +42,9 @@ def _root_of_unity(log_n):
 class SyntheticCircuit:
     """What `CircuitBuilder::build` leaves behind for the prover: the committed constants/sigmas oracle."""
 
-    def __init__(self, ctx, constants_sigmas, shape=LEAF_SHAPE):
+    def __init__(self, ctx, constants_sigmas, shape=LEAF_SHAPE, sigma_col0=None):
         self.ctx, self.shape = ctx, dict(shape)
+        self.sigma_col0 = sigma_col0     # first sigma column inside constants_sigmas (needed for the device quotient)
         self.log_n = shape["log_n"]
         self.constants_sigmas = PolynomialBatch.from_values(ctx, constants_sigmas, RATE_BITS, None, CAP_HEIGHT)
         self.circuit_digest = np.arange(4, dtype=np.uint64) + 11   # stands for the verifier-data digest
@@ -67,8 +72,14 @@ def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public
                                                    betas_gammas[nz:], quotient_degree_factor)
     zs_b = PolynomialBatch.from_values(ctx, zs_partial_products, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(zs_b)
-    alphas = ch.get_n_challenges(2)                            # would feed the quotient (a17)
-    quot_b = PolynomialBatch.from_coeffs(ctx, quotient_coeffs, RATE_BITS, None, CAP_HEIGHT)
+    alphas = ch.get_n_challenges(nz)
+    if quotient_coeffs is None:                                # permutation argument only (no gate terms)
+        num_routed = np.asarray(sigmas).shape[0]
+        quot_b = PolynomialBatch.commit_quotient(circuit.constants_sigmas, wires_b, zs_b, circuit.sigma_col0, num_routed,
+                                                 betas_gammas[:nz], betas_gammas[nz:], alphas, CAP_HEIGHT,
+                                                 quotient_degree_factor)
+    else:
+        quot_b = PolynomialBatch.from_coeffs(ctx, quotient_coeffs, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(quot_b)
     zeta = ch.get_extension_challenge()
     g = _root_of_unity(circuit.log_n)

@@ -441,3 +441,110 @@ def test_prove_synthetic_with_device_partial_products(ctx, qpzk, orc):
     assert (got["fri_proof"] == want["fri_proof"]).all()
     assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], want["openings"], want["params"],
                           want["verifier_challenger"], got["fri_proof"]) == 0
+
+
+# ---- quotient polynomials of the permutation argument (row a17) ----------------------------------------------------
+def _gateless_batches(ctx, qpzk, orc, log_n, R, num_wires, num_consts, seed, rate_bits=3):
+    from perm_util import satisfied_permutation
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=seed)
+    wires = np.concatenate([routed, rng.integers(0, P, size=(num_wires - R, n), dtype=np.uint64)])
+    cs = np.concatenate([rng.integers(0, P, size=(num_consts, n), dtype=np.uint64), sigmas])
+    ch = rng.integers(0, P, size=(3, 2), dtype=np.uint64)
+    zs = orc.partial_products(routed, sigmas, ch[0], ch[1], 8)
+    g = [qpzk.PolynomialBatch.from_values(ctx, a, rate_bits, None, 2) for a in (cs, wires, zs)]
+    o = [orc.PolynomialBatch.from_values(a, rate_bits, 2) for a in (cs, wires, zs)]
+    return g, o, ch
+
+
+@pytest.mark.parametrize("log_n,R,num_wires,num_consts,G", [(5, 19, 22, 2, 0), (9, 80, 135, 5, 0), (6, 8, 8, 0, 0),
+                                                           (7, 60, 135, 4, 5), (3, 1, 2, 1, 2)])
+def test_quotient_polys_match_oracle(ctx, qpzk, orc, log_n, R, num_wires, num_consts, G):
+    import torch
+    g, o, ch = _gateless_batches(ctx, qpzk, orc, log_n, R, num_wires, num_consts, seed=300 + log_n)
+    gate = gate_dev = None
+    if G:
+        gate = np.random.default_rng(log_n).integers(0, P, size=(8 << log_n, G), dtype=np.uint64)
+        gate_t = torch.from_numpy(gate.view(np.int64)).cuda()
+        gate_dev = gate_t.data_ptr()
+    want = orc.quotient_polys(o[0], o[1], o[2], num_consts, R, ch[0], ch[1], ch[2], gate_terms=gate)
+    got = qpzk.PolynomialBatch.quotient_polys(g[0], g[1], g[2], num_consts, R, ch[0], ch[1], ch[2],
+                                              gate_terms_dev=gate_dev, num_gate_terms=G)
+    assert got.shape == want.shape == (16, 1 << log_n)
+    assert (got == want).all()
+    qb = qpzk.PolynomialBatch.commit_quotient(g[0], g[1], g[2], num_consts, R, ch[0], ch[1], ch[2], 2,
+                                              gate_terms_dev=gate_dev, num_gate_terms=G)
+    assert (qb.cap == orc.PolynomialBatch.from_coeffs(want, 3, 2).cap()).all()
+    assert (qb.polynomials == want).all()
+
+
+def test_quotient_with_smaller_degree_factor_than_blowup(ctx, qpzk, orc):
+    """quotient_degree_factor 4 on rate_bits 3 batches: the quotient domain is every second LDE point = the first
+    half of the leaf rows."""
+    from perm_util import satisfied_permutation
+    log_n, R = 6, 11
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=8)
+    rng = np.random.default_rng(8)
+    ch = rng.integers(0, P, size=(3, 1), dtype=np.uint64)
+    zs = orc.partial_products(routed, sigmas, ch[0], ch[1], 4)
+    g = [qpzk.PolynomialBatch.from_values(ctx, a, 3, None, 2) for a in (sigmas, routed, zs)]
+    o = [orc.PolynomialBatch.from_values(a, 3, 2) for a in (sigmas, routed, zs)]
+    want = orc.quotient_polys(o[0], o[1], o[2], 0, R, ch[0], ch[1], ch[2], quotient_degree_factor=4)
+    got = qpzk.PolynomialBatch.quotient_polys(g[0], g[1], g[2], 0, R, ch[0], ch[1], ch[2], quotient_degree_factor=4)
+    assert got.shape == (4, 1 << log_n) and (got == want).all()
+
+
+def test_quotient_rejects_bad_arguments(ctx, qpzk):
+    n = 16
+    z = np.zeros((4, n), np.uint64)
+    b = qpzk.PolynomialBatch.from_values(ctx, z, 3, None, 2)
+    small = qpzk.PolynomialBatch.from_values(ctx, z[:, :8], 3, None, 2)
+    Q = qpzk.PolynomialBatch.quotient_polys
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, small, 0, 4, [1], [1], [1])                    # different degrees
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, b, 2, 4, [1], [1], [1])                        # sigma columns out of range
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, b, 0, 4, [1], [1], [1], quotient_degree_factor=6)
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, b, 0, 4, [1], [1], [1], quotient_degree_factor=16)   # exceeds the blowup
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, b, 0, 4, [P], [1], [1])                        # non-canonical challenge
+    with pytest.raises(qpzk.QpzkError):
+        Q(b, b, b, 0, 4, [1] * 5, [1] * 5, [1] * 5)            # more than 4 challenges
+
+
+def test_gateless_plonk_proof_end_to_end(ctx, qpzk, orc):
+    """wires -> partial products -> quotient -> openings -> FRI, everything on the device from the routed wires and
+    the circuit's sigmas: bit-exact with the oracle, FRI accepted by the oracle verifier, and the vanishing identity
+    holds on the OPENED values (what upstream's verifier checks) -- a complete proof of a circuit without gates."""
+    from qpzk import prover
+    from perm_util import satisfied_permutation, verify_gateless_openings
+    log_n, R, num_consts = 8, 80, 5
+    n = 1 << log_n
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n)
+    rng = np.random.default_rng(123)
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=17)
+    wires = np.concatenate([routed, rng.integers(0, P, size=(shape["wires"] - R, n), dtype=np.uint64)])
+    cs = np.concatenate([rng.integers(0, P, size=(num_consts, n), dtype=np.uint64), sigmas])
+    circuit = prover.SyntheticCircuit(ctx, cs, shape, sigma_col0=num_consts)
+    pih = rng.integers(0, P, size=4, dtype=np.uint64)
+    got = prover.prove_synthetic(circuit, wires, None, None, pih, sigmas=sigmas)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=num_consts)
+    for a, b in zip(got["caps"], want["caps"]):
+        assert (a == b).all()
+    assert (got["openings"] == want["openings"]).all()
+    assert (got["fri_proof"] == want["fri_proof"]).all()
+    assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], got["openings"], want["params"],
+                          want["verifier_challenger"], got["fri_proof"]) == 0
+    bg, alphas, zeta = got["challenges"]
+    assert verify_gateless_openings(log_n, got["openings"], num_consts, R, shape["wires"], 2, 8, bg[:2], bg[2:], alphas, zeta)
+    # a wire that breaks a copy constraint: the proof is still produced, and the vanishing check rejects it
+    bad = wires.copy()
+    bad[2, 5] = (int(bad[2, 5]) + 1) % P
+    got_bad = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas)
+    bg, alphas, zeta = got_bad["challenges"]
+    assert not verify_gateless_openings(log_n, got_bad["openings"], num_consts, R, shape["wires"], 2, 8, bg[:2], bg[2:],
+                                        alphas, zeta)

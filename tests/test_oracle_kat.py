@@ -278,3 +278,89 @@ def test_partial_products_close_for_satisfied_copy_constraints(orc):
     bad[3, 7] = (int(bad[3, 7]) + 1) % P
     _, z_bad = _partial_products_bigint(bad, sigmas, betas, gammas, chunk)
     assert z_bad != 1
+
+
+# ---- quotient polynomials of the permutation argument ---------------------------------------
+def _gateless_instance(orc, log_n, R, extra_wires, num_consts, seed, break_wire=False):
+    from perm_util import satisfied_permutation
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=seed)
+    if break_wire:
+        routed = routed.copy()
+        routed[1, 3] = (int(routed[1, 3]) + 1) % P
+    wires = np.concatenate([routed, rng.integers(0, P, size=(extra_wires, n), dtype=np.uint64)])
+    consts = rng.integers(0, P, size=(num_consts, n), dtype=np.uint64)
+    cs_b = orc.PolynomialBatch.from_values(np.concatenate([consts, sigmas]), 3, 2)
+    w_b = orc.PolynomialBatch.from_values(wires, 3, 2)
+    ch = rng.integers(0, P, size=(3, 2), dtype=np.uint64)
+    zs = orc.partial_products(routed, sigmas, ch[0], ch[1], 8)
+    z_b = orc.PolynomialBatch.from_values(zs, 3, 2)
+    return dict(cs=cs_b, wires=w_b, zs=z_b, betas=ch[0], gammas=ch[1], alphas=ch[2], R=R, sigma_col0=num_consts, rng=rng)
+
+
+def test_quotient_satisfies_the_verifier_identity(orc):
+    """For wires that satisfy the copy constraints the quotient chunks pass the verifier's identity at a random point;
+    with one wire changed they do not (the vanishing polynomial is no longer divisible by Z_H)."""
+    from perm_util import quotient_identity_holds
+    log_n, R = 5, 19
+    for broken in (False, True):
+        inst = _gateless_instance(orc, log_n, R, extra_wires=3, num_consts=2, seed=21, break_wire=broken)
+        q = orc.quotient_polys(inst["cs"], inst["wires"], inst["zs"], inst["sigma_col0"], R, inst["betas"], inst["gammas"],
+                               inst["alphas"])
+        assert q.shape == (16, 1 << log_n)
+        wc, sc, zc = inst["wires"].coeffs()[:R], inst["cs"].coeffs()[2:2 + R], inst["zs"].coeffs()
+        for zeta in (0x123456789abcdef % P, 3):
+            ok = quotient_identity_holds(log_n, wc, sc, zc, q, inst["betas"], inst["gammas"], inst["alphas"], 8, zeta)
+            assert ok == (not broken)
+
+
+def test_quotient_gate_terms_enter_the_alpha_combination(orc):
+    """Gate terms of the form Z_H(x) r_g(x) (they vanish on the subgroup, as satisfied gate constraints do): the
+    quotient still passes the verifier's identity, with the gate values Z_H(zeta) r_g(zeta) appended to the terms."""
+    from perm_util import quotient_identity_holds, horner
+    log_n, R, G = 4, 9, 3
+    n, Lq = 1 << log_n, 8 << log_n
+    inst = _gateless_instance(orc, log_n, R, extra_wires=1, num_consts=1, seed=5)
+    rng = inst["rng"]
+    r_coeffs = rng.integers(0, P, size=(G, n), dtype=np.uint64)
+    g_pow_n = pow(orc.GENERATOR, n, P)
+    w8 = pow(7277203076849721926, 1 << (32 - 3), P)
+    gate = np.zeros((Lq, G), np.uint64)
+    for g in range(G):
+        padded = np.zeros(Lq, np.uint64)
+        padded[:n] = r_coeffs[g]
+        vals = orc.coset_fft(padded)                               # r_g on the quotient coset, natural order
+        for i in range(Lq):
+            zh = (g_pow_n * pow(w8, i % 8, P) - 1) % P
+            gate[int(format(i, "0%db" % (log_n + 3))[::-1], 2), g] = int(vals[i]) * zh % P
+    q = orc.quotient_polys(inst["cs"], inst["wires"], inst["zs"], inst["sigma_col0"], R, inst["betas"], inst["gammas"],
+                           inst["alphas"], gate_terms=gate)
+    wc, sc, zc = inst["wires"].coeffs()[:R], inst["cs"].coeffs()[1:1 + R], inst["zs"].coeffs()
+    zeta = 0xabcdef0123456789 % P
+    zh_z = (pow(zeta, n, P) - 1) % P
+    gv = [zh_z * horner(r_coeffs[g], zeta) % P for g in range(G)]
+    assert quotient_identity_holds(log_n, wc, sc, zc, q, inst["betas"], inst["gammas"], inst["alphas"], 8, zeta, gv)
+    assert not quotient_identity_holds(log_n, wc, sc, zc, q, inst["betas"], inst["gammas"], inst["alphas"], 8, zeta)
+
+
+def test_oracle_gateless_proof_passes_the_vanishing_check_on_opened_values(orc):
+    """The CPU mirror of the whole flow (wires -> partial products -> quotient -> openings -> FRI): FRI verifies and the
+    plonk vanishing identity holds on the opened extension-field values."""
+    from perm_util import satisfied_permutation, verify_gateless_openings
+    log_n, R, num_consts, num_wires = 6, 20, 2, 24
+    n = 1 << log_n
+    rng = np.random.default_rng(31)
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=4)
+    wires = np.concatenate([routed, rng.integers(0, P, size=(num_wires - R, n), dtype=np.uint64)])
+    cs = np.concatenate([rng.integers(0, P, size=(num_consts, n), dtype=np.uint64), sigmas])
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    pih = rng.integers(0, P, size=4, dtype=np.uint64)
+    out = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=num_consts, pow_bits=8)
+    assert orc.fri_verify(log_n, out["leaf_lens"], out["all_caps"], out["instance"], out["openings"], out["params"],
+                          out["verifier_challenger"], out["fri_proof"]) == 0
+    bg, alphas, zeta = out["challenges"]
+    assert verify_gateless_openings(log_n, out["openings"], num_consts, R, num_wires, 2, 8, bg[:2], bg[2:], alphas, zeta)
+    tampered = out["openings"].copy()
+    tampered[num_consts + R + 1, 0] ^= np.uint64(1)
+    assert not verify_gateless_openings(log_n, tampered, num_consts, R, num_wires, 2, 8, bg[:2], bg[2:], alphas, zeta)
