@@ -151,14 +151,67 @@ def gpu_prove_synthetic(ctx, proofs=16):
     return 1e3 * dt, (ctx.launch_count() - l0) // proofs
 
 
-def native_prove_bench(device, threads, proofs=32):
+def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_consts=5, nch=2, chunk=8):
+    """SURVEY.md 8a rows a16/a17 at the leaf-circuit column counts: partial products + Z from device-resident routed
+    wires and sigmas, then the quotient of the permutation argument from the three committed batches.  Device times
+    (CUDA events on the context stream) and algorithmic bytes: every operand read once, every result written once."""
+    import numpy as np
+    import torch
+    import qpzk
+    n = 1 << log_n
+    gen = torch.Generator(device=dev).manual_seed(99 + log_n)
+    rnd = lambda r: torch.randint(0, 2**63 - 1, (r, n), generator=gen, device=dev, dtype=torch.int64)
+    wires, cs = rnd(num_wires), rnd(num_consts + routed)
+    nchunks = (routed + chunk - 1) // chunk
+    zs = torch.empty((nch * nchunks, n), dtype=torch.int64, device=dev)
+    ch = np.random.default_rng(log_n).integers(0, P, size=(3, nch), dtype=np.uint64)
+    sig_ptr = cs.data_ptr() + num_consts * n * 8
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    pp_ms = timed(lambda: ctx.partial_products_device(wires.data_ptr(), sig_ptr, log_n, routed, ch[0], ch[1], zs.data_ptr(), chunk))
+    batches = [qpzk.PolynomialBatch.from_device(ctx, t.data_ptr(), log_n, t.shape[0], RATE_BITS, CAP_HEIGHT) for t in (cs, wires, zs)]
+    ctx.set_timing(True)
+    commit_ms = [0.0]
+
+    def quot():
+        qb = qpzk.PolynomialBatch.commit_quotient(batches[0], batches[1], batches[2], num_consts, routed, ch[0], ch[1], ch[2],
+                                                  CAP_HEIGHT, chunk)
+        commit_ms[0] = sum(ctx.last_commit_timing().values())
+        qb.free()
+
+    total_ms = timed(quot)
+    for b in batches:
+        b.free()
+    Lq = n * chunk
+    pp_bytes = 8 * n * (2 * routed + nch * nchunks)
+    q_bytes = 8 * Lq * (2 * routed + nch * nchunks + nch) + 8 * 3 * nch * Lq   # operands once; values out, iNTT in/out
+    q_ms = total_ms - commit_ms[0]
+    return {"log_n": log_n, "routed": routed, "challenges": nch,
+            "partial_products_ms": pp_ms, "partial_products_GBps": pp_bytes / pp_ms / 1e6,
+            "quotient_ms": q_ms, "quotient_GBps": q_bytes / q_ms / 1e6 if q_ms > 0 else None,
+            "quotient_commit_ms": commit_ms[0],
+            "what": "a16: qpzk_partial_products_dev; a17: qpzk_commit_quotient minus the time of its 16-column commit"}
+
+
+def native_prove_bench(device, threads, proofs=32, perm=0):
     """The same synthetic prove driven from native code (qp-zk-circuits_b200/host/prove_bench.cpp: C++ threads on the
     C ABI, one context per thread, pinned host buffers).  Returns the parsed JSON line or None."""
     exe = os.path.join(ROOT, "qp-zk-circuits_b200", "prove_bench")
     if not os.path.exists(exe):
         return None
     try:
-        r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs)],
+        r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm)],
                            capture_output=True, text=True, timeout=300)
         return json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
@@ -252,6 +305,8 @@ def main():
         tmax = max(1, min(4, (os.cpu_count() or 4) // world))
         native[1] = native_prove_bench(local_rank, 1, 64)          # also warms the clocks
         native[tmax] = native_prove_bench(local_rank, tmax, 64)
+        native["perm1"] = native_prove_bench(local_rank, 1, 64, perm=1)
+        native["perm%d" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1)
         native["tmax"] = tmax
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -448,10 +503,19 @@ def main():
                 "latency_ms_1_thread": n1["latency_ms"], "proofs_per_s_1_thread": n1["proofs_per_s"],
                 "proofs_per_s_%d_threads" % native["tmax"]: n4["proofs_per_s"], "gpu_launches_per_proof": n1["launches_per_proof"],
                 "what": "same proof from C++ host threads on the C ABI (host/prove_bench.cpp), one context per thread, pinned buffers"}
+        p1, p4 = native.get("perm1"), native.get("perm%d" % native.get("tmax", 0))
+        if p1 and p4:
+            out["prove_synthetic"]["native_with_permutation_argument"] = {
+                "latency_ms_1_thread": p1["latency_ms"], "proofs_per_s_1_thread": p1["proofs_per_s"],
+                "proofs_per_s_%d_threads" % native["tmax"]: p4["proofs_per_s"], "gpu_launches_per_proof": p1["launches_per_proof"],
+                "what": "as above, but the zs/partial-product columns and the quotient chunks are computed on the device from the "
+                        "routed wires, the circuit's sigmas and the transcript's challenges (rows a16/a17, permutation argument only)"}
         if not args.no_cpu_baseline:
             cms, cores = cpu_prove_synthetic()
             out["prove_synthetic"]["cpu_port_latency_ms"] = cms
             out["prove_synthetic"]["cpu_cores"] = cores
+    if not args.no_prove:
+        out["perm_argument"] = [gpu_perm_argument(ctx, dev, k) for k in (13, 18)]
     if not args.no_cpu_baseline:
         v, cores, secs = cpu_commit_sample(16)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -65,6 +65,9 @@ int qpzk_ctx_synchronize(qpzk_ctx* ctx);
 int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on);
 /* Stage timing with CUDA events on the context stream.  After a commit:
  *   ms[0]=iNTT  ms[1]=LDE passes  ms[2]=leaf hashing  ms[3]=Merkle levels  (0 when a stage did not run) */
+/* Batches created by from_values keep their input VALUES (on the subgroup) on the device as well -- what the
+ * permutation argument needs from the wires and the sigmas (qpzk_commit_zs_partial_products).  Default: off. */
+int qpzk_ctx_set_keep_values(qpzk_ctx* ctx, int on);
 int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on);
 int qpzk_ctx_last_commit_timing(qpzk_ctx* ctx, float ms[4]);
 /* number of kernel launches issued through this context since creation */
@@ -152,6 +155,7 @@ int qpzk_batches_eval_ext(qpzk_ctx* ctx, const qpzk_batch* const* batches, uint3
 /* device views for zero-copy consumers (quotient evaluation, next tier): valid until qpzk_batch_free */
 const uint64_t* qpzk_batch_leaves_dev(const qpzk_batch* b);
 const uint64_t* qpzk_batch_coeffs_dev(const qpzk_batch* b);
+const uint64_t* qpzk_batch_values_dev(const qpzk_batch* b);   /* NULL unless committed with keep_values on */
 
 /* ---- Challenger<F, PoseidonHash> ----------------------------------------------------------------- */
 typedef struct {
@@ -232,6 +236,13 @@ int qpzk_partial_products(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* 
 int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires_dev, const uint64_t* sigmas_dev, uint32_t log_n,
                               uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                               const uint64_t* gammas, uint64_t* out_dev);
+
+/* The same from two committed batches that kept their values (qpzk_ctx_set_keep_values), followed by the
+ * zs/partial-products commitment (from_values, rate_bits of `wires`) -- nothing leaves the device:
+ * sigma_j = column sigma_col0 + j of constants_sigmas, routed wires = columns [0, num_routed) of wires. */
+int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                    uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
+                                    const uint64_t* betas, const uint64_t* gammas, uint32_t cap_height, qpzk_batch** out);
 
 /* ---- quotient polynomials: compute_quotient_polys for the permutation argument -----------------------
  * Replaces the gate-independent part of qp-plonky2 `compute_quotient_polys` (plonk/prover.rs) and

@@ -57,6 +57,7 @@ struct qpzk_ctx {
     bool zeroize = true;
     bool legacy_ntt = false;   // QPZK_LEGACY_NTT=1: generic strided passes only (A/B testing of ntt_fwd.cu)
     bool timing = false;
+    bool keep_values = false;  // from_values batches keep their input values on the device (qpzk_ctx_set_keep_values)
     cudaStream_t copy_stream = nullptr;   // H2D of host-buffer commits, overlapped with the per-column stages
     cudaEvent_t copy_done = nullptr;
     cudaEvent_t ev[5] = {};
@@ -79,6 +80,7 @@ struct qpzk_batch {
     uint64_t num_leaves = 0;
     uint32_t log_leaves = 0, num_levels = 0;  // levels[0] = leaf digests ... levels[num_levels-1] = cap
     uint64_t* coeffs = nullptr;               // num_cols x n (null for a bare MerkleTree)
+    uint64_t* values = nullptr;               // num_cols x n values on the subgroup (only with keep_values)
     uint64_t* leaves = nullptr;
     uint64_t* digests = nullptr;
     bool own_leaves = true;
@@ -270,6 +272,7 @@ extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
     return 0;
 }
 extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->zeroize = on != 0; return 0; }
+extern "C" int qpzk_ctx_set_keep_values(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->keep_values = on != 0; return 0; }
 extern "C" int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->timing = on != 0; return 0; }
 extern "C" uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // Page-locked host buffers for callers that want the host<->device copies of the commit / proof calls to be truly
@@ -481,6 +484,7 @@ static void batch_release(qpzk_batch* b) {
     cudaSetDevice(ctx->device);
     uint64_t n = 1ull << b->log_n;
     dev_free(ctx, b->coeffs, (uint64_t)b->num_cols * n);
+    dev_free(ctx, b->values, (uint64_t)b->num_cols * n);
     if (b->own_leaves) dev_free(ctx, b->leaves, b->num_leaves * b->leaf_width);
     dev_free(ctx, b->digests);
     delete b;
@@ -581,7 +585,17 @@ static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32
     if (!num_cols) mark(ctx, 1);
     rc = lde.run_last();
     lde.release();
-    if (src.host && from_values) dev_free(ctx, src.staging, (uint64_t)num_cols * n);
+    const bool keep = from_values && ctx->keep_values && coset_count == cosets && num_cols;
+    if (src.host && from_values) {
+        if (keep && !rc) b->values = src.staging;      // the staged input stays with the batch (no copy)
+        else dev_free(ctx, src.staging, (uint64_t)num_cols * n);
+    } else if (keep && !rc) {
+        if ((rc = dev_alloc(ctx, &b->values, (uint64_t)num_cols * n)) == 0) {
+            cudaError_t e = cudaMemcpyAsync(b->values, src.dev, (uint64_t)num_cols * n * sizeof(uint64_t),
+                                            cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) { batch_release(b); CK(e); }
+        }
+    }
     if (rc) { batch_release(b); return rc; }
     if (salt_dev) {
         cudaError_t e = launch_salt_scatter(salt_dev, b->leaves, log_L, num_cols, b->leaf_width, b->salt_cols, ctx->stream);
@@ -719,6 +733,7 @@ extern "C" uint32_t qpzk_batch_leaf_len(const qpzk_batch* b) { return b ? b->lea
 extern "C" uint32_t qpzk_batch_cap_len(const qpzk_batch* b) { return b ? 1u << b->cap_height : 0; }
 extern "C" const uint64_t* qpzk_batch_leaves_dev(const qpzk_batch* b) { return b ? b->leaves : nullptr; }
 extern "C" const uint64_t* qpzk_batch_coeffs_dev(const qpzk_batch* b) { return b ? b->coeffs : nullptr; }
+extern "C" const uint64_t* qpzk_batch_values_dev(const qpzk_batch* b) { return b ? b->values : nullptr; }
 
 static int d2h(const qpzk_batch* b, uint64_t* dst, const uint64_t* src, uint64_t words) {
     CK(cudaSetDevice(b->ctx->device));
@@ -1219,8 +1234,9 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
         }
     }
     DevBufs bufs(ctx);
-    uint64_t *d_par, *d_chunk, *d_row, *d_w = nullptr, *d_s = nullptr, *d_out = nullptr;
+    uint64_t *d_par, *d_chunk, *d_row, *d_blk, *d_w = nullptr, *d_s = nullptr, *d_out = nullptr;
     if ((rc = bufs.alloc(&d_par, par.size()))) return rc;
+    if ((rc = bufs.alloc(&d_blk, (uint64_t)num_challenges * pp_num_blocks(log_n)))) return rc;
     if ((rc = bufs.alloc(&d_chunk, out_words))) return rc;
     if ((rc = bufs.alloc(&d_row, (uint64_t)num_challenges * n))) return rc;
     if (host) {
@@ -1236,7 +1252,7 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
     a.log_n = log_n; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = nchunks; a.num_challenges = num_challenges;
     a.betas = d_par; a.gammas = d_par + num_challenges; a.beta_k = d_par + 2 * num_challenges;
     a.tw_lo = tw.lo; a.tw_hi = tw.hi;
-    a.chunkprod = d_chunk; a.rowprod = d_row; a.out = host ? d_out : out;
+    a.chunkprod = d_chunk; a.rowprod = d_row; a.blockprod = d_blk; a.out = host ? d_out : out;
     CK(launch_partial_products(a, ctx->stream));
     ctx->launches += 3;
     if (host) CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1248,7 +1264,9 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
             CK(cudaMemsetAsync(d_out, 0, out_words * sizeof(uint64_t), ctx->stream));
         }
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // `par` (pageable) and the caller's host buffers are released on return
+    // host variant: the caller's buffers are released on return.  (`par` is pageable: its copy was staged by the
+    // driver before cudaMemcpyAsync returned, so the device variant need not wait.)
+    if (host) CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 extern "C" int qpzk_partial_products(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
@@ -1260,6 +1278,35 @@ extern "C" int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires, c
                                          uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                                          const uint64_t* gammas, uint64_t* out) {
     GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, false, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+}
+
+extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                               uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk,
+                                               uint32_t num_challenges, const uint64_t* betas, const uint64_t* gammas,
+                                               uint32_t cap_height, qpzk_batch** out) {
+    GUARD_BEGIN
+    if (!out) return fail(QPZK_EINVAL, "null argument");
+    *out = nullptr;
+    if (!ctx || !constants_sigmas || !wires) return fail(QPZK_EINVAL, "null argument");
+    if (constants_sigmas->ctx != ctx || wires->ctx != ctx) return fail(QPZK_EINVAL, "batch belongs to another context");
+    if (!constants_sigmas->values || !wires->values)
+        return fail(QPZK_EINVAL, "batches hold no values: commit them with from_values after qpzk_ctx_set_keep_values(ctx, 1)");
+    if (constants_sigmas->log_n != wires->log_n) return fail(QPZK_EINVAL, "batches must have the same degree");
+    if (!num_routed || num_routed > wires->num_cols || (uint64_t)sigma_col0 + num_routed > constants_sigmas->num_cols)
+        return fail(QPZK_EINVAL, "routed wires / sigma columns out of range");
+    if (!chunk || !num_challenges) return fail(QPZK_EINVAL, "chunk and num_challenges must be positive");
+    const uint64_t n = 1ull << wires->log_n;
+    const uint32_t cols = num_challenges * ((num_routed + chunk - 1) / chunk);
+    uint64_t* d_out;
+    int rc = dev_alloc(ctx, &d_out, (uint64_t)cols * n);
+    if (rc) return rc;
+    rc = partial_products_impl(ctx, wires->values, constants_sigmas->values + (uint64_t)sigma_col0 * n, false, wires->log_n,
+                               num_routed, chunk, num_challenges, betas, gammas, d_out);
+    if (!rc) rc = commit_impl(ctx, dev_source(d_out), true, wires->log_n, cols, wires->rate_bits, cap_height, nullptr, 0,
+                              1u << wires->rate_bits, true, out);
+    dev_free(ctx, d_out, (uint64_t)cols * n);
+    return rc;
+    GUARD_END
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -184,8 +184,10 @@ struct PartialProductsArgs {
     const uint64_t *tw_lo, *tw_hi;    // powers of w_n
     uint64_t* chunkprod;              // scratch: [challenge][chunk][row]
     uint64_t* rowprod;                // scratch: [challenge][row]
+    uint64_t* blockprod;              // scratch: [challenge][pp_num_blocks(log_n)]
     uint64_t* out;                    // [Z of every challenge | partial products of challenge 0, 1, ...] x n
 };
+inline unsigned pp_num_blocks(uint32_t log_n) { return (unsigned)(((1ull << log_n) + 127) / 128); }
 cudaError_t launch_partial_products(const PartialProductsArgs& a, cudaStream_t st);
 
 // ---- quotient.cu ----

@@ -60,21 +60,33 @@ __global__ void __launch_bounds__(QUOT_THREADS) quotient_perm_kernel(QuotientArg
         uint64_t pn[NCH], pd[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; c++) pn[c] = pd[c] = 1;
-        const uint32_t j1 = min(a.num_routed, (k + 1) * a.chunk);
-        for (uint32_t r = k * a.chunk; r < j1; r++) {
-            const uint64_t w = __ldg(wrow + r), sg = __ldg(srow + r);
+        const uint32_t j0 = k * a.chunk, j1 = min(a.num_routed, j0 + a.chunk);
+        // operands in groups of 8 words = 64 B of the thread's own rows, loaded back to back so that both sectors of
+        // a group are fetched once (the access pattern of the leaf-hash kernel)
+        for (uint32_t r0 = j0; r0 < j1; r0 += 8) {
+            uint64_t w[8], sg[8];
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const uint64_t wg = gl_add(w, gamma[c]);
-                pn[c] = gl_mul(pn[c], gl_add(wg, gl_mul(a.beta_k[(size_t)c * a.num_routed + r], x)));
-                pd[c] = gl_mul(pd[c], gl_add(wg, gl_mul(beta[c], sg)));
+            for (int u = 0; u < 8; u++) {
+                const bool in = r0 + u < j1;
+                w[u] = in ? __ldg(wrow + r0 + u) : 0;
+                sg[u] = in ? __ldg(srow + r0 + u) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (r0 + u >= j1) break;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {   // arbitrary u64 representatives inside the products
+                    const uint64_t wg = add_canon_p(w[u], gamma[c]);
+                    pn[c] = mulp(pn[c], mul_addp(a.beta_k[(size_t)c * a.num_routed + r0 + u], x, wg));
+                    pd[c] = mulp(pd[c], mul_addp(beta[c], sg[u], wg));
+                }
             }
         }
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const uint64_t prev = k == 0 ? zrow[c] : zrow[NCH + c * np + k - 1];
             const uint64_t next = k == np ? znrow[c] : zrow[NCH + c * np + k];
-            const uint64_t term = gl_sub(gl_mul(prev, pn[c]), gl_mul(next, pd[c]));
+            const uint64_t term = gl_sub(gl_canon(mulp(prev, pn[c])), gl_canon(mulp(next, pd[c])));
             const uint32_t t = NCH + c * a.nchunks + k;
 #pragma unroll
             for (int e = 0; e < NCH; e++) res[e] = gl_add(res[e], gl_mul(term, a.apow[(size_t)e * T + t]));

@@ -7,7 +7,10 @@
 // aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
-//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13] [--pinned 1]
+//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1]
+// --perm 1: the zs/partial-products columns and the quotient chunks are not random stand-ins but computed on the device
+// from the routed wires, the circuit's sigma columns and the transcript's challenges (qpzk_commit_zs_partial_products,
+// qpzk_commit_quotient: SURVEY.md 8a rows a16/a17, permutation argument only -- the gate set is not part of this repo).
 // prints one JSON line: proofs/s over all threads, mean latency per proof, and a checksum of every thread's first
 // proof (identical inputs must give identical proofs on every thread).
 #include <atomic>
@@ -45,7 +48,7 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
     }
 };
 
-static bool g_pinned = true, g_breakdown = false;
+static bool g_pinned = true, g_breakdown = false, g_perm = false;
 
 struct HostBuf {   // pinned (default) or pageable host buffer
     uint64_t* p = nullptr;
@@ -76,7 +79,7 @@ static HostBuf random_columns(uint64_t seed, size_t cols, size_t n) {
         if (rc_ != 0) { fprintf(stderr, "%s -> %d: %s\n", #call, rc_, qpzk_last_error()); exit(2); } \
     } while (0)
 
-struct Shape { unsigned log_n = 13, constants_sigmas = 85, wires = 135, zs_pp = 20, quotient = 16, num_zs = 2; };
+struct Shape { unsigned log_n = 13, constants_sigmas = 85, wires = 135, zs_pp = 20, quotient = 16, num_zs = 2, routed = 80, sigma_col0 = 5; };
 
 struct Worker {
     int device;
@@ -93,7 +96,9 @@ struct Worker {
         // what CircuitBuilder::build leaves behind: the committed constants/sigmas oracle
         auto cs = random_columns(1, sh.constants_sigmas, n);
         qpzk_batch* cs_b;
+        if (g_perm) QCHECK(qpzk_ctx_set_keep_values(ctx, 1));   // the permutation argument reads the sigma VALUES
         QCHECK(qpzk_commit_from_values(ctx, cs.data(), sh.log_n, sh.constants_sigmas, 3, 4, nullptr, &cs_b));
+        QCHECK(qpzk_ctx_set_keep_values(ctx, 0));
         // four witnesses' worth of columns, reused round robin
         std::vector<HostBuf> wires, zs, quot;
         for (int s = 0; s < 4; s++) {
@@ -131,15 +136,24 @@ struct Worker {
             QCHECK(qpzk_challenger_observe(ch, pih, 4));
             qpzk_batch *w_b, *z_b, *q_b;
             uint64_t chal[4], zeta[2];
+            if (g_perm) QCHECK(qpzk_ctx_set_keep_values(ctx, 1));
             QCHECK(qpzk_commit_from_values(ctx, wires[s].data(), sh.log_n, sh.wires, 3, 4, nullptr, &w_b));
+            QCHECK(qpzk_ctx_set_keep_values(ctx, 0));
             QCHECK(qpzk_challenger_observe_cap(ch, w_b));
-            QCHECK(qpzk_challenger_get(ch, chal, 4));   // betas, gammas (would feed the partial products)
+            QCHECK(qpzk_challenger_get(ch, chal, 4));   // betas, gammas
             lap(0, tp);
-            QCHECK(qpzk_commit_from_values(ctx, zs[s].data(), sh.log_n, sh.zs_pp, 3, 4, nullptr, &z_b));
+            if (g_perm)
+                QCHECK(qpzk_commit_zs_partial_products(ctx, cs_b, w_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, 4, &z_b));
+            else
+                QCHECK(qpzk_commit_from_values(ctx, zs[s].data(), sh.log_n, sh.zs_pp, 3, 4, nullptr, &z_b));
             QCHECK(qpzk_challenger_observe_cap(ch, z_b));
-            QCHECK(qpzk_challenger_get(ch, chal, 2));   // alphas (would feed the quotient)
+            uint64_t alphas[2];
+            QCHECK(qpzk_challenger_get(ch, alphas, 2));
             lap(1, tp);
-            QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
+            if (g_perm)
+                QCHECK(qpzk_commit_quotient(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, nullptr, 0, 4, &q_b));
+            else
+                QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
             QCHECK(qpzk_challenger_observe_cap(ch, q_b));
             QCHECK(qpzk_challenger_get(ch, zeta, 2));
             lap(2, tp);
@@ -195,6 +209,7 @@ int main(int argc, char** argv) {
         else if (k == "--log-n") sh.log_n = (unsigned)v;
         else if (k == "--pinned") g_pinned = v != 0;
         else if (k == "--breakdown") g_breakdown = v != 0;
+        else if (k == "--perm") g_perm = v != 0;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);
@@ -216,9 +231,9 @@ int main(int argc, char** argv) {
         lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum;
         if (w.seconds > wall) wall = w.seconds;
     }
-    printf("{\"threads\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+    printf("{\"threads\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\"}\n",
-           threads, proofs, sh.log_n, threads * proofs / wall, 1e3 * lat / threads,
+           threads, proofs, sh.log_n, g_perm ? 1 : 0, threads * proofs / wall, 1e3 * lat / threads,
            (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum);
     return same ? 0 : 3;
 }

@@ -80,6 +80,9 @@ def load_library():
         "qpzk_ctx_synchronize": (i, [vp]),
         "qpzk_ctx_set_zeroize": (i, [vp, i]),
         "qpzk_ctx_set_timing": (i, [vp, i]),
+        "qpzk_ctx_set_keep_values": (i, [vp, i]),
+        "qpzk_batch_values_dev": (vp, [vp]),
+        "qpzk_commit_zs_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, u32, C.POINTER(vp)]),
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
         "qpzk_ctx_trim": (i, [vp]),
@@ -163,6 +166,10 @@ class Context:
     def set_zeroize(self, on):
         _check(self.L.qpzk_ctx_set_zeroize(self.h, int(on)))
 
+    def set_keep_values(self, on):
+        """from_values batches also keep their input values on the device (needed by commit_zs_partial_products)."""
+        _check(self.L.qpzk_ctx_set_keep_values(self.h, int(on)))
+
     def set_timing(self, on):
         _check(self.L.qpzk_ctx_set_timing(self.h, int(on)))
 
@@ -210,6 +217,14 @@ class Context:
         _check(self.L.qpzk_partial_products(self.h, wp, sp, n.bit_length() - 1, R, chunk, b.size, bp, gp,
                                             out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def partial_products_device(self, wires_ptr, sigmas_ptr, log_n, num_routed, betas, gammas, out_ptr, chunk=8):
+        """The same on raw device addresses (wires / sigmas: num_routed x 2^log_n column-major; out: Z and partial
+        product columns, ready for PolynomialBatch.from_device)."""
+        b, bp = _host(betas)
+        g, gp = _host(gammas)
+        _check(self.L.qpzk_partial_products_dev(self.h, C.c_void_p(wires_ptr), C.c_void_p(sigmas_ptr), log_n, num_routed,
+                                                chunk, b.size, bp, gp, C.c_void_p(out_ptr)))
 
     def bench_imad(self, iters=4096):
         v = C.c_double()
@@ -364,6 +379,20 @@ class PolynomialBatch:
         keep = (b, g, al)
         return keep, (wires.ctx.h, constants_sigmas.h, wires.h, zs_partial_products.h, sigma_col0, num_routed), \
             (b.size, bp, gp, ap, C.c_void_p(gate_terms_dev) if gate_terms_dev else None, num_gate_terms)
+
+    @classmethod
+    def commit_zs_partial_products(cls, constants_sigmas, wires, sigma_col0, num_routed, betas, gammas, cap_height,
+                                   quotient_degree_factor=8):
+        """all_wires_permutation_partial_products + the zs/partial-products commitment on the device, from two batches
+        committed with Context.set_keep_values(True)."""
+        b, bp = _host(betas)
+        g, gp = _host(gammas)
+        h = C.c_void_p()
+        ctx = wires.ctx
+        _check(ctx.L.qpzk_commit_zs_partial_products(ctx.h, constants_sigmas.h, wires.h, sigma_col0, num_routed,
+                                                     quotient_degree_factor, b.size, bp, gp, cap_height, C.byref(h)))
+        cols = b.size * ((num_routed + quotient_degree_factor - 1) // quotient_degree_factor)
+        return cls(ctx, h, wires.degree_log, cols, wires.rate_bits, cap_height, False)
 
     @classmethod
     def quotient_polys(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,

@@ -45,8 +45,11 @@ class SyntheticCircuit:
     def __init__(self, ctx, constants_sigmas, shape=LEAF_SHAPE, sigma_col0=None):
         self.ctx, self.shape = ctx, dict(shape)
         self.sigma_col0 = sigma_col0     # first sigma column inside constants_sigmas (needed for the device quotient)
+        if sigma_col0 is not None:       # the permutation argument reads the sigma VALUES from this batch
+            ctx.set_keep_values(True)
         self.log_n = shape["log_n"]
         self.constants_sigmas = PolynomialBatch.from_values(ctx, constants_sigmas, RATE_BITS, None, CAP_HEIGHT)
+        ctx.set_keep_values(False)
         self.circuit_digest = np.arange(4, dtype=np.uint64) + 11   # stands for the verifier-data digest
         self.fri_params = fri_params(self.log_n, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, ARITY_BITS, FINAL_POLY_BITS)
 
@@ -62,15 +65,23 @@ def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public
     ch = Challenger(ctx)
     ch.observe_hash(circuit.circuit_digest)
     ch.observe_hash(public_inputs_hash)
+    on_device = zs_partial_products is None and circuit.sigma_col0 is not None
+    ctx.set_keep_values(on_device)                             # the wires batch keeps its values for the partial products
     wires_b = PolynomialBatch.from_values(ctx, wires, RATE_BITS, None, CAP_HEIGHT)
+    ctx.set_keep_values(False)
     ch.observe_cap(wires_b)
     nz = sh["num_zs"]
     betas_gammas = ch.get_n_challenges(2 * nz)                 # betas, then gammas (num_challenges each)
-    if zs_partial_products is None:
-        sg = np.asarray(sigmas, dtype=np.uint64)
-        zs_partial_products = ctx.partial_products(np.asarray(wires)[:sg.shape[0]], sg, betas_gammas[:nz],
-                                                   betas_gammas[nz:], quotient_degree_factor)
-    zs_b = PolynomialBatch.from_values(ctx, zs_partial_products, RATE_BITS, None, CAP_HEIGHT)
+    if on_device:                                              # wires and sigmas never leave the device
+        zs_b = PolynomialBatch.commit_zs_partial_products(circuit.constants_sigmas, wires_b, circuit.sigma_col0,
+                                                          np.asarray(sigmas).shape[0], betas_gammas[:nz], betas_gammas[nz:],
+                                                          CAP_HEIGHT, quotient_degree_factor)
+    else:
+        if zs_partial_products is None:
+            sg = np.asarray(sigmas, dtype=np.uint64)
+            zs_partial_products = ctx.partial_products(np.asarray(wires)[:sg.shape[0]], sg, betas_gammas[:nz],
+                                                       betas_gammas[nz:], quotient_degree_factor)
+        zs_b = PolynomialBatch.from_values(ctx, zs_partial_products, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(zs_b)
     alphas = ch.get_n_challenges(nz)
     if quotient_coeffs is None:                                # permutation argument only (no gate terms)
