@@ -75,4 +75,58 @@ extern "C" {
                           instance: *const qpzk_fri_instance, params: *const qpzk_fri_params,
                           ch: *mut qpzk_challenger, pow_witness_in: u64, proof_out: *mut u64,
                           openings_out: *mut u64) -> c_int;
+    // ---- remaining entry points of include/qpzk.h (device-pointer variants, accessors, challenger, permutation
+    // argument, microbenchmarks): every symbol the header declares is bound here (tests/test_capi_cpu.py checks it)
+    pub fn qpzk_version() -> *const c_char;
+    pub fn qpzk_ctx_set_zeroize(ctx: *mut qpzk_ctx, on: c_int) -> c_int;
+    pub fn qpzk_ctx_set_keep_values(ctx: *mut qpzk_ctx, on: c_int) -> c_int;
+    pub fn qpzk_ctx_set_timing(ctx: *mut qpzk_ctx, on: c_int) -> c_int;
+    pub fn qpzk_ctx_last_commit_timing(ctx: *mut qpzk_ctx, ms: *mut f32) -> c_int;
+    pub fn qpzk_ctx_launch_count(ctx: *const qpzk_ctx) -> u64;
+    pub fn qpzk_commit_from_values_dev(ctx: *mut qpzk_ctx, cols_dev: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
+                                       cap_height: u32, salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_commit_from_coeffs_dev(ctx: *mut qpzk_ctx, cols_dev: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
+                                       cap_height: u32, salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_commit_cosets_from_coeffs_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, log_n: u32, num_cols: u32,
+                                              rate_bits: u32, cap_height: u32, coset_begin: u32, coset_count: u32,
+                                              out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_intt_columns_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, coeffs_dev: *mut u64, log_n: u32,
+                                 num_cols: u32) -> c_int;
+    pub fn qpzk_selftest_mds_layer(ctx: *mut qpzk_ctx, states: *const u64, count: u64, next_round: u32, out: *mut u64) -> c_int;
+    pub fn qpzk_merkle_new_dev(ctx: *mut qpzk_ctx, leaves_dev: *const u64, num_leaves: u64, leaf_len: u32, cap_height: u32,
+                               out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_batch_num_leaves(b: *const qpzk_batch) -> u64;
+    pub fn qpzk_batch_leaf_len(b: *const qpzk_batch) -> u32;
+    pub fn qpzk_batch_digests(b: *const qpzk_batch, level: u32, out: *mut u64) -> c_int;
+    pub fn qpzk_batch_leaves_dev(b: *const qpzk_batch) -> *const u64;
+    pub fn qpzk_batch_coeffs_dev(b: *const qpzk_batch) -> *const u64;
+    pub fn qpzk_batch_values_dev(b: *const qpzk_batch) -> *const u64;
+    pub fn qpzk_challenger_observe(ch: *mut qpzk_challenger, elems: *const u64, n: u32) -> c_int;
+    pub fn qpzk_challenger_observe_cap(ch: *mut qpzk_challenger, b: *const qpzk_batch) -> c_int;
+    pub fn qpzk_challenger_get(ch: *mut qpzk_challenger, out: *mut u64, n: u32) -> c_int;
+    pub fn qpzk_fri_params_constant_arity(p: *mut qpzk_fri_params, log_n: u32, rate_bits: u32, cap_height: u32,
+                                          proof_of_work_bits: u32, num_query_rounds: u32, arity_bits: u32,
+                                          final_poly_bits: u32) -> c_int;
+    // all_wires_permutation_partial_products (plonk/prover.rs) and the zs/partial-products commitment
+    pub fn qpzk_partial_products(ctx: *mut qpzk_ctx, wires: *const u64, sigmas: *const u64, log_n: u32, num_routed: u32,
+                                 chunk: u32, num_challenges: u32, betas: *const u64, gammas: *const u64, out: *mut u64) -> c_int;
+    pub fn qpzk_partial_products_dev(ctx: *mut qpzk_ctx, wires_dev: *const u64, sigmas_dev: *const u64, log_n: u32,
+                                     num_routed: u32, chunk: u32, num_challenges: u32, betas: *const u64,
+                                     gammas: *const u64, out_dev: *mut u64) -> c_int;
+    pub fn qpzk_commit_zs_partial_products(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
+                                           sigma_col0: u32, num_routed: u32, chunk: u32, num_challenges: u32,
+                                           betas: *const u64, gammas: *const u64, cap_height: u32,
+                                           out: *mut *mut qpzk_batch) -> c_int;
+    // compute_quotient_polys for the permutation argument (+ caller-supplied gate terms) and the quotient commitment
+    pub fn qpzk_quotient_polys(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
+                               zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
+                               quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
+                               alphas: *const u64, gate_terms_dev: *const u64, num_gate_terms: u32, out: *mut u64) -> c_int;
+    pub fn qpzk_commit_quotient(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
+                                zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
+                                quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
+                                alphas: *const u64, gate_terms_dev: *const u64, num_gate_terms: u32, cap_height: u32,
+                                out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_bench_imad(ctx: *mut qpzk_ctx, iters: u32, imad_per_sec: *mut f64) -> c_int;
+    pub fn qpzk_bench_poseidon(ctx: *mut qpzk_ctx, perms_per_thread: u32, perms_per_sec: *mut f64) -> c_int;
 }

@@ -25,6 +25,17 @@ def test_library_exports_every_declared_symbol(qpzk):
     assert sorted(lib._qpzk_symbols) == declared
 
 
+def test_rust_sys_crate_binds_every_declared_symbol(qpzk):
+    """rust/qpzk-sys/src/lib.rs (the -sys crate a qp-plonky2 fork links) declares every entry point of
+    include/qpzk.h.  Source-level check: there is no cargo/rustc in this image."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rs = open(os.path.join(root, "rust", "qpzk-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (qpzk_[a-z0-9_]+)\s*\(", rs))
+    declared = set(_declared_symbols(qpzk.HEADER_PATH))
+    assert declared - bound == set(), sorted(declared - bound)
+    assert bound - declared == set(), sorted(bound - declared)
+
+
 def test_version_string(qpzk):
     assert b"sm_100a" in qpzk.load_library().qpzk_version()
 
