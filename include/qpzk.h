@@ -273,6 +273,33 @@ int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, cons
                          const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
                          uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out);
 
+/* ---- wire format: ProofWithPublicInputs::to_bytes / from_bytes ----------------------------------------
+ * Replaces qp-plonky2 `util/serialization`: `write_proof_with_public_inputs` / `read_proof_with_public_inputs`
+ * (what the reference passes between prover, aggregator and verifier:
+ * wormhole/tests/src/prover/prover_tests.rs:118, field inventory wormhole/aggregator/src/common/utils.rs:349-537).
+ * Host functions, no device work.  Byte layout in qp-zk-circuits_b200/csrc/wire.cu (upstream's order as recalled;
+ * PARITY UNPINNED).
+ *   openings : the (k, 2) array in FRI-instance order, as qpzk_fri_prove / the prover produce it:
+ *              constants | sigmas | wires | zs | partial products | quotient chunks | zs at g*zeta
+ *   fri_proof: the flat words of qpzk_fri_prove for the four oracles with leaf lengths leaf_lens
+ *              (constants_sigmas, wires, zs_partial_products, quotient; + QPZK_SALT_SIZE where blinded). */
+typedef struct {
+    uint32_t log_n;
+    uint32_t num_constants, num_sigmas, num_wires, num_zs, num_partial_products, num_quotient_polys;
+    uint32_t leaf_lens[4];
+    uint32_t num_public_inputs;
+} qpzk_proof_shape;
+size_t qpzk_proof_bytes_len(const qpzk_fri_params* p, const qpzk_proof_shape* s);   /* 0 = invalid shape */
+int qpzk_proof_to_bytes(const qpzk_fri_params* p, const qpzk_proof_shape* s, const uint64_t* wires_cap,
+                        const uint64_t* zs_partial_products_cap, const uint64_t* quotient_polys_cap,
+                        const uint64_t* openings, const uint64_t* fri_proof, const uint64_t* public_inputs,
+                        uint8_t* out, size_t out_len);
+/* The inverse; fails (QPZK_EINVAL) on a wrong total length, a sibling count that does not match the circuit, or a
+ * non-canonical field element. */
+int qpzk_proof_from_bytes(const qpzk_fri_params* p, const qpzk_proof_shape* s, const uint8_t* bytes, size_t len,
+                          uint64_t* wires_cap, uint64_t* zs_partial_products_cap, uint64_t* quotient_polys_cap,
+                          uint64_t* openings, uint64_t* fri_proof, uint64_t* public_inputs);
+
 /* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------------- */
 /* IMAD.WIDE throughput: returns 32x32+64 multiply-adds per second measured over `iters` dependent-chain
  * iterations on every SM. */

@@ -397,3 +397,80 @@ def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient
     return dict(caps=[wires_b.cap(), zs_b.cap(), quot_b.cap()], openings=openings, fri_proof=proof,
                 challenges=(betas_gammas, alphas, zeta), instance=inst, params=params, verifier_challenger=verifier_ch,
                 leaf_lens=[b.leaf_len for b in oracles], all_caps=[b.cap() for b in oracles])
+
+
+# ---- wire format (upstream util/serialization, recalled order -- parity unpinned, Appendix B A6) -----
+def parse_fri_proof(words, params, log_n, leaf_lens):
+    """Flat FriProof words -> the structured proof upstream holds: dict(commit_phase_merkle_caps, query_round_proofs
+    [dict(initial_trees_proof=[(evals, siblings)], steps=[(evals, siblings)])], final_poly, pow_witness)."""
+    w = [int(x) for x in _u64(words)]
+    pos = [0]
+
+    def take(n):
+        v = w[pos[0]:pos[0] + n]
+        assert len(v) == n
+        pos[0] += n
+        return v
+
+    H, R = 1 << params.cap_height, params.num_rounds
+    log_L = log_n + params.rate_bits
+    caps = [[take(4) for _ in range(H)] for _ in range(R)]
+    rounds = []
+    for _ in range(params.num_queries):
+        init = []
+        for ll in leaf_lens:
+            init.append((take(int(ll)), [take(4) for _ in range(log_L - params.cap_height)]))
+        steps, lg = [], log_L
+        for r in range(R):
+            ab = params.arity_bits[r]
+            evals = take(2 << ab)
+            steps.append((evals, [take(4) for _ in range(max(lg - ab - params.cap_height, 0))]))
+            lg -= ab
+        rounds.append(dict(initial_trees_proof=init, steps=steps))
+    final_poly = take(2 << (log_n - sum(params.arity_bits[r] for r in range(R))))
+    pow_witness = take(1)[0]
+    assert pos[0] == len(w)
+    return dict(commit_phase_merkle_caps=caps, query_round_proofs=rounds, final_poly=final_poly, pow_witness=pow_witness)
+
+
+def proof_to_bytes(caps3, opening_set, fri, public_inputs):
+    """write_proof_with_public_inputs: caps3 = (wires, zs_partial_products, quotient) caps as lists of 4-word hashes;
+    opening_set = dict of the upstream OpeningSet fields (lists of (a, b) extension elements); fri = parse_fri_proof()."""
+    import struct
+    out = bytearray()
+    felt = lambda v: out.extend(struct.pack("<Q", int(v)))
+
+    def merkle_proof(sibs):
+        out.append(len(sibs))
+        for h in sibs:
+            for v in h:
+                felt(v)
+
+    for cap in caps3:
+        for h in cap:
+            for v in h:
+                felt(v)
+    for name in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys",
+                 "lookup_zs", "lookup_zs_next"):
+        for e in opening_set.get(name, []):
+            felt(e[0]); felt(e[1])
+    for cap in fri["commit_phase_merkle_caps"]:
+        for h in cap:
+            for v in h:
+                felt(v)
+    for rd in fri["query_round_proofs"]:
+        for evals, sibs in rd["initial_trees_proof"]:
+            for v in evals:
+                felt(v)
+            merkle_proof(sibs)
+        for evals, sibs in rd["steps"]:
+            for v in evals:
+                felt(v)
+            merkle_proof(sibs)
+    for v in fri["final_poly"]:
+        felt(v)
+    felt(fri["pow_witness"])
+    out.extend(struct.pack("<Q", len(public_inputs)))
+    for v in public_inputs:
+        felt(v)
+    return bytes(out)

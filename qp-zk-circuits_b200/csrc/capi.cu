@@ -22,6 +22,7 @@ using namespace qpzk;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+namespace qpzk { int wire_fail(int code, const std::string& msg) { return fail(code, msg); } }   // wire.cu
 
 #define CK(call)                                                                                       \
     do {                                                                                               \

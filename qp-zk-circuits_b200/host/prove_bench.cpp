@@ -7,7 +7,9 @@
 // aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
-//   prove_bench [--device D] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1]
+//   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1]
+// --devices G: one process drives G GPUs, thread t on device D + (t mod G) -- the aggregator's dispatch (independent leaf
+// proofs, one context per worker thread and device, no collective; reference wormhole/aggregator/src/aggregator.rs:187-227).
 // --perm 1: the zs/partial-products columns and the quotient chunks are not random stand-ins but computed on the device
 // from the routed wires, the circuit's sigma columns and the transcript's challenges (qpzk_commit_zs_partial_products,
 // qpzk_commit_quotient: SURVEY.md 8a rows a16/a17, permutation argument only -- the gate set is not part of this repo).
@@ -198,12 +200,13 @@ struct Worker {
 };
 
 int main(int argc, char** argv) {
-    int device = 0, threads = 1, proofs = 16;
+    int device = 0, devices = 1, threads = 1, proofs = 16;
     Shape sh;
     for (int i = 1; i + 1 < argc; i += 2) {
         std::string k = argv[i];
         int v = atoi(argv[i + 1]);
         if (k == "--device") device = v;
+        else if (k == "--devices") devices = v > 0 ? v : 1;
         else if (k == "--threads") threads = v;
         else if (k == "--proofs") proofs = v;
         else if (k == "--log-n") sh.log_n = (unsigned)v;
@@ -217,7 +220,7 @@ int main(int argc, char** argv) {
     std::atomic<int> ready{0};
     std::atomic<bool> go{false};
     for (int t = 0; t < threads; t++) {
-        ws[t].device = device; ws[t].sh = sh; ws[t].proofs = proofs;
+        ws[t].device = device + t % devices; ws[t].sh = sh; ws[t].proofs = proofs;
         th.emplace_back([&, t] { ws[t].run(&ready, &go); });
     }
     while (ready.load() < threads) std::this_thread::yield();
@@ -231,9 +234,9 @@ int main(int argc, char** argv) {
         lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum;
         if (w.seconds > wall) wall = w.seconds;
     }
-    printf("{\"threads\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\"}\n",
-           threads, proofs, sh.log_n, g_perm ? 1 : 0, threads * proofs / wall, 1e3 * lat / threads,
+           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, threads * proofs / wall, 1e3 * lat / threads,
            (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum);
     return same ? 0 : 3;
 }

@@ -53,6 +53,13 @@ class _FriInstance(C.Structure):
                 ("poly_oracle", U32P), ("poly_index", U32P)]
 
 
+class ProofShape(C.Structure):
+    """qpzk_proof_shape: how many polynomials of each kind a proof of this circuit opens (wire format)."""
+    _fields_ = [("log_n", C.c_uint32), ("num_constants", C.c_uint32), ("num_sigmas", C.c_uint32),
+                ("num_wires", C.c_uint32), ("num_zs", C.c_uint32), ("num_partial_products", C.c_uint32),
+                ("num_quotient_polys", C.c_uint32), ("leaf_lens", C.c_uint32 * 4), ("num_public_inputs", C.c_uint32)]
+
+
 class ChallengerState(C.Structure):
     _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8),
                 ("output_buffer", C.c_uint64 * 8), ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
@@ -126,6 +133,9 @@ def load_library():
         "qpzk_partial_products_dev": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "qpzk_quotient_polys": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, vp]),
         "qpzk_commit_quotient": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, u32, C.POINTER(vp)]),
+        "qpzk_proof_bytes_len": (C.c_size_t, [C.POINTER(FriParams), C.POINTER(ProofShape)]),
+        "qpzk_proof_to_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, vp, vp, vp, vp, vp, vp, C.c_size_t]),
+        "qpzk_proof_from_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -496,6 +506,52 @@ def fri_params(log_n, rate_bits=3, cap_height=4, proof_of_work_bits=16, num_quer
     _check(load_library().qpzk_fri_params_constant_arity(C.byref(p), log_n, rate_bits, cap_height, proof_of_work_bits,
                                                          num_query_rounds, arity_bits, final_poly_bits))
     return p
+
+
+def proof_shape(log_n, num_constants, num_sigmas, num_wires, num_zs, num_partial_products, num_quotient_polys,
+                num_public_inputs, salted=(False, False, False, False)):
+    s = ProofShape(log_n, num_constants, num_sigmas, num_wires, num_zs, num_partial_products, num_quotient_polys)
+    lens = [num_constants + num_sigmas, num_wires, num_zs + num_partial_products, num_quotient_polys]
+    for k in range(4):
+        s.leaf_lens[k] = lens[k] + (SALT_SIZE if salted[k] else 0)
+    s.num_public_inputs = num_public_inputs
+    return s
+
+
+def proof_to_bytes(params, shape, wires_cap, zs_cap, quotient_cap, openings, fri_proof, public_inputs):
+    """ProofWithPublicInputs::to_bytes from the pieces the prover returns (openings in FRI-instance order)."""
+    L = load_library()
+    n = L.qpzk_proof_bytes_len(C.byref(params), C.byref(shape))
+    if not n:
+        raise QpzkError(-1, L.qpzk_last_error().decode())
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1) for a in (wires_cap, zs_cap, quotient_cap, openings, fri_proof, public_inputs)]
+    H = 4 << params.cap_height
+    want = [H, H, H, 2 * (shape.num_constants + shape.num_sigmas + shape.num_wires + 2 * shape.num_zs +
+                          shape.num_partial_products + shape.num_quotient_polys),
+            L.qpzk_fri_proof_words(C.byref(params), shape.log_n, 4, shape.leaf_lens), shape.num_public_inputs]
+    if [a.size for a in arrs] != want:
+        raise QpzkError(-1, "proof pieces have sizes %s, the circuit needs %s" % ([a.size for a in arrs], want))
+    out = np.zeros(n, np.uint8)
+    _check(L.qpzk_proof_to_bytes(C.byref(params), C.byref(shape), *[a.ctypes.data_as(C.c_void_p) for a in arrs],
+                                 out.ctypes.data_as(C.c_void_p), n))
+    return out.tobytes()
+
+
+def proof_from_bytes(params, shape, data):
+    """The inverse: dict(wires_cap, zs_cap, quotient_cap, openings (k, 2), fri_proof, public_inputs)."""
+    L = load_library()
+    H = 1 << params.cap_height
+    k = (shape.num_constants + shape.num_sigmas + shape.num_wires + 2 * shape.num_zs + shape.num_partial_products +
+         shape.num_quotient_polys)
+    out = dict(wires_cap=np.zeros((H, 4), np.uint64), zs_cap=np.zeros((H, 4), np.uint64), quotient_cap=np.zeros((H, 4), np.uint64),
+               openings=np.zeros((k, 2), np.uint64),
+               fri_proof=np.zeros(L.qpzk_fri_proof_words(C.byref(params), shape.log_n, 4, shape.leaf_lens), np.uint64),
+               public_inputs=np.zeros(shape.num_public_inputs, np.uint64))
+    buf = np.frombuffer(bytes(data), np.uint8)
+    _check(L.qpzk_proof_from_bytes(C.byref(params), C.byref(shape), buf.ctypes.data_as(C.c_void_p), buf.size,
+                                   *[out[f].ctypes.data_as(C.c_void_p) for f in ("wires_cap", "zs_cap", "quotient_cap", "openings",
+                                                                                 "fri_proof", "public_inputs")]))
+    return out
 
 
 class Challenger:

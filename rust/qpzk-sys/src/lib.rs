@@ -32,6 +32,20 @@ pub struct qpzk_fri_params {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
+pub struct qpzk_proof_shape {
+    pub log_n: u32,
+    pub num_constants: u32,
+    pub num_sigmas: u32,
+    pub num_wires: u32,
+    pub num_zs: u32,
+    pub num_partial_products: u32,
+    pub num_quotient_polys: u32,
+    pub leaf_lens: [u32; 4],
+    pub num_public_inputs: u32,
+}
+
+#[repr(C)]
 pub struct qpzk_fri_instance {
     pub num_batches: u32,
     pub points: *const u64,
@@ -127,6 +141,14 @@ extern "C" {
                                 quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
                                 alphas: *const u64, gate_terms_dev: *const u64, num_gate_terms: u32, cap_height: u32,
                                 out: *mut *mut qpzk_batch) -> c_int;
+    // ProofWithPublicInputs::to_bytes / from_bytes (host functions)
+    pub fn qpzk_proof_bytes_len(p: *const qpzk_fri_params, s: *const qpzk_proof_shape) -> usize;
+    pub fn qpzk_proof_to_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, wires_cap: *const u64,
+                               zs_partial_products_cap: *const u64, quotient_polys_cap: *const u64, openings: *const u64,
+                               fri_proof: *const u64, public_inputs: *const u64, out: *mut u8, out_len: usize) -> c_int;
+    pub fn qpzk_proof_from_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, bytes: *const u8, len: usize,
+                                 wires_cap: *mut u64, zs_partial_products_cap: *mut u64, quotient_polys_cap: *mut u64,
+                                 openings: *mut u64, fri_proof: *mut u64, public_inputs: *mut u64) -> c_int;
     pub fn qpzk_bench_imad(ctx: *mut qpzk_ctx, iters: u32, imad_per_sec: *mut f64) -> c_int;
     pub fn qpzk_bench_poseidon(ctx: *mut qpzk_ctx, perms_per_thread: u32, perms_per_sec: *mut f64) -> c_int;
 }
