@@ -65,7 +65,10 @@ cudaError_t upload_poseidon_constants() {
 // One thread per row; overwrite-mode sponge, rate 8.  The next chunk is loaded before the
 // permutation of the current one so the (strided, L1-served) loads hide under ~20k integer ops.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HASH_THREADS)
+#ifndef QPZK_HASH_MINBLOCKS
+#define QPZK_HASH_MINBLOCKS 6   // <= 80 registers: the limb-domain partial rounds would take 96 (5 blocks per SM) otherwise
+#endif
+__global__ void __launch_bounds__(HASH_THREADS, QPZK_HASH_MINBLOCKS)
 hash_rows_kernel(const uint64_t* __restrict__ leaves, uint64_t num_rows, uint32_t leaf_len, uint64_t row_stride,
                  uint64_t* __restrict__ digests) {
     uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -184,6 +184,61 @@ __device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = limb_combine(y0[i], y1[i], y2[i]);
 }
+
+#ifndef QPZK_PARTIAL_LIMB
+#define QPZK_PARTIAL_LIMB 1
+#endif
+#if QPZK_PARTIAL_LIMB
+// ---- the 22 partial rounds with lanes 1..11 kept in the limb domain -------------------------------------------------
+// Only lane 0 passes through an S-box in a partial round; the other eleven lanes see nothing but the linear layer, so
+// they need not be recombined into 64-bit words and split again between rounds.  What they do need is a carry
+// normalisation, because a layer grows a limb by up to 2^8.15 (sum of a matrix row = 284):
+//     t1 = y1 + (y0 >> 22),  t2 = y2 + (t1 >> 22),  h = t2 >> 20   (h * 2^64 = h * 2^32 - h mod p)
+//     n0 = (y0 & M22) + 4096 - h,   n1 = (t1 & M22) + (h << 10),   n2 = t2 & M20
+// 10 instructions per lane instead of 12 (combine) + 5 (split).  The table constants carry -4096 (see limb_combine), so
+// adding 4096 restores the true value and keeps n0 positive (h <= 2^11).  Bounds: n0 < 2^22 + 2^12, n1 < 2^22 + 2^21 +
+// 2^10, n2 < 2^20, hence every output of the next layer is < 284 * (2^22 + 2^21 + 2^10) + 2^22 < 2^31: exact in the
+// wrapping 32-bit arithmetic of mds_limb.
+__device__ __forceinline__ void limb_normalize(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t& n0, uint32_t& n1, uint32_t& n2) {
+    const uint32_t t1 = y1 + (y0 >> 22);
+    const uint32_t t2 = y2 + (t1 >> 22);
+    const uint32_t h = t2 >> 20;
+    n0 = (y0 & 0x3FFFFFu) + 4096u - h;
+    n1 = (t1 & 0x3FFFFFu) + (h << 10);
+    n2 = t2 & 0xFFFFFu;
+}
+
+// rounds 4..25: in s = state after the linear layer of round 3 (constants of round 4 added); out s = state after the
+// linear layer of round 25 (constants of round 26 added)
+__device__ __forceinline__ void partial_rounds_limb(uint64_t (&s)[12]) {
+    uint32_t l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) {
+        l0[i] = (uint32_t)s[i] & 0x3FFFFFu;
+        l1[i] = (uint32_t)(s[i] >> 22) & 0x3FFFFFu;
+        l2[i] = (uint32_t)(s[i] >> 44);
+    }
+    uint64_t s0 = s[0];
+#pragma unroll 1
+    for (int r = 4; r < 26; r++) {
+        s0 = sbox7_nc(s0);
+        l0[0] = (uint32_t)s0 & 0x3FFFFFu;
+        l1[0] = (uint32_t)(s0 >> 22) & 0x3FFFFFu;
+        l2[0] = (uint32_t)(s0 >> 44);
+        const uint32_t* rc = c_rc_limb + 36 * (r + 1);
+        uint32_t y0[12], y1[12], y2[12];
+        mds_limb(l0, rc, y0);
+        mds_limb(l1, rc + 12, y1);
+        mds_limb(l2, rc + 24, y2);
+        s0 = limb_combine(y0[0], y1[0], y2[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) limb_normalize(y0[i], y1[i], y2[i], l0[i], l1[i], l2[i]);
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = limb_combine(l0[i] - 4096u, l1[i], l2[i]);   // limb_combine adds the 4096 back
+}
+#endif  // QPZK_PARTIAL_LIMB
 #else
 // s <- MDS * s + table row `next`
 __device__ __forceinline__ void mds_layer_rc(uint64_t (&s)[12], int next) {
@@ -245,6 +300,12 @@ __device__ __forceinline__ void poseidon_permute(uint64_t (&s)[12]) {
             sparse_segment(s);
             r = 26;
         }
+#if QPZK_MDS_FFT && QPZK_PARTIAL_LIMB
+        if (SPARSE_ROUNDS == 0 && r == 4) {
+            partial_rounds_limb(s);
+            r = 26;
+        }
+#endif
         if (r < 4 || r >= 26) {
 #if QPZK_SBOX_PASSES == 1
 #pragma unroll

@@ -36,6 +36,30 @@ def test_poseidon_permute_matches_oracle_and_kats(ctx, orc):
     assert (ctx.poseidon_permute(nc) == want[:64]).all()
 
 
+def test_poseidon_permute_bulk_and_extreme_states(ctx, orc):
+    """60 k permutations against the oracle: uniform states, states of extreme words (all limbs saturated: the limb-domain
+    partial rounds carry between limbs and wrap the top limb in every round), sparse states and non-canonical words."""
+    import ctypes as C
+    rng = np.random.default_rng(2024)
+    ext = np.array([0, 1, P - 1, P - 2, 2**32 - 1, 2**32, 2**44 - 1, 2**44, 2**22 - 1, 2**22, 0xFFFFFFFF00000000,
+                    0xFFFFF00000000000, 0x00000FFFFFFFFFFF, 0x003FFFFF003FFFFF & (2**64 - 1), 0x8000000000000000], dtype=np.uint64)
+    a = rng.integers(0, P, size=(40000, 12), dtype=np.uint64)
+    b = ext[rng.integers(0, ext.size, size=(15000, 12))]
+    c = np.zeros((5000, 12), np.uint64)
+    c[np.arange(5000), rng.integers(0, 12, 5000)] = ext[rng.integers(0, ext.size, 5000)]
+    states = np.concatenate([a, b, c])
+    got = ctx.poseidon_permute(states)
+    want = states.copy()
+    L = orc.lib()
+    for row in want:
+        L.orc_poseidon(row.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert (got == want).all()
+    nc = np.full((64, 12), 2**64 - 1, np.uint64)              # 2^64 - 1 = 2^32 - 2 (mod p)
+    nc[:, ::2] = np.uint64(P)                                  # p = 0 (mod p)
+    canon = nc % np.uint64(P)
+    assert (ctx.poseidon_permute(nc) == np.stack([orc.poseidon(r) for r in canon])).all()
+
+
 def test_mds_layer_carry_paths(ctx, orc):
     """One linear layer (limb-domain MDS + next round's constants) on states chosen to hit every carry/wrap path:
     all-ones words, values just below/above p and 2^64, single hot lanes, limb boundaries (2^22, 2^44)."""
