@@ -211,9 +211,15 @@ def native_prove_bench(device, threads, proofs=32, perm=0):
     if not os.path.exists(exe):
         return None
     try:
-        r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm)],
-                           capture_output=True, text=True, timeout=300)
-        return json.loads(r.stdout.strip().splitlines()[-1])
+        runs = []
+        for _ in range(3 if threads > 1 else 1):   # multi-threaded throughput varies from run to run: report the median
+            r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm)],
+                               capture_output=True, text=True, timeout=300)
+            runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+        runs.sort(key=lambda d: d["proofs_per_s"])
+        out = runs[len(runs) // 2]
+        out["proofs_per_s_runs"] = [d["proofs_per_s"] for d in runs]
+        return out
     except Exception:
         return None
 

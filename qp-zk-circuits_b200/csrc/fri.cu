@@ -143,29 +143,97 @@ __global__ void __launch_bounds__(COMBINE_THREADS) fri_combine_kernel(FriCombine
         }
     }
     const uint32_t count = L - p0 < 32 ? (uint32_t)(L - p0) : 32u;
-    for (uint32_t pt = 0; pt < count; pt++) {
-        const uint64_t p = p0 + pt;
+    // Batch 0 is the big one (every polynomial of every oracle at zeta: ~276 for the leaf circuit).  The polynomials a
+    // lane is responsible for do not change from point to point, so their column address, row stride and alpha power
+    // are fetched ONCE per warp (they were four dependent loads per polynomial and point) and the point loop is left
+    // with one independent load and one extension-by-base multiplication per polynomial.
+    constexpr uint32_t PL = 10;                       // polynomials per lane kept in registers: 320 per batch
+    const uint32_t k0 = a.batch_off[1] - a.batch_off[0];
+    const bool hoist = k0 <= 32 * PL;
+    const uint64_t* cptr[PL];
+    uint32_t cstr[PL];
+    ext2 cap[PL];
+#pragma unroll
+    for (uint32_t t = 0; t < PL; t++) {
+        const uint32_t j = lane + 32 * t;
+        cptr[t] = a.leaves[0]; cstr[t] = 0; cap[t] = ext_make(0, 0);     // harmless slot: value * 0
+        if (hoist && j < k0) {
+            const uint32_t o = a.poly_oracle[a.batch_off[0] + j];
+            cptr[t] = a.leaves[o] + a.poly_index[a.batch_off[0] + j];
+            cstr[t] = a.leaf_width[o];
+            cap[t] = ext_make(a.apow[2 * j], a.apow[2 * j + 1]);
+        }
+    }
+    // Points in groups of 8.  Every lane accumulates, for the 8 points of the group, the part of the sum that belongs
+    // to ITS polynomials (8 independent loads per polynomial); a recursive-halving exchange (xor 16: keep 4 of the 8
+    // partial sums and receive the partner's, xor 8: 2, xor 4: 1, then plain butterflies for xor 2 and 1) leaves the
+    // total of point q = lane >> 2 on lanes 4q..4q+3: 9 exchange steps per group instead of 8 x 5, and the per-point
+    // arithmetic that follows (two extension multiplications per batch) runs for 8 points at once instead of being
+    // repeated by all 32 lanes for one point.  (ncu, before: 1940 instructions per point and lane, 3x the arithmetic.)
+    (void)count;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const uint32_t q = lane >> 2;
+    for (uint32_t grp = 0; grp < 4; grp++) {
+        const uint64_t pg = p0 + 8 * grp;                 // first point of the group
+        if (pg >= L) break;
         ext2 sum = ext_make(0, 0);
 #pragma unroll
         for (uint32_t b = 0; b < MAX_FRI_BATCHES; b++) {
             if (b >= a.num_batches) break;
-            uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
-            ext2 acc = ext_make(0, 0);
-            for (uint32_t j = lane; j < k; j += 32) {
-                uint32_t o = a.poly_oracle[off + j], idx = a.poly_index[off + j];
-                uint64_t v = a.leaves[o][p * a.leaf_width[o] + idx];
-                acc = ext_add(acc, ext_scale(ext_make(a.apow[2 * j], a.apow[2 * j + 1]), v));
+            const uint32_t off = a.batch_off[b], k = a.batch_off[b + 1] - off;
+            ext2 acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc[u] = ext_make(0, 0);
+            if (b == 0 && hoist) {
+#pragma unroll
+                for (uint32_t t = 0; t < PL; t++) {
+                    if (32 * t >= k0) break;
+                    uint64_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = cptr[t][min(pg + u, L - 1) * cstr[t]];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc[u] = ext_add(acc[u], ext_scale(cap[t], v[u]));
+                }
+            } else {
+                for (uint32_t jj = lane; jj < k; jj += 32) {
+                    const uint32_t o = a.poly_oracle[off + jj], idx = a.poly_index[off + jj];
+                    const ext2 ap = ext_make(a.apow[2 * jj], a.apow[2 * jj + 1]);
+                    const uint64_t* col = a.leaves[o] + idx;
+                    const uint64_t wdt = a.leaf_width[o];
+                    uint64_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = col[min(pg + u, L - 1) * wdt];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc[u] = ext_add(acc[u], ext_scale(ap, v[u]));
+                }
+            }
+            ext2 h4[4], h2[2], tot;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const ext2 keep = b4 ? acc[u + 4] : acc[u], give = b4 ? acc[u] : acc[u + 4];
+                h4[u] = ext_add(keep, ext_shfl_xor(give, 16));
             }
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) acc = ext_add(acc, ext_shfl_xor(acc, sft));
-            ext2 numer = ext_sub(acc, ext_make(a.reduced[2 * b], a.reduced[2 * b + 1]));
+            for (int u = 0; u < 2; u++) {
+                const ext2 keep = b3 ? h4[u + 2] : h4[u], give = b3 ? h4[u] : h4[u + 2];
+                h2[u] = ext_add(keep, ext_shfl_xor(give, 8));
+            }
+            {
+                const ext2 keep = b2 ? h2[1] : h2[0], give = b2 ? h2[0] : h2[1];
+                tot = ext_add(keep, ext_shfl_xor(give, 4));
+            }
+            tot = ext_add(tot, ext_shfl_xor(tot, 2));
+            tot = ext_add(tot, ext_shfl_xor(tot, 1));
+            // tot = sum over all polynomials of the batch at point pg + q  (q = 4*b4 + 2*b3 + b2 = lane >> 2)
+            const ext2 numer = ext_sub(tot, ext_make(a.reduced[2 * b], a.reduced[2 * b + 1]));
             ext2 dinv;
-            dinv.a = __shfl_sync(0xffffffffu, inv[b].a, pt);
-            dinv.b = __shfl_sync(0xffffffffu, inv[b].b, pt);
-            ext2 q = ext_mul(numer, dinv);
-            sum = ext_add(ext_mul(sum, ext_make(a.apow[2 * k], a.apow[2 * k + 1])), q);
+            dinv.a = __shfl_sync(0xffffffffu, inv[b].a, 8 * grp + q);
+            dinv.b = __shfl_sync(0xffffffffu, inv[b].b, 8 * grp + q);
+            const ext2 quo = ext_mul(numer, dinv);
+            sum = ext_add(ext_mul(sum, ext_make(a.apow[2 * k], a.apow[2 * k + 1])), quo);
         }
-        if (lane == 0) { a.values[2 * p] = sum.a; a.values[2 * p + 1] = sum.b; }
+        const uint64_t p = pg + q;
+        if ((lane & 3) == 0 && p < L) { a.values[2 * p] = sum.a; a.values[2 * p + 1] = sum.b; }
     }
 }
 

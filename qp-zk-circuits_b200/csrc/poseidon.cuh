@@ -345,24 +345,28 @@ __device__ __forceinline__ void poseidon_permute(uint64_t (&s)[12]) {
 // lanes must call it; lanes >= 12 carry don't-care values.  Constants: d_rc_flat[12*r + i] (31 rows, row 30 zero).
 __device__ uint64_t d_rc_flat[372];
 
-template <int I>
+// W = 32: one permutation per warp.  W = 16: TWO independent permutations per warp, one per half-warp (shuffles of
+// width 16; `lane` = index inside the half): twice the throughput per warp instruction for levels / leaf sets that are
+// wide enough to be throughput bound, the same latency per permutation.
+template <int I, int W>
 struct WarpMds {
     static __device__ __forceinline__ void run(uint64_t& lo, uint64_t& hi, uint32_t l, uint32_t h, int lane) {
         constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
         int src = lane + I;
         if (src >= 12) src -= 12;
-        const uint32_t vl = __shfl_sync(0xffffffffu, l, src), vh = __shfl_sync(0xffffffffu, h, src);
+        const uint32_t vl = __shfl_sync(0xffffffffu, l, src, W), vh = __shfl_sync(0xffffffffu, h, src, W);
         lo += (uint64_t)vl * CIRC[I];
         hi += (uint64_t)vh * CIRC[I];
-        WarpMds<I + 1>::run(lo, hi, l, h, lane);
+        WarpMds<I + 1, W>::run(lo, hi, l, h, lane);
     }
 };
-template <>
-struct WarpMds<12> {
+template <int W>
+struct WarpMds<12, W> {
     static __device__ __forceinline__ void run(uint64_t&, uint64_t&, uint32_t, uint32_t, int) {}
 };
 
-__device__ __forceinline__ uint64_t poseidon_permute_warp(uint64_t s, int lane) {
+template <int W>
+__device__ __forceinline__ uint64_t poseidon_permute_sub(uint64_t s, int lane) {
     const int li = lane < 12 ? lane : 0;
     s = add_canon_p(s, d_rc_flat[li]);
 #pragma unroll 1
@@ -371,11 +375,12 @@ __device__ __forceinline__ uint64_t poseidon_permute_warp(uint64_t s, int lane) 
         const uint64_t rc = d_rc_flat[12 * (r + 1) + li];
         uint64_t lo = (uint32_t)rc, hi = rc >> 32;
         const uint32_t l = (uint32_t)s, h = (uint32_t)(s >> 32);
-        WarpMds<0>::run(lo, hi, l, h, lane);
+        WarpMds<0, W>::run(lo, hi, l, h, lane);
         if (lane == 0) { lo += 8ull * l; hi += 8ull * h; }
         s = mds_combine(lo, hi);
     }
     return s;
 }
+__device__ __forceinline__ uint64_t poseidon_permute_warp(uint64_t s, int lane) { return poseidon_permute_sub<32>(s, lane); }
 
 }  // namespace qpzk
