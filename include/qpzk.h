@@ -83,6 +83,8 @@ int qpzk_ctx_trim(qpzk_ctx* ctx);
 void* qpzk_pinned_alloc(size_t bytes);
 void qpzk_pinned_free(void* p);
 uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx);
+/* number of cudaMalloc calls the context's block cache has made since creation (does not grow in steady state) */
+uint64_t qpzk_ctx_device_allocs(const qpzk_ctx* ctx);
 
 /* ---- PolynomialBatch::from_values / from_coeffs --------------------------------------------------
  * Replaces qp-plonky2 `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing,

@@ -64,6 +64,7 @@ struct qpzk_ctx {
     cudaEvent_t ev[5] = {};
     bool ev_valid[5] = {};
     uint64_t launches = 0;
+    uint64_t device_allocs = 0;   // cudaMalloc calls of the block cache (0 in steady state)
     // The context stays alive until qpzk_ctx_destroy has been called AND every batch / challenger created
     // from it has been freed, whatever order a binding's finalizers run in.
     int refs = 1;
@@ -125,6 +126,7 @@ static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
         return 0;
     }
     void* q = nullptr;
+    ctx->device_allocs++;
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
@@ -223,6 +225,11 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     int count = 0;
     CK(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(QPZK_EINVAL, "no such CUDA device");
+    {   // QPZK_BLOCKING_SYNC=1: host threads sleep in cudaStreamSynchronize instead of spinning (many prover threads
+        // on few or quota-limited cores); must precede the creation of the device's primary context
+        const char* e = getenv("QPZK_BLOCKING_SYNC");
+        if (e && e[0] == '1') { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
+    }
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -291,6 +298,7 @@ extern "C" int qpzk_ctx_trim(qpzk_ctx* ctx) {
     return 0;
 }
 extern "C" uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx) { return ctx ? ctx->cached_bytes : 0; }
+extern "C" uint64_t qpzk_ctx_device_allocs(const qpzk_ctx* ctx) { return ctx ? ctx->device_allocs : 0; }
 
 static void mark(qpzk_ctx* ctx, int i) {
     if (ctx->timing) { cudaEventRecord(ctx->ev[i], ctx->stream); ctx->ev_valid[i] = true; }

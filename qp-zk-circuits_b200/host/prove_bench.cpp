@@ -51,6 +51,7 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
 };
 
 static bool g_pinned = true, g_breakdown = false, g_perm = false;
+static int g_stagger_us = 0;   // thread t starts t * g_stagger_us after the others (spreads the phases of concurrent provers)
 
 struct HostBuf {   // pinned (default) or pageable host buffer
     uint64_t* p = nullptr;
@@ -85,11 +86,13 @@ struct Shape { unsigned log_n = 13, constants_sigmas = 85, wires = 135, zs_pp = 
 
 struct Worker {
     int device;
+    int index = 0;
     Shape sh;
     int proofs;
     double seconds = 0;
     uint64_t checksum = 0;
-    uint64_t launches = 0;
+    uint64_t launches = 0, allocs = 0;
+    double max_proof_s = 0;
 
     void run(std::atomic<int>* ready, std::atomic<bool>* go) {
         const size_t n = (size_t)1 << sh.log_n;
@@ -121,13 +124,15 @@ struct Worker {
         const uint64_t digest[4] = {11, 12, 13, 14}, pih[4] = {21, 22, 23, 24};
         const uint64_t g = root_of_unity(sh.log_n);
 
-        double phase[8] = {0};
+        double phase[8] = {0}, phase_max[8] = {0};
         auto now = [] { return std::chrono::steady_clock::now(); };
         auto lap = [&](int k, std::chrono::steady_clock::time_point& t) {
             if (!g_breakdown) return;
             QCHECK(qpzk_ctx_synchronize(ctx));
             auto t1 = now();
-            phase[k] += std::chrono::duration<double>(t1 - t).count();
+            const double dt = std::chrono::duration<double>(t1 - t).count();
+            phase[k] += dt;
+            if (dt > phase_max[k]) phase_max[k] = dt;
             t = t1;
         };
         auto prove_one = [&](int s) {
@@ -179,16 +184,28 @@ struct Worker {
         };
         prove_one(0); prove_one(1);   // warm-up: tables, block cache
         for (double& x : phase) x = 0;
+        for (double& x : phase_max) x = 0;
         for (size_t i = 0; i < proof.size(); i++) checksum = (checksum ^ proof.p[i]) * 0x100000001B3ULL;
         QCHECK(qpzk_ctx_synchronize(ctx));
         ready->fetch_add(1);
         while (!go->load()) std::this_thread::yield();
-        const uint64_t l0 = qpzk_ctx_launch_count(ctx);
+        if (g_stagger_us) std::this_thread::sleep_for(std::chrono::microseconds((long)g_stagger_us * index));
+        const uint64_t l0 = qpzk_ctx_launch_count(ctx), a0 = qpzk_ctx_device_allocs(ctx);
         auto t0 = std::chrono::steady_clock::now();
-        for (int i = 0; i < proofs; i++) prove_one(i & 3);
+        for (int i = 0; i < proofs; i++) {
+            auto tp0 = std::chrono::steady_clock::now();
+            prove_one(i & 3);
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
+            if (dt > max_proof_s) max_proof_s = dt;
+        }
         QCHECK(qpzk_ctx_synchronize(ctx));
         seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         launches = qpzk_ctx_launch_count(ctx) - l0;
+        allocs = qpzk_ctx_device_allocs(ctx) - a0;
+        if (g_breakdown)
+            fprintf(stderr, "thread %d longest single phase (ms): wires %.1f | zs %.1f | quotient %.1f | openings %.1f | observe %.1f | fri %.1f | free %.1f\n",
+                    index, 1e3 * phase_max[0], 1e3 * phase_max[1], 1e3 * phase_max[2], 1e3 * phase_max[3], 1e3 * phase_max[4],
+                    1e3 * phase_max[5], 1e3 * phase_max[6]);
         if (g_breakdown)
             fprintf(stderr, "per proof (ms): wires commit+challenges %.3f | zs commit %.3f | quotient commit %.3f | openings %.3f | "
                             "observe openings %.3f | fri_prove %.3f | free %.3f\n",
@@ -213,6 +230,7 @@ int main(int argc, char** argv) {
         else if (k == "--pinned") g_pinned = v != 0;
         else if (k == "--breakdown") g_breakdown = v != 0;
         else if (k == "--perm") g_perm = v != 0;
+        else if (k == "--stagger-us") g_stagger_us = v;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);
@@ -220,7 +238,7 @@ int main(int argc, char** argv) {
     std::atomic<int> ready{0};
     std::atomic<bool> go{false};
     for (int t = 0; t < threads; t++) {
-        ws[t].device = device + t % devices; ws[t].sh = sh; ws[t].proofs = proofs;
+        ws[t].device = device + t % devices; ws[t].index = t; ws[t].sh = sh; ws[t].proofs = proofs;
         th.emplace_back([&, t] { ws[t].run(&ready, &go); });
     }
     while (ready.load() < threads) std::this_thread::yield();
@@ -228,15 +246,19 @@ int main(int argc, char** argv) {
     go.store(true);
     for (auto& t : th) t.join();
     (void)t0;
-    double lat = 0, wall = 0;   // wall = the slowest thread's proving loop (threads start together; teardown excluded)
+    double lat = 0, wall = 0, fastest = 1e30, maxp = 0;
+    uint64_t allocs = 0;   // wall = the slowest thread's proving loop (threads start together; teardown excluded)
     bool same = true;
     for (auto& w : ws) {
         lat += w.seconds / proofs; same = same && w.checksum == ws[0].checksum;
         if (w.seconds > wall) wall = w.seconds;
+        if (w.seconds < fastest) fastest = w.seconds;
+        if (w.max_proof_s > maxp) maxp = w.max_proof_s;
+        allocs += w.allocs;
     }
     printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
-           "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\"}\n",
+           "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\", \"slowest_thread_s\": %.4f, \"fastest_thread_s\": %.4f, \"max_proof_ms\": %.2f, \"device_allocs_in_loop\": %llu}\n",
            threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, threads * proofs / wall, 1e3 * lat / threads,
-           (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum);
+           (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum, wall, fastest, 1e3 * maxp, (unsigned long long)allocs);
     return same ? 0 : 3;
 }

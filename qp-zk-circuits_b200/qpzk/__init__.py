@@ -99,6 +99,7 @@ def load_library():
         "qpzk_poseidon_permute": (i, [vp, vp, u64, vp]),
         "qpzk_selftest_mds_layer": (i, [vp, vp, u64, u32, vp]),
         "qpzk_ctx_cached_bytes": (u64, [vp]),
+        "qpzk_ctx_device_allocs": (u64, [vp]),
         "qpzk_commit_from_values": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_coeffs": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_values_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
@@ -194,6 +195,9 @@ class Context:
     def trim(self):
         """Return the cached device blocks to the driver."""
         _check(self.L.qpzk_ctx_trim(self.h))
+
+    def device_allocs(self):
+        return int(self.L.qpzk_ctx_device_allocs(self.h))
 
     def cached_bytes(self):
         return int(self.L.qpzk_ctx_cached_bytes(self.h))

@@ -67,6 +67,7 @@ extern "C" {
     pub fn qpzk_pinned_free(p: *mut c_void);
     pub fn qpzk_poseidon_permute(ctx: *mut qpzk_ctx, states: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn qpzk_ctx_cached_bytes(ctx: *const qpzk_ctx) -> u64;
+    pub fn qpzk_ctx_device_allocs(ctx: *const qpzk_ctx) -> u64;
     pub fn qpzk_commit_from_values(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
                                    cap_height: u32, salt: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_commit_from_coeffs(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
