@@ -204,7 +204,7 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
             "what": "a16: qpzk_partial_products_dev; a17: qpzk_commit_quotient minus the time of its 16-column commit"}
 
 
-def native_prove_bench(device, threads, proofs=32, perm=0):
+def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1):
     """The same synthetic prove driven from native code (qp-zk-circuits_b200/host/prove_bench.cpp: C++ threads on the
     C ABI, one context per thread, pinned host buffers).  Returns the parsed JSON line or None."""
     exe = os.path.join(ROOT, "qp-zk-circuits_b200", "prove_bench")
@@ -213,7 +213,8 @@ def native_prove_bench(device, threads, proofs=32, perm=0):
     try:
         runs = []
         for _ in range(3 if threads > 1 else 1):   # multi-threaded throughput varies from run to run: report the median
-            r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm)],
+            r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm),
+                                "--zeroize", str(zeroize)],
                                capture_output=True, text=True, timeout=300)
             runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
         runs.sort(key=lambda d: d["proofs_per_s"])
@@ -313,6 +314,7 @@ def main():
         native[tmax] = native_prove_bench(local_rank, tmax, 64)
         native["perm1"] = native_prove_bench(local_rank, 1, 64, perm=1)
         native["perm%d" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1)
+        native["perm%d_deferred" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1, zeroize=2)
         native["tmax"] = tmax
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -446,7 +448,7 @@ def main():
     # ---- independent proofs, one prover per GPU (BASELINE configs 4/5: replicas, no data-path collective) ----
     native_all = None
     if world > 1 and not args.no_prove:
-        r = native.get(native.get("tmax"))
+        r = native.get("perm%d_deferred" % native.get("tmax", 0))
         v = torch.tensor([r["proofs_per_s"] if r else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(v)
         native_all = float(v.item())
@@ -482,7 +484,7 @@ def main():
                      "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": measured_traffic(log_n, world),
                      "traffic_unit": "DRAM bytes read+written per launch (ncu --set full, profiles/r1_traffic.json)",
                      "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src + " (of measured)",
-                     "pipes": "ncu: issue slots 73% busy, ALU pipe 80% of peak, FMA-heavy pipe ~79% (profiles/r1_summary.md C)",
+                     "pipes": "ncu: issue slots 71% busy, ALU pipe 80% of peak (profiles/r1_summary.md F)",
                      "note": "integer-pipe bound, not HBM bound: see int_pipe; HBM fraction reported because the contract asks for it"},
         "roofline_lde": {"kernels": "ntt_pass_kernel (iNTT) + ntt_fwd_kernel x2 + lde_last32_tma_kernel", "bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": lde_gbs / hbm_peak if lde_gbs else None, "bytes": lde_bytes},
@@ -502,7 +504,8 @@ def main():
                                           "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
                                           "restatement (tests/test_gpu_parity.py); witness generation and quotient evaluation are not part of it"}
         if native_all is not None:
-            out["prove_synthetic"]["proofs_per_s_all_gpus"] = native_all   # min(4, cores/N) host threads per GPU, every rank at once
+            # min(4, cores/N) host threads per GPU, every rank at once; permutation argument on the device, deferred zeroize
+            out["prove_synthetic"]["proofs_per_s_all_gpus"] = native_all
         n1, n4 = native.get(1), native.get(native.get("tmax"))
         if n1 and n4:
             out["prove_synthetic"]["native"] = {
@@ -514,8 +517,17 @@ def main():
             out["prove_synthetic"]["native_with_permutation_argument"] = {
                 "latency_ms_1_thread": p1["latency_ms"], "proofs_per_s_1_thread": p1["proofs_per_s"],
                 "proofs_per_s_%d_threads" % native["tmax"]: p4["proofs_per_s"], "gpu_launches_per_proof": p1["launches_per_proof"],
+                "proofs_per_s_%d_threads_runs" % native["tmax"]: p4.get("proofs_per_s_runs"),
                 "what": "as above, but the zs/partial-product columns and the quotient chunks are computed on the device from the "
                         "routed wires, the circuit's sigmas and the transcript's challenges (rows a16/a17, permutation argument only)"}
+            pd = native.get("perm%d_deferred" % native["tmax"])
+            if pd:
+                out["prove_synthetic"]["native_with_permutation_argument"].update({
+                    "proofs_per_s_%d_threads_deferred_zeroize" % native["tmax"]: pd["proofs_per_s"],
+                    "proofs_per_s_%d_threads_deferred_zeroize_runs" % native["tmax"]: pd.get("proofs_per_s_runs"),
+                    "zeroize_note": "default: secret-derived buffers are zeroed when released; with several provers on one GPU those "
+                                    "fills trigger stalls of 0.2-2 s in about half of the runs (median of 3 reported); "
+                                    "qpzk_ctx_set_zeroize(ctx, 2) zeroes them before they leave the context's block cache instead"})
         if not args.no_cpu_baseline:
             cms, cores = cpu_prove_synthetic()
             out["prove_synthetic"]["cpu_port_latency_ms"] = cms

@@ -60,9 +60,14 @@ int qpzk_ctx_create(int device, qpzk_ctx** out);
 int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx** out);
 void qpzk_ctx_destroy(qpzk_ctx* ctx);
 int qpzk_ctx_synchronize(qpzk_ctx* ctx);
-/* Zero wire/LDE buffers before they are released (secret hygiene, reference
- * wormhole/circuit/src/sensitive.rs:1-16).  Default: on. */
-int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on);
+/* Zero wire/LDE buffers that held secret-derived data (secret hygiene, reference wormhole/circuit/src/sensitive.rs:1-16).
+ *   1 (default)  when the buffer is released (qpzk_batch_free, end of a call)
+ *   2            deferred: released buffers stay in the context's private block cache as they are and are zeroed before
+ *                they are returned to the driver (qpzk_ctx_trim, qpzk_ctx_destroy, switching the mode back).  For several
+ *                prover contexts on one device: the zero fills at release were measured to trigger stalls of 0.2-2 s in
+ *                about half of the runs of 4 concurrent provers, none without them.
+ *   0            never */
+int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int mode);
 /* Stage timing with CUDA events on the context stream.  After a commit:
  *   ms[0]=iNTT  ms[1]=LDE passes  ms[2]=leaf hashing  ms[3]=Merkle levels  (0 when a stage did not run) */
 /* Batches created by from_values keep their input VALUES (on the subgroup) on the device as well -- what the

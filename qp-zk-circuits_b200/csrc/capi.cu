@@ -55,7 +55,8 @@ struct qpzk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int num_sms = 0;
-    bool zeroize = true;
+    int zeroize = 1;           // 0 off, 1 at release, 2 deferred until the block leaves the library (qpzk_ctx_set_zeroize)
+    std::map<void*, bool> dirty;   // mode 2: cached blocks that held secrets and have not been zeroed yet
     bool legacy_ntt = false;   // QPZK_LEGACY_NTT=1: generic strided passes only (A/B testing of ntt_fwd.cu)
     bool timing = false;
     bool keep_values = false;  // from_values batches keep their input values on the device (qpzk_ctx_set_keep_values)
@@ -107,8 +108,30 @@ static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++;
 // the cache is released once and the request retried.  (cudaMallocAsync was measured to stall the host for
 // 0.1-3 s per commit when commits are issued back to back: its pool cannot reuse blocks whose frees are still
 // pending and keeps mapping new memory instead.)
+// zero `words` words of a block that held secret-derived data: now (mode 1) or before the block leaves the library (2)
+static void scrub(qpzk_ctx* ctx, void* p, uint64_t words) {
+    if (!p || !words || !ctx->zeroize) return;
+    if (ctx->zeroize == 1) launch_fill_words(p, words, 0, ctx->stream);
+    else ctx->dirty[p] = true;
+}
+// mode 2: zero every dirty block that is about to be returned to the driver (whole block: the cache does not track
+// which part the last owner used)
+static void scrub_dirty(qpzk_ctx* ctx, bool only_cached) {
+    for (auto it = ctx->dirty.begin(); it != ctx->dirty.end();) {
+        auto bb = ctx->block_bytes.find(it->first);
+        bool cached = false;
+        if (only_cached) for (auto& kv : ctx->cache) if (kv.second == it->first) { cached = true; break; }
+        if (bb != ctx->block_bytes.end() && (!only_cached || cached)) {
+            launch_fill_words(it->first, bb->second / sizeof(uint64_t), 0, ctx->stream);
+            it = ctx->dirty.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
 static void cache_trim(qpzk_ctx* ctx) {
     if (ctx->cache.empty()) return;
+    scrub_dirty(ctx, true);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->cache) { cudaFree(kv.second); ctx->block_bytes.erase(kv.second); }
     ctx->cache.clear();
@@ -140,7 +163,7 @@ static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
 }
 static void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words = 0) {
     if (!p) return;
-    if (zero_words && ctx->zeroize) cudaMemsetAsync(p, 0, zero_words * sizeof(uint64_t), ctx->stream);
+    scrub(ctx, p, zero_words);
     auto it = ctx->block_bytes.find(p);
     if (it == ctx->block_bytes.end()) { cudaFree(p); return; }  // not ours (cannot happen)
     ctx->cache.emplace(it->second, p);
@@ -228,7 +251,11 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     {   // QPZK_BLOCKING_SYNC=1: host threads sleep in cudaStreamSynchronize instead of spinning (many prover threads
         // on few or quota-limited cores); must precede the creation of the device's primary context
         const char* e = getenv("QPZK_BLOCKING_SYNC");
-        if (e && e[0] == '1') { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
+        const char* l = getenv("QPZK_LMEM_MAX");
+        unsigned flags = 0;
+        if (e && e[0] == '1') flags |= cudaDeviceScheduleBlockingSync;
+        if (l && l[0] == '1') flags |= cudaDeviceLmemResizeToMax;
+        if (flags) { cudaSetDeviceFlags(flags); cudaGetLastError(); }
     }
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -238,6 +265,7 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("QPZK_LEGACY_NTT"); ctx->legacy_ntt = e && e[0] == '1'; }
+    { const char* e = getenv("QPZK_ZEROIZE"); if (e && e[0] >= '0' && e[0] <= '2') ctx->zeroize = e[0] - '0'; }   // dev aid; qpzk_ctx_set_zeroize is the API
     if (own) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
@@ -261,6 +289,7 @@ extern "C" int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx
 static void ctx_unref(qpzk_ctx* ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
+    scrub_dirty(ctx, false);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->block_bytes) cudaFree(kv.first);   // cached blocks (every live handle has been freed by now)
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
@@ -279,7 +308,13 @@ extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
-extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->zeroize = on != 0; return 0; }
+extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int mode) {
+    if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
+    if (mode < 0 || mode > 2) return fail(QPZK_EINVAL, "zeroize mode must be 0, 1 or 2");
+    if (ctx->zeroize == 2 && mode != 2) { cudaSetDevice(ctx->device); scrub_dirty(ctx, false); }   // nothing stays deferred
+    ctx->zeroize = mode;
+    return 0;
+}
 extern "C" int qpzk_ctx_set_keep_values(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->keep_values = on != 0; return 0; }
 extern "C" int qpzk_ctx_set_timing(qpzk_ctx* ctx, int on) { if (!ctx) return fail(QPZK_EINVAL, "ctx is null"); ctx->timing = on != 0; return 0; }
 extern "C" uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -910,7 +945,8 @@ extern "C" int qpzk_challenger_create(qpzk_ctx* ctx, qpzk_challenger** out) {
     ch->scratch_words = 4096;
     ch->dev = reinterpret_cast<ChallengerDev*>(dev);
     ch->scratch = scratch;
-    CK(cudaMemsetAsync(ch->dev, 0, sizeof(ChallengerDev), ctx->stream));
+    static_assert(sizeof(ChallengerDev) % 8 == 0, "challenger state is a whole number of words");
+    CK(launch_fill_words(ch->dev, sizeof(ChallengerDev) / 8, 0, ctx->stream));
     *out = ch;
     return 0;
     GUARD_END
@@ -1265,14 +1301,10 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
     CK(launch_partial_products(a, ctx->stream));
     ctx->launches += 3;
     if (host) CK(cudaMemcpyAsync(out, d_out, out_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->zeroize) {   // everything here is a function of the (secret) wires
-        CK(cudaMemsetAsync(d_chunk, 0, out_words * sizeof(uint64_t), ctx->stream));
-        CK(cudaMemsetAsync(d_row, 0, (uint64_t)num_challenges * n * sizeof(uint64_t), ctx->stream));
-        if (host) {
-            CK(cudaMemsetAsync(d_w, 0, in_words * sizeof(uint64_t), ctx->stream));
-            CK(cudaMemsetAsync(d_out, 0, out_words * sizeof(uint64_t), ctx->stream));
-        }
-    }
+    // everything here is a function of the (secret) wires
+    scrub(ctx, d_chunk, out_words);
+    scrub(ctx, d_row, (uint64_t)num_challenges * n);
+    if (host) { scrub(ctx, d_w, in_words); scrub(ctx, d_out, out_words); }
     // host variant: the caller's buffers are released on return.  (`par` is pageable: its copy was staged by the
     // driver before cudaMemcpyAsync returned, so the device variant need not wait.)
     if (host) CK(cudaStreamSynchronize(ctx->stream));
@@ -1422,7 +1454,7 @@ static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* 
     if ((e = launch_coset_unshift(d_coeffs, log_q, num_challenges, un.lo, un.hi, ctx->stream)) != cudaSuccess)
         return bail(e, "coset_unshift_kernel");
     ctx->launches++;
-    if (ctx->zeroize) cudaMemsetAsync(d_vals, 0, (uint64_t)num_challenges * Lq * sizeof(uint64_t), ctx->stream);
+    scrub(ctx, d_vals, (uint64_t)num_challenges * Lq);
     // `par` is pageable host memory: the copy above was staged by the driver before cudaMemcpyAsync returned
     *coeffs_out = d_coeffs;
     *qbits_out = qbits;

@@ -399,7 +399,7 @@ cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witn
                        unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices, uint32_t* status,
                        cudaStream_t st) {
     if (forced_witness == ~0ULL) {
-        cudaError_t e = cudaMemsetAsync(found_dev, 0xFF, sizeof(unsigned long long), st);
+        cudaError_t e = launch_fill_words(found_dev, 1, ~0ULL, st);
         if (e != cudaSuccess) return e;
         uint64_t blocks = (window_count + HASH_THREADS - 1) / HASH_THREADS;
         pow_grind_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(c, pow_bits, window_base, window_count, found_dev);

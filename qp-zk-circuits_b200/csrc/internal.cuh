@@ -77,6 +77,7 @@ constexpr int LDE_LAST32_MAX_THREADS = 384;
 bool lde_last32_supported(const LdeLastArgs& a);                       // ntt_fwd.cu: 32-point in-register last pass
 cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms);
 cudaError_t launch_lde_last(const LdeLastArgs& a, cudaStream_t st);
+cudaError_t launch_fill_words(void* p, uint64_t words, uint64_t value, cudaStream_t st);   // replaces cudaMemsetAsync
 cudaError_t launch_bitrev_copy(const uint64_t* in, uint64_t* out, uint32_t log_n, uint64_t num_arrays,
                                uint64_t in_stride, uint64_t out_stride, cudaStream_t st);
 cudaError_t launch_salt_scatter(const uint64_t* salt, uint64_t* leaves, uint32_t log_L, uint32_t num_cols,

@@ -16,6 +16,7 @@
 //           leaves [j*n, (j+1)*n).  The LAST pass holds ALL columns of 2^s consecutive
 //           rows in shared memory and writes whole rows, so the transpose and the bit reversal cost no
 //           extra pass and every store is a full contiguous row range.
+#include <cstdlib>
 #include "internal.cuh"
 #include "goldilocks.cuh"
 #include "ntt_local.cuh"
@@ -218,6 +219,33 @@ cudaError_t launch_salt_scatter(const uint64_t* salt, uint64_t* leaves, uint32_t
     uint64_t L = 1ull << log_L;
     salt_scatter_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(salt, leaves, log_L, num_cols, leaf_width,
                                                                     salt_cols);
+    return cudaGetLastError();
+}
+
+// Fill `words` 64-bit words with `value`.  Used instead of cudaMemsetAsync everywhere: with several prover contexts
+// (streams) active on one device, cudaMemsetAsync calls stalled EVERY stream for 0.2-2 s at random (about one run of
+// 64 proofs x 4 threads in three; none in any run with the memsets removed or with a single hardware work queue) --
+// a plain kernel on the context's stream has no such side effect.
+__global__ void __launch_bounds__(256) fill_words_kernel(uint64_t* __restrict__ p, uint64_t words, uint64_t value) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {          // 16-byte stores for the bulk
+        ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+        const uint64_t pairs = words >> 1;
+        for (uint64_t k = i; k < pairs; k += stride) q[k] = make_ulonglong2(value, value);
+        if (i == 0 && (words & 1)) p[words - 1] = value;
+    } else {
+        for (; i < words; i += stride) p[i] = value;
+    }
+}
+
+cudaError_t launch_fill_words(void* p, uint64_t words, uint64_t value, cudaStream_t st) {
+    if (!words) return cudaSuccess;
+    uint64_t blocks = (words / 2 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    static const uint64_t cap = [] { const char* e = getenv("QPZK_FILL_BLOCKS"); return (uint64_t)(e ? atoi(e) : 148 * 8); }();
+    if (blocks > cap) blocks = cap;
+    fill_words_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<uint64_t*>(p), words, value);
     return cudaGetLastError();
 }
 

@@ -338,8 +338,9 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
     }
     // chunks per block: enough (column, chunk) items for ~256 threads, within ~96 KB of shared memory
     uint32_t log_ch = 0;
+    static const size_t smem_cap = [] { const char* e = getenv("QPZK_LAST32_SMEM_KB"); return (size_t)(e ? atoi(e) : 96) * 1024; }();
     while (log_ch < 5 && ((uint64_t)a.num_cols << log_ch) < 224 && a.log_n > 5 + log_ch &&
-           (size_t)a.num_cols * ((64u << log_ch) + 1) * 8 <= 96 * 1024) log_ch++;
+           (size_t)a.num_cols * ((64u << log_ch) + 1) * 8 <= smem_cap) log_ch++;
     const uint32_t items = a.num_cols << log_ch;
     uint32_t threads = (items + 31) / 32 * 32;
     if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;

@@ -7,7 +7,7 @@
 // aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
-//   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1]
+//   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1] [--zeroize 0|1|2]
 // --devices G: one process drives G GPUs, thread t on device D + (t mod G) -- the aggregator's dispatch (independent leaf
 // proofs, one context per worker thread and device, no collective; reference wormhole/aggregator/src/aggregator.rs:187-227).
 // --perm 1: the zs/partial-products columns and the quotient chunks are not random stand-ins but computed on the device
@@ -51,6 +51,7 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
 };
 
 static bool g_pinned = true, g_breakdown = false, g_perm = false;
+static int g_zeroize = 1;      // qpzk_ctx_set_zeroize mode
 static int g_stagger_us = 0;   // thread t starts t * g_stagger_us after the others (spreads the phases of concurrent provers)
 
 struct HostBuf {   // pinned (default) or pageable host buffer
@@ -98,6 +99,7 @@ struct Worker {
         const size_t n = (size_t)1 << sh.log_n;
         qpzk_ctx* ctx;
         QCHECK(qpzk_ctx_create(device, &ctx));
+        QCHECK(qpzk_ctx_set_zeroize(ctx, g_zeroize));
         // what CircuitBuilder::build leaves behind: the committed constants/sigmas oracle
         auto cs = random_columns(1, sh.constants_sigmas, n);
         qpzk_batch* cs_b;
@@ -231,6 +233,7 @@ int main(int argc, char** argv) {
         else if (k == "--breakdown") g_breakdown = v != 0;
         else if (k == "--perm") g_perm = v != 0;
         else if (k == "--stagger-us") g_stagger_us = v;
+        else if (k == "--zeroize") g_zeroize = v;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);
@@ -256,9 +259,9 @@ int main(int argc, char** argv) {
         if (w.max_proof_s > maxp) maxp = w.max_proof_s;
         allocs += w.allocs;
     }
-    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"zeroize\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\", \"slowest_thread_s\": %.4f, \"fastest_thread_s\": %.4f, \"max_proof_ms\": %.2f, \"device_allocs_in_loop\": %llu}\n",
-           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, threads * proofs / wall, 1e3 * lat / threads,
+           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, g_zeroize, threads * proofs / wall, 1e3 * lat / threads,
            (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum, wall, fastest, 1e3 * maxp, (unsigned long long)allocs);
     return same ? 0 : 3;
 }

@@ -174,8 +174,9 @@ class Context:
     def synchronize(self):
         _check(self.L.qpzk_ctx_synchronize(self.h))
 
-    def set_zeroize(self, on):
-        _check(self.L.qpzk_ctx_set_zeroize(self.h, int(on)))
+    def set_zeroize(self, mode):
+        """0 never, 1 (default) when a buffer is released, 2 deferred until the block leaves the library (trim / destroy)."""
+        _check(self.L.qpzk_ctx_set_zeroize(self.h, int(mode)))
 
     def set_keep_values(self, on):
         """from_values batches also keep their input values on the device (needed by commit_zs_partial_products)."""

@@ -572,3 +572,44 @@ def test_gateless_plonk_proof_end_to_end(ctx, qpzk, orc):
     bg, alphas, zeta = got_bad["challenges"]
     assert not verify_gateless_openings(log_n, got_bad["openings"], num_consts, R, shape["wires"], 2, 8, bg[:2], bg[2:],
                                         alphas, zeta)
+
+
+# ---- secret hygiene: zeroize modes ----------------------------------------------------------------------------------
+def _peek(dev_ptr, words):
+    from cuda import cudart
+    out = np.zeros(words, np.uint64)
+    err, = cudart.cudaMemcpy(out.ctypes.data, dev_ptr, 8 * words, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0
+    return out
+
+
+def test_zeroize_modes(qpzk):
+    """Mode 1 zeroes the LDE / coefficient buffers when the batch is freed; mode 2 leaves them in the context's private
+    block cache and zeroes them before they go back to the driver (here: when the mode is switched back)."""
+    c = qpzk.Context(0)
+    cols = np.random.default_rng(3).integers(1, P, size=(5, 64), dtype=np.uint64)
+    b = qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2)
+    leaves, coeffs = c.L.qpzk_batch_leaves_dev(b.h), c.L.qpzk_batch_coeffs_dev(b.h)
+    assert _peek(leaves, 5 * 512).any() and _peek(coeffs, 5 * 64).any()
+    b.free()
+    c.synchronize()
+    assert not _peek(leaves, 5 * 512).any() and not _peek(coeffs, 5 * 64).any()      # mode 1 (default): zero at release
+    c.set_zeroize(2)
+    b = qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2)
+    cap = b.cap.copy()
+    leaves = c.L.qpzk_batch_leaves_dev(b.h)
+    b.free()
+    c.synchronize()
+    assert _peek(leaves, 5 * 512).any()                                               # still in the private cache
+    b2 = qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2)                        # steady state: same block, same result
+    assert (b2.cap == cap).all()
+    b2.free()
+    c.set_zeroize(1)                                                                  # nothing stays deferred
+    c.synchronize()
+    assert not _peek(leaves, 5 * 512).any()
+    with pytest.raises(qpzk.QpzkError):
+        c.set_zeroize(3)
+    c.set_zeroize(2)
+    qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2).free()
+    c.trim()                                                                          # scrubbed, then returned to the driver
+    assert c.cached_bytes() == 0
