@@ -368,15 +368,34 @@ struct WarpMds<12, W> {
 template <int W>
 __device__ __forceinline__ uint64_t poseidon_permute_sub(uint64_t s, int lane) {
     const int li = lane < 12 ? lane : 0;
+    // coefficient of state word 0 in output word `lane`: circ[(12 - lane) mod 12], + the diagonal 8 for lane 0
+    constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t c0 = 25;
+#pragma unroll
+    for (int k = 1; k < 12; k++) if (li == k) c0 = CIRC[12 - k];
     s = add_canon_p(s, d_rc_flat[li]);
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
-        if (r < 4 || r >= 26 || lane == 0) s = sbox7_nc(s);
         const uint64_t rc = d_rc_flat[12 * (r + 1) + li];
         uint64_t lo = (uint32_t)rc, hi = rc >> 32;
-        const uint32_t l = (uint32_t)s, h = (uint32_t)(s >> 32);
-        WarpMds<0, W>::run(lo, hi, l, h, lane);
-        if (lane == 0) { lo += 8ull * l; hi += 8ull * h; }
+        if (r < 4 || r >= 26) {
+            s = sbox7_nc(s);
+            const uint32_t l = (uint32_t)s, h = (uint32_t)(s >> 32);
+            WarpMds<0, W>::run(lo, hi, l, h, lane);
+            if (lane == 0) { lo += 8ull * l; hi += 8ull * h; }
+        } else {
+            // Partial round: only word 0 passes through the S-box, so the eleven other terms of every output do not
+            // depend on it.  They are accumulated from the OLD words (lane 0 contributes zero) in the same basic block as
+            // the S-box: the scheduler fills the stalls of the S-box's dependent multiplication chain with the shuffles
+            // and multiply-adds of the linear layer, and only word 0's term is added afterwards.
+            const uint32_t l = lane == 0 ? 0u : (uint32_t)s, h = lane == 0 ? 0u : (uint32_t)(s >> 32);
+            WarpMds<0, W>::run(lo, hi, l, h, lane);
+            const uint64_t x0 = sbox7_nc(s);                       // meaningful on lane 0 only
+            const uint32_t x0l = __shfl_sync(0xffffffffu, (uint32_t)x0, 0, W);
+            const uint32_t x0h = __shfl_sync(0xffffffffu, (uint32_t)(x0 >> 32), 0, W);
+            lo += (uint64_t)x0l * c0;
+            hi += (uint64_t)x0h * c0;
+        }
         s = mds_combine(lo, hi);
     }
     return s;
