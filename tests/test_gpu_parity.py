@@ -613,3 +613,34 @@ def test_zeroize_modes(qpzk):
     qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2).free()
     c.trim()                                                                          # scrubbed, then returned to the driver
     assert c.cached_bytes() == 0
+
+
+def test_zs_partial_products_from_device_resident_batches(ctx, qpzk, orc):
+    """keep_values with DEVICE inputs (from_values_dev copies the values next to the batch): the partial products
+    computed from two such batches give the same commitment as the host path and as the oracle."""
+    import torch
+    from perm_util import satisfied_permutation
+    log_n, R, num_consts = 7, 12, 3
+    rng = np.random.default_rng(91)
+    routed, sigmas, _ = satisfied_permutation(log_n, R, seed=91)
+    wires = np.concatenate([routed, rng.integers(0, P, size=(4, 1 << log_n), dtype=np.uint64)])
+    cs = np.concatenate([rng.integers(0, P, size=(num_consts, 1 << log_n), dtype=np.uint64), sigmas])
+    betas, gammas = rng.integers(0, P, size=2, dtype=np.uint64), rng.integers(0, P, size=2, dtype=np.uint64)
+    dw = torch.from_numpy(wires.view(np.int64)).cuda()
+    dc = torch.from_numpy(cs.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ctx.set_keep_values(True)
+    try:
+        wb = qpzk.PolynomialBatch.from_device(ctx, dw.data_ptr(), log_n, wires.shape[0], 3, 2)
+        cb = qpzk.PolynomialBatch.from_device(ctx, dc.data_ptr(), log_n, cs.shape[0], 3, 2)
+    finally:
+        ctx.set_keep_values(False)
+    assert ctx.L.qpzk_batch_values_dev(wb.h) and ctx.L.qpzk_batch_values_dev(wb.h) != dw.data_ptr()
+    zb = qpzk.PolynomialBatch.commit_zs_partial_products(cb, wb, num_consts, R, betas, gammas, 2)
+    want = orc.partial_products(routed, sigmas, betas, gammas, 8)
+    assert (zb.cap == orc.PolynomialBatch.from_values(want, 3, 2).cap()).all()
+    assert (zb.polynomials == orc.PolynomialBatch.from_values(want, 3, 2).coeffs()).all()
+    plain = qpzk.PolynomialBatch.from_values(ctx, wires, 3, None, 2)       # without the flag a batch holds no values ...
+    assert not ctx.L.qpzk_batch_values_dev(plain.h)
+    with pytest.raises(qpzk.QpzkError):                                    # ... and cannot feed the permutation argument
+        qpzk.PolynomialBatch.commit_zs_partial_products(cb, plain, num_consts, R, betas, gammas, 2)
