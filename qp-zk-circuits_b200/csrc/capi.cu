@@ -547,6 +547,11 @@ struct ColumnSource {
 
 static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uint32_t c0, uint32_t c1) {
     if (!src.host || c1 <= c0) return 0;
+    if (src.chunks <= 1) {   // one piece: nothing to overlap, so no second stream and no cross-stream waits
+        CK(cudaMemcpyAsync(src.staging + (uint64_t)c0 * n, src.host + (uint64_t)c0 * n, (uint64_t)(c1 - c0) * n * sizeof(uint64_t),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    }
     CK(cudaMemcpyAsync(src.staging + (uint64_t)c0 * n, src.host + (uint64_t)c0 * n, (uint64_t)(c1 - c0) * n * sizeof(uint64_t),
                        cudaMemcpyHostToDevice, ctx->copy_stream));
     CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
@@ -594,8 +599,11 @@ static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32
         } else {
             src.staging = b->coeffs;
         }
-        cudaError_t e = cudaEventRecord(ctx->copy_done, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0);
+        cudaError_t e = cudaSuccess;
+        if (src.chunks > 1) {
+            e = cudaEventRecord(ctx->copy_done, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0);
+        }
         if (e != cudaSuccess) { if (from_values) dev_free(ctx, src.staging); batch_release(b); CK(e); }
     }
     const uint64_t* in_dev = src.host ? src.staging : src.dev;
