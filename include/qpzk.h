@@ -280,6 +280,34 @@ int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, cons
                          const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
                          uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out);
 
+/* Gate constraints handed over as DATA: a straight-line register program over the base field that computes, for one
+ * point, what upstream's `evaluate_gate_constraints` / `eval_unfiltered_base_batch` (plonk/vanishing_poly.rs, gates/*.rs)
+ * computes -- selector filters included.  The fork obtains it by running its gates' constraint code once over a
+ * recording field type; the gate set itself stays in its crate.  The library interprets the program on the device at
+ * every point of the quotient domain and feeds the emitted terms to the alpha combination after the permutation terms.
+ *   code : num_ops x 4 words {op, dst, a, b}
+ *          0 LOAD_WIRE  r[dst] = wires column a          3 ADD r[dst] = r[a] + r[b]     6 EMIT constraint term = r[a]
+ *          1 LOAD_CONST r[dst] = constants_sigmas col a  4 SUB r[dst] = r[a] - r[b]
+ *          2 LOAD_IMM   r[dst] = imm[a]                  5 MUL r[dst] = r[a] * r[b]
+ *   registers 0..num_regs-1 (num_regs <= 64); a register must be written before it is read (checked). */
+typedef struct {
+    const uint32_t* code;
+    uint32_t num_ops;
+    const uint64_t* imm;   /* canonical */
+    uint32_t num_imm;
+    uint32_t num_regs;
+} qpzk_gate_program;
+/* qpzk_quotient_polys / qpzk_commit_quotient with the gate terms computed from `prog` (NULL = no gates). */
+int qpzk_quotient_polys_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                             const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                             uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                             const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog, uint64_t* out);
+int qpzk_commit_quotient_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                              const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                              uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                              const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog,
+                              uint32_t cap_height, qpzk_batch** out);
+
 /* ---- wire format: ProofWithPublicInputs::to_bytes / from_bytes ----------------------------------------
  * Replaces qp-plonky2 `util/serialization`: `write_proof_with_public_inputs` / `read_proof_with_public_inputs`
  * (what the reference passes between prover, aggregator and verifier:

@@ -519,6 +519,43 @@ int orc_quotient_polys(const orc_batch* cs, const orc_batch* wires, const orc_ba
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Gate constraints as a straight-line program (the data format of qpzk_gate_program, include/qpzk.h): evaluates the
+ * program at every point of the quotient domain from the LDE rows of the constants/sigmas and wires batches.
+ * out: [n Q][num_terms], row = leaf index of the quotient domain.  Returns the number of emitted terms, < 0 on a bad
+ * program.  (Test infrastructure like the rest of this file: restates the interpreter of quotient.cu in plain C.)
+ * ------------------------------------------------------------------------------------------ */
+int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, const uint32_t* code, unsigned num_ops,
+                   const uint64_t* imm, uint64_t* out) {
+    unsigned qbits = 0, emits = 0;
+    while ((1u << qbits) < chunk) qbits++;
+    for (unsigned pc = 0; pc < num_ops; pc++) if (code[4 * pc] == 6) emits++; else if (code[4 * pc] > 6 || code[4 * pc + 1] >= 64) return -1;
+    if (!out) return (int)emits;
+    const unsigned log_n = wires->log_n, log_L = log_n + wires->rate_bits, log_q = log_n + qbits;
+    const size_t Lq = (size_t)1 << log_q, step = (size_t)1 << (wires->rate_bits - qbits);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < Lq; i++) {
+        const size_t row = bitrev(i * step, log_L), leaf_q = bitrev(i, log_q);
+        const uint64_t* lw = orc_merkle_leaf(wires->tree, row);
+        const uint64_t* lc = orc_merkle_leaf(cs->tree, row);
+        uint64_t r[64] = {0};
+        unsigned e = 0;
+        for (unsigned pc = 0; pc < num_ops; pc++) {
+            const uint32_t op = code[4 * pc], d = code[4 * pc + 1], a = code[4 * pc + 2], b = code[4 * pc + 3];
+            switch (op) {
+                case 0: r[d] = lw[a]; break;
+                case 1: r[d] = lc[a]; break;
+                case 2: r[d] = imm[a]; break;
+                case 3: r[d] = gl_add(r[a], r[b]); break;
+                case 4: r[d] = gl_sub(r[a], r[b]); break;
+                case 5: r[d] = gl_mul(r[a], r[b]); break;
+                default: out[leaf_q * emits + e++] = r[a]; break;
+            }
+        }
+    }
+    return (int)emits;
+}
+
 void orc_challenger_init(orc_challenger* c) { memset(c, 0, sizeof *c); }
 
 static void duplexing(orc_challenger* c) {

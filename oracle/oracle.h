@@ -70,6 +70,10 @@ int orc_quotient_polys(const orc_batch* cs, const orc_batch* wires, const orc_ba
                        const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms,
                        unsigned num_gate_terms, uint64_t* out);
 
+/* gate constraints as a straight-line program (the format of qpzk_gate_program): [n Q][num_terms] gate-term matrix */
+int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, const uint32_t* code, unsigned num_ops,
+                   const uint64_t* imm, uint64_t* out);
+
 /* ---- Challenger ---- */
 typedef struct {
     uint64_t state[12];

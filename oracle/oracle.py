@@ -62,6 +62,8 @@ def lib():
         L.orc_quotient_polys.restype = C.c_int
         L.orc_quotient_polys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                          U64P, U64P, U64P, U64P, C.c_uint, U64P]
+        L.orc_gate_terms.restype = C.c_int
+        L.orc_gate_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, U32P, C.c_uint, U64P, U64P]
         for f in (L.orc_hash_no_pad, L.orc_hash_or_noop):
             f.restype = None; f.argtypes = [U64P, C.c_size_t, U64P]
         L.orc_two_to_one.restype = None; L.orc_two_to_one.argtypes = [U64P, U64P, U64P]
@@ -143,6 +145,20 @@ def quotient_polys(constants_sigmas, wires, zs_partial_products, sigma_col0, num
                                   _p64(gt) if gt is not None else None, G, _p64(out))
     assert rc == 0, rc
     return out
+
+
+def gate_terms(constants_sigmas, wires, code, imm, quotient_degree_factor=8):
+    """Interpret a gate program (qpzk_gate_program format: (num_ops, 4) uint32 code, uint64 immediates) at every point
+    of the quotient domain: (n*Q, num_terms) matrix, row = leaf index."""
+    code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
+    imm = _u64(imm if len(imm) else [0])
+    cp = code.ctypes.data_as(U32P)
+    nt = lib().orc_gate_terms(constants_sigmas.h, wires.h, quotient_degree_factor, cp, code.shape[0], _p64(imm), None)
+    assert nt >= 0, "bad gate program"
+    out = np.zeros(((quotient_degree_factor << wires.log_n), max(nt, 1)), np.uint64)
+    if nt:
+        lib().orc_gate_terms(constants_sigmas.h, wires.h, quotient_degree_factor, cp, code.shape[0], _p64(imm), _p64(out))
+    return out[:, :nt]
 
 
 def round_constants():
@@ -362,7 +378,7 @@ def num_threads():
 # ---- the commitment / opening half of prove() on the CPU (mirror of qpzk/prover.py) ----------------
 def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient_coeffs, public_inputs_hash,
                     log_n, num_zs=2, rate_bits=3, cap_height=4, pow_bits=16, num_queries=28, arity_bits=4,
-                    final_poly_bits=5, sigmas=None, quotient_degree_factor=8, sigma_col0=None):
+                    final_poly_bits=5, sigmas=None, quotient_degree_factor=8, sigma_col0=None, gate_program=None):
     """Same transcript and the same outputs as qpzk.prover.prove_synthetic, computed by the CPU restatement."""
     ch = Challenger()
     ch.observe(np.arange(4, dtype=np.uint64) + 11)
@@ -378,8 +394,11 @@ def prove_synthetic(constants_sigmas_batch, wires, zs_partial_products, quotient
     ch.observe(zs_b.cap())
     alphas = ch.get(num_zs)
     if quotient_coeffs is None:
+        gt = None
+        if gate_program is not None:      # (code, imm) in the format of qpzk_gate_program
+            gt = gate_terms(constants_sigmas_batch, wires_b, gate_program[0], gate_program[1], quotient_degree_factor)
         quotient_coeffs = quotient_polys(constants_sigmas_batch, wires_b, zs_b, sigma_col0, _u64(sigmas).shape[0],
-                                         betas_gammas[:num_zs], betas_gammas[num_zs:], alphas, quotient_degree_factor)
+                                         betas_gammas[:num_zs], betas_gammas[num_zs:], alphas, quotient_degree_factor, gt)
     quot_b = PolynomialBatch.from_coeffs(quotient_coeffs, rate_bits, cap_height)
     ch.observe(quot_b.cap())
     zeta = ch.get(2)

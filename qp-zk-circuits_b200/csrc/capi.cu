@@ -1471,6 +1471,89 @@ static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* 
     return 0;
 }
 
+// Validates a gate program and evaluates it at every quotient-domain point: *terms_out (device, [n Q][num_terms]) is
+// left to the caller (dev_free); *num_terms_out = number of EMITs.  prog == NULL: no gates, nothing allocated.
+static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk,
+                                   const qpzk_gate_program* prog, uint64_t** terms_out, uint32_t* num_terms_out) {
+    *terms_out = nullptr; *num_terms_out = 0;
+    if (!prog) return 0;
+    if (!ctx || !cs || !wires) return fail(QPZK_EINVAL, "null argument");
+    if (!prog->code || (!prog->imm && prog->num_imm)) return fail(QPZK_EINVAL, "gate program: null code / imm");
+    if (!prog->num_regs || prog->num_regs > GATE_MAX_REGS) return fail(QPZK_EINVAL, "gate program: num_regs must be in 1..64");
+    if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
+    if (ilog2(chunk) > wires->rate_bits || cs->log_n != wires->log_n || cs->rate_bits != wires->rate_bits)
+        return fail(QPZK_EINVAL, "batches must have the same degree and rate, quotient_degree_factor <= blowup");
+    std::vector<bool> written(prog->num_regs, false);
+    uint32_t emits = 0;
+    for (uint32_t pc = 0; pc < prog->num_ops; pc++) {
+        const uint32_t op = prog->code[4 * pc], dst = prog->code[4 * pc + 1], a = prog->code[4 * pc + 2], b = prog->code[4 * pc + 3];
+        auto bad = [&](const char* what) { return fail(QPZK_EINVAL, std::string("gate program, instruction ") + std::to_string(pc) + ": " + what); };
+        if (op > 6) return bad("unknown opcode");
+        if (op <= 5 && dst >= prog->num_regs) return bad("destination register out of range");
+        if (op == 0 && a >= wires->num_cols) return bad("wire column out of range");
+        if (op == 1 && a >= cs->num_cols) return bad("constants/sigmas column out of range");
+        if (op == 2 && a >= prog->num_imm) return bad("immediate out of range");
+        if (op >= 3 && op <= 5 && (a >= prog->num_regs || b >= prog->num_regs || !written[a] || !written[b])) return bad("source register out of range or not yet written");
+        if (op == 6 && (a >= prog->num_regs || !written[a])) return bad("emitted register out of range or not yet written");
+        if (op <= 5) written[dst] = true; else emits++;
+    }
+    for (uint32_t i = 0; i < prog->num_imm; i++) if (prog->imm[i] >= GL_P) return fail(QPZK_EINVAL, "gate program: immediate is not canonical");
+    if (!emits) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t points = (1ull << wires->log_n) * chunk;
+    DevBufs bufs(ctx);
+    uint64_t *d_code, *d_imm, *d_terms;
+    int rc;
+    if ((rc = bufs.alloc(&d_code, 2ull * prog->num_ops + 2))) return rc;          // 4 x u32 per instruction, 16-byte aligned
+    if ((rc = bufs.alloc(&d_imm, prog->num_imm ? prog->num_imm : 1))) return rc;
+    if ((rc = dev_alloc(ctx, &d_terms, points * emits))) return rc;
+    cudaError_t e = cudaMemcpyAsync(d_code, prog->code, 16ull * prog->num_ops, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && prog->num_imm)
+        e = cudaMemcpyAsync(d_imm, prog->imm, 8ull * prog->num_imm, cudaMemcpyHostToDevice, ctx->stream);
+    GateProgramArgs g{};
+    g.cs_leaves = cs->leaves; g.w_leaves = wires->leaves; g.cs_width = cs->leaf_width; g.w_width = wires->leaf_width;
+    g.code = reinterpret_cast<const uint32_t*>(d_code); g.imm = d_imm; g.num_ops = prog->num_ops; g.num_terms = emits;
+    g.num_points = points; g.terms = d_terms;
+    if (e == cudaSuccess) { e = launch_gate_program(g, ctx->stream); ctx->launches++; }
+    // the program came from caller memory: it must be on the device before the call returns (the scratch copies are
+    // released to the block cache, where stream order protects them until the kernel has run)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { dev_free(ctx, d_terms); CK(e); }
+    *terms_out = d_terms; *num_terms_out = emits;
+    return 0;
+}
+
+extern "C" int qpzk_quotient_polys_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                        const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                                        uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                                        const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog, uint64_t* out) {
+    GUARD_BEGIN
+    uint64_t* terms; uint32_t nt;
+    int rc = gate_terms_from_program(ctx, constants_sigmas, wires, quotient_degree_factor, prog, &terms, &nt);
+    if (rc) return rc;
+    rc = qpzk_quotient_polys(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
+                             num_challenges, betas, gammas, alphas, terms, nt, out);
+    if (terms) dev_free(ctx, terms, ((1ull << wires->log_n) * quotient_degree_factor) * nt);
+    return rc;
+    GUARD_END
+}
+extern "C" int qpzk_commit_quotient_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                         const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
+                                         uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
+                                         const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog,
+                                         uint32_t cap_height, qpzk_batch** out) {
+    GUARD_BEGIN
+    if (out) *out = nullptr;
+    uint64_t* terms; uint32_t nt;
+    int rc = gate_terms_from_program(ctx, constants_sigmas, wires, quotient_degree_factor, prog, &terms, &nt);
+    if (rc) return rc;
+    rc = qpzk_commit_quotient(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
+                              num_challenges, betas, gammas, alphas, terms, nt, cap_height, out);
+    if (terms) dev_free(ctx, terms, ((1ull << wires->log_n) * quotient_degree_factor) * nt);
+    return rc;
+    GUARD_END
+}
+
 extern "C" int qpzk_quotient_polys(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
                                    const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                                    uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,

@@ -113,6 +113,44 @@ __global__ void __launch_bounds__(256) coset_unshift_kernel(uint64_t* __restrict
     coeffs[t] = gl_mul(coeffs[t], tw_get(lo, hi, t & (len - 1)));
 }
 
+// ---- gate constraints as a straight-line program ---------------------------------------------------------------------
+// The gate set of a circuit lives in the prover's crate, not here; what this library can do is EVALUATE it on the device
+// when it is handed over as data: a register program over the base field (what upstream's `eval_unfiltered_base_batch`
+// computes per point, selector filters included) that the host side obtains by running its gates' constraint code over
+// a recording field type.  One thread per quotient-domain point interprets the program -- every thread executes the same
+// instruction, so there is no divergence; the register file sits in local memory -- and writes one row of the gate-term
+// matrix that quotient_perm_kernel consumes.
+//   op  dst a b      0 LOAD_WIRE  r[dst] = wires[a]            3 ADD  r[dst] = r[a] + r[b]      6 EMIT  term = r[a]
+//                    1 LOAD_CONST r[dst] = constants_sigmas[a] 4 SUB  r[dst] = r[a] - r[b]
+//                    2 LOAD_IMM   r[dst] = imm[a]              5 MUL  r[dst] = r[a] * r[b]
+__global__ void __launch_bounds__(QUOT_THREADS) gate_program_kernel(GateProgramArgs a) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.num_points) return;
+    const uint64_t* __restrict__ wrow = a.w_leaves + j * a.w_width;
+    const uint64_t* __restrict__ crow = a.cs_leaves + j * a.cs_width;
+    uint64_t* __restrict__ out = a.terms + j * a.num_terms;
+    uint64_t r[GATE_MAX_REGS];
+    uint32_t emitted = 0;
+    for (uint32_t pc = 0; pc < a.num_ops; pc++) {
+        const uint4 ins = __ldg(reinterpret_cast<const uint4*>(a.code) + pc);
+        switch (ins.x) {
+            case 0: r[ins.y] = __ldg(wrow + ins.z); break;
+            case 1: r[ins.y] = __ldg(crow + ins.z); break;
+            case 2: r[ins.y] = __ldg(a.imm + ins.z); break;
+            case 3: r[ins.y] = gl_add(r[ins.z], r[ins.w]); break;
+            case 4: r[ins.y] = gl_sub(r[ins.z], r[ins.w]); break;
+            case 5: r[ins.y] = gl_mul(r[ins.z], r[ins.w]); break;
+            default: out[emitted++] = r[ins.z]; break;
+        }
+    }
+}
+
+cudaError_t launch_gate_program(const GateProgramArgs& a, cudaStream_t st) {
+    if (!a.num_points) return cudaSuccess;
+    gate_program_kernel<<<(unsigned)((a.num_points + QUOT_THREADS - 1) / QUOT_THREADS), QUOT_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_quotient_perm(const QuotientArgs& a, cudaStream_t st) {
     const uint64_t Lq = 1ull << (a.log_n + a.qbits);
     const unsigned blocks = (unsigned)((Lq + QUOT_THREADS - 1) / QUOT_THREADS);

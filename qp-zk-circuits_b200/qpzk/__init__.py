@@ -60,6 +60,19 @@ class ProofShape(C.Structure):
                 ("num_quotient_polys", C.c_uint32), ("leaf_lens", C.c_uint32 * 4), ("num_public_inputs", C.c_uint32)]
 
 
+class GateProgram(C.Structure):
+    """qpzk_gate_program: gate constraints as a straight-line register program (see include/qpzk.h)."""
+    _fields_ = [("code", U32P), ("num_ops", C.c_uint32), ("imm", U64P), ("num_imm", C.c_uint32), ("num_regs", C.c_uint32)]
+
+    @classmethod
+    def make(cls, code, imm, num_regs):
+        code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
+        imm = np.ascontiguousarray(imm, dtype=np.uint64).reshape(-1)
+        g = cls(code.ctypes.data_as(U32P), code.shape[0], imm.ctypes.data_as(U64P) if imm.size else None, imm.size, num_regs)
+        g._keep = (code, imm)
+        return g
+
+
 class ChallengerState(C.Structure):
     _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8),
                 ("output_buffer", C.c_uint64 * 8), ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
@@ -137,6 +150,8 @@ def load_library():
         "qpzk_proof_bytes_len": (C.c_size_t, [C.POINTER(FriParams), C.POINTER(ProofShape)]),
         "qpzk_proof_to_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, vp, vp, vp, vp, vp, vp, C.c_size_t]),
         "qpzk_proof_from_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
+        "qpzk_quotient_polys_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), vp]),
+        "qpzk_commit_quotient_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), u32, C.POINTER(vp)]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -428,6 +443,28 @@ class PolynomialBatch:
                                               betas, gammas, alphas, gate_terms_dev, num_gate_terms)
         h = C.c_void_p()
         _check(wires.ctx.L.qpzk_commit_quotient(*head, quotient_degree_factor, *tail, cap_height, C.byref(h)))
+        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, False)
+
+    @classmethod
+    def quotient_polys_prog(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                            program, quotient_degree_factor=8):
+        """quotient_polys with the gate terms computed on the device from a GateProgram (None = no gates)."""
+        keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
+                                              betas, gammas, alphas, None, 0)
+        out = np.zeros((tail[0] * quotient_degree_factor, 1 << wires.degree_log), np.uint64)
+        _check(wires.ctx.L.qpzk_quotient_polys_prog(*head, quotient_degree_factor, *tail[:4],
+                                                    C.byref(program) if program is not None else None,
+                                                    out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @classmethod
+    def commit_quotient_prog(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
+                             program, cap_height, quotient_degree_factor=8):
+        keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
+                                              betas, gammas, alphas, None, 0)
+        h = C.c_void_p()
+        _check(wires.ctx.L.qpzk_commit_quotient_prog(*head, quotient_degree_factor, *tail[:4],
+                                                     C.byref(program) if program is not None else None, cap_height, C.byref(h)))
         return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, False)
 
     @property

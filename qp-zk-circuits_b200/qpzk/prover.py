@@ -17,7 +17,9 @@ routed wires and the betas/gammas drawn from the transcript (`Context.partial_pr
 is None the quotient chunks are computed and committed on the device from the three committed batches and the alphas
 (`PolynomialBatch.commit_quotient`; the circuit's sigma columns are then `SyntheticCircuit.sigma_col0 ...`).  With both,
 and wires that satisfy the copy constraints, the result is a complete PLONK proof of a circuit without gates: the
-vanishing identity holds on the opened values (tests/perm_util.py: verify_gateless_openings).  The constants/sigmas oracle is committed once per circuit
+vanishing identity holds on the opened values (tests/perm_util.py: verify_gateless_openings).  A circuit WITH gates hands
+its constraints over as a `GateProgram` (a straight-line register program, include/qpzk.h): they are then interpreted on
+the device at every quotient point, and the proof covers gates and copy constraints alike.  The constants/sigmas oracle is committed once per circuit
 (`CircuitBuilder::build`, reference wormhole/circuit/src/circuit.rs:206-216), not per proof.
 
 Shapes of the leaf circuit: degree 2^13, 85 constants+sigmas, 135 wires, 20 zs/partial
@@ -55,7 +57,7 @@ class SyntheticCircuit:
 
 
 def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public_inputs_hash, pow_witness=None,
-                    keep_batches=False, sigmas=None, quotient_degree_factor=8):
+                    keep_batches=False, sigmas=None, quotient_degree_factor=8, gate_program=None):
     """One proof's worth of commitments + FRI.  Inputs are host arrays (values / coefficients, column-major).
     zs_partial_products may be None when `sigmas` (num_routed x n sigma values) is given: the columns are then
     computed from wires[:num_routed] with the transcript's betas and gammas (upstream
@@ -86,9 +88,10 @@ def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public
     alphas = ch.get_n_challenges(nz)
     if quotient_coeffs is None:                                # permutation argument only (no gate terms)
         num_routed = np.asarray(sigmas).shape[0]
-        quot_b = PolynomialBatch.commit_quotient(circuit.constants_sigmas, wires_b, zs_b, circuit.sigma_col0, num_routed,
-                                                 betas_gammas[:nz], betas_gammas[nz:], alphas, CAP_HEIGHT,
-                                                 quotient_degree_factor)
+        # gate_program (a qpzk.GateProgram): the circuit's gate constraints as data, interpreted on the device
+        quot_b = PolynomialBatch.commit_quotient_prog(circuit.constants_sigmas, wires_b, zs_b, circuit.sigma_col0, num_routed,
+                                                      betas_gammas[:nz], betas_gammas[nz:], alphas, gate_program, CAP_HEIGHT,
+                                                      quotient_degree_factor)
     else:
         quot_b = PolynomialBatch.from_coeffs(ctx, quotient_coeffs, RATE_BITS, None, CAP_HEIGHT)
     ch.observe_cap(quot_b)

@@ -45,6 +45,16 @@ pub struct qpzk_proof_shape {
     pub num_public_inputs: u32,
 }
 
+/// Gate constraints as a straight-line register program (see include/qpzk.h).
+#[repr(C)]
+pub struct qpzk_gate_program {
+    pub code: *const u32,
+    pub num_ops: u32,
+    pub imm: *const u64,
+    pub num_imm: u32,
+    pub num_regs: u32,
+}
+
 #[repr(C)]
 pub struct qpzk_fri_instance {
     pub num_batches: u32,
@@ -142,6 +152,15 @@ extern "C" {
                                 quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
                                 alphas: *const u64, gate_terms_dev: *const u64, num_gate_terms: u32, cap_height: u32,
                                 out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_quotient_polys_prog(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
+                                    zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
+                                    quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
+                                    alphas: *const u64, prog: *const qpzk_gate_program, out: *mut u64) -> c_int;
+    pub fn qpzk_commit_quotient_prog(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
+                                     zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
+                                     quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
+                                     alphas: *const u64, prog: *const qpzk_gate_program, cap_height: u32,
+                                     out: *mut *mut qpzk_batch) -> c_int;
     // ProofWithPublicInputs::to_bytes / from_bytes (host functions)
     pub fn qpzk_proof_bytes_len(p: *const qpzk_fri_params, s: *const qpzk_proof_shape) -> usize;
     pub fn qpzk_proof_to_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, wires_cap: *const u64,

@@ -101,7 +101,22 @@ def e_pow(x, e):
     return r
 
 
-def verify_gateless_openings(log_n, openings, num_consts, num_routed, num_wires, nch, chunk, betas, gammas, alphas, zeta):
+def interpret_program_ext(code, imm, wires, consts):
+    """The gate program over extension-field values (the opened values of the wires / constants)."""
+    r, out = {}, []
+    for op, d, a, b in [tuple(int(x) for x in row) for row in code]:
+        if op == 0: r[d] = wires[a]
+        elif op == 1: r[d] = consts[a]
+        elif op == 2: r[d] = (int(imm[a]) % P, 0)
+        elif op == 3: r[d] = e_add(r[a], r[b])
+        elif op == 4: r[d] = e_sub(r[a], r[b])
+        elif op == 5: r[d] = e_mul(r[a], r[b])
+        else: out.append(r[a])
+    return out
+
+
+def verify_gateless_openings(log_n, openings, num_consts, num_routed, num_wires, nch, chunk, betas, gammas, alphas, zeta,
+                             program=None):
     """The plonk verifier's vanishing check on OPENED values (upstream plonk/verifier.rs: eval_vanishing_poly at zeta
     against Z_H(zeta) * reduce_with_powers(quotient chunk openings, zeta^n)) for a circuit without gates.
     openings: (k, 2) array in the order constants | sigmas | wires | zs | partial products | quotient chunks | zs at g zeta."""
@@ -130,6 +145,8 @@ def verify_gateless_openings(log_n, openings, num_consts, num_routed, num_wires,
                 pn = e_mul(pn, e_add(e_add(wires[j], e_scale(z, b * pow(G, j, P) % P)), (g, 0)))
                 pd = e_mul(pd, e_add(e_add(wires[j], e_scale(sig[j], b)), (g, 0)))
             terms.append(e_sub(e_mul(accs[k], pn), e_mul(accs[k + 1], pd)))
+    if program is not None:      # gate constraints, evaluated on the opened wires and constants
+        terms += interpret_program_ext(program[0], program[1], wires, op[:num_consts])
     zn = e_pow(z, n)
     for a in range(nch):
         lhs = (0, 0)
@@ -141,3 +158,100 @@ def verify_gateless_openings(log_n, openings, num_consts, num_routed, num_wires,
         if lhs != e_mul(zh, q):
             return False
     return True
+
+
+# ---- a small circuit WITH gates: arithmetic gates chained by copy constraints ---------------------------------------
+class ProgramBuilder:
+    """Assembles a gate program in the format of qpzk_gate_program: (num_ops, 4) uint32 code + uint64 immediates."""
+    WIRE, CONST, IMM, ADD, SUB, MUL, EMIT = range(7)
+
+    def __init__(self):
+        self.code, self.imm, self.next = [], [], 0
+
+    def _new(self):
+        self.next += 1
+        return self.next - 1
+
+    def load(self, kind, idx):
+        d = self._new()
+        self.code.append([kind, d, idx, 0])
+        return d
+
+    def wire(self, j): return self.load(self.WIRE, j)
+    def const(self, j): return self.load(self.CONST, j)
+
+    def immediate(self, v):
+        self.imm.append(int(v) % P)
+        return self.load(self.IMM, len(self.imm) - 1)
+
+    def op(self, kind, a, b):
+        d = self._new()
+        self.code.append([kind, d, a, b])
+        return d
+
+    def add(self, a, b): return self.op(self.ADD, a, b)
+    def sub(self, a, b): return self.op(self.SUB, a, b)
+    def mul(self, a, b): return self.op(self.MUL, a, b)
+    def emit(self, a): self.code.append([self.EMIT, 0, a, 0])
+
+    def arrays(self):
+        return np.array(self.code, dtype=np.uint32).reshape(-1, 4), np.array(self.imm, dtype=np.uint64)
+
+
+def interpret_program(code, imm, wires, consts):
+    """Big-integer interpreter of a gate program at one point: wires / consts are lists of field elements."""
+    r, out = {}, []
+    for op, d, a, b in [tuple(int(x) for x in row) for row in code]:
+        if op == 0: r[d] = int(wires[a]) % P
+        elif op == 1: r[d] = int(consts[a]) % P
+        elif op == 2: r[d] = int(imm[a]) % P
+        elif op == 3: r[d] = (r[a] + r[b]) % P
+        elif op == 4: r[d] = (r[a] - r[b]) % P
+        elif op == 5: r[d] = r[a] * r[b] % P
+        else: out.append(r[a])
+    return out
+
+
+ARITH_OPS = 4   # operations per row: wires [m0, m1, addend, out] x 4; constants columns [selector, c0, c1]
+
+
+def arithmetic_program():
+    """constraint_k = selector * (out_k - (c0 * m0_k * m1_k + c1 * addend_k)),  k < 4   (upstream ArithmeticGate with
+    a selector filter)."""
+    b = ProgramBuilder()
+    s, c0, c1 = b.const(0), b.const(1), b.const(2)
+    for k in range(ARITH_OPS):
+        m0, m1, ad, out = (b.wire(4 * k + t) for t in range(4))
+        t = b.add(b.mul(b.mul(m0, m1), c0), b.mul(ad, c1))
+        b.emit(b.mul(b.sub(out, t), s))
+    return b
+
+
+def arithmetic_circuit(log_n, seed, inactive_rows=3):
+    """A satisfying instance: (wires (16, n), constants (3, n), sigmas (16, n)).  Copy constraints: out_0 of row i feeds
+    m0_0 of row i + 1 (a chain through the active rows), and m1_2 = m0_3 inside every active row."""
+    rng = np.random.default_rng(seed)
+    n, R = 1 << log_n, 4 * ARITH_OPS
+    act = n - inactive_rows
+    w = root_of_unity(log_n)
+    xs = [pow(w, i, P) for i in range(n)]
+    ids = [[pow(G, j, P) * x % P for x in xs] for j in range(R)]
+    rnd = lambda: int(rng.integers(0, P, dtype=np.uint64))
+    consts = [[1 if i < act else 0 for i in range(n)], [rnd() for _ in range(n)], [rnd() for _ in range(n)]]
+    wires = [[rnd() for _ in range(n)] for _ in range(R)]
+    nxt = {}                                            # position -> next position of its cycle
+    link = lambda a, b: (nxt.__setitem__(a, b), nxt.__setitem__(b, a))
+    for i in range(act):
+        if i > 0:
+            wires[0][i] = wires[3][i - 1]               # m0_0(i) = out_0(i - 1)
+            link((3, i - 1), (0, i))
+        wires[12][i] = wires[9][i]                      # m0_3(i) = m1_2(i)
+        link((9, i), (12, i))
+        for k in range(ARITH_OPS):
+            m0, m1, ad = wires[4 * k][i], wires[4 * k + 1][i], wires[4 * k + 2][i]
+            wires[4 * k + 3][i] = (consts[1][i] * m0 % P * m1 + consts[2][i] * ad) % P
+    sig = [[ids[j][i] for i in range(n)] for j in range(R)]
+    for (j, i), (j2, i2) in nxt.items():
+        sig[j][i] = ids[j2][i2]
+    u = lambda a: np.array(a, dtype=np.uint64)
+    return u(wires), u(consts), u(sig)

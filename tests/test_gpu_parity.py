@@ -644,3 +644,68 @@ def test_zs_partial_products_from_device_resident_batches(ctx, qpzk, orc):
     assert not ctx.L.qpzk_batch_values_dev(plain.h)
     with pytest.raises(qpzk.QpzkError):                                    # ... and cannot feed the permutation argument
         qpzk.PolynomialBatch.commit_zs_partial_products(cb, plain, num_consts, R, betas, gammas, 2)
+
+
+# ---- gate constraints handed over as a program (qpzk_gate_program) ---------------------------------------------------
+def test_gate_program_quotient_matches_oracle(ctx, qpzk, orc):
+    from perm_util import arithmetic_circuit, arithmetic_program
+    log_n = 7
+    wires, consts, sigmas = arithmetic_circuit(log_n, 5)
+    b = arithmetic_program()
+    code, imm = b.arrays()
+    prog = qpzk.GateProgram.make(code, imm, b.next)
+    ch = np.random.default_rng(6).integers(0, P, size=(3, 2), dtype=np.uint64)
+    zs = orc.partial_products(wires, sigmas, ch[0], ch[1], 8)
+    cs = np.concatenate([consts, sigmas])
+    g = [qpzk.PolynomialBatch.from_values(ctx, a, 3, None, 2) for a in (cs, wires, zs)]
+    o = [orc.PolynomialBatch.from_values(a, 3, 2) for a in (cs, wires, zs)]
+    gt = orc.gate_terms(o[0], o[1], code, imm)
+    want = orc.quotient_polys(o[0], o[1], o[2], 3, 16, ch[0], ch[1], ch[2], gate_terms=gt)
+    got = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], prog)
+    assert (got == want).all()
+    none = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], None)
+    assert (none == orc.quotient_polys(o[0], o[1], o[2], 3, 16, ch[0], ch[1], ch[2])).all() and not (none == want).all()
+    qb = qpzk.PolynomialBatch.commit_quotient_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], prog, 2)
+    assert (qb.polynomials == want).all()
+    # malformed programs are rejected at the boundary, with the instruction number in the message
+    for bad, what in ((np.array([[9, 0, 0, 0]], np.uint32), "opcode"), (np.array([[0, 70, 0, 0]], np.uint32), "destination"),
+                      (np.array([[0, 0, 99, 0]], np.uint32), "wire column"), (np.array([[1, 0, 99, 0]], np.uint32), "column"),
+                      (np.array([[2, 0, 3, 0]], np.uint32), "immediate"), (np.array([[3, 0, 1, 2]], np.uint32), "not yet written"),
+                      (np.array([[6, 0, 5, 0]], np.uint32), "not yet written")):
+        with pytest.raises(qpzk.QpzkError) as e:
+            qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], qpzk.GateProgram.make(bad, imm, 8))
+        assert what in str(e.value)
+
+
+def test_plonk_proof_with_gates_end_to_end(ctx, qpzk, orc):
+    """Arithmetic gates chained by copy constraints, the gates handed to the device as a program: wires -> partial
+    products -> quotient (permutation AND gate terms) -> openings -> FRI.  Bit-exact with the oracle, FRI accepted, and
+    the plonk verifier's vanishing identity -- gate constraints interpreted on the OPENED values -- holds; it fails when a
+    gate output is wrong."""
+    from qpzk import prover
+    from perm_util import arithmetic_circuit, arithmetic_program, verify_gateless_openings
+    log_n = 8
+    wires, consts, sigmas = arithmetic_circuit(log_n, 12)
+    b = arithmetic_program()
+    code, imm = b.arrays()
+    prog = qpzk.GateProgram.make(code, imm, b.next)
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n, wires=16, constants_sigmas=19, zs_partial_products=4, quotient=16)
+    cs = np.concatenate([consts, sigmas])
+    circuit = prover.SyntheticCircuit(ctx, cs, shape, sigma_col0=3)
+    pih = np.arange(4, dtype=np.uint64) + 100
+    got = prover.prove_synthetic(circuit, wires, None, None, pih, sigmas=sigmas, gate_program=prog)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=3, gate_program=(code, imm))
+    for a, c in zip(got["caps"], want["caps"]):
+        assert (a == c).all()
+    assert (got["openings"] == want["openings"]).all() and (got["fri_proof"] == want["fri_proof"]).all()
+    assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], got["openings"], want["params"],
+                          want["verifier_challenger"], got["fri_proof"]) == 0
+    bg, alphas, zeta = got["challenges"]
+    assert verify_gateless_openings(log_n, got["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+    assert not verify_gateless_openings(log_n, got["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta)   # gates matter
+    bad = wires.copy()
+    bad[7, 9] = (int(bad[7, 9]) + 1) % P
+    gb = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas, gate_program=prog)
+    bg, alphas, zeta = gb["challenges"]
+    assert not verify_gateless_openings(log_n, gb["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))

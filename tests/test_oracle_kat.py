@@ -364,3 +364,61 @@ def test_oracle_gateless_proof_passes_the_vanishing_check_on_opened_values(orc):
     tampered = out["openings"].copy()
     tampered[num_consts + R + 1, 0] ^= np.uint64(1)
     assert not verify_gateless_openings(log_n, tampered, num_consts, R, num_wires, 2, 8, bg[:2], bg[2:], alphas, zeta)
+
+
+# ---- gate constraints handed over as a program -------------------------------------------------------------------------
+def _arith_instance(orc, log_n, seed, break_gate=False, break_copy=False):
+    from perm_util import arithmetic_circuit
+    wires, consts, sigmas = arithmetic_circuit(log_n, seed)
+    if break_gate:
+        wires = wires.copy(); wires[7, 2] = (int(wires[7, 2]) + 1) % P          # an output no gate produces
+    if break_copy:
+        wires = wires.copy(); wires[9, 1] = (int(wires[9, 1]) + 1) % P          # m1_2 != m0_3 (and its gate re-satisfied)
+        wires[11, 1] = (int(consts[1, 1]) * int(wires[8, 1]) % P * int(wires[9, 1]) + int(consts[2, 1]) * int(wires[10, 1])) % P
+    rng = np.random.default_rng(seed + 1)
+    ch = rng.integers(0, P, size=(3, 2), dtype=np.uint64)
+    cs_b = orc.PolynomialBatch.from_values(np.concatenate([consts, sigmas]), 3, 2)
+    w_b = orc.PolynomialBatch.from_values(wires, 3, 2)
+    zs = orc.partial_products(wires, sigmas, ch[0], ch[1], 8)
+    z_b = orc.PolynomialBatch.from_values(zs, 3, 2)
+    return dict(cs=cs_b, wires=w_b, zs=z_b, ch=ch, consts=consts, arrays=(wires, consts, sigmas))
+
+
+def test_gate_program_quotient_passes_the_verifier_identity(orc):
+    """An arithmetic-gate circuit whose gates arrive as a program: the oracle interprets it at every quotient point, the
+    quotient passes the verifier's identity with the gate values computed by a big-integer interpreter from the
+    polynomials at zeta -- and fails when a gate or a copy constraint is violated."""
+    from perm_util import arithmetic_program, interpret_program, quotient_identity_holds, horner
+    log_n = 5
+    code, imm = arithmetic_program().arrays()
+    for kind in ("ok", "gate", "copy"):
+        inst = _arith_instance(orc, log_n, 77, break_gate=kind == "gate", break_copy=kind == "copy")
+        ch = inst["ch"]
+        gt = orc.gate_terms(inst["cs"], inst["wires"], code, imm)
+        assert gt.shape == (8 << log_n, 4)
+        q = orc.quotient_polys(inst["cs"], inst["wires"], inst["zs"], 3, 16, ch[0], ch[1], ch[2], gate_terms=gt)
+        wc, cc, zc = inst["wires"].coeffs(), inst["cs"].coeffs(), inst["zs"].coeffs()
+        zeta = 0x0123456789abcdef % P
+        gv = interpret_program(code, imm, [horner(c, zeta) for c in wc], [horner(c, zeta) for c in cc[:3]])
+        ok = quotient_identity_holds(log_n, wc, cc[3:19], zc, q, ch[0], ch[1], ch[2], 8, zeta, gv)
+        assert ok == (kind == "ok"), kind
+    # on the subgroup itself a satisfied gate evaluates to zero in every row
+    wires, consts, _ = _arith_instance(orc, log_n, 77)["arrays"]
+    for i in (0, 5, (1 << log_n) - 1):
+        assert interpret_program(code, imm, wires[:, i], consts[:, i]) == [0, 0, 0, 0]
+
+
+def test_oracle_proof_with_gates_passes_the_vanishing_check_on_opened_values(orc):
+    from perm_util import arithmetic_circuit, arithmetic_program, verify_gateless_openings
+    log_n = 6
+    wires, consts, sigmas = arithmetic_circuit(log_n, 33)
+    code, imm = arithmetic_program().arrays()
+    cs = np.concatenate([consts, sigmas])
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    pih = np.arange(4, dtype=np.uint64)
+    out = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=3, gate_program=(code, imm), pow_bits=8)
+    assert orc.fri_verify(log_n, out["leaf_lens"], out["all_caps"], out["instance"], out["openings"], out["params"],
+                          out["verifier_challenger"], out["fri_proof"]) == 0
+    bg, alphas, zeta = out["challenges"]
+    assert verify_gateless_openings(log_n, out["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+    assert not verify_gateless_openings(log_n, out["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta)
