@@ -529,7 +529,7 @@ int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, 
                    const uint64_t* imm, uint64_t* out) {
     unsigned qbits = 0, emits = 0;
     while ((1u << qbits) < chunk) qbits++;
-    for (unsigned pc = 0; pc < num_ops; pc++) if (code[4 * pc] == 6) emits++; else if (code[4 * pc] > 6 || code[4 * pc + 1] >= 64) return -1;
+    for (unsigned pc = 0; pc < num_ops; pc++) if (code[4 * pc] == 6) emits++; else if (code[4 * pc] > 6 || code[4 * pc + 1] >= 256) return -1;
     if (!out) return (int)emits;
     const unsigned log_n = wires->log_n, log_L = log_n + wires->rate_bits, log_q = log_n + qbits;
     const size_t Lq = (size_t)1 << log_q, step = (size_t)1 << (wires->rate_bits - qbits);
@@ -538,7 +538,7 @@ int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, 
         const size_t row = bitrev(i * step, log_L), leaf_q = bitrev(i, log_q);
         const uint64_t* lw = orc_merkle_leaf(wires->tree, row);
         const uint64_t* lc = orc_merkle_leaf(cs->tree, row);
-        uint64_t r[64] = {0};
+        uint64_t r[256] = {0};
         unsigned e = 0;
         for (unsigned pc = 0; pc < num_ops; pc++) {
             const uint32_t op = code[4 * pc], d = code[4 * pc + 1], a = code[4 * pc + 2], b = code[4 * pc + 3];

@@ -1479,7 +1479,7 @@ static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qp
     if (!prog) return 0;
     if (!ctx || !cs || !wires) return fail(QPZK_EINVAL, "null argument");
     if (!prog->code || (!prog->imm && prog->num_imm)) return fail(QPZK_EINVAL, "gate program: null code / imm");
-    if (!prog->num_regs || prog->num_regs > GATE_MAX_REGS) return fail(QPZK_EINVAL, "gate program: num_regs must be in 1..64");
+    if (!prog->num_regs || prog->num_regs > GATE_MAX_REGS) return fail(QPZK_EINVAL, "gate program: num_regs must be in 1..256");
     if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
     if (ilog2(chunk) > wires->rate_bits || cs->log_n != wires->log_n || cs->rate_bits != wires->rate_bits)
         return fail(QPZK_EINVAL, "batches must have the same degree and rate, quotient_degree_factor <= blowup");
@@ -1512,7 +1512,7 @@ static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qp
         e = cudaMemcpyAsync(d_imm, prog->imm, 8ull * prog->num_imm, cudaMemcpyHostToDevice, ctx->stream);
     GateProgramArgs g{};
     g.cs_leaves = cs->leaves; g.w_leaves = wires->leaves; g.cs_width = cs->leaf_width; g.w_width = wires->leaf_width;
-    g.code = reinterpret_cast<const uint32_t*>(d_code); g.imm = d_imm; g.num_ops = prog->num_ops; g.num_terms = emits;
+    g.code = reinterpret_cast<const uint32_t*>(d_code); g.imm = d_imm; g.num_ops = prog->num_ops; g.num_terms = emits; g.num_regs = prog->num_regs;
     g.num_points = points; g.terms = d_terms;
     if (e == cudaSuccess) { e = launch_gate_program(g, ctx->stream); ctx->launches++; }
     // the program came from caller memory: it must be on the device before the call returns (the scratch copies are

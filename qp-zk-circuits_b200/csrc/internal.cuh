@@ -207,13 +207,13 @@ struct QuotientArgs {
     uint64_t* values;                  // [challenge][n << qbits], natural order
 };
 cudaError_t launch_quotient_perm(const QuotientArgs& a, cudaStream_t st);
-constexpr uint32_t GATE_MAX_REGS = 64;
+constexpr uint32_t GATE_MAX_REGS = 256;
 struct GateProgramArgs {
     const uint64_t *cs_leaves, *w_leaves;   // leaf matrices (row = quotient-domain point in leaf order)
     uint32_t cs_width, w_width;
     const uint32_t* code;                   // device, num_ops x {op, dst, a, b}
     const uint64_t* imm;                    // device
-    uint32_t num_ops, num_terms;
+    uint32_t num_ops, num_terms, num_regs;
     uint64_t num_points;
     uint64_t* terms;                        // device, [num_points][num_terms]
 };

@@ -123,13 +123,14 @@ __global__ void __launch_bounds__(256) coset_unshift_kernel(uint64_t* __restrict
 //   op  dst a b      0 LOAD_WIRE  r[dst] = wires[a]            3 ADD  r[dst] = r[a] + r[b]      6 EMIT  term = r[a]
 //                    1 LOAD_CONST r[dst] = constants_sigmas[a] 4 SUB  r[dst] = r[a] - r[b]
 //                    2 LOAD_IMM   r[dst] = imm[a]              5 MUL  r[dst] = r[a] * r[b]
+template <int NR>   // size of the register file: 64 (fits L1 comfortably) or GATE_MAX_REGS
 __global__ void __launch_bounds__(QUOT_THREADS) gate_program_kernel(GateProgramArgs a) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.num_points) return;
     const uint64_t* __restrict__ wrow = a.w_leaves + j * a.w_width;
     const uint64_t* __restrict__ crow = a.cs_leaves + j * a.cs_width;
     uint64_t* __restrict__ out = a.terms + j * a.num_terms;
-    uint64_t r[GATE_MAX_REGS];
+    uint64_t r[NR];
     uint32_t emitted = 0;
     for (uint32_t pc = 0; pc < a.num_ops; pc++) {
         const uint4 ins = __ldg(reinterpret_cast<const uint4*>(a.code) + pc);
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(QUOT_THREADS) gate_program_kernel(GateProgramA
 
 cudaError_t launch_gate_program(const GateProgramArgs& a, cudaStream_t st) {
     if (!a.num_points) return cudaSuccess;
-    gate_program_kernel<<<(unsigned)((a.num_points + QUOT_THREADS - 1) / QUOT_THREADS), QUOT_THREADS, 0, st>>>(a);
+    const unsigned blocks = (unsigned)((a.num_points + QUOT_THREADS - 1) / QUOT_THREADS);
+    if (a.num_regs <= 64) gate_program_kernel<64><<<blocks, QUOT_THREADS, 0, st>>>(a);
+    else gate_program_kernel<GATE_MAX_REGS><<<blocks, QUOT_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -669,6 +669,7 @@ def test_gate_program_quotient_matches_oracle(ctx, qpzk, orc):
     assert (qb.polynomials == want).all()
     # malformed programs are rejected at the boundary, with the instruction number in the message
     for bad, what in ((np.array([[9, 0, 0, 0]], np.uint32), "opcode"), (np.array([[0, 70, 0, 0]], np.uint32), "destination"),
+                      (np.array([[0, 300, 0, 0]], np.uint32), "destination"),
                       (np.array([[0, 0, 99, 0]], np.uint32), "wire column"), (np.array([[1, 0, 99, 0]], np.uint32), "column"),
                       (np.array([[2, 0, 3, 0]], np.uint32), "immediate"), (np.array([[3, 0, 1, 2]], np.uint32), "not yet written"),
                       (np.array([[6, 0, 5, 0]], np.uint32), "not yet written")):
@@ -709,3 +710,27 @@ def test_plonk_proof_with_gates_end_to_end(ctx, qpzk, orc):
     gb = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas, gate_program=prog)
     bg, alphas, zeta = gb["challenges"]
     assert not verify_gateless_openings(log_n, gb["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+
+
+def test_gate_program_with_a_large_register_file(ctx, qpzk, orc):
+    """More than 64 registers selects the 256-register interpreter; same results as the oracle's interpreter."""
+    from perm_util import arithmetic_circuit, ProgramBuilder
+    log_n = 5
+    wires, consts, sigmas = arithmetic_circuit(log_n, 2)
+    b = ProgramBuilder()
+    regs = [b.wire(j % 16) if j % 3 else b.const(j % 3) for j in range(120)]
+    acc = b.immediate(12345)
+    for j, r in enumerate(regs):
+        acc = b.add(b.mul(acc, r), regs[(7 * j + 1) % 120]) if b.next < 250 else acc
+        if j % 40 == 39:
+            b.emit(acc)
+    assert 64 < b.next <= 256
+    code, imm = b.arrays()
+    ch = np.random.default_rng(1).integers(0, P, size=(3, 1), dtype=np.uint64)
+    zs = orc.partial_products(wires, sigmas, ch[0], ch[1], 8)
+    cs = np.concatenate([consts, sigmas])
+    g = [qpzk.PolynomialBatch.from_values(ctx, a, 3, None, 2) for a in (cs, wires, zs)]
+    o = [orc.PolynomialBatch.from_values(a, 3, 2) for a in (cs, wires, zs)]
+    want = orc.quotient_polys(o[0], o[1], o[2], 3, 16, ch[0], ch[1], ch[2], gate_terms=orc.gate_terms(o[0], o[1], code, imm))
+    got = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], qpzk.GateProgram.make(code, imm, b.next))
+    assert (got == want).all()
