@@ -192,17 +192,18 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
 
     total_ms = timed(quot)
 
-    # gate constraints as a program: a synthetic program of the size of a Poseidon-gate row (about 3000 field operations,
-    # 123 constraints) interpreted at every quotient point (qpzk_commit_quotient_prog minus the plain quotient above)
-    ops, code = 3000, []
-    for r in range(16):
-        code.append([0 if r % 2 == 0 else 1, r, r % 80, 0])
-    for k in range(ops):
-        d, a_, b_ = 16 + k % 48, (k * 7) % 16 if k < 48 else 16 + (k * 7) % 48, (k * 5 + 3) % 16 if k < 48 else 16 + (k * 5 + 3) % 48
-        code.append([3 + k % 3, d, a_, b_])
-        if k % 24 == 23:
-            code.append([6, 0, d, 0])
-    prog = qpzk.GateProgram.make(np.array(code, np.uint32), np.zeros(0, np.uint64), 64)
+    # gate constraints as a program: upstream's PoseidonGate -- the gate behind the reference's 135-wire configuration,
+    # 123 constraints of degree 7 -- recorded by qpzk/gates.py (about 5300 instructions, 37 registers) and interpreted at
+    # every quotient point (qpzk_commit_quotient_prog minus the plain quotient above)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_poseidon_constants as gen
+    from qpzk import gates
+    rc = gen.round_constants()
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, gen.derive_fast_partial(rc), selector=rec.const(0))
+    code, imm, regs = rec.finish()
+    prog = qpzk.GateProgram.make(code, imm, regs)
+    ops = int(code.shape[0])
 
     def quot_prog():
         qb = qpzk.PolynomialBatch.commit_quotient_prog(batches[0], batches[1], batches[2], num_consts, routed, ch[0], ch[1], ch[2],
@@ -220,7 +221,8 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
             "partial_products_ms": pp_ms, "partial_products_GBps": pp_bytes / pp_ms / 1e6,
             "quotient_ms": q_ms, "quotient_GBps": q_bytes / q_ms / 1e6 if q_ms > 0 else None,
             "quotient_commit_ms": commit_ms[0],
-            "gate_program_ms": prog_total_ms - total_ms, "gate_program_ops": ops, "gate_program_terms": ops // 24,
+            "gate_program": "PoseidonGate (qpzk/gates.py)", "gate_program_ms": prog_total_ms - total_ms, "gate_program_ops": ops,
+            "gate_program_terms": int((code[:, 0] == 6).sum()), "gate_program_registers": int(regs),
             "gate_program_ns_per_op_and_point": 1e6 * (prog_total_ms - total_ms) / (ops * n * chunk),
             "what": "a16: qpzk_partial_products_dev; a17: qpzk_commit_quotient minus the time of its 16-column commit"}
 

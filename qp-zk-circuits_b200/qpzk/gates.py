@@ -1,0 +1,225 @@
+"""Gate constraints recorded as `qpzk_gate_program`s (include/qpzk.h): the host-side half of SURVEY.md 8a row a17.
+
+The reference's gate set lives in the un-vendored crate qp-plonky2 =1.5.5 (`gates/*.rs`); a fork records it by running
+its constraint code over a recording field type.  This module is that recorder in Python, plus two
+gates written from upstream plonky2 as recalled [upstream-memory] -- `ArithmeticGate` and `PoseidonGate`, the gate that
+fixes the reference's 135-wire configuration (reference common/src/circuit.rs:428-431) -- so that the device interpreter
+is exercised and measured on a program of the real shape: 135 wires, 123 constraints of degree 7.
+
+    rec = Recorder();  poseidon_gate(rec, round_constants, fast_partial, selector=rec.const(0));  prog = rec.finish()
+"""
+import numpy as np
+
+from . import GateProgram, P
+
+WIRE, CONST, IMM, ADD, SUB, MUL, EMIT = range(7)
+
+
+class Recorder:
+    """Records field operations on virtual registers; finish() maps them onto at most `max_regs` physical registers
+    (linear scan over the straight-line program: a register is free again after the last read of its value)."""
+
+    def __init__(self):
+        self.ops, self.imms, self.n = [], [], 0
+
+    def _new(self):
+        self.n += 1
+        return self.n - 1
+
+    def wire(self, j):
+        d = self._new(); self.ops.append((WIRE, d, j, 0)); return d
+
+    def const(self, j):
+        d = self._new(); self.ops.append((CONST, d, j, 0)); return d
+
+    def imm(self, v):
+        v = int(v) % P
+        d = self._new(); self.imms.append(v); self.ops.append((IMM, d, len(self.imms) - 1, 0)); return d
+
+    def add(self, a, b):
+        d = self._new(); self.ops.append((ADD, d, a, b)); return d
+
+    def sub(self, a, b):
+        d = self._new(); self.ops.append((SUB, d, a, b)); return d
+
+    def mul(self, a, b):
+        d = self._new(); self.ops.append((MUL, d, a, b)); return d
+
+    def emit(self, a):
+        self.ops.append((EMIT, 0, a, 0))
+
+    def finish(self, max_regs=256):
+        """(code (num_ops, 4) uint32, imm uint64, num_regs) with physical registers."""
+        last = {}
+        for i, (op, d, a, b) in enumerate(self.ops):
+            if op in (ADD, SUB, MUL):
+                last[a] = i; last[b] = i
+            elif op == EMIT:
+                last[a] = i
+        free, phys, used, code = [], {}, 0, []
+        for i, (op, d, a, b) in enumerate(self.ops):
+            pa = phys.get(a, 0) if op in (ADD, SUB, MUL, EMIT) else a
+            pb = phys.get(b, 0) if op in (ADD, SUB, MUL) else b
+            # sources whose last use is this instruction are released BEFORE the destination is chosen (dst may reuse them)
+            for v in ({a, b} if op in (ADD, SUB, MUL) else {a} if op == EMIT else set()):
+                if last.get(v) == i:
+                    free.append(phys.pop(v))
+            if op != EMIT:
+                if d not in last:                      # value never read: still needs a slot for the write
+                    last[d] = i
+                if free:
+                    pd = free.pop()
+                else:
+                    pd = used; used += 1
+                    if used > max_regs:
+                        raise ValueError("gate program needs more than %d registers" % max_regs)
+                phys[d] = pd
+                if last[d] == i:
+                    free.append(phys.pop(d))
+                code.append((op, pd, pa, pb))
+            else:
+                code.append((EMIT, 0, pa, 0))
+        return np.array(code, dtype=np.uint32).reshape(-1, 4), np.array(self.imms, dtype=np.uint64), max(used, 1)
+
+    def program(self, max_regs=256):
+        code, imm, regs = self.finish(max_regs)
+        return GateProgram.make(code, imm, regs)
+
+
+def arithmetic_gate(rec, num_ops, selector=None, const_base=1):
+    """upstream ArithmeticGate: wires [multiplicand_0, multiplicand_1, addend, output] x num_ops, constants c0, c1:
+    constraint_k = output_k - (c0 * m0_k * m1_k + c1 * addend_k)   (times the selector filter)."""
+    c0, c1 = rec.const(const_base), rec.const(const_base + 1)
+    for k in range(num_ops):
+        m0, m1, ad, out = (rec.wire(4 * k + t) for t in range(4))
+        c = rec.sub(out, rec.add(rec.mul(rec.mul(m0, m1), c0), rec.mul(ad, c1)))
+        rec.emit(rec.mul(c, selector) if selector is not None else c)
+
+
+# ---- PoseidonGate [upstream-memory: plonky2/src/gates/poseidon.rs] ------------------------------------------------------
+WIRE_SWAP, START_DELTA, START_FULL_0, START_PARTIAL, START_FULL_1, POSEIDON_GATE_WIRES = 24, 25, 29, 65, 87, 135
+MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
+
+
+def wire_input(i): return i
+def wire_output(i): return 12 + i
+def wire_delta(i): return START_DELTA + i
+def wire_full_sbox_0(r, i): return START_FULL_0 + 12 * (r - 1) + i     # rounds 1..3 (round 0 reads the state itself)
+def wire_partial_sbox(r): return START_PARTIAL + r
+def wire_full_sbox_1(r, i): return START_FULL_1 + 12 * r + i
+
+
+def poseidon_gate(rec, rc, fast, selector=None):
+    """123 constraints: swap is a bit (1), delta_i = swap * (rhs_i - lhs_i) (4), the S-box inputs of full rounds 1-3
+    (36), of the 22 partial rounds (22) and of the last 4 full rounds (48) equal the running state, and the outputs (12).
+    rc: the 360 round constants; fast = (K, INIT, W, VHAT, POST), the sparse form of the partial rounds
+    (tools/gen_poseidon_constants.py: derive_fast_partial) -- the S-box inputs are the same field elements as in the
+    literal rounds, so the witness does not depend on this choice."""
+    ks, init, w_l, vhat_l, post = fast
+    out = (lambda c: rec.emit(rec.mul(c, selector))) if selector is not None else rec.emit
+    consts = {}
+
+    def k(v):
+        # the small MDS entries are used in every round and stay in registers; a round constant or a coefficient of
+        # the sparse matrices is used once and is loaded where it is needed (a cached one would pin a register)
+        v = int(v) % P
+        if v >= 64:
+            return rec.imm(v)
+        if v not in consts:
+            consts[v] = rec.imm(v)
+        return consts[v]
+
+    def sbox(x):
+        x2 = rec.mul(x, x); x4 = rec.mul(x2, x2); x3 = rec.mul(x, x2)
+        return rec.mul(x3, x4)
+
+    def mds(s):
+        res = []
+        for r in range(12):
+            acc = None
+            for i in range(12):
+                c = MDS_CIRC[i] + (8 if (r == 0 and i == 0) else 0)
+                t = rec.mul(s[(i + r) % 12], k(c))
+                acc = t if acc is None else rec.add(acc, t)
+            res.append(acc)
+        return res
+
+    swap = rec.wire(WIRE_SWAP)
+    out(rec.mul(swap, rec.sub(swap, k(1))))
+    state = [None] * 12
+    for i in range(4):
+        lhs, rhs, delta = rec.wire(wire_input(i)), rec.wire(wire_input(i + 4)), rec.wire(wire_delta(i))
+        out(rec.sub(rec.mul(swap, rec.sub(rhs, lhs)), delta))
+        state[i], state[i + 4] = rec.add(lhs, delta), rec.sub(rhs, delta)
+    for i in range(8, 12):
+        state[i] = rec.wire(wire_input(i))
+    for r in range(4):                                                   # first full rounds
+        state = [rec.add(state[i], k(rc[12 * r + i])) for i in range(12)]
+        if r:
+            for i in range(12):
+                sin = rec.wire(wire_full_sbox_0(r, i))
+                out(rec.sub(state[i], sin))
+                state[i] = sin
+        state = mds([sbox(x) for x in state])
+    rest = []                                                            # x[1..] <- INIT * x[1..]
+    for i in range(11):
+        acc = None
+        for j in range(11):
+            if init[i][j]:
+                t = rec.mul(state[1 + j], k(init[i][j]))
+                acc = t if acc is None else rec.add(acc, t)
+        rest.append(acc)
+    state = [state[0]] + rest
+    for r in range(22):                                                  # partial rounds, sparse form
+        sin = rec.wire(wire_partial_sbox(r))
+        out(rec.sub(rec.add(state[0], k(ks[r])), sin))
+        x0 = sbox(sin)
+        d = rec.mul(x0, k(25))
+        for i in range(11):
+            d = rec.add(d, rec.mul(state[1 + i], k(vhat_l[r][i])))
+        state = [d] + [rec.add(state[1 + i], rec.mul(x0, k(w_l[r][i]))) for i in range(11)]
+    state = [rec.add(state[i], k(post[i])) for i in range(12)]
+    for r in range(4):                                                   # last full rounds
+        state = [rec.add(state[i], k(rc[12 * (26 + r) + i])) for i in range(12)]
+        for i in range(12):
+            sin = rec.wire(wire_full_sbox_1(r, i))
+            out(rec.sub(state[i], sin))
+            state[i] = sin
+        state = mds([sbox(x) for x in state])
+    for i in range(12):
+        out(rec.sub(state[i], rec.wire(wire_output(i))))
+
+
+def poseidon_gate_witness(inputs, swap, rc):
+    """The 135 wire values of one PoseidonGate row for `inputs` (12 field elements) and a swap bit: literal rounds."""
+    w = [0] * POSEIDON_GATE_WIRES
+    inputs = [int(x) % P for x in inputs]
+    for i in range(12):
+        w[wire_input(i)] = inputs[i]
+    w[WIRE_SWAP] = int(swap)
+    s = list(inputs)
+    for i in range(4):
+        d = int(swap) * (inputs[i + 4] - inputs[i]) % P
+        w[wire_delta(i)] = d
+        s[i], s[i + 4] = (inputs[i] + d) % P, (inputs[i + 4] - d) % P
+
+    def mds(v):
+        return [sum((MDS_CIRC[i] + (8 if (r == 0 and i == 0) else 0)) * v[(i + r) % 12] for i in range(12)) % P for r in range(12)]
+
+    for r in range(30):
+        s = [(x + c) % P for x, c in zip(s, rc[12 * r:12 * r + 12])]
+        if r < 4 or r >= 26:
+            if 1 <= r < 4:
+                for i in range(12):
+                    w[wire_full_sbox_0(r, i)] = s[i]
+            if r >= 26:
+                for i in range(12):
+                    w[wire_full_sbox_1(r - 26, i)] = s[i]
+            s = [pow(x, 7, P) for x in s]
+        else:
+            w[wire_partial_sbox(r - 4)] = s[0]
+            s[0] = pow(s[0], 7, P)
+        s = mds(s)
+    for i in range(12):
+        w[wire_output(i)] = s[i]
+    return w

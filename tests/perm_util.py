@@ -255,3 +255,35 @@ def arithmetic_circuit(log_n, seed, inactive_rows=3):
         sig[j][i] = ids[j2][i2]
     u = lambda a: np.array(a, dtype=np.uint64)
     return u(wires), u(consts), u(sig)
+
+
+def poseidon_chain_circuit(log_n, seed, rc, routed=80, inactive_rows=2):
+    """A hash chain in the reference's shape: every active row is one PoseidonGate (135 wires, the first 80 routed),
+    output words 0..3 of row i are copied to input words 0..3 of row i + 1, the other input words are free.
+    Returns (wires (135, n), constants (1, n) = the gate's selector, sigmas (routed, n))."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qp-zk-circuits_b200"))
+    from qpzk import gates
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    act = n - inactive_rows
+    rnd = lambda: int(rng.integers(0, P, dtype=np.uint64))
+    w = root_of_unity(log_n)
+    xs = [pow(w, i, P) for i in range(n)]
+    ids = [[pow(G, j, P) * x % P for x in xs] for j in range(routed)]
+    sig = [list(r) for r in ids]
+    wires = [[rnd() for _ in range(n)] for _ in range(gates.POSEIDON_GATE_WIRES)]
+    prev = None
+    for i in range(act):
+        inp = [rnd() for _ in range(12)]
+        if prev is not None:
+            inp[:4] = prev[:4]
+            for t in range(4):                        # out_t(i - 1) <-> in_t(i): a 2-cycle of the permutation
+                a, b = (gates.wire_output(t), i - 1), (gates.wire_input(t), i)
+                sig[a[0]][a[1]], sig[b[0]][b[1]] = ids[b[0]][b[1]], ids[a[0]][a[1]]
+        row = gates.poseidon_gate_witness(inp, i & 1, rc)
+        for j in range(gates.POSEIDON_GATE_WIRES):
+            wires[j][i] = row[j]
+        prev = row[12:24] if not (i & 1) else row[12:24]
+    u = lambda a: np.array(a, dtype=np.uint64)
+    return u(wires), u([[1 if i < act else 0 for i in range(n)]]), u(sig)

@@ -734,3 +734,39 @@ def test_gate_program_with_a_large_register_file(ctx, qpzk, orc):
     want = orc.quotient_polys(o[0], o[1], o[2], 3, 16, ch[0], ch[1], ch[2], gate_terms=orc.gate_terms(o[0], o[1], code, imm))
     got = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], qpzk.GateProgram.make(code, imm, b.next))
     assert (got == want).all()
+
+
+def test_poseidon_hash_chain_proved_end_to_end(ctx, qpzk, orc):
+    """The reference's shape in miniature: 135 wires of which 80 routed, one PoseidonGate per row (123 constraints of
+    degree 7, recorded as a gate program of ~5300 instructions), rows chained by copy constraints on the digest words.
+    Device path = oracle bit for bit, FRI accepted, and the vanishing identity -- the gate program interpreted over the
+    opened extension-field values -- holds; a wrong S-box wire is rejected."""
+    import gen_poseidon_constants as gen
+    from qpzk import prover, gates
+    from perm_util import poseidon_chain_circuit, verify_gateless_openings
+    log_n = 6
+    rc = gen.round_constants()
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, gen.derive_fast_partial(rc), selector=rec.const(0))
+    code, imm, regs = rec.finish()
+    prog = qpzk.GateProgram.make(code, imm, regs)
+    wires, consts, sigmas = poseidon_chain_circuit(log_n, 4, rc)
+    cs = np.concatenate([consts, sigmas])
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n, constants_sigmas=81)
+    circuit = prover.SyntheticCircuit(ctx, cs, shape, sigma_col0=1)
+    pih = np.arange(4, dtype=np.uint64) + 7
+    got = prover.prove_synthetic(circuit, wires, None, None, pih, sigmas=sigmas, gate_program=prog)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=1, gate_program=(code, imm))
+    for a, c in zip(got["caps"], want["caps"]):
+        assert (a == c).all()
+    assert (got["openings"] == want["openings"]).all() and (got["fri_proof"] == want["fri_proof"]).all()
+    assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], got["openings"], want["params"],
+                          want["verifier_challenger"], got["fri_proof"]) == 0
+    bg, alphas, zeta = got["challenges"]
+    assert verify_gateless_openings(log_n, got["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+    bad = wires.copy()
+    bad[gates.wire_partial_sbox(7), 3] = (int(bad[gates.wire_partial_sbox(7), 3]) + 1) % P
+    gb = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas, gate_program=prog)
+    bg, alphas, zeta = gb["challenges"]
+    assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))

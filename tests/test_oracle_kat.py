@@ -422,3 +422,76 @@ def test_oracle_proof_with_gates_passes_the_vanishing_check_on_opened_values(orc
     bg, alphas, zeta = out["challenges"]
     assert verify_gateless_openings(log_n, out["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
     assert not verify_gateless_openings(log_n, out["openings"], 3, 16, 16, 2, 8, bg[:2], bg[2:], alphas, zeta)
+
+
+# ---- PoseidonGate as a gate program ------------------------------------------------------------------------------------
+def test_poseidon_gate_program_vanishes_on_a_correct_trace(orc):
+    """The reference's dominant gate (135 wires, 123 constraints of degree 7) recorded as a gate program: every
+    constraint is zero on the wires of a real permutation trace -- whose outputs are the KAT-pinned permutation -- with
+    and without the swap, and some constraint is non-zero when any single wire is changed."""
+    from qpzk import gates
+    from perm_util import interpret_program
+    rc = gen.round_constants()
+    fast = gen.derive_fast_partial(rc)
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, fast)
+    code, imm, regs = rec.finish()
+    assert (code[:, 0] == 6).sum() == 123 and regs <= 256
+    assert code.shape[0] < 6000                                       # ~4.9 k field operations and loads
+    rng = np.random.default_rng(8)
+    for swap in (0, 1):
+        inp = [int(x) for x in rng.integers(0, P, size=12, dtype=np.uint64)]
+        w = gates.poseidon_gate_witness(inp, swap, rc)
+        perm_in = inp if not swap else inp[4:8] + inp[0:4] + inp[8:]
+        assert w[12:24] == [int(x) for x in orc.poseidon(np.array(perm_in, np.uint64))]
+        assert interpret_program(code, imm, w, []) == [0] * 123
+        for j in (0, 5, 24, 26, 30, 64, 65, 86, 87, 134, 12, 23):     # one wire of every group
+            bad = list(w)
+            bad[j] = (bad[j] + 1) % P
+            assert any(interpret_program(code, imm, bad, []))
+    # the three upstream vectors through the gate
+    for inp, want in gen.KATS:
+        w = gates.poseidon_gate_witness(inp, 0, rc)
+        assert w[12:24] == [int(x, 16) for x in want.split()]
+
+
+def test_recorder_register_allocation(orc):
+    from qpzk import gates
+    from perm_util import interpret_program
+    rec = gates.Recorder()
+    a, b = rec.wire(0), rec.wire(1)
+    t = rec.add(a, b)
+    for _ in range(500):                                              # a long chain needs only a handful of registers
+        t = rec.add(rec.mul(t, a), b)
+    rec.emit(t)
+    code, imm, regs = rec.finish()
+    assert regs <= 4
+    x, y, acc = 3, 5, 8
+    for _ in range(500):
+        acc = (acc * x + y) % P
+    assert interpret_program(code, imm, [x, y], []) == [acc]
+    rec = gates.Recorder()
+    for v in [rec.mul(rec.wire(i % 7), rec.wire((i + 1) % 7)) for i in range(300)][::-1]:   # 300 values alive at once
+        rec.emit(v)
+    with pytest.raises(ValueError):
+        rec.finish(256)
+
+
+def test_oracle_poseidon_hash_chain_passes_the_vanishing_check(orc):
+    """CPU mirror of the hash-chain proof (PoseidonGate program, 135 wires, 80 routed) at a small size."""
+    from qpzk import gates
+    from perm_util import poseidon_chain_circuit, verify_gateless_openings
+    log_n = 4
+    rc = gen.round_constants()
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, gen.derive_fast_partial(rc), selector=rec.const(0))
+    code, imm, _ = rec.finish()
+    wires, consts, sigmas = poseidon_chain_circuit(log_n, 9, rc)
+    cs = np.concatenate([consts, sigmas])
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    out = orc.prove_synthetic(ocs, wires, None, None, np.arange(4, dtype=np.uint64), log_n, sigmas=sigmas, sigma_col0=1,
+                              gate_program=(code, imm), pow_bits=6, final_poly_bits=2)
+    assert orc.fri_verify(log_n, out["leaf_lens"], out["all_caps"], out["instance"], out["openings"], out["params"],
+                          out["verifier_challenger"], out["fri_proof"]) == 0
+    bg, alphas, zeta = out["challenges"]
+    assert verify_gateless_openings(log_n, out["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
