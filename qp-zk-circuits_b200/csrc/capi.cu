@@ -163,7 +163,15 @@ static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
 }
 static void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words = 0) {
     if (!p) return;
-    scrub(ctx, p, zero_words);
+    auto dirty = ctx->dirty.find(p);
+    if (dirty != ctx->dirty.end() && ctx->zeroize == 1) {
+        // a block that still carries deferred (mode 2) contents and is released under mode 1: zero all of it now
+        auto bb = ctx->block_bytes.find(p);
+        if (bb != ctx->block_bytes.end()) launch_fill_words(p, bb->second / sizeof(uint64_t), 0, ctx->stream);
+        ctx->dirty.erase(dirty);
+    } else {
+        scrub(ctx, p, zero_words);
+    }
     auto it = ctx->block_bytes.find(p);
     if (it == ctx->block_bytes.end()) { cudaFree(p); return; }  // not ours (cannot happen)
     ctx->cache.emplace(it->second, p);
@@ -311,7 +319,8 @@ extern "C" int qpzk_ctx_synchronize(qpzk_ctx* ctx) {
 extern "C" int qpzk_ctx_set_zeroize(qpzk_ctx* ctx, int mode) {
     if (!ctx) return fail(QPZK_EINVAL, "ctx is null");
     if (mode < 0 || mode > 2) return fail(QPZK_EINVAL, "zeroize mode must be 0, 1 or 2");
-    if (ctx->zeroize == 2 && mode != 2) { cudaSetDevice(ctx->device); scrub_dirty(ctx, false); }   // nothing stays deferred
+    // nothing stays deferred: cached blocks are zeroed now, blocks that live handles still use when they are released
+    if (ctx->zeroize == 2 && mode != 2) { cudaSetDevice(ctx->device); scrub_dirty(ctx, true); }
     ctx->zeroize = mode;
     return 0;
 }

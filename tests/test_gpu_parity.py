@@ -603,10 +603,22 @@ def test_zeroize_modes(qpzk):
     assert _peek(leaves, 5 * 512).any()                                               # still in the private cache
     b2 = qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2)                        # steady state: same block, same result
     assert (b2.cap == cap).all()
+    b2_coeffs = b2.polynomials
     b2.free()
     c.set_zeroize(1)                                                                  # nothing stays deferred
     c.synchronize()
     assert not _peek(leaves, 5 * 512).any()
+    # switching the mode while a batch lives in a block that carries deferred contents must not touch the live batch
+    c.set_zeroize(2)
+    qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2).free()
+    live = qpzk.PolynomialBatch.from_values(c, cols, 3, None, 2)                      # reuses the dirty blocks
+    c.set_zeroize(1)
+    c.synchronize()
+    assert (live.cap == cap).all() and (live.polynomials == b2_coeffs).all()
+    lp = c.L.qpzk_batch_leaves_dev(live.h)
+    live.free()
+    c.synchronize()
+    assert not _peek(lp, 5 * 512).any()
     with pytest.raises(qpzk.QpzkError):
         c.set_zeroize(3)
     c.set_zeroize(2)
