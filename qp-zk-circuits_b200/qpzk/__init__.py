@@ -550,6 +550,18 @@ def fri_params(log_n, rate_bits=3, cap_height=4, proof_of_work_bits=16, num_quer
     return p
 
 
+def hash_no_pad(ctx, elements):
+    """PoseidonHash::hash_no_pad on the device: overwrite-mode sponge of rate 8, no padding, first 4 state words
+    (upstream hashing.rs; `public_inputs_hash = hash_no_pad(public_inputs)` in prove())."""
+    x = np.ascontiguousarray(elements, dtype=np.uint64).reshape(-1)
+    state = np.zeros(12, np.uint64)
+    for off in range(0, max(x.size, 1), 8):
+        chunk = x[off:off + 8]
+        state[:chunk.size] = chunk
+        state = ctx.poseidon_permute(state.reshape(1, 12))[0]
+    return state[:4].copy()
+
+
 def proof_shape(log_n, num_constants, num_sigmas, num_wires, num_zs, num_partial_products, num_quotient_polys,
                 num_public_inputs, salted=(False, False, False, False)):
     s = ProofShape(log_n, num_constants, num_sigmas, num_wires, num_zs, num_partial_products, num_quotient_polys)

@@ -28,7 +28,8 @@ products, 16 quotient chunks; FRI rate_bits 3, cap_height 4, 16 PoW bits, 28 que
 """
 import numpy as np
 
-from . import GENERATOR, P, Challenger, FriInstanceInfo, PolynomialBatch, fri_params  # noqa: F401
+from . import (GENERATOR, P, Challenger, FriInstanceInfo, PolynomialBatch, fri_params, hash_no_pad,  # noqa: F401
+               proof_shape, proof_to_bytes)
 
 LEAF_SHAPE = dict(log_n=13, constants_sigmas=85, wires=135, zs_partial_products=20, quotient=16, num_zs=2)
 RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, ARITY_BITS, FINAL_POLY_BITS = 3, 4, 16, 28, 4, 5
@@ -123,3 +124,23 @@ def synthetic_inputs(seed, shape=LEAF_SHAPE):
     mk = lambda c: rng.integers(0, P, size=(c, n), dtype=np.uint64)
     return dict(wires=mk(shape["wires"]), zs_partial_products=mk(shape["zs_partial_products"]),
                 quotient_coeffs=mk(shape["quotient"]), public_inputs_hash=rng.integers(0, P, size=4, dtype=np.uint64))
+
+
+def prove(circuit, wires, public_inputs, num_routed, gate_program=None, quotient_degree_factor=8, pow_witness=None):
+    """`prove()` for a circuit given as data -- the committed constants/sigmas batch (sigma columns from
+    circuit.sigma_col0), the number of routed wires and the gate program -- and a witness (the wire values):
+    public-inputs hash, wires commitment, partial products, quotient, openings, FRI, then
+    `ProofWithPublicInputs::to_bytes`.  Returns (proof bytes, the qpzk_proof_shape they were written with)."""
+    ctx, sh = circuit.ctx, circuit.shape
+    pih = hash_no_pad(ctx, public_inputs)
+    sig_dummy = np.zeros((num_routed, 0), np.uint64)            # only its row count is read on the device path
+    r = prove_synthetic(circuit, wires, None, None, pih, pow_witness=pow_witness, sigmas=sig_dummy,
+                        quotient_degree_factor=quotient_degree_factor, gate_program=gate_program)
+    nz = sh["num_zs"]
+    nchunks = (num_routed + quotient_degree_factor - 1) // quotient_degree_factor
+    shape = proof_shape(circuit.log_n, circuit.sigma_col0, circuit.constants_sigmas.num_cols - circuit.sigma_col0,
+                        np.asarray(wires).shape[0], nz, nz * (nchunks - 1), nz * quotient_degree_factor,
+                        np.asarray(public_inputs).size)
+    data = proof_to_bytes(circuit.fri_params, shape, r["caps"][0], r["caps"][1], r["caps"][2], r["openings"], r["fri_proof"],
+                          public_inputs)
+    return data, shape

@@ -287,3 +287,34 @@ def poseidon_chain_circuit(log_n, seed, rc, routed=80, inactive_rows=2):
         prev = row[12:24] if not (i & 1) else row[12:24]
     u = lambda a: np.array(a, dtype=np.uint64)
     return u(wires), u([[1 if i < act else 0 for i in range(n)]]), u(sig)
+
+
+# ---- a verifier over the serialized proof ---------------------------------------------------------------------------
+def verify_proof_bytes(orc, qpzk, data, params_q, params_o, shape, cs_cap, circuit_digest, num_routed, chunk=8, program=None):
+    """What upstream's `verify()` does with `ProofWithPublicInputs::from_bytes` output, for a circuit given as data:
+    re-derive every challenge from the transcript (circuit digest, public-inputs hash, the three caps, the openings),
+    check the vanishing identity on the opened values (gate program included) and verify the FRI proof.
+    params_q / params_o: the same FRI parameters as qpzk / oracle structures.  Returns True iff the proof is accepted."""
+    pr = qpzk.proof_from_bytes(params_q, shape, data)
+    log_n, nch = shape.log_n, shape.num_zs
+    ch = orc.Challenger()
+    ch.observe(np.asarray(circuit_digest, np.uint64))
+    ch.observe(orc.hash_no_pad(pr["public_inputs"]) if pr["public_inputs"].size else np.zeros(4, np.uint64))
+    ch.observe(pr["wires_cap"].reshape(-1))
+    bg = ch.get(2 * nch)
+    ch.observe(pr["zs_cap"].reshape(-1))
+    alphas = ch.get(nch)
+    ch.observe(pr["quotient_cap"].reshape(-1))
+    zeta = ch.get(2)
+    if not verify_gateless_openings(log_n, pr["openings"], shape.num_constants, num_routed, shape.num_wires, nch, chunk,
+                                    bg[:nch], bg[nch:], alphas, zeta, program=program):
+        return False
+    ch.observe(pr["openings"].reshape(-1))
+    g = root_of_unity(log_n)
+    g_zeta = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
+    lens = [shape.num_constants + shape.num_sigmas, shape.num_wires, shape.num_zs + shape.num_partial_products,
+            shape.num_quotient_polys]
+    all_polys = [(o, i) for o in range(4) for i in range(lens[o])]
+    inst = orc.Instance([([int(zeta[0]), int(zeta[1])], all_polys), (g_zeta, [(2, i) for i in range(nch)])])
+    caps = [np.asarray(cs_cap, np.uint64).reshape(-1, 4), pr["wires_cap"], pr["zs_cap"], pr["quotient_cap"]]
+    return orc.fri_verify(log_n, list(shape.leaf_lens), caps, inst, pr["openings"], params_o, ch, pr["fri_proof"]) == 0

@@ -782,3 +782,36 @@ def test_poseidon_hash_chain_proved_end_to_end(ctx, qpzk, orc):
     gb = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas, gate_program=prog)
     bg, alphas, zeta = gb["challenges"]
     assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+
+
+def test_prove_to_bytes_and_verify_from_bytes(ctx, qpzk, orc):
+    """prove() for a circuit given as data (Poseidon hash chain, gates as a program) returns serialized bytes; an
+    independent verifier parses them, re-derives every challenge from the transcript, checks the vanishing identity on
+    the opened values and the FRI proof.  Any flipped byte of the proof is rejected."""
+    import gen_poseidon_constants as gen
+    from qpzk import prover, gates
+    from perm_util import poseidon_chain_circuit, verify_proof_bytes
+    log_n = 5
+    rc = gen.round_constants()
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, gen.derive_fast_partial(rc), selector=rec.const(0))
+    code, imm, regs = rec.finish()
+    wires, consts, sigmas = poseidon_chain_circuit(log_n, 21, rc)
+    cs = np.concatenate([consts, sigmas])
+    circuit = prover.SyntheticCircuit(ctx, cs, dict(prover.LEAF_SHAPE, log_n=log_n, constants_sigmas=81), sigma_col0=1)
+    public_inputs = wires[12:16, (1 << log_n) - 3].copy()           # the last digest of the chain
+    data, shape = prover.prove(circuit, wires, public_inputs, 80, qpzk.GateProgram.make(code, imm, regs))
+    assert len(data) == qpzk.load_library().qpzk_proof_bytes_len(circuit.fri_params, shape)
+    po = orc.fri_params(log_n, 3, 4, 16, 28, 4, 5)
+    args = (circuit.fri_params, po, shape, circuit.constants_sigmas.cap, circuit.circuit_digest, 80)
+    assert verify_proof_bytes(orc, qpzk, data, *args, program=(code, imm))
+    assert not verify_proof_bytes(orc, qpzk, data, *args)                       # a verifier without the gates rejects
+    rng = np.random.default_rng(0)
+    for pos in [0, 600, len(data) // 2, len(data) - 40, len(data) - 9] + [int(x) for x in rng.integers(0, len(data) - 48, 6)]:
+        bad = bytearray(data)
+        bad[pos] ^= 1
+        try:
+            ok = verify_proof_bytes(orc, qpzk, bytes(bad), *args, program=(code, imm))
+        except qpzk.QpzkError:
+            ok = False                                                           # not even well formed any more
+        assert not ok, pos
