@@ -193,7 +193,7 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
     total_ms = timed(quot)
 
     # gate constraints as a program: upstream's PoseidonGate -- the gate behind the reference's 135-wire configuration,
-    # 123 constraints of degree 7 -- recorded by qpzk/gates.py (about 5300 instructions, 37 registers) and interpreted at
+    # 123 constraints of degree 7 -- recorded by qpzk/gates.py (about 2900 instructions after multiply-add fusion, 24 registers) and interpreted at
     # every quotient point (qpzk_commit_quotient_prog minus the plain quotient above)
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_poseidon_constants as gen

@@ -289,6 +289,9 @@ int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, cons
  *          0 LOAD_WIRE  r[dst] = wires column a          3 ADD r[dst] = r[a] + r[b]     6 EMIT constraint term = r[a]
  *          1 LOAD_CONST r[dst] = constants_sigmas col a  4 SUB r[dst] = r[a] - r[b]
  *          2 LOAD_IMM   r[dst] = imm[a]                  5 MUL r[dst] = r[a] * r[b]
+ *          fused forms, third source register c in bits 8..15 of the op word:
+ *          7 MULADD r[dst] = r[a]*r[b] + r[c]   8 MULI r[dst] = r[a]*imm[b]   9 ADDI r[dst] = r[a] + imm[b]
+ *          10 MULIADD r[dst] = r[a]*imm[b] + r[c]
  *   registers 0..num_regs-1 (num_regs <= 256; up to 64 stay in L1); a register must be written before it is read (checked). */
 typedef struct {
     const uint32_t* code;

@@ -529,7 +529,7 @@ int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, 
                    const uint64_t* imm, uint64_t* out) {
     unsigned qbits = 0, emits = 0;
     while ((1u << qbits) < chunk) qbits++;
-    for (unsigned pc = 0; pc < num_ops; pc++) if (code[4 * pc] == 6) emits++; else if (code[4 * pc] > 6 || code[4 * pc + 1] >= 256) return -1;
+    for (unsigned pc = 0; pc < num_ops; pc++) if ((code[4 * pc] & 0xff) == 6) emits++; else if ((code[4 * pc] & 0xff) > 10 || code[4 * pc + 1] >= 256) return -1;
     if (!out) return (int)emits;
     const unsigned log_n = wires->log_n, log_L = log_n + wires->rate_bits, log_q = log_n + qbits;
     const size_t Lq = (size_t)1 << log_q, step = (size_t)1 << (wires->rate_bits - qbits);
@@ -541,7 +541,8 @@ int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, 
         uint64_t r[256] = {0};
         unsigned e = 0;
         for (unsigned pc = 0; pc < num_ops; pc++) {
-            const uint32_t op = code[4 * pc], d = code[4 * pc + 1], a = code[4 * pc + 2], b = code[4 * pc + 3];
+            const uint32_t op = code[4 * pc] & 0xff, c = (code[4 * pc] >> 8) & 0xff, d = code[4 * pc + 1], a = code[4 * pc + 2],
+                           b = code[4 * pc + 3];
             switch (op) {
                 case 0: r[d] = lw[a]; break;
                 case 1: r[d] = lc[a]; break;
@@ -549,6 +550,10 @@ int orc_gate_terms(const orc_batch* cs, const orc_batch* wires, unsigned chunk, 
                 case 3: r[d] = gl_add(r[a], r[b]); break;
                 case 4: r[d] = gl_sub(r[a], r[b]); break;
                 case 5: r[d] = gl_mul(r[a], r[b]); break;
+                case 7: r[d] = gl_add(gl_mul(r[a], r[b]), r[c]); break;
+                case 8: r[d] = gl_mul(r[a], imm[b]); break;
+                case 9: r[d] = gl_add(r[a], imm[b]); break;
+                case 10: r[d] = gl_add(gl_mul(r[a], imm[b]), r[c]); break;
                 default: out[leaf_q * emits + e++] = r[a]; break;
             }
         }

@@ -1495,16 +1495,21 @@ static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qp
     std::vector<bool> written(prog->num_regs, false);
     uint32_t emits = 0;
     for (uint32_t pc = 0; pc < prog->num_ops; pc++) {
-        const uint32_t op = prog->code[4 * pc], dst = prog->code[4 * pc + 1], a = prog->code[4 * pc + 2], b = prog->code[4 * pc + 3];
+        const uint32_t w0 = prog->code[4 * pc], op = w0 & 0xffu, c = (w0 >> 8) & 0xffu, dst = prog->code[4 * pc + 1],
+                       a = prog->code[4 * pc + 2], b = prog->code[4 * pc + 3];
         auto bad = [&](const char* what) { return fail(QPZK_EINVAL, std::string("gate program, instruction ") + std::to_string(pc) + ": " + what); };
-        if (op > 6) return bad("unknown opcode");
-        if (op <= 5 && dst >= prog->num_regs) return bad("destination register out of range");
+        auto reg_ok = [&](uint32_t r) { return r < prog->num_regs && written[r]; };
+        if (op > 10 || (w0 >> 16)) return bad("unknown opcode");
+        if (op != 6 && dst >= prog->num_regs) return bad("destination register out of range");
         if (op == 0 && a >= wires->num_cols) return bad("wire column out of range");
         if (op == 1 && a >= cs->num_cols) return bad("constants/sigmas column out of range");
         if (op == 2 && a >= prog->num_imm) return bad("immediate out of range");
-        if (op >= 3 && op <= 5 && (a >= prog->num_regs || b >= prog->num_regs || !written[a] || !written[b])) return bad("source register out of range or not yet written");
-        if (op == 6 && (a >= prog->num_regs || !written[a])) return bad("emitted register out of range or not yet written");
-        if (op <= 5) written[dst] = true; else emits++;
+        if ((op == 3 || op == 4 || op == 5 || op == 7) && (!reg_ok(a) || !reg_ok(b))) return bad("source register out of range or not yet written");
+        if ((op == 8 || op == 9 || op == 10) && !reg_ok(a)) return bad("source register out of range or not yet written");
+        if ((op == 8 || op == 9 || op == 10) && b >= prog->num_imm) return bad("immediate out of range");
+        if ((op == 7 || op == 10) && !reg_ok(c)) return bad("source register out of range or not yet written");
+        if (op == 6 && !reg_ok(a)) return bad("emitted register out of range or not yet written");
+        if (op != 6) written[dst] = true; else emits++;
     }
     for (uint32_t i = 0; i < prog->num_imm; i++) if (prog->imm[i] >= GL_P) return fail(QPZK_EINVAL, "gate program: immediate is not canonical");
     if (!emits) return 0;

@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(256) coset_unshift_kernel(uint64_t* __restrict
 //   op  dst a b      0 LOAD_WIRE  r[dst] = wires[a]            3 ADD  r[dst] = r[a] + r[b]      6 EMIT  term = r[a]
 //                    1 LOAD_CONST r[dst] = constants_sigmas[a] 4 SUB  r[dst] = r[a] - r[b]
 //                    2 LOAD_IMM   r[dst] = imm[a]              5 MUL  r[dst] = r[a] * r[b]
+//   fused forms (third source register c in bits 8..15 of the op word; the recorder's peephole pass produces them):
+//                    7 MULADD  r[dst] = r[a] * r[b] + r[c]     8 MULI r[dst] = r[a] * imm[b]    9 ADDI r[dst] = r[a] + imm[b]
+//                    10 MULIADD r[dst] = r[a] * imm[b] + r[c]
+// A linear layer is multiply-adds by constants: fused, upstream's PoseidonGate shrinks from 5290 to about half as
+// many steps, and each step is one 128-bit product with the addend folded in before the single reduction.
 template <int NR>   // size of the register file: 64 (fits L1 comfortably) or GATE_MAX_REGS
 __global__ void __launch_bounds__(QUOT_THREADS) gate_program_kernel(GateProgramArgs a) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,13 +139,17 @@ __global__ void __launch_bounds__(QUOT_THREADS) gate_program_kernel(GateProgramA
     uint32_t emitted = 0;
     for (uint32_t pc = 0; pc < a.num_ops; pc++) {
         const uint4 ins = __ldg(reinterpret_cast<const uint4*>(a.code) + pc);
-        switch (ins.x) {
+        switch (ins.x & 0xffu) {
             case 0: r[ins.y] = __ldg(wrow + ins.z); break;
             case 1: r[ins.y] = __ldg(crow + ins.z); break;
             case 2: r[ins.y] = __ldg(a.imm + ins.z); break;
             case 3: r[ins.y] = gl_add(r[ins.z], r[ins.w]); break;
             case 4: r[ins.y] = gl_sub(r[ins.z], r[ins.w]); break;
             case 5: r[ins.y] = gl_mul(r[ins.z], r[ins.w]); break;
+            case 7: r[ins.y] = gl_canon(mul_addp(r[ins.z], r[ins.w], r[(ins.x >> 8) & 0xffu])); break;
+            case 8: r[ins.y] = gl_mul(r[ins.z], __ldg(a.imm + ins.w)); break;
+            case 9: r[ins.y] = gl_add(r[ins.z], __ldg(a.imm + ins.w)); break;
+            case 10: r[ins.y] = gl_canon(mul_addp(r[ins.z], __ldg(a.imm + ins.w), r[(ins.x >> 8) & 0xffu])); break;
             default: out[emitted++] = r[ins.z]; break;
         }
     }

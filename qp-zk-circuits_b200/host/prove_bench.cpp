@@ -7,7 +7,9 @@
 // aggregators (wormhole/aggregator/src/aggregator.rs:22-43 proves on detached worker threads without a lock, which is
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
-//   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1] [--zeroize 0|1|2]
+//   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1] [--zeroize 0|1|2] [--gates FILE]
+// --gates FILE (with --perm 1): the circuit's gate constraints as a qpzk_gate_program written by
+// tools/export_gate_program.py (upstream's PoseidonGate on every row), interpreted on the device for the quotient.
 // --devices G: one process drives G GPUs, thread t on device D + (t mod G) -- the aggregator's dispatch (independent leaf
 // proofs, one context per worker thread and device, no collective; reference wormhole/aggregator/src/aggregator.rs:187-227).
 // --perm 1: the zs/partial-products columns and the quotient chunks are not random stand-ins but computed on the device
@@ -52,6 +54,9 @@ struct SplitMix {  // SURVEY.md 8d input recipe: SplitMix64, rejection-sampled b
 
 static bool g_pinned = true, g_breakdown = false, g_perm = false;
 static int g_zeroize = 1;      // qpzk_ctx_set_zeroize mode
+static std::vector<uint32_t> g_gate_code;   // --gates: program shared by all threads (read only)
+static std::vector<uint64_t> g_gate_imm;
+static uint32_t g_gate_regs = 0;
 static int g_stagger_us = 0;   // thread t starts t * g_stagger_us after the others (spreads the phases of concurrent provers)
 
 struct HostBuf {   // pinned (default) or pageable host buffer
@@ -159,7 +164,11 @@ struct Worker {
             uint64_t alphas[2];
             QCHECK(qpzk_challenger_get(ch, alphas, 2));
             lap(1, tp);
-            if (g_perm)
+            if (g_perm && g_gate_regs) {
+                qpzk_gate_program prog{g_gate_code.data(), (uint32_t)(g_gate_code.size() / 4), g_gate_imm.data(),
+                                       (uint32_t)g_gate_imm.size(), g_gate_regs};
+                QCHECK(qpzk_commit_quotient_prog(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, &prog, 4, &q_b));
+            } else if (g_perm)
                 QCHECK(qpzk_commit_quotient(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, nullptr, 0, 4, &q_b));
             else
                 QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
@@ -223,6 +232,15 @@ int main(int argc, char** argv) {
     Shape sh;
     for (int i = 1; i + 1 < argc; i += 2) {
         std::string k = argv[i];
+        if (k == "--gates") {
+            FILE* f = fopen(argv[i + 1], "rb");
+            uint32_t hdr[4];
+            if (!f || fread(hdr, 4, 4, f) != 4 || memcmp(hdr, "QPGP", 4) != 0) { fprintf(stderr, "cannot read gate program %s\n", argv[i + 1]); return 1; }
+            g_gate_code.resize(4ull * hdr[1]); g_gate_imm.resize(hdr[2]); g_gate_regs = hdr[3];
+            if (fread(g_gate_code.data(), 16, hdr[1], f) != hdr[1] || fread(g_gate_imm.data(), 8, hdr[2], f) != hdr[2]) { fprintf(stderr, "truncated gate program\n"); return 1; }
+            fclose(f);
+            continue;
+        }
         int v = atoi(argv[i + 1]);
         if (k == "--device") device = v;
         else if (k == "--devices") devices = v > 0 ? v : 1;
@@ -259,9 +277,9 @@ int main(int argc, char** argv) {
         if (w.max_proof_s > maxp) maxp = w.max_proof_s;
         allocs += w.allocs;
     }
-    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"zeroize\": %d, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"zeroize\": %d, \"gate_program_ops\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\", \"slowest_thread_s\": %.4f, \"fastest_thread_s\": %.4f, \"max_proof_ms\": %.2f, \"device_allocs_in_loop\": %llu}\n",
-           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, g_zeroize, threads * proofs / wall, 1e3 * lat / threads,
+           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, g_zeroize, (unsigned)(g_gate_code.size() / 4), threads * proofs / wall, 1e3 * lat / threads,
            (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum, wall, fastest, 1e3 * maxp, (unsigned long long)allocs);
     return same ? 0 : 3;
 }

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import GateProgram, P
 
-WIRE, CONST, IMM, ADD, SUB, MUL, EMIT = range(7)
+WIRE, CONST, IMM, ADD, SUB, MUL, EMIT, MULADD, MULI, ADDI, MULIADD = range(11)
 
 
 class Recorder:
@@ -48,37 +48,89 @@ class Recorder:
     def emit(self, a):
         self.ops.append((EMIT, 0, a, 0))
 
-    def finish(self, max_regs=256):
+    @staticmethod
+    def _sources(o):
+        """register operands of an internal op tuple (op, dst, a, b, c)"""
+        op, _, a, b, c = o
+        if op in (ADD, SUB, MUL): return (a, b)
+        if op == MULADD: return (a, b, c)
+        if op in (MULI, ADDI): return (a,)
+        if op == MULIADD: return (a, c)
+        if op == EMIT: return (a,)
+        return ()
+
+    def _peephole(self):
+        """Immediate operands and multiply-adds: MUL/ADD with an immediate operand become MULI/ADDI, an ADD whose
+        operand is a single-use MUL/MULI becomes MULADD/MULIADD; loads and products that lose their last use are dropped.
+        The ops are in SSA form (every value has its own virtual register), so moving a product to the place of its sum
+        is always valid."""
+        ops = [(op, d, a, b, 0) for op, d, a, b in self.ops]
+        for _ in range(2):
+            defs = {o[1]: o for o in ops if o[0] != EMIT}
+            for i, o in enumerate(ops):
+                op, d, a, b, c = o
+                if op in (MUL, ADD):
+                    if defs[b][0] == IMM:
+                        ops[i] = (MULI if op == MUL else ADDI, d, a, defs[b][2], 0)
+                    elif defs[a][0] == IMM:
+                        ops[i] = (MULI if op == MUL else ADDI, d, b, defs[a][2], 0)
+            uses = {}
+            for o in ops:
+                for r in self._sources(o):
+                    uses[r] = uses.get(r, 0) + 1
+            defs = {o[1]: o for o in ops if o[0] != EMIT}
+            for i, o in enumerate(ops):
+                op, d, a, b, c = o
+                if op != ADD:
+                    continue
+                for x, y in ((a, b), (b, a)):
+                    m = defs[x]
+                    if m[0] in (MUL, MULI) and uses.get(x, 0) == 1:
+                        ops[i] = (MULADD, d, m[2], m[3], y) if m[0] == MUL else (MULIADD, d, m[2], m[3], y)
+                        uses[x] = 0
+                        break
+            while True:                                  # drop values nobody reads any more
+                uses = {}
+                for o in ops:
+                    for r in self._sources(o):
+                        uses[r] = uses.get(r, 0) + 1
+                keep = [o for o in ops if o[0] == EMIT or uses.get(o[1], 0) > 0]
+                if len(keep) == len(ops):
+                    break
+                ops = keep
+        return ops
+
+    def finish(self, max_regs=256, fuse=True):
         """(code (num_ops, 4) uint32, imm uint64, num_regs) with physical registers."""
+        ops = self._peephole() if fuse else [(op, d, a, b, 0) for op, d, a, b in self.ops]
         last = {}
-        for i, (op, d, a, b) in enumerate(self.ops):
-            if op in (ADD, SUB, MUL):
-                last[a] = i; last[b] = i
-            elif op == EMIT:
-                last[a] = i
+        for i, o in enumerate(ops):
+            for r in self._sources(o):
+                last[r] = i
         free, phys, used, code = [], {}, 0, []
-        for i, (op, d, a, b) in enumerate(self.ops):
-            pa = phys.get(a, 0) if op in (ADD, SUB, MUL, EMIT) else a
-            pb = phys.get(b, 0) if op in (ADD, SUB, MUL) else b
-            # sources whose last use is this instruction are released BEFORE the destination is chosen (dst may reuse them)
-            for v in ({a, b} if op in (ADD, SUB, MUL) else {a} if op == EMIT else set()):
+        for i, o in enumerate(ops):
+            op, d, a, b, c = o
+            src = self._sources(o)
+            pa = phys[a] if a in src else a
+            pb = phys[b] if b in src and op in (ADD, SUB, MUL, MULADD) else b
+            pc = phys[c] if op in (MULADD, MULIADD) else 0
+            for v in set(src):                         # released BEFORE the destination is chosen (dst may reuse them)
                 if last.get(v) == i:
                     free.append(phys.pop(v))
-            if op != EMIT:
-                if d not in last:                      # value never read: still needs a slot for the write
-                    last[d] = i
-                if free:
-                    pd = free.pop()
-                else:
-                    pd = used; used += 1
-                    if used > max_regs:
-                        raise ValueError("gate program needs more than %d registers" % max_regs)
-                phys[d] = pd
-                if last[d] == i:
-                    free.append(phys.pop(d))
-                code.append((op, pd, pa, pb))
-            else:
+            if op == EMIT:
                 code.append((EMIT, 0, pa, 0))
+                continue
+            if free:
+                pd = free.pop()
+            else:
+                pd = used; used += 1
+                if used > max_regs:
+                    raise ValueError("gate program needs more than %d registers" % max_regs)
+            if d in last:
+                phys[d] = pd
+            else:
+                free.append(pd)                        # value never read: the slot is free again at once
+            code.append((op | (pc << 8), pd, pa, pb))
         return np.array(code, dtype=np.uint32).reshape(-1, 4), np.array(self.imms, dtype=np.uint64), max(used, 1)
 
     def program(self, max_regs=256):

@@ -104,13 +104,18 @@ def e_pow(x, e):
 def interpret_program_ext(code, imm, wires, consts):
     """The gate program over extension-field values (the opened values of the wires / constants)."""
     r, out = {}, []
-    for op, d, a, b in [tuple(int(x) for x in row) for row in code]:
+    for w0, d, a, b in [tuple(int(x) for x in row) for row in code]:
+        op, c = w0 & 0xff, (w0 >> 8) & 0xff
         if op == 0: r[d] = wires[a]
         elif op == 1: r[d] = consts[a]
         elif op == 2: r[d] = (int(imm[a]) % P, 0)
         elif op == 3: r[d] = e_add(r[a], r[b])
         elif op == 4: r[d] = e_sub(r[a], r[b])
         elif op == 5: r[d] = e_mul(r[a], r[b])
+        elif op == 7: r[d] = e_add(e_mul(r[a], r[b]), r[c])
+        elif op == 8: r[d] = e_scale(r[a], int(imm[b]) % P)
+        elif op == 9: r[d] = e_add(r[a], (int(imm[b]) % P, 0))
+        elif op == 10: r[d] = e_add(e_scale(r[a], int(imm[b]) % P), r[c])
         else: out.append(r[a])
     return out
 
@@ -201,13 +206,18 @@ class ProgramBuilder:
 def interpret_program(code, imm, wires, consts):
     """Big-integer interpreter of a gate program at one point: wires / consts are lists of field elements."""
     r, out = {}, []
-    for op, d, a, b in [tuple(int(x) for x in row) for row in code]:
+    for w0, d, a, b in [tuple(int(x) for x in row) for row in code]:
+        op, c = w0 & 0xff, (w0 >> 8) & 0xff
         if op == 0: r[d] = int(wires[a]) % P
         elif op == 1: r[d] = int(consts[a]) % P
         elif op == 2: r[d] = int(imm[a]) % P
         elif op == 3: r[d] = (r[a] + r[b]) % P
         elif op == 4: r[d] = (r[a] - r[b]) % P
         elif op == 5: r[d] = r[a] * r[b] % P
+        elif op == 7: r[d] = (r[a] * r[b] + r[c]) % P
+        elif op == 8: r[d] = r[a] * int(imm[b]) % P
+        elif op == 9: r[d] = (r[a] + int(imm[b])) % P
+        elif op == 10: r[d] = (r[a] * int(imm[b]) + r[c]) % P
         else: out.append(r[a])
     return out
 

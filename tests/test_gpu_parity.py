@@ -680,7 +680,8 @@ def test_gate_program_quotient_matches_oracle(ctx, qpzk, orc):
     qb = qpzk.PolynomialBatch.commit_quotient_prog(g[0], g[1], g[2], 3, 16, ch[0], ch[1], ch[2], prog, 2)
     assert (qb.polynomials == want).all()
     # malformed programs are rejected at the boundary, with the instruction number in the message
-    for bad, what in ((np.array([[9, 0, 0, 0]], np.uint32), "opcode"), (np.array([[0, 70, 0, 0]], np.uint32), "destination"),
+    for bad, what in ((np.array([[11, 0, 0, 0]], np.uint32), "opcode"), (np.array([[0x10003, 0, 0, 0]], np.uint32), "opcode"),
+                      (np.array([[0, 0, 0, 0], [8, 1, 0, 900]], np.uint32), "immediate"), (np.array([[0, 0, 0, 0], [0x0507, 1, 0, 0]], np.uint32), "not yet written"), (np.array([[0, 70, 0, 0]], np.uint32), "destination"),
                       (np.array([[0, 300, 0, 0]], np.uint32), "destination"),
                       (np.array([[0, 0, 99, 0]], np.uint32), "wire column"), (np.array([[1, 0, 99, 0]], np.uint32), "column"),
                       (np.array([[2, 0, 3, 0]], np.uint32), "immediate"), (np.array([[3, 0, 1, 2]], np.uint32), "not yet written"),
