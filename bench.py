@@ -227,7 +227,7 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
             "what": "a16: qpzk_partial_products_dev; a17: qpzk_commit_quotient minus the time of its 16-column commit"}
 
 
-def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1):
+def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1, gates=None):
     """The same synthetic prove driven from native code (qp-zk-circuits_b200/host/prove_bench.cpp: C++ threads on the
     C ABI, one context per thread, pinned host buffers).  Returns the parsed JSON line or None."""
     exe = os.path.join(ROOT, "qp-zk-circuits_b200", "prove_bench")
@@ -237,7 +237,7 @@ def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1):
         runs = []
         for _ in range(3 if threads > 1 else 1):   # multi-threaded throughput varies from run to run: report the median
             r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm),
-                                "--zeroize", str(zeroize)],
+                                "--zeroize", str(zeroize)] + (["--gates", gates] if gates else []),
                                capture_output=True, text=True, timeout=300)
             runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
         runs.sort(key=lambda d: d["proofs_per_s"])
@@ -338,6 +338,10 @@ def main():
         native["perm1"] = native_prove_bench(local_rank, 1, 64, perm=1)
         native["perm%d" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1)
         native["perm%d_deferred" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1, zeroize=2)
+        gp = os.path.join(ROOT, "qp-zk-circuits_b200", "host", "poseidon_gate.qpgp")   # written by __graft_entry__.build()
+        if os.path.exists(gp):
+            native["gates1"] = native_prove_bench(local_rank, 1, 64, perm=1, gates=gp)
+            native["gates%d_deferred" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1, zeroize=2, gates=gp)
         native["tmax"] = tmax
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -543,6 +547,15 @@ def main():
                 "proofs_per_s_%d_threads_runs" % native["tmax"]: p4.get("proofs_per_s_runs"),
                 "what": "as above, but the zs/partial-product columns and the quotient chunks are computed on the device from the "
                         "routed wires, the circuit's sigmas and the transcript's challenges (rows a16/a17, permutation argument only)"}
+            g1, g4 = native.get("gates1"), native.get("gates%d_deferred" % native["tmax"])
+            if g1 and g4:
+                out["prove_synthetic"]["native_with_permutation_argument_and_poseidon_gates"] = {
+                    "latency_ms_1_thread": g1["latency_ms"], "proofs_per_s_1_thread": g1["proofs_per_s"],
+                    "proofs_per_s_%d_threads_deferred_zeroize" % native["tmax"]: g4["proofs_per_s"],
+                    "gate_program_ops": g1.get("gate_program_ops"), "gpu_launches_per_proof": g1["launches_per_proof"],
+                    "what": "as above, plus the gate constraints of a circuit with upstream's PoseidonGate on every row (123 constraints of "
+                            "degree 7), handed over as a qpzk_gate_program and interpreted on the device: everything prove() does after "
+                            "witness generation"}
             pd = native.get("perm%d_deferred" % native["tmax"])
             if pd:
                 out["prove_synthetic"]["native_with_permutation_argument"].update({
