@@ -555,7 +555,7 @@ def hash_no_pad(ctx, elements):
     (upstream hashing.rs; `public_inputs_hash = hash_no_pad(public_inputs)` in prove())."""
     x = np.ascontiguousarray(elements, dtype=np.uint64).reshape(-1)
     state = np.zeros(12, np.uint64)
-    for off in range(0, max(x.size, 1), 8):
+    for off in range(0, x.size, 8):                  # no input, no permutation: the hash of nothing is four zeros
         chunk = x[off:off + 8]
         state[:chunk.size] = chunk
         state = ctx.poseidon_permute(state.reshape(1, 12))[0]

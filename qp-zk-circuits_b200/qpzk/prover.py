@@ -1,4 +1,4 @@
-"""Leaf-shaped synthetic prove: the commitment / opening half of plonky2's `prove()` driven through the C ABI.
+"""plonky2's `prove()` after witness generation, driven through the C ABI.
 
 `prove_with_partition_witness` (qp-plonky2 =1.5.5; reached from the reference at wormhole/prover/src/lib.rs:171-175)
 does, per proof (transcript in Appendix A.7):
@@ -8,19 +8,20 @@ does, per proof (transcript in Appendix A.7):
     quotient chunks (coefficients) -> from_coeffs -> observe cap -> zeta
     openings of all four oracles at zeta, of zs at g*zeta -> observe -> PolynomialBatch::prove_openings (FRI)
 
-Witness generation and the quotient evaluation need the gate set of the un-vendored crate and
-are NOT part of this repo; here their outputs are stood in for by caller-supplied (random) columns of the right shapes,
-so the function exercises exactly the part of `prove()` this backend replaces and is labelled *synthetic* wherever it
-is reported.  The permutation argument (rows a16/a17) is gate independent: when the caller passes the sigma values
-(`sigmas`, num_routed x n) instead of ready-made zs/partial-product columns, they are computed on the device from the
-routed wires and the betas/gammas drawn from the transcript (`Context.partial_products`); and when `quotient_coeffs`
-is None the quotient chunks are computed and committed on the device from the three committed batches and the alphas
-(`PolynomialBatch.commit_quotient`; the circuit's sigma columns are then `SyntheticCircuit.sigma_col0 ...`).  With both,
-and wires that satisfy the copy constraints, the result is a complete PLONK proof of a circuit without gates: the
-vanishing identity holds on the opened values (tests/perm_util.py: verify_gateless_openings).  A circuit WITH gates hands
-its constraints over as a `GateProgram` (a straight-line register program, include/qpzk.h): they are then interpreted on
-the device at every quotient point, and the proof covers gates and copy constraints alike.  The constants/sigmas oracle is committed once per circuit
-(`CircuitBuilder::build`, reference wormhole/circuit/src/circuit.rs:206-216), not per proof.
+Two ways to use this module:
+
+* `prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, ...)` with caller-supplied (random) columns for
+  the zs/partial products and the quotient: exactly the commitment / opening half of `prove()`, the part measured as
+  the *leaf-shaped synthetic prove* (BASELINE.json configs 1/2 stand-in).
+* with `zs_partial_products=None` / `quotient_coeffs=None` those two steps run on the device as well: the partial
+  products from the routed wires and the circuit's sigma columns (`PolynomialBatch.commit_zs_partial_products`, row a16),
+  the quotient from the three committed batches (`commit_quotient_prog`, row a17) with the circuit's gate constraints
+  handed over as a `GateProgram` (qpzk/gates.py records them; None = a circuit without gates).  `prove()` below wraps
+  this into "circuit data + witness + public inputs -> ProofWithPublicInputs bytes".  What stays outside is what is
+  specific to the reference's circuits: witness generation and the Rust-side recording of its gate set.
+
+The constants/sigmas oracle is committed once per circuit (`CircuitBuilder::build`, reference
+wormhole/circuit/src/circuit.rs:206-216), not per proof.
 
 Shapes of the leaf circuit: degree 2^13, 85 constants+sigmas, 135 wires, 20 zs/partial
 products, 16 quotient chunks; FRI rate_bits 3, cap_height 4, 16 PoW bits, 28 queries, arity 4, final poly <= 2^5

@@ -309,7 +309,7 @@ def verify_proof_bytes(orc, qpzk, data, params_q, params_o, shape, cs_cap, circu
     log_n, nch = shape.log_n, shape.num_zs
     ch = orc.Challenger()
     ch.observe(np.asarray(circuit_digest, np.uint64))
-    ch.observe(orc.hash_no_pad(pr["public_inputs"]) if pr["public_inputs"].size else np.zeros(4, np.uint64))
+    ch.observe(orc.hash_no_pad(pr["public_inputs"]))
     ch.observe(pr["wires_cap"].reshape(-1))
     bg = ch.get(2 * nch)
     ch.observe(pr["zs_cap"].reshape(-1))

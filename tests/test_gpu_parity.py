@@ -785,6 +785,14 @@ def test_poseidon_hash_chain_proved_end_to_end(ctx, qpzk, orc):
     assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
 
 
+def test_hash_no_pad_matches_oracle(ctx, qpzk, orc):
+    rng = np.random.default_rng(17)
+    for k in (0, 1, 4, 7, 8, 9, 16, 21, 135):
+        x = rng.integers(0, P, size=k, dtype=np.uint64)
+        assert (qpzk.hash_no_pad(ctx, x) == orc.hash_no_pad(x)).all(), k
+    assert not qpzk.hash_no_pad(ctx, []).any()
+
+
 def test_prove_to_bytes_and_verify_from_bytes(ctx, qpzk, orc):
     """prove() for a circuit given as data (Poseidon hash chain, gates as a program) returns serialized bytes; an
     independent verifier parses them, re-derives every challenge from the transcript, checks the vanishing identity on
