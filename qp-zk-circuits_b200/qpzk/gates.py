@@ -148,6 +148,67 @@ def arithmetic_gate(rec, num_ops, selector=None, const_base=1):
         rec.emit(rec.mul(c, selector) if selector is not None else c)
 
 
+# ---- selectors and the sum over gates [upstream-memory: plonky2/src/gates/gate.rs, plonk/vanishing_poly.rs] ---------------
+UNUSED_SELECTOR = 0xFFFFFFFF
+
+
+def selector_filter(rec, s, row, group, many_selectors=False):
+    """upstream `compute_filter(row, group_range, s, many_selector)`: the product over the other gate indices i of the
+    selector group of (i - s), times (UNUSED_SELECTOR - s) when the circuit has several selector polynomials.  It is
+    non-zero exactly on the rows whose selector value is `row`."""
+    f = None
+    for i in list(group) + ([UNUSED_SELECTOR] if many_selectors else []):
+        if i == row:
+            continue
+        t = rec.sub(rec.imm(i), s)
+        f = t if f is None else rec.mul(f, t)
+    return f if f is not None else rec.imm(1)
+
+
+class _Collector:
+    """Stands in for the recorder while ONE gate is recorded: its constraints are kept, not emitted."""
+
+    def __init__(self, rec):
+        self._rec, self.constraints = rec, []
+
+    def __getattr__(self, name):
+        return getattr(self._rec, name)
+
+    def emit(self, a):
+        self.constraints.append(a)
+
+
+def evaluate_gate_constraints(rec, gate_list):
+    """upstream `evaluate_gate_constraints`: constraint slot i of the circuit is the sum over the gates of
+    filter_g * constraint_{g,i}.  gate_list: [(record_fn(recorder), filter register), ...]; emits max_g(#constraints)
+    terms."""
+    slots = []
+    for record, filt in gate_list:
+        col = _Collector(rec)
+        record(col)
+        for i, c in enumerate(col.constraints):
+            t = rec.mul(c, filt)
+            if i < len(slots):
+                slots[i] = rec.add(slots[i], t)
+            else:
+                slots.append(t)
+    for t in slots:
+        rec.emit(t)
+    return len(slots)
+
+
+def constant_gate(rec, num_consts, const_base):
+    """upstream ConstantGate: wire_i - constant_i."""
+    for i in range(num_consts):
+        rec.emit(rec.sub(rec.const(const_base + i), rec.wire(i)))
+
+
+def public_input_gate(rec, public_inputs_hash):
+    """upstream PublicInputGate: wires 0..3 carry the hash of the public inputs (immediates of THIS proof's program)."""
+    for i in range(4):
+        rec.emit(rec.sub(rec.wire(i), rec.imm(public_inputs_hash[i])))
+
+
 # ---- PoseidonGate [upstream-memory: plonky2/src/gates/poseidon.rs] ------------------------------------------------------
 WIRE_SWAP, START_DELTA, START_FULL_0, START_PARTIAL, START_FULL_1, POSEIDON_GATE_WIRES = 24, 25, 29, 65, 87, 135
 MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]

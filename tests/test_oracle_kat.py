@@ -495,3 +495,43 @@ def test_oracle_poseidon_hash_chain_passes_the_vanishing_check(orc):
                           out["verifier_challenger"], out["fri_proof"]) == 0
     bg, alphas, zeta = out["challenges"]
     assert verify_gateless_openings(log_n, out["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+
+
+def test_several_gates_share_constraint_slots_through_selector_filters(orc):
+    """upstream's evaluate_gate_constraints: every gate's constraints are multiplied by its selector filter and summed
+    slot by slot.  A circuit with Poseidon, arithmetic, constant and public-input rows: the combined program vanishes on
+    a correct row of every kind (selected by the row's selector value), not on a row checked against the wrong gate."""
+    from qpzk import gates
+    from perm_util import interpret_program
+    rc = gen.round_constants()
+    fast = gen.derive_fast_partial(rc)
+    pih = [11, 22, 33, 44]
+    rec = gates.Recorder()
+    s = rec.const(0)                                                   # selector polynomial: the gate index of the row
+    group = range(4)
+    n = gates.evaluate_gate_constraints(rec, [
+        (lambda r: gates.poseidon_gate(r, rc, fast), gates.selector_filter(rec, s, 0, group, many_selectors=True)),
+        (lambda r: gates.arithmetic_gate(r, 20, const_base=1), gates.selector_filter(rec, s, 1, group, many_selectors=True)),
+        (lambda r: gates.constant_gate(r, 2, const_base=1), gates.selector_filter(rec, s, 2, group, many_selectors=True)),
+        (lambda r: gates.public_input_gate(r, pih), gates.selector_filter(rec, s, 3, group, many_selectors=True)),
+    ])
+    assert n == 123
+    code, imm, regs = rec.finish()
+    assert (code[:, 0] & 0xff == 6).sum() == 123 and regs <= 256
+    rng = np.random.default_rng(3)
+    rnd = lambda k: [int(x) for x in rng.integers(0, P, size=k, dtype=np.uint64)]
+    # row kinds: wires (135) and constants [selector, c0, c1]
+    pos = gates.poseidon_gate_witness(rnd(12), 1, rc)
+    c0, c1 = rnd(1)[0], rnd(1)[0]
+    ar = rnd(135)
+    for k in range(20):
+        ar[4 * k + 3] = (c0 * ar[4 * k] % P * ar[4 * k + 1] + c1 * ar[4 * k + 2]) % P
+    co = rnd(135); co[0], co[1] = c0, c1
+    pi = rnd(135); pi[:4] = pih
+    rows = {0: (pos, [0, 5, 6]), 1: (ar, [1, c0, c1]), 2: (co, [2, c0, c1]), 3: (pi, [3, 7, 8])}
+    for kind, (w, consts) in rows.items():
+        assert interpret_program(code, imm, w, consts) == [0] * 123, kind
+        wrong = [(kind + 1) % 4] + consts[1:]                           # the same wires under another gate's selector
+        assert any(interpret_program(code, imm, w, wrong)), kind
+    unused = [gates.UNUSED_SELECTOR, 1, 2]                              # a row of another selector group: every filter is 0
+    assert interpret_program(code, imm, rnd(135), unused) == [0] * 123
