@@ -529,7 +529,7 @@ def main():
                                   "what": "leaf-shaped synthetic prove (BASELINE configs 1/2 stand-in): 2^13 rows; commits of 135 / 20 / 16 "
                                           "random columns, openings at zeta and g*zeta over 256 polynomials, FRI (rate 3, cap 4, 16 PoW bits, "
                                           "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
-                                          "restatement (tests/test_gpu_parity.py); witness generation and quotient evaluation are not part of it"}
+                                          "restatement (tests/test_gpu_parity.py); witness generation, partial products and quotient evaluation are not part of THIS figure (see native_with_permutation_argument*)"}
         if native_all is not None:
             # min(4, cores/N) host threads per GPU, every rank at once; permutation argument on the device, deferred zeroize
             out["prove_synthetic"]["proofs_per_s_all_gpus"] = native_all

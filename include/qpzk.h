@@ -159,7 +159,7 @@ int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t point[2], uint64_t* 
  * out = (sum of num_cols) x 2 words, batches in the given order.  (OpeningSet::new evaluates all four oracles at zeta.) */
 int qpzk_batches_eval_ext(qpzk_ctx* ctx, const qpzk_batch* const* batches, uint32_t num_batches,
                           const uint64_t point[2], uint64_t* out);
-/* device views for zero-copy consumers (quotient evaluation, next tier): valid until qpzk_batch_free */
+/* device views for zero-copy consumers (e.g. a caller's own gate-term kernel): valid until qpzk_batch_free */
 const uint64_t* qpzk_batch_leaves_dev(const qpzk_batch* b);
 const uint64_t* qpzk_batch_coeffs_dev(const qpzk_batch* b);
 const uint64_t* qpzk_batch_values_dev(const qpzk_batch* b);   /* NULL unless committed with keep_values on */
