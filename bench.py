@@ -18,9 +18,15 @@ inputs (synthetic).  Default log_n = 22, the largest size of the sweep; it fits 
   roofline  the dominant kernel (Poseidon leaf hashing) against the measured HBM peak, as the contract asks; the
             LDE stage (HBM-bound by design) and the integer pipe (what actually bounds Poseidon) are reported
             beside it as roofline_lde / int_pipe.
-  --impl reference   the CPU restatement of the reference algorithm (oracle/, OpenMP on all host cores) on a bounded
-            sample (2^16 x 135) of the same workload.  The Rust reference itself cannot be built here (no cargo,
-            un-vendored qp-plonky2), see DESIGN.md.
+  --impl reference   the CPU restatement of the reference algorithm (oracle/, OpenMP on every host core, set
+            explicitly: torchrun exports OMP_NUM_THREADS=1) on a bounded sample (2^k x 135, k <= 16 sized to the host)
+            of the same workload.  The Rust reference itself cannot be built here (no cargo, un-vendored qp-plonky2),
+            see DESIGN.md; `cpu_baseline.calibration` states the port's us per permutation per core and the
+            reference's published whole-prove() time so that no ratio is read as "x times the reference".
+  parity_check       outside the timed region the benchmarked commitment is verified against the oracle
+            (oracle/scale_check.py) and the caps of the timed path, the e2e path and a fresh commit must agree; a
+            mismatch fails the run.
+  output    ONE compact JSON line (<= 1.4 kB); the long-form record goes to gpurun_out/bench_detail_n<N>.json.
 """
 import argparse
 import json
@@ -50,17 +56,38 @@ def perms(log_n, num_cols=NUM_COLS, rate_bits=RATE_BITS, cap_height=CAP_HEIGHT):
     return L * ((num_cols + 7) // 8) + (L - (1 << cap_height))
 
 
-def measured_traffic(log_n, world):
-    """DRAM bytes (read + write) of one hash_rows_kernel launch from the committed `ncu --set full` capture of the same
-    configuration (profiles/r1_traffic.json); None when that configuration was not captured."""
-    if world != 1:
-        return None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            e = json.load(f)["per_log_n"][str(log_n)]
-        return e["dram_read_bytes"] + e["dram_write_bytes"]
-    except Exception:
-        return None
+def splitmix_columns_device(seed, num_cols, n, device):
+    """SURVEY.md 8d input recipe on the device: SplitMix64 stream seeded `seed`, rejection-sampled < p, filled
+    column-major; returns a (num_cols, n) int64 tensor holding the canonical u64 bit patterns (identical to
+    tests/conftest.py splitmix_columns and to host/prove_bench.cpp's SplitMix)."""
+    import torch
+    total = num_cols * n
+    m = total + 64 + total // (1 << 24)                 # rejection probability 2^-32 per draw
+    s64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+    lsr = lambda z, k: (z >> k) & ((1 << (64 - k)) - 1)
+    z = torch.arange(1, m + 1, dtype=torch.int64, device=device) * s64(0x9E3779B97F4A7C15) + s64(seed & ((1 << 64) - 1))
+    z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    bad = (z < 0) & (z >= -4294967295)                  # unsigned value >= p = 2^64 - 2^32 + 1
+    if bool(bad.any()):
+        z = z[~bad]
+    return z[:total].reshape(num_cols, n).contiguous()
+
+
+def ncu_record():
+    """Numbers taken from the committed `ncu --set full` capture of hash_rows_kernel at the benchmarked configuration
+    (profiles/r2_traffic.json, else r1): DRAM traffic per launch by log_n, warp-level instructions per permutation."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                e = json.load(f)
+            return {"source": "profiles/" + name,
+                    "traffic": {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in e["per_log_n"].items()},
+                    "inst_per_permutation": e.get("inst_executed_per_permutation")}
+        except Exception:
+            continue
+    return {}
 
 
 def measured_peaks():
@@ -248,6 +275,26 @@ def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1, gates=None
         return None
 
 
+def native_prove_suite(device, world):
+    """Leaf-shaped synthetic prove (BASELINE configs 1/2/5 stand-in) from native code: latency of one prover, throughput
+    of several on one GPU; permutation argument on the device, with and without the PoseidonGate program on every row."""
+    tmax = max(1, min(4, (os.cpu_count() or 4) // world))
+    gp = os.path.join(ROOT, "qp-zk-circuits_b200", "host", "poseidon_gate.qpgp")   # written by __graft_entry__.build()
+    gp = gp if os.path.exists(gp) else None
+    runs = {"perm_1t": native_prove_bench(device, 1, 64, perm=1),
+            "perm_%dt" % tmax: native_prove_bench(device, tmax, 64, perm=1)}
+    if gp:
+        runs["gates_1t"] = native_prove_bench(device, 1, 64, perm=1, gates=gp)
+        runs["gates_%dt" % tmax] = native_prove_bench(device, tmax, 64, perm=1, gates=gp)
+    get = lambda k, f: (runs.get(k) or {}).get(f)
+    return {"threads": tmax, "runs": runs,
+            "latency_ms": get("perm_1t", "latency_ms"), "latency_ms_gates": get("gates_1t", "latency_ms"),
+            "proofs_per_s": get("perm_%dt" % tmax, "proofs_per_s"), "proofs_per_s_gates": get("gates_%dt" % tmax, "proofs_per_s"),
+            "what": "2^13 rows; commits of 135 / 20 / 16 columns, partial products + quotient (+ PoseidonGate program) on the "
+                    "device, 276 openings, FRI (rate 3, cap 4, 16 PoW bits, 28 queries, arity 4); host buffers in, proof out; "
+                    "witness generation excluded; host/prove_bench.cpp"}
+
+
 def cpu_prove_synthetic(proofs=2):
     """The same synthetic prove on the CPU restatement (all host cores); ms per proof."""
     import numpy as np
@@ -268,17 +315,49 @@ def cpu_prove_synthetic(proofs=2):
     return 1e3 * best, orc.num_threads()
 
 
+WORKLOAD = "raw commit (BASELINE config 3): 2^%d rows x %d cols, rate_bits %d, cap_height %d, Poseidon-12 Merkle, blinding off"
+# published whole-prove() time of the reference's own CPU prover (other hardware; context for every ratio below)
+PUBLISHED_LEAF_PROVE = {"ms": 20.0, "hardware": "Apple M2 Max, 12 cores", "source": "paper/main.tex:449,455"}
+
+
+def cpu_sample_log_n(cores, budget_s=6.0):
+    """Largest size of the sweep's shape (2^k x 135, k <= 16) one step of which fits `budget_s` on `cores` threads,
+    assuming 7 us per permutation per core (the port's measured rate; the permutations dominate)."""
+    k = 16
+    while k > 10 and 7e-6 * perms(k) / max(cores, 1) > budget_s:
+        k -= 1
+    return k
+
+
+def port_calibration(orc):
+    """us per Poseidon permutation on ONE core of this host (the port's unit of work)."""
+    import numpy as np
+    rows = np.arange(256 * 128, dtype=np.uint64).reshape(256, 128)
+    orc.set_num_threads(1)
+    t0 = time.perf_counter()
+    orc.MerkleTree(rows, 0)
+    dt = time.perf_counter() - t0
+    orc.set_num_threads()
+    return 1e6 * dt / (256 * 16 + 255)
+
+
 def run_reference(args):
+    """The reference arm: the CPU restatement of the same algorithm (oracle/, C + OpenMP) on every host core, each step
+    one from_values of a bounded sample of the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
     from oracle import oracle as orc
     orc.build()
-    sample = 16
-    rng = np.random.default_rng(16)
-    cols = rng.integers(0, P, size=(NUM_COLS, 1 << sample), dtype=np.uint64)
+    cores = orc.set_num_threads()            # torchrun exports OMP_NUM_THREADS=1: use the host's cores explicitly
+    us_perm = port_calibration(orc)
+    sample = cpu_sample_log_n(cores)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import splitmix_columns
+    cols = splitmix_columns(0x51575A4B00000000 + sample, NUM_COLS, 1 << sample)
     times = []
+    t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         b = orc.PolynomialBatch.from_values(cols, RATE_BITS, CAP_HEIGHT)
@@ -286,21 +365,59 @@ def run_reference(args):
         del b
         if i >= args.warmup:
             times.append(dt)
+        if time.perf_counter() - t_start > 150 and times:      # bound the arm's wall time whatever the host is
+            break
     ms = 1e3 * sum(times) / len(times)
     v = bytes_alg(sample) / (ms * 1e-3) / 1e9
-    desc = "one from_values of 2^%d x %d (rate_bits 3, cap_height 4) per step" % (sample, NUM_COLS)
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    desc = "one from_values of 2^%d x %d per step (same shape, bounded size), %d steps timed" % (sample, NUM_COLS, len(times))
+    print(json.dumps(compact({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64 (Goldilocks)", "data": "synthetic",
-        "config": {"workload": "raw commit 2^%d x %d, rate_bits 3, cap_height 4 (bounded CPU sample of config 3)" % (sample, NUM_COLS)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": desc,
-                         "note": "restated CPU baseline (oracle/, C + OpenMP) -- not the reference binary: no cargo/rustc here"},
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % (args.log_n, NUM_COLS, RATE_BITS, CAP_HEIGHT)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "calibration": {"port_us_per_permutation_per_core": us_perm, "published_leaf_prove": PUBLISHED_LEAF_PROVE},
+                         "note": "restated CPU baseline (oracle/), not the reference binary: no cargo here"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "prove_synthetic": (lambda r: {"latency_ms": r[0], "proofs_per_s": 1e3 / r[0], "cores": r[1],
-                                       "what": "leaf-shaped synthetic prove (2^13; 135/20/16-column commits, openings, FRI) on the CPU restatement"})(cpu_prove_synthetic()),
-    }))
+    })))
+
+
+def compact(x, sig=5):
+    """Round floats to `sig` significant digits (the driver keeps ~1.5 kB of the line)."""
+    if isinstance(x, float):
+        return float("%.*g" % (sig, x))
+    if isinstance(x, dict):
+        return {k: compact(v, sig) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [compact(v, sig) for v in x]
+    return x
+
+
+def parity_check_commit(qpzk, ctx, dev, log_n, values_dev, cap_timed, cap_e2e, seed=22):
+    """Outside the timed region: the commitment the benchmark times, checked against the oracle.
+    values_dev: the full (C, n) input on this device.  A fresh single-GPU device-resident commit of it must
+      (1) pass oracle/scale_check.check_commit: coefficients vs the committed VALUES at a random point for every
+          column, 1024 leaf rows x all columns on subgroup cosets in all 8 leaf blocks, their Merkle paths, tree top;
+      (2) have the cap the timed loop produced (N > 1: the all-gathered cap of the coset split) and
+      (3) the cap of the end-to-end host-buffer path.
+    Returns the dict that goes into the JSON line; any mismatch raises."""
+    import numpy as np
+    from oracle import scale_check
+    from oracle import oracle as orc
+    orc.set_num_threads()
+    t0 = time.perf_counter()
+    b = qpzk.PolynomialBatch.from_device(ctx, values_dev.data_ptr(), log_n, values_dev.shape[0], RATE_BITS, CAP_HEIGHT, values=True)
+    cap = b.cap
+    host = values_dev.cpu().numpy().view(np.uint64)
+    r = scale_check.check_commit(b, host, RATE_BITS, num_rows=1024, seed=seed)
+    b.free()
+    r["cap_timed_path_equal"] = bool((np.asarray(cap_timed).reshape(-1) == cap.reshape(-1)).all())
+    r["cap_e2e_path_equal"] = None if cap_e2e is None else bool((np.asarray(cap_e2e).reshape(-1) == cap.reshape(-1)).all())
+    r["ok"] = bool(r["ok"] and r["cap_timed_path_equal"] and r["cap_e2e_path_equal"] is not False)
+    r["seconds"] = time.perf_counter() - t0
+    r["cap0"] = "%016x" % int(cap.reshape(-1)[0])
+    return r
 
 
 def main():
@@ -313,6 +430,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--detail", default=None, help="side file for the long-form record (default gpurun_out/bench_detail_n<N>.json)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -332,17 +451,7 @@ def main():
     # prover per GPU = BASELINE configs 4/5, replicas without a data-path collective).
     native = {}
     if not args.no_prove:
-        tmax = max(1, min(4, (os.cpu_count() or 4) // world))
-        native[1] = native_prove_bench(local_rank, 1, 64)          # also warms the clocks
-        native[tmax] = native_prove_bench(local_rank, tmax, 64)
-        native["perm1"] = native_prove_bench(local_rank, 1, 64, perm=1)
-        native["perm%d" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1)
-        native["perm%d_deferred" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1, zeroize=2)
-        gp = os.path.join(ROOT, "qp-zk-circuits_b200", "host", "poseidon_gate.qpgp")   # written by __graft_entry__.build()
-        if os.path.exists(gp):
-            native["gates1"] = native_prove_bench(local_rank, 1, 64, perm=1, gates=gp)
-            native["gates%d_deferred" % tmax] = native_prove_bench(local_rank, tmax, 64, perm=1, zeroize=2, gates=gp)
-        native["tmax"] = tmax
+        native = native_prove_suite(local_rank, world)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -362,21 +471,27 @@ def main():
     ctx = qpzk.Context(local_rank, stream=stream.cuda_stream)
     ctx.set_timing(True)
 
-    # ---- synthetic input: this rank's column slice, canonical uniform values, resident in HBM
+    # ---- synthetic input: SplitMix64 seeded 0x51575a4b00000000 + k, rejection-sampled < p, column-major;
+    # this rank's column slice resident in HBM (rank 0 keeps the whole matrix for the parity check)
     q = (C_ + world - 1) // world                      # columns per rank (last rank is zero padded)
     c0, c1 = rank * q, min((rank + 1) * q, C_)
-    gen = torch.Generator(device=dev).manual_seed(0x5157 + log_n)
-    full = torch.randint(0, 2**63 - 1, (C_, n), generator=gen, device=dev, dtype=torch.int64)  # < 2^63 < p: canonical
-    mine = torch.zeros((q, n), dtype=torch.int64, device=dev)
-    mine[: c1 - c0] = full[c0:c1]
-    del full
-    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev)
+    full = splitmix_columns_device(0x51575A4B00000000 + log_n, C_, n, dev)
+    if world == 1:
+        mine = full
+    else:
+        mine = torch.zeros((q, n), dtype=torch.int64, device=dev)
+        mine[: c1 - c0] = full[c0:c1]
+        if rank != 0 or args.no_parity:
+            del full
+            full = None
+    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev) if world > 1 else None
     coeff_all = torch.empty((world * q, n), dtype=torch.int64, device=dev) if world > 1 else None
     cosets_per = B // world
     cap_all = torch.empty((world, (1 << CAP_HEIGHT) // world * 4), dtype=torch.int64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
     stage = {"intt_ms": 0.0, "lde_ms": 0.0, "leaf_hash_ms": 0.0, "merkle_levels_ms": 0.0, "allgather_ms": 0.0}
+    last_cap = [None]
 
     def step(record):
         if world == 1:
@@ -398,9 +513,12 @@ def main():
         return b
 
     def finish(b):
-        cap = torch.from_numpy(b.cap.view(np.int64).reshape(-1))  # tiny D2H read of this rank's cap slice
+        cap = b.cap                                   # tiny D2H read of this rank's cap slice
         if world > 1:
-            dist.all_gather_into_tensor(cap_all, cap.to(dev).reshape(1, -1))
+            dist.all_gather_into_tensor(cap_all, torch.from_numpy(cap.view(np.int64).reshape(1, -1)).to(dev))
+            last_cap[0] = cap_all
+        else:
+            last_cap[0] = cap
         b.free()
 
     # ---- device-resident timing: W warm-up, then exactly K steps between barriers + synchronize
@@ -423,6 +541,7 @@ def main():
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
+    cap_timed = last_cap[0].cpu().numpy().view(np.uint64).copy() if world > 1 else last_cap[0].copy()
     # per-stage durations from a separate pass (stage events synchronise the stream, so they stay out of the timed loop)
     for _ in range(args.steps):
         finish(step(True))
@@ -435,22 +554,40 @@ def main():
     value = bytes_alg(log_n) / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C-ABI call (pinned host input, H2D inside, cap D2H inside)
-    e2e = None
+    e2e, cap_e2e = None, None
     if not args.no_e2e:
         host = torch.empty((c1 - c0 if world > 1 else C_, n), dtype=torch.int64).pin_memory()
         host.copy_(mine[: host.shape[0]])
         torch.cuda.synchronize()
         hnp = host.numpy().view(np.uint64)
+        copy_stream = torch.cuda.Stream(device=dev)
+        pieces = max(1, min(8, host.shape[0]))
+        bounds = [host.shape[0] * i // pieces for i in range(pieces + 1)]
 
         def e2e_step():
             if world == 1:
                 bb = qpzk.PolynomialBatch.from_values(ctx, hnp, RATE_BITS, None, CAP_HEIGHT)
-                cap = bb.cap
-                bb.free()
-                return cap
-            mine[: host.shape[0]].copy_(host, non_blocking=True)
-            bb = step(False)
-            finish(bb)
+                finish(bb)
+                return
+            # N > 1: this rank's column slice comes from pinned host memory in column ranges on a copy stream; the
+            # iNTT of one range runs while the next is in flight (what qpzk_commit_from_values does on one GPU)
+            copy_stream.wait_stream(stream)
+            evs = []
+            with torch.cuda.stream(copy_stream):
+                for a, z in zip(bounds[:-1], bounds[1:]):
+                    mine[a:z].copy_(host[a:z], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    evs.append(ev)
+            for (a, z), ev in zip(zip(bounds[:-1], bounds[1:]), evs):
+                stream.wait_event(ev)
+                if z > a:
+                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[a:z].data_ptr(), coeff_mine[a:z].data_ptr(), log_n, z - a))
+            if q > host.shape[0]:                      # zero padding columns of the last rank
+                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[host.shape[0]:].data_ptr(), coeff_mine[host.shape[0]:].data_ptr(), log_n, q - host.shape[0]))
+            dist.all_gather_into_tensor(coeff_all, coeff_mine)
+            finish(qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
+                                                                  rank * cosets_per, cosets_per))
 
         for _ in range(2):
             e2e_step()
@@ -459,31 +596,39 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ts = time.perf_counter()
             e2e_step()
-            if os.environ.get("QPZK_BENCH_DEBUG"):
-                torch.cuda.synchronize()
-                print("e2e step %.1f ms" % (1e3 * (time.perf_counter() - ts)), file=sys.stderr)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_ms = 1e3 * float(dt.item()) / args.steps
+        cap_e2e = last_cap[0].cpu().numpy().view(np.uint64).copy() if world > 1 else last_cap[0].copy()
         e2e = {"value": bytes_alg(log_n) / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(host.numel() * 8), "d2h_bytes_per_step": int((1 << CAP_HEIGHT) // world * 32)}
+        del host, hnp
 
     # ---- independent proofs, one prover per GPU (BASELINE configs 4/5: replicas, no data-path collective) ----
-    native_all = None
+    proofs_all = None
     if world > 1 and not args.no_prove:
-        r = native.get("perm%d_deferred" % native.get("tmax", 0))
-        v = torch.tensor([r["proofs_per_s"] if r else 0.0], device=dev, dtype=torch.float64)
+        v = torch.tensor([native.get("proofs_per_s", 0.0) or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(v)
-        native_all = float(v.item())
+        proofs_all = float(v.item())
 
     if rank != 0:
         if world > 1:
+            dist.barrier()                            # rank 0 finishes its parity check before NCCL goes away
             dist.destroy_process_group()
         return
+
+    # ---- parity of what was timed (outside the timed region; a mismatch fails the run)
+    parity = None
+    if not args.no_parity:
+        del mine
+        ctx.trim()
+        try:
+            parity = parity_check_commit(qpzk, ctx, dev, log_n, full, cap_timed, cap_e2e, seed=log_n)
+        except AssertionError as ex:
+            parity = {"ok": False, "error": str(ex)[:200]}
 
     # ---- rooflines
     hbm_peak, peak_src = measured_peaks()
@@ -495,89 +640,81 @@ def main():
     lde_ms = stage["intt_ms"] + stage["lde_ms"]
     lde_gbs = lde_bytes / (lde_ms * 1e-3) / 1e9 if lde_ms else None
     imad_peak = ctx.bench_imad(8192)
-    perm_rate_kernel = rows_here * ((C_ + 7) // 8) / (stage["leaf_hash_ms"] * 1e-3) if stage["leaf_hash_ms"] else None
+    perms_launch = rows_here * ((C_ + 7) // 8)
+    perm_rate_kernel = perms_launch / (stage["leaf_hash_ms"] * 1e-3) if stage["leaf_hash_ms"] else None
+    ncu = ncu_record()
+    sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+    int_issue = None
+    if ncu.get("inst_per_permutation") and stage["leaf_hash_ms"]:
+        # warp instructions issued by one launch (ncu: smsp__inst_executed.sum per permutation x permutations / 32 lanes)
+        # over the issue slots of the launch: SMs x 4 schedulers x cycles
+        int_issue = ncu["inst_per_permutation"] * perms_launch / 32 / (148 * 4 * sm_hz * stage["leaf_hash_ms"] * 1e-3)
+    detail = {
+        "config_long": {"l2": "inputs (%.2f GB per rank) and the LDE are larger than the 126 MB L2; no flush needed" % (C_ * n * 8 / world / 1e9),
+                        "inputs": "SplitMix64 seed 0x51575a4b00000000 + log_n, rejection-sampled < p, column-major (SURVEY.md 8d)",
+                        "bytes_alg": bytes_alg(log_n), "permutations": perms(log_n)},
+        "roofline_long": {"kernel": "hash_rows_kernel (Poseidon leaf sponge, %d permutations per row)" % ((C_ + 7) // 8),
+                          "traffic_unit": "DRAM bytes read+written per launch (ncu --set full, %s)" % ncu.get("source"),
+                          "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src + " (of measured)",
+                          "note": "integer-pipe bound, not HBM bound: int_issue = issued warp instructions / issue slots; "
+                                  "HBM fraction reported because the contract asks for it"},
+        "roofline_commit": {"bound": "hbm", "achieved": value, "peak": hbm_peak * world, "unit": "GB/s", "frac": value / (hbm_peak * world)},
+        "native": native,
+    }
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64 (Goldilocks)", "data": "synthetic",
-        "config": {"workload": "raw commit (BASELINE config 3): 2^%d rows x %d cols, rate_bits %d, cap_height %d, "
-                               "Poseidon-12 Merkle, blinding off" % (log_n, C_, RATE_BITS, CAP_HEIGHT),
-                   "l2": "inputs (%.2f GB per rank) and the LDE are larger than the 126 MB L2; no flush needed" % (mine.numel() * 8 / 1e9),
-                   "parallelism": "coset split x%d (iNTT column split + NCCL all-gather of coefficients)" % world if world > 1 else "single GPU",
-                   "bytes_alg": bytes_alg(log_n), "permutations": perms(log_n)},
-        "stages_ms": stage,
-        "roofline": {"kernel": "hash_rows_kernel (Poseidon leaf sponge, %d permutations per row)" % ((C_ + 7) // 8),
-                     "bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": measured_traffic(log_n, world),
-                     "traffic_unit": "DRAM bytes read+written per launch (ncu --set full, profiles/r1_traffic.json)",
-                     "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": peak_src + " (of measured)",
-                     "pipes": "ncu: issue slots 71% busy, ALU pipe 80% of peak (profiles/r1_summary.md F)",
-                     "note": "integer-pipe bound, not HBM bound: see int_pipe; HBM fraction reported because the contract asks for it"},
-        "roofline_lde": {"kernels": "ntt_pass_kernel (iNTT) + ntt_fwd_kernel x2 + lde_last32_tma_kernel", "bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": lde_gbs / hbm_peak if lde_gbs else None, "bytes": lde_bytes},
-        "roofline_commit": {"bound": "hbm", "achieved": value, "peak": hbm_peak * world, "unit": "GB/s",
-                            "frac": value / (hbm_peak * world)},
-        "int_pipe": {"imad_wide_per_s_measured": imad_peak, "poseidon_perms_per_s_in_kernel": perm_rate_kernel,
-                     "poseidon_perms_per_s_microbench": ctx.bench_poseidon(32)},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % (log_n, C_, RATE_BITS, CAP_HEIGHT),
+                   "parallelism": "coset split x%d + NCCL all-gather of coefficients" % world if world > 1 else "single GPU",
+                   "l2": "inputs > L2"},
+        "roofline": {"bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": ncu.get("traffic", {}).get(str(log_n)) if world == 1 else None,
+                     "kernel": "hash_rows_kernel", "int_issue": int_issue},
+        "roofline_lde": {"bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": lde_gbs / hbm_peak if lde_gbs else None},
+        "int_pipe": {"imad_wide_per_s": imad_peak, "perms_per_s_in_kernel": perm_rate_kernel,
+                     "perms_per_s_microbench": ctx.bench_poseidon(32)},
+        "stages_ms": stage, "gpu_launches": int(launches), "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
     }
     if e2e:
         out["e2e"] = e2e
+    if parity is not None:
+        out["parity_check"] = {k: parity.get(k) for k in ("ok", "rows_checked", "columns", "cap_timed_path_equal", "cap_e2e_path_equal", "error") if parity.get(k) is not None}
+        detail["parity_check"] = parity
     if not args.no_prove:
-        ms, nl = gpu_prove_synthetic(ctx)
-        out["prove_synthetic"] = {"latency_ms": ms, "proofs_per_s": 1e3 / ms, "gpu_launches_per_proof": int(nl),
-                                  "what": "leaf-shaped synthetic prove (BASELINE configs 1/2 stand-in): 2^13 rows; commits of 135 / 20 / 16 "
-                                          "random columns, openings at zeta and g*zeta over 256 polynomials, FRI (rate 3, cap 4, 16 PoW bits, "
-                                          "28 queries, arity 4); host buffers in, proof out; sequential on one GPU; bit-exact with the CPU "
-                                          "restatement (tests/test_gpu_parity.py); witness generation, partial products and quotient evaluation are not part of THIS figure (see native_with_permutation_argument*)"}
-        if native_all is not None:
-            # min(4, cores/N) host threads per GPU, every rank at once; permutation argument on the device, deferred zeroize
-            out["prove_synthetic"]["proofs_per_s_all_gpus"] = native_all
-        n1, n4 = native.get(1), native.get(native.get("tmax"))
-        if n1 and n4:
-            out["prove_synthetic"]["native"] = {
-                "latency_ms_1_thread": n1["latency_ms"], "proofs_per_s_1_thread": n1["proofs_per_s"],
-                "proofs_per_s_%d_threads" % native["tmax"]: n4["proofs_per_s"], "gpu_launches_per_proof": n1["launches_per_proof"],
-                "what": "same proof from C++ host threads on the C ABI (host/prove_bench.cpp), one context per thread, pinned buffers"}
-        p1, p4 = native.get("perm1"), native.get("perm%d" % native.get("tmax", 0))
-        if p1 and p4:
-            out["prove_synthetic"]["native_with_permutation_argument"] = {
-                "latency_ms_1_thread": p1["latency_ms"], "proofs_per_s_1_thread": p1["proofs_per_s"],
-                "proofs_per_s_%d_threads" % native["tmax"]: p4["proofs_per_s"], "gpu_launches_per_proof": p1["launches_per_proof"],
-                "proofs_per_s_%d_threads_runs" % native["tmax"]: p4.get("proofs_per_s_runs"),
-                "what": "as above, but the zs/partial-product columns and the quotient chunks are computed on the device from the "
-                        "routed wires, the circuit's sigmas and the transcript's challenges (rows a16/a17, permutation argument only)"}
-            g1, g4 = native.get("gates1"), native.get("gates%d_deferred" % native["tmax"])
-            if g1 and g4:
-                out["prove_synthetic"]["native_with_permutation_argument_and_poseidon_gates"] = {
-                    "latency_ms_1_thread": g1["latency_ms"], "proofs_per_s_1_thread": g1["proofs_per_s"],
-                    "proofs_per_s_%d_threads_deferred_zeroize" % native["tmax"]: g4["proofs_per_s"],
-                    "gate_program_ops": g1.get("gate_program_ops"), "gpu_launches_per_proof": g1["launches_per_proof"],
-                    "what": "as above, plus the gate constraints of a circuit with upstream's PoseidonGate on every row (123 constraints of "
-                            "degree 7), handed over as a qpzk_gate_program and interpreted on the device: everything prove() does after "
-                            "witness generation"}
-            pd = native.get("perm%d_deferred" % native["tmax"])
-            if pd:
-                out["prove_synthetic"]["native_with_permutation_argument"].update({
-                    "proofs_per_s_%d_threads_deferred_zeroize" % native["tmax"]: pd["proofs_per_s"],
-                    "proofs_per_s_%d_threads_deferred_zeroize_runs" % native["tmax"]: pd.get("proofs_per_s_runs"),
-                    "zeroize_note": "default: secret-derived buffers are zeroed when released; with several provers on one GPU those "
-                                    "fills trigger stalls of 0.2-2 s in about half of the runs (median of 3 reported); "
-                                    "qpzk_ctx_set_zeroize(ctx, 2) zeroes them before they leave the context's block cache instead"})
-        if not args.no_cpu_baseline:
-            cms, cores = cpu_prove_synthetic()
-            out["prove_synthetic"]["cpu_port_latency_ms"] = cms
-            out["prove_synthetic"]["cpu_cores"] = cores
+        out["prove"] = {k: native.get(k) for k in ("latency_ms", "latency_ms_gates", "proofs_per_s", "proofs_per_s_gates") if native.get(k) is not None}
+        if proofs_all is not None:
+            out["prove"]["proofs_per_s_all_gpus"] = proofs_all
+        out["prove"]["published_cpu_ms"] = PUBLISHED_LEAF_PROVE["ms"]
     if not args.no_prove:
-        out["perm_argument"] = [gpu_perm_argument(ctx, dev, k) for k in (13, 18)]
+        detail["perm_argument"] = [gpu_perm_argument(ctx, dev, k) for k in (13, 18)]
     if not args.no_cpu_baseline:
-        v, cores, secs = cpu_commit_sample(16)
+        from oracle import oracle as orc
+        cores = orc.set_num_threads()
+        us_perm = port_calibration(orc)
+        k = cpu_sample_log_n(cores, 12.0)
+        v, cores, secs = cpu_commit_sample(k)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "one from_values of 2^16 x %d (same shape, smallest size of the sweep), %.1f s" % (C_, secs),
-                               "note": "restated CPU baseline (oracle/, C + OpenMP) -- not the reference binary"}
-    print(json.dumps(out))
+                               "sample": "one from_values of 2^%d x %d, %.1f s" % (k, C_, secs),
+                               "calibration": {"port_us_per_perm_per_core": us_perm, "published_leaf_prove_ms": PUBLISHED_LEAF_PROVE["ms"],
+                                               "published_on": PUBLISHED_LEAF_PROVE["hardware"]}}
+        if not args.no_prove:
+            cms, _ = cpu_prove_synthetic()
+            out["prove"]["cpu_port_ms"] = cms
+    path = args.detail or os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % world)
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump({"line": out, "detail": detail}, f, indent=1, default=str)
+    except OSError:
+        pass
+    print(json.dumps(compact(out), separators=(",", ":")))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity.get("ok"):
+        raise SystemExit("parity check FAILED: %s" % parity)
 
 
 if __name__ == "__main__":

@@ -90,6 +90,13 @@ void qpzk_pinned_free(void* p);
 uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx);
 /* number of cudaMalloc calls the context's block cache has made since creation (does not grow in steady state) */
 uint64_t qpzk_ctx_device_allocs(const qpzk_ctx* ctx);
+/* High-water mark of the device memory this context holds (buffers in use + cached blocks), in bytes -- the role of the
+ * reference's peak-RSS figure (wormhole/memprof/src/report.rs:18-54; common/src/circuit.rs:393-395 quotes 1.5 / 2.5 GB
+ * for the 2^15 / 2^16 private-batch prover).  qpzk_ctx_reset_peak restarts the measurement from the current holding.
+ * Every stage of the path is also an NVTX range ("qpzk:from_values", "qpzk:ifft", "qpzk:lde passes",
+ * "qpzk:MerkleTree::new", "qpzk:prove_openings", ...) for nsys / ncu --nvtx. */
+uint64_t qpzk_ctx_peak_bytes(const qpzk_ctx* ctx);
+void qpzk_ctx_reset_peak(qpzk_ctx* ctx);
 
 /* ---- PolynomialBatch::from_values / from_coeffs --------------------------------------------------
  * Replaces qp-plonky2 `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing,
@@ -246,10 +253,14 @@ int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires_dev, const ui
 
 /* The same from two committed batches that kept their values (qpzk_ctx_set_keep_values), followed by the
  * zs/partial-products commitment (from_values, rate_bits of `wires`) -- nothing leaves the device:
- * sigma_j = column sigma_col0 + j of constants_sigmas, routed wires = columns [0, num_routed) of wires. */
+ * sigma_j = column sigma_col0 + j of constants_sigmas, routed wires = columns [0, num_routed) of wires.
+ * salt_dev: NULL, or the DEVICE blinding columns of this oracle (QPZK_SALT_SIZE x 2^(log_n+rate_bits), as for
+ * qpzk_commit_from_values_dev): upstream blinds WIRES, ZS_PARTIAL_PRODUCTS and QUOTIENT when the circuit is
+ * zero-knowledge (PlonkOracle::*.blinding; the leaf and private-batch configurations, common/src/circuit.rs:378-402). */
 int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
                                     uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
-                                    const uint64_t* betas, const uint64_t* gammas, uint32_t cap_height, qpzk_batch** out);
+                                    const uint64_t* betas, const uint64_t* gammas, uint32_t cap_height,
+                                    const uint64_t* salt_dev, qpzk_batch** out);
 
 /* ---- quotient polynomials: compute_quotient_polys for the permutation argument -----------------------
  * Replaces the gate-independent part of qp-plonky2 `compute_quotient_polys` (plonk/prover.rs) and
@@ -268,7 +279,8 @@ int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_s
  *                          The gate set itself lives in the un-vendored crate and is not part of this library.
  *   out                  : (num_challenges * Q) x 2^log_n coefficients, column-major: chunk k of challenge a is
  *                          column a*Q + k -- the input of the quotient commitment (from_coeffs).
- * qpzk_commit_quotient does the same and commits the chunks without leaving the device (rate_bits of the inputs). */
+ * qpzk_commit_quotient does the same and commits the chunks without leaving the device (rate_bits of the inputs;
+ * salt_dev as for qpzk_commit_zs_partial_products). */
 int qpzk_quotient_polys(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
                         const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                         uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
@@ -278,7 +290,7 @@ int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, cons
                          const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                          uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
                          const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
-                         uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out);
+                         uint32_t num_gate_terms, uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out);
 
 /* Gate constraints handed over as DATA: a straight-line register program over the base field that computes, for one
  * point, what upstream's `evaluate_gate_constraints` / `eval_unfiltered_base_batch` (plonk/vanishing_poly.rs, gates/*.rs)
@@ -309,7 +321,7 @@ int qpzk_commit_quotient_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas,
                               const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                               uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
                               const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog,
-                              uint32_t cap_height, qpzk_batch** out);
+                              uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out);
 
 /* ---- wire format: ProofWithPublicInputs::to_bytes / from_bytes ----------------------------------------
  * Replaces qp-plonky2 `util/serialization`: `write_proof_with_public_inputs` / `read_proof_with_public_inputs`

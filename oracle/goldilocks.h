@@ -23,26 +23,32 @@ typedef unsigned __int128 u128;
 #define GL_TWO_ADICITY 32
 #define GL_EXT_W 7ULL                       /* X^2 = 7 */
 
-static inline uint64_t gl_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+static inline uint64_t gl_canon(uint64_t x) { return x - (GL_P & (0 - (uint64_t)(x >= GL_P))); }
 
 static inline uint64_t gl_add(uint64_t a, uint64_t b) {
+    /* branch-free: a,b < p so one subtraction suffices; (s < a) is the carry out of the 64-bit add */
     uint64_t s = a + b;
-    if (s < a || s >= GL_P) s -= GL_P; /* a,b < p so one subtraction suffices */
-    return s;
+    uint64_t over = (uint64_t)(s < a) | (uint64_t)(s >= GL_P);
+    return s - (GL_P & (0 - over));
 }
-static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    return d + (GL_P & (0 - (uint64_t)(a < b)));
+}
 static inline uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
 
 /* x = lo + 2^64*(hh*2^32 + hl)  ==  lo - hh + hl*(2^32-1)  (mod p), since 2^64 = 2^32-1, 2^96 = -1. */
 static inline uint64_t gl_reduce128(u128 x) {
+    /* branch-free form of upstream's reduce128 (the two fix-ups are data-dependent: a branchy version
+     * mispredicts about once per multiplication on random data) */
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & GL_EPSILON;
     uint64_t t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPSILON;
+    t0 -= GL_EPSILON & (0 - (uint64_t)(lo < hh));
     uint64_t t1 = hl * GL_EPSILON;
     uint64_t r = t0 + t1;
-    if (r < t0) r += GL_EPSILON;
-    return gl_canon(r);
+    r += GL_EPSILON & (0 - (uint64_t)(r < t0));
+    return r - (GL_P & (0 - (uint64_t)(r >= GL_P)));
 }
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }
 static inline uint64_t gl_sqr(uint64_t a) { return gl_mul(a, a); }

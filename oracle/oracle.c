@@ -39,6 +39,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU baseline must use the host's cores anyway */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }
 uint64_t orc_gl_inv(uint64_t a) { return gl_inv(a); }
 uint64_t orc_gl_exp(uint64_t a, uint64_t e) { return gl_exp(a, e); }
@@ -366,6 +375,88 @@ void orc_batch_eval_ext(const orc_batch* b, const uint64_t point[2], uint64_t* o
         for (size_t i = n; i-- > 0;) acc = ext_add(ext_mul(acc, z), ext_from(p[i]));
         out[2 * c] = acc.a; out[2 * c + 1] = acc.b;
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Size-independent checks for the sizes the full restatement above cannot reach in seconds (SURVEY.md 8d:
+ * "larger k: cap + 1024 sampled rows/paths"; used by tests/ and bench.py's parity_check, never by the product).
+ * They restate DEFINITIONS, not the FFT: a polynomial evaluated from its values by the barycentric formula,
+ * from its coefficients by Horner's rule, and on a whole coset of a small subgroup by folding.
+ * ------------------------------------------------------------------------------------------ */
+
+/* out[c] = P_c(r) with P_c the interpolant of column c's VALUES on <w_n> (what PolynomialValues::ifft inverts):
+ *   P(r) = (r^n - 1)/n * sum_i v_i * w^i / (r - w^i).   r must lie outside the subgroup.  -1 if it does not. */
+int orc_eval_from_values(const uint64_t* values, size_t col_stride, size_t num_cols, unsigned log_n, uint64_t r,
+                         uint64_t* out) {
+    const size_t n = (size_t)1 << log_n;
+    const uint64_t zh = gl_sub(gl_exp(r, n), 1);
+    if (!zh) return -1;
+    uint64_t* wt = (uint64_t*)malloc(n * sizeof(uint64_t));   /* w^i / (r - w^i) */
+    uint64_t* pre = (uint64_t*)malloc(n * sizeof(uint64_t));
+    if (!wt || !pre) { free(wt); free(pre); return -3; }
+    const uint64_t w = gl_root_of_unity(log_n);
+    uint64_t x = 1, acc = 1;
+    for (size_t i = 0; i < n; i++) { wt[i] = gl_sub(r, x); pre[i] = acc; acc = gl_mul(acc, wt[i]); x = gl_mul(x, w); }
+    uint64_t inv = gl_inv(acc);
+    for (size_t i = n; i-- > 0;) { uint64_t d = wt[i]; wt[i] = gl_mul(inv, pre[i]); inv = gl_mul(inv, d); }
+    x = 1;
+    for (size_t i = 0; i < n; i++) { wt[i] = gl_mul(wt[i], x); x = gl_mul(x, w); }
+    const uint64_t scale = gl_mul(zh, gl_inv((uint64_t)n % GL_P));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < num_cols; c++) {
+        const uint64_t* v = values + c * col_stride;
+        uint64_t s0 = 0, s1 = 0;
+        size_t i = 0;
+        for (; i + 1 < n; i += 2) { s0 = gl_add(s0, gl_mul(v[i], wt[i])); s1 = gl_add(s1, gl_mul(v[i + 1], wt[i + 1])); }
+        if (i < n) s0 = gl_add(s0, gl_mul(v[i], wt[i]));
+        out[c] = gl_mul(gl_add(s0, s1), scale);
+    }
+    free(wt); free(pre);
+    return 0;
+}
+
+/* out[c] = sum_k coeffs[c][k] r^k (Horner) */
+int orc_eval_from_coeffs(const uint64_t* coeffs, size_t col_stride, size_t num_cols, unsigned log_n, uint64_t r,
+                         uint64_t* out) {
+    const size_t n = (size_t)1 << log_n;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (size_t c = 0; c < num_cols; c++) {
+        const uint64_t* p = coeffs + c * col_stride;
+        uint64_t acc = 0;
+        for (size_t k = n; k-- > 0;) acc = gl_add(gl_mul(acc, r), p[k]);
+        out[c] = acc;
+    }
+    return 0;
+}
+
+/* The LDE of every column at the m = 2^log_m points with natural LDE index i0 + k * (L / m), k < m, L = n << rate_bits:
+ * x_k = s * w_m^k with s = g * w_L^i0, so P(x_k) = sum_{r<m} (sum_q c_{r+qm} s^{r+qm}) w_m^{rk}: fold the coefficients
+ * (n multiplications per column) and run one size-m transform.  out: m x num_cols, row k = point k.  log_m <= log_n + rate_bits. */
+int orc_lde_subgroup_rows(const uint64_t* coeffs, size_t col_stride, size_t num_cols, unsigned log_n, unsigned rate_bits,
+                          uint64_t i0, unsigned log_m, uint64_t* out) {
+    const unsigned log_L = log_n + rate_bits;
+    if (log_m > log_L) return -1;
+    const size_t n = (size_t)1 << log_n, m = (size_t)1 << log_m;
+    const uint64_t s = gl_mul(GL_GENERATOR, gl_exp(gl_root_of_unity(log_L), i0));
+    uint64_t* sp = (uint64_t*)malloc(n * sizeof(uint64_t));
+    if (!sp) return -3;
+    uint64_t v = 1;
+    for (size_t k = 0; k < n; k++) { sp[k] = v; v = gl_mul(v, s); }
+#pragma omp parallel
+    {
+        uint64_t* q = (uint64_t*)malloc(m * sizeof(uint64_t));
+#pragma omp for schedule(dynamic, 1)
+        for (size_t c = 0; c < num_cols; c++) {
+            const uint64_t* p = coeffs + c * col_stride;
+            memset(q, 0, m * sizeof(uint64_t));
+            for (size_t k = 0; k < n; k++) q[k & (m - 1)] = gl_add(q[k & (m - 1)], gl_mul(p[k], sp[k]));
+            orc_fft(q, log_m);
+            for (size_t k = 0; k < m; k++) out[k * num_cols + c] = q[k];
+        }
+        free(q);
+    }
+    free(sp);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -64,6 +64,12 @@ size_t orc_batch_leaf_len(const orc_batch* b);
 /* evaluate every (unsalted) polynomial at an extension point; out = num_cols x 2 words */
 void orc_batch_eval_ext(const orc_batch* b, const uint64_t point[2], uint64_t* out);
 
+/* ---- size-independent checks for the benchmarked sizes (definitions, not the FFT; see oracle.c) ---- */
+int orc_eval_from_values(const uint64_t* values, size_t col_stride, size_t num_cols, unsigned log_n, uint64_t r, uint64_t* out);
+int orc_eval_from_coeffs(const uint64_t* coeffs, size_t col_stride, size_t num_cols, unsigned log_n, uint64_t r, uint64_t* out);
+int orc_lde_subgroup_rows(const uint64_t* coeffs, size_t col_stride, size_t num_cols, unsigned log_n, unsigned rate_bits,
+                          uint64_t i0, unsigned log_m, uint64_t* out);
+
 /* quotient polynomials of the permutation argument + caller-supplied gate terms (row a17, next tier, parity unpinned) */
 int orc_quotient_polys(const orc_batch* cs, const orc_batch* wires, const orc_batch* zs, unsigned sigma_col0,
                        unsigned num_routed, unsigned chunk, unsigned num_challenges, const uint64_t* betas,
@@ -118,6 +124,7 @@ int orc_fri_verify(unsigned log_n, unsigned num_oracles, const uint32_t* leaf_le
                    orc_challenger* ch, const uint64_t* proof);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* OpenMP threads of every later call (overrides OMP_NUM_THREADS) */
 #ifdef __cplusplus
 }
 #endif

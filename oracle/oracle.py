@@ -99,7 +99,12 @@ def lib():
         L.orc_fri_verify.restype = C.c_int
         L.orc_fri_verify.argtypes = [C.c_uint, C.c_uint, U32P, U64P, C.POINTER(FriInstance), U64P,
                                      C.POINTER(FriParams), C.POINTER(ChallengerState), U64P]
+        for f in (L.orc_eval_from_values, L.orc_eval_from_coeffs):
+            f.restype = C.c_int; f.argtypes = [U64P, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint64, U64P]
+        L.orc_lde_subgroup_rows.restype = C.c_int
+        L.orc_lde_subgroup_rows.argtypes = [U64P, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.c_uint64, C.c_uint, U64P]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.restype = None; L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -371,8 +376,47 @@ def fri_verify(log_n, leaf_lens, caps, instance, openings, params, challenger, p
                                 C.byref(params), C.byref(challenger.s), _p64(proof))
 
 
+def eval_from_values(values, r):
+    """P_c(r) for every column c, from the column's VALUES on the subgroup (barycentric formula; r outside the subgroup)."""
+    v = _u64(values)
+    out = np.zeros(v.shape[0], np.uint64)
+    rc = lib().orc_eval_from_values(_p64(v), v.shape[1], v.shape[0], v.shape[1].bit_length() - 1, int(r), _p64(out))
+    assert rc == 0, rc
+    return out
+
+
+def eval_from_coeffs(coeffs, r):
+    """P_c(r) for every column c by Horner's rule on the coefficients."""
+    c = _u64(coeffs)
+    out = np.zeros(c.shape[0], np.uint64)
+    rc = lib().orc_eval_from_coeffs(_p64(c), c.shape[1], c.shape[0], c.shape[1].bit_length() - 1, int(r), _p64(out))
+    assert rc == 0, rc
+    return out
+
+
+def lde_subgroup_rows(coeffs, rate_bits, i0, log_m):
+    """LDE values of every column at the natural LDE indices i0 + k * (L >> log_m), k < 2^log_m: (2^log_m, C) array."""
+    c = _u64(coeffs)
+    out = np.zeros((1 << log_m, c.shape[0]), np.uint64)
+    rc = lib().orc_lde_subgroup_rows(_p64(c), c.shape[1], c.shape[0], c.shape[1].bit_length() - 1, rate_bits, int(i0), log_m, _p64(out))
+    assert rc == 0, rc
+    return out
+
+
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n=None):
+    """Use n OpenMP threads (default: every core this process may run on) whatever OMP_NUM_THREADS says --
+    torch.distributed.run sets it to 1 for every rank."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 # ---- the commitment / opening half of prove() on the CPU (mirror of qpzk/prover.py; SURVEY.md A.7) ----------------

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/qpzk.h"
 #include "goldilocks.cuh"
 #include "internal.cuh"
@@ -33,6 +35,13 @@ namespace qpzk { int wire_fail(int code, const std::string& msg) { return fail(c
             return fail(e_ == cudaErrorMemoryAllocation ? QPZK_ENOMEM : QPZK_ECUDA, buf_);              \
         }                                                                                              \
     } while (0)
+
+// NVTX range per stage of the path (the role of the reference's phase brackets, wormhole/memprof/src/report.rs:18-54,
+// and of plonky2's TimingTree scopes): visible in nsys / ncu --nvtx, free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define GUARD_BEGIN try {
 #define GUARD_END                                                  \
@@ -62,6 +71,7 @@ struct qpzk_ctx {
     bool keep_values = false;  // from_values batches keep their input values on the device (qpzk_ctx_set_keep_values)
     cudaStream_t copy_stream = nullptr;   // H2D of host-buffer commits, overlapped with the per-column stages
     cudaEvent_t copy_done = nullptr;
+    cudaEvent_t h2d_done = nullptr, h2d_done2 = nullptr;   // last read of the caller's column / salt buffers (host-buffer calls wait on them before returning)
     cudaEvent_t ev[5] = {};
     bool ev_valid[5] = {};
     uint64_t launches = 0;
@@ -72,6 +82,7 @@ struct qpzk_ctx {
     std::multimap<uint64_t, void*> cache;                              // free device blocks by size in bytes
     std::map<void*, uint64_t> block_bytes;                             // every block this context allocated
     uint64_t cached_bytes = 0;
+    uint64_t owned_bytes = 0, peak_owned_bytes = 0;   // device memory this context holds (in use + cached) and its high-water mark
     std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
     std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
     std::map<uint32_t, PowTables> unshift_tables;                       // log_size -> powers of g^-1 (coset_ifft)
@@ -133,7 +144,7 @@ static void cache_trim(qpzk_ctx* ctx) {
     if (ctx->cache.empty()) return;
     scrub_dirty(ctx, true);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->cache) { cudaFree(kv.second); ctx->block_bytes.erase(kv.second); }
+    for (auto& kv : ctx->cache) { cudaFree(kv.second); ctx->block_bytes.erase(kv.second); ctx->owned_bytes -= kv.first; }
     ctx->cache.clear();
     ctx->cached_bytes = 0;
 }
@@ -158,6 +169,8 @@ static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
     }
     CK(e);
     ctx->block_bytes[q] = bytes;
+    ctx->owned_bytes += bytes;
+    if (ctx->owned_bytes > ctx->peak_owned_bytes) ctx->peak_owned_bytes = ctx->owned_bytes;
     *p = (uint64_t*)q;
     return 0;
 }
@@ -250,9 +263,18 @@ static int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, C
 extern "C" const char* qpzk_last_error(void) { return g_err.c_str(); }
 extern "C" const char* qpzk_version(void) { return "qpzk-b200 0.1 (sm_100a)"; }
 
+static void ctx_unref(qpzk_ctx* ctx);
+static int ctx_create_body(int device, void* stream, bool own, qpzk_ctx** out);
 static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     if (!out) return fail(QPZK_EINVAL, "out is null");
     *out = nullptr;
+    qpzk_ctx* ctx = nullptr;
+    const int rc = ctx_create_body(device, stream, own, &ctx);
+    if (rc) { if (ctx) ctx_unref(ctx); return rc; }   // a failed step leaves nothing behind (stream, events, the struct)
+    *out = ctx;
+    return 0;
+}
+static int ctx_create_body(int device, void* stream, bool own, qpzk_ctx** out) {
     int count = 0;
     CK(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(QPZK_EINVAL, "no such CUDA device");
@@ -270,6 +292,7 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(QPZK_ECUDA, "libqpzk is built for sm_100a only; device is older than Blackwell");
     qpzk_ctx* ctx = new qpzk_ctx();
+    *out = ctx;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     { const char* e = getenv("QPZK_LEGACY_NTT"); ctx->legacy_ntt = e && e[0] == '1'; }
@@ -284,7 +307,8 @@ static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev[i]));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
-    *out = ctx;
+    CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->h2d_done2, cudaEventDisableTiming));
     return 0;
 }
 
@@ -298,14 +322,17 @@ static void ctx_unref(qpzk_ctx* ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     scrub_dirty(ctx, false);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->block_bytes) cudaFree(kv.first);   // cached blocks (every live handle has been freed by now)
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (auto& kv : ctx->coset_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    for (auto& kv : ctx->unshift_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
+    if (ctx->h2d_done2) cudaEventDestroy(ctx->h2d_done2);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 extern "C" void qpzk_ctx_destroy(qpzk_ctx* ctx) {
@@ -343,6 +370,8 @@ extern "C" int qpzk_ctx_trim(qpzk_ctx* ctx) {
 }
 extern "C" uint64_t qpzk_ctx_cached_bytes(const qpzk_ctx* ctx) { return ctx ? ctx->cached_bytes : 0; }
 extern "C" uint64_t qpzk_ctx_device_allocs(const qpzk_ctx* ctx) { return ctx ? ctx->device_allocs : 0; }
+extern "C" uint64_t qpzk_ctx_peak_bytes(const qpzk_ctx* ctx) { return ctx ? ctx->peak_owned_bytes : 0; }
+extern "C" void qpzk_ctx_reset_peak(qpzk_ctx* ctx) { if (ctx) ctx->peak_owned_bytes = ctx->owned_bytes; }
 
 static void mark(qpzk_ctx* ctx, int i) {
     if (ctx->timing) { cudaEventRecord(ctx->ev[i], ctx->stream); ctx->ev_valid[i] = true; }
@@ -380,6 +409,7 @@ static uint32_t tile_width(uint32_t s, uint32_t room_bits) {
 // values (natural order, column-major) -> coefficients (natural order, column-major)
 static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
     if (!num_cols) return 0;
+    NvtxRange nvtx_intt("qpzk:ifft");
     if (num_cols > 65535) return fail(QPZK_EINVAL, "num_cols > 65535");
     PowTables inv;
     int rc = get_pow_tables(ctx, log_n, true, &inv);
@@ -469,6 +499,7 @@ struct LdePlan {
     // strided passes for columns [c0, c1)
     int run_passes(uint32_t c0, uint32_t c1) {
         if (passes.empty() || c1 <= c0) return 0;
+        NvtxRange nvtx_lde("qpzk:lde passes");
         const uint64_t n = 1ull << log_n;
         uint32_t b_hi = log_n;
         for (size_t i = 0; i < passes.size(); i++) {
@@ -501,6 +532,7 @@ struct LdePlan {
     }
     int run_last() {
         if (!num_cols) return 0;
+        NvtxRange nvtx_last("qpzk:lde last pass + transpose");
         LdeLastArgs la{};
         la.leaves = leaves; la.log_n = log_n; la.s = s_last; la.num_cols = num_cols; la.leaf_width = leaf_width;
         la.num_cosets = coset_count; la.tw_lo = fwd.lo; la.tw_hi = fwd.hi; la.cs_lo = cs_lo; la.cs_hi = cs_hi;
@@ -519,6 +551,7 @@ struct LdePlan {
 };
 
 static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
+    NvtxRange nvtx_tree("qpzk:MerkleTree::new");
     uint64_t words = 8 * b->num_leaves;  // all levels fit in 8N words
     int rc = dev_alloc(ctx, &b->digests, words);
     if (rc) return rc;
@@ -559,10 +592,12 @@ static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uin
     if (src.chunks <= 1) {   // one piece: nothing to overlap, so no second stream and no cross-stream waits
         CK(cudaMemcpyAsync(src.staging + (uint64_t)c0 * n, src.host + (uint64_t)c0 * n, (uint64_t)(c1 - c0) * n * sizeof(uint64_t),
                            cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->h2d_done, ctx->stream));
         return 0;
     }
     CK(cudaMemcpyAsync(src.staging + (uint64_t)c0 * n, src.host + (uint64_t)c0 * n, (uint64_t)(c1 - c0) * n * sizeof(uint64_t),
                        cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->h2d_done, ctx->copy_stream));
     CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
     return 0;
@@ -571,6 +606,7 @@ static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uin
 static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin,
                        uint32_t coset_count, bool keep_coeffs_copy, qpzk_batch** out) {
+    NvtxRange nvtx_commit(from_values ? "qpzk:from_values" : "qpzk:from_coeffs");
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
     if (!src.dev && !src.host && num_cols) return fail(QPZK_EINVAL, "cols is null");
@@ -708,6 +744,7 @@ static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, ui
     if (salt_words) {
         if ((rc = dev_alloc(ctx, &d_salt, salt_words))) return rc;
         cudaError_t e = cudaMemcpyAsync(d_salt, salt, salt_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->h2d_done2, ctx->stream);
         if (e != cudaSuccess) { dev_free(ctx, d_salt); CK(e); }
     }
     ColumnSource src;
@@ -719,6 +756,11 @@ static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, ui
     if (!num_cols) { src.host = nullptr; src.dev = nullptr; }
     rc = commit_impl(ctx, src, from_values, log_n, num_cols, rate_bits, cap_height, d_salt, 0, 1u << rate_bits, true, out);
     dev_free(ctx, d_salt, salt_words);
+    // The caller's buffers are "only read during the call" (qpzk.h): wait for the host->device reads -- and only for
+    // them; the kernels behind them stay asynchronous -- so that a caller may reuse or zeroize its witness buffer
+    // (reference wormhole/circuit/src/sensitive.rs) as soon as the call returns, pinned or not.
+    if (src.host) { cudaError_t e = cudaEventSynchronize(ctx->h2d_done); if (!rc) CK(e); }
+    if (salt_words) { cudaError_t e = cudaEventSynchronize(ctx->h2d_done2); if (!rc) CK(e); }
     return rc;
 }
 extern "C" int qpzk_commit_from_values(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
@@ -781,7 +823,10 @@ extern "C" int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t n
     uint64_t* copy;
     if ((rc = dev_alloc(ctx, &copy, num_leaves * leaf_len))) return rc;
     CK(cudaMemcpyAsync(copy, leaves, num_leaves * leaf_len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    return merkle_impl(ctx, copy, nullptr, num_leaves, leaf_len, cap_height, out);
+    CK(cudaEventRecord(ctx->h2d_done, ctx->stream));
+    rc = merkle_impl(ctx, copy, nullptr, num_leaves, leaf_len, cap_height, out);
+    { cudaError_t e = cudaEventSynchronize(ctx->h2d_done); if (!rc) CK(e); }   // the caller's leaves have been read
+    return rc;
     GUARD_END
 }
 
@@ -1049,7 +1094,9 @@ extern "C" int qpzk_fri_params_constant_arity(qpzk_fri_params* p, uint32_t log_n
     memset(p, 0, sizeof *p);
     p->rate_bits = rate_bits; p->cap_height = cap_height; p->proof_of_work_bits = pow_bits; p->num_query_rounds = num_queries;
     uint32_t d = log_n;
-    while (d > final_poly_bits && d + rate_bits - arity_bits >= cap_height && p->num_rounds < QPZK_MAX_FRI_ROUNDS) {
+    while (d > final_poly_bits && d + rate_bits - arity_bits >= cap_height) {
+        if (p->num_rounds == QPZK_MAX_FRI_ROUNDS)    // upstream's ConstantArityBits would keep reducing: refuse, do not truncate
+            return fail(QPZK_EINVAL, "reduction needs more than QPZK_MAX_FRI_ROUNDS rounds");
         p->arity_bits[p->num_rounds++] = arity_bits;
         d -= arity_bits;
     }
@@ -1071,16 +1118,21 @@ extern "C" size_t qpzk_fri_proof_words(const qpzk_fri_params* p, uint32_t log_n,
 
 struct DevBufs {  // frees everything it holds on scope exit
     qpzk_ctx* ctx;
-    std::vector<void*> ptrs;
+    std::vector<std::pair<void*, uint64_t>> ptrs;   // block, words to scrub at release (0 = holds nothing secret)
     explicit DevBufs(qpzk_ctx* c) : ctx(c) {}
-    ~DevBufs() { for (void* p : ptrs) dev_free(ctx, p); }
-    int alloc(uint64_t** p, uint64_t words) { int rc = dev_alloc(ctx, p, words); if (!rc) ptrs.push_back(*p); return rc; }
+    ~DevBufs() { for (auto& p : ptrs) dev_free(ctx, p.first, p.second); }
+    int alloc(uint64_t** p, uint64_t words, bool secret = false) {
+        int rc = dev_alloc(ctx, p, words);
+        if (!rc) ptrs.emplace_back(*p, secret ? (words ? words : 1) : 0);
+        return rc;
+    }
 };
 
 extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
                               const qpzk_fri_instance* inst, const qpzk_fri_params* p, qpzk_challenger* ch,
                               uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out) {
     GUARD_BEGIN
+    NvtxRange nvtx_fri("qpzk:prove_openings");
     if (!ctx || !oracles || !inst || !p || !ch || !proof_out) return fail(QPZK_EINVAL, "null argument");
     if (!num_oracles || num_oracles > MAX_ORACLES) return fail(QPZK_EINVAL, "num_oracles must be in 1..8");
     if (!inst->num_batches || inst->num_batches > MAX_FRI_BATCHES) return fail(QPZK_EINVAL, "num_batches must be in 1..8");
@@ -1143,7 +1195,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
             ca.eval_off[b * num_oracles + o] = (uint32_t)eval_words;
             if (used[b * num_oracles + o]) eval_words += oracles[o]->num_cols;
         }
-    if ((rc = bufs.alloc(&d_evals, 2 * eval_words))) return rc;
+    if ((rc = bufs.alloc(&d_evals, 2 * eval_words, true))) return rc;
     if ((rc = bufs.alloc(&d_reduced, 2ull * inst->num_batches))) return rc;
     if ((rc = bufs.alloc(&d_open, 2ull * total_polys))) return rc;
     if ((rc = bufs.alloc(&d_found, 4 + p->num_query_rounds))) return rc;  // [0]=found, [1]=witness, [2]=status, [4..]=indices
@@ -1175,7 +1227,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
     const uint64_t L = 1ull << log_L;
     std::vector<uint64_t*> layer(p->num_rounds + 1);
-    if ((rc = bufs.alloc(&layer[0], 2 * L))) return rc;
+    if ((rc = bufs.alloc(&layer[0], 2 * L, true))) return rc;
     ca.log_n = log_n; ca.rate_bits = rate_bits; ca.num_batches = inst->num_batches; ca.num_oracles = num_oracles;
     for (uint32_t o = 0; o < num_oracles; o++) { ca.leaves[o] = oracles[o]->leaves; ca.leaf_width[o] = oracles[o]->leaf_width; }
     ca.poly_oracle = d_po; ca.poly_index = d_pi; ca.apow = d_apow; ca.evals = d_evals; ca.reduced = d_reduced;
@@ -1190,7 +1242,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     const size_t final_len = (size_t)1 << (log_n - total_arity);
     const size_t query_base = p->num_rounds * cap_words;
     const size_t query_words = p->num_query_rounds ? (proof_words - 1 - 2 * final_len - query_base) / p->num_query_rounds : 0;
-    if ((rc = bufs.alloc(&d_proof, proof_words))) return rc;
+    if ((rc = bufs.alloc(&d_proof, proof_words, true))) return rc;
 
     // ---- commit phase
     std::vector<uint64_t*> round_digests(p->num_rounds);
@@ -1200,7 +1252,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     for (uint32_t r = 0; r < p->num_rounds; r++) {
         const uint32_t ab = p->arity_bits[r];
         const uint64_t rows = 1ull << (lg - ab);
-        if ((rc = bufs.alloc(&round_digests[r], 8 * rows))) return rc;
+        if ((rc = bufs.alloc(&round_digests[r], 8 * rows, true))) return rc;
         CK(launch_hash_rows(layer[r], rows, 2u << ab, 2u << ab, round_digests[r], st)); ctx->launches++;
         const uint32_t levels = (lg - ab) - p->cap_height + 1;
         CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += merkle_levels_launches(levels, rows);
@@ -1208,7 +1260,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         CK(cudaMemcpyAsync(d_proof + r * cap_words, cap, cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         CK(launch_challenger_observe(ch->dev, cap, (uint32_t)cap_words, st)); ctx->launches++;
         CK(launch_challenger_get(ch->dev, d_beta, 2, st)); ctx->launches++;
-        if ((rc = bufs.alloc(&layer[r + 1], 2 * rows))) return rc;
+        if ((rc = bufs.alloc(&layer[r + 1], 2 * rows, true))) return rc;
         FriFoldArgs fa{};
         fa.in = layer[r]; fa.out = layer[r + 1]; fa.lg = lg; fa.log_L = log_L; fa.beta = d_beta;
         fa.shift_inv = gl_inv_host(shift);
@@ -1274,6 +1326,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
 static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, bool host, uint32_t log_n,
                                  uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                                  const uint64_t* gammas, uint64_t* out) {
+    NvtxRange nvtx_pp("qpzk:partial_products");
     if (!ctx || !wires || !sigmas || !betas || !gammas || !out) return fail(QPZK_EINVAL, "null argument");
     if (log_n > 28) return fail(QPZK_EINVAL, "log_n must be <= 28");
     if (!num_routed || !chunk) return fail(QPZK_EINVAL, "num_routed and chunk must be positive");
@@ -1343,7 +1396,7 @@ extern "C" int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires, c
 extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
                                                uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk,
                                                uint32_t num_challenges, const uint64_t* betas, const uint64_t* gammas,
-                                               uint32_t cap_height, qpzk_batch** out) {
+                                               uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out) {
     GUARD_BEGIN
     if (!out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
@@ -1362,7 +1415,7 @@ extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* 
     if (rc) return rc;
     rc = partial_products_impl(ctx, wires->values, constants_sigmas->values + (uint64_t)sigma_col0 * n, false, wires->log_n,
                                num_routed, chunk, num_challenges, betas, gammas, d_out);
-    if (!rc) rc = commit_impl(ctx, dev_source(d_out), true, wires->log_n, cols, wires->rate_bits, cap_height, nullptr, 0,
+    if (!rc) rc = commit_impl(ctx, dev_source(d_out), true, wires->log_n, cols, wires->rate_bits, cap_height, salt_dev, 0,
                               1u << wires->rate_bits, true, out);
     dev_free(ctx, d_out, (uint64_t)cols * n);
     return rc;
@@ -1394,6 +1447,7 @@ static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* 
                          uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
                          const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
                          const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out) {
+    NvtxRange nvtx_q("qpzk:compute_quotient_polys");
     *coeffs_out = nullptr;
     if (!ctx || !cs || !wires || !zs || !betas || !gammas || !alphas) return fail(QPZK_EINVAL, "null argument");
     if (cs->ctx != ctx || wires->ctx != ctx || zs->ctx != ctx) return fail(QPZK_EINVAL, "batch belongs to another context");
@@ -1555,14 +1609,14 @@ extern "C" int qpzk_commit_quotient_prog(qpzk_ctx* ctx, const qpzk_batch* consta
                                          const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                                          uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
                                          const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog,
-                                         uint32_t cap_height, qpzk_batch** out) {
+                                         uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out) {
     GUARD_BEGIN
     if (out) *out = nullptr;
     uint64_t* terms; uint32_t nt;
     int rc = gate_terms_from_program(ctx, constants_sigmas, wires, quotient_degree_factor, prog, &terms, &nt);
     if (rc) return rc;
     rc = qpzk_commit_quotient(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
-                              num_challenges, betas, gammas, alphas, terms, nt, cap_height, out);
+                              num_challenges, betas, gammas, alphas, terms, nt, cap_height, salt_dev, out);
     if (terms) dev_free(ctx, terms, ((1ull << wires->log_n) * quotient_degree_factor) * nt);
     return rc;
     GUARD_END
@@ -1593,7 +1647,7 @@ extern "C" int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_s
                                     const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,
                                     uint32_t quotient_degree_factor, uint32_t num_challenges, const uint64_t* betas,
                                     const uint64_t* gammas, const uint64_t* alphas, const uint64_t* gate_terms_dev,
-                                    uint32_t num_gate_terms, uint32_t cap_height, qpzk_batch** out) {
+                                    uint32_t num_gate_terms, uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out) {
     GUARD_BEGIN
     if (!out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
@@ -1603,7 +1657,7 @@ extern "C" int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_s
                            num_challenges, betas, gammas, alphas, gate_terms_dev, num_gate_terms, &d, &qbits);
     if (rc) return rc;
     const uint32_t cols = num_challenges << qbits;
-    rc = commit_impl(ctx, dev_source(d), false, wires->log_n, cols, wires->rate_bits, cap_height, nullptr, 0,
+    rc = commit_impl(ctx, dev_source(d), false, wires->log_n, cols, wires->rate_bits, cap_height, salt_dev, 0,
                      1u << wires->rate_bits, true, out);
     dev_free(ctx, d, (uint64_t)cols << wires->log_n);
     return rc;

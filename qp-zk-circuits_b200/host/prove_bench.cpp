@@ -157,7 +157,7 @@ struct Worker {
             QCHECK(qpzk_challenger_get(ch, chal, 4));   // betas, gammas
             lap(0, tp);
             if (g_perm)
-                QCHECK(qpzk_commit_zs_partial_products(ctx, cs_b, w_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, 4, &z_b));
+                QCHECK(qpzk_commit_zs_partial_products(ctx, cs_b, w_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, 4, nullptr, &z_b));
             else
                 QCHECK(qpzk_commit_from_values(ctx, zs[s].data(), sh.log_n, sh.zs_pp, 3, 4, nullptr, &z_b));
             QCHECK(qpzk_challenger_observe_cap(ch, z_b));
@@ -167,9 +167,9 @@ struct Worker {
             if (g_perm && g_gate_regs) {
                 qpzk_gate_program prog{g_gate_code.data(), (uint32_t)(g_gate_code.size() / 4), g_gate_imm.data(),
                                        (uint32_t)g_gate_imm.size(), g_gate_regs};
-                QCHECK(qpzk_commit_quotient_prog(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, &prog, 4, &q_b));
+                QCHECK(qpzk_commit_quotient_prog(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, &prog, 4, nullptr, &q_b));
             } else if (g_perm)
-                QCHECK(qpzk_commit_quotient(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, nullptr, 0, 4, &q_b));
+                QCHECK(qpzk_commit_quotient(ctx, cs_b, w_b, z_b, sh.sigma_col0, sh.routed, 8, 2, chal, chal + 2, alphas, nullptr, 0, 4, nullptr, &q_b));
             else
                 QCHECK(qpzk_commit_from_coeffs(ctx, quot[s].data(), sh.log_n, sh.quotient, 3, 4, nullptr, &q_b));
             QCHECK(qpzk_challenger_observe_cap(ch, q_b));

@@ -102,7 +102,7 @@ def load_library():
         "qpzk_ctx_set_timing": (i, [vp, i]),
         "qpzk_ctx_set_keep_values": (i, [vp, i]),
         "qpzk_batch_values_dev": (vp, [vp]),
-        "qpzk_commit_zs_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, u32, C.POINTER(vp)]),
+        "qpzk_commit_zs_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, u32, vp, C.POINTER(vp)]),
         "qpzk_ctx_last_commit_timing": (i, [vp, C.POINTER(C.c_float)]),
         "qpzk_ctx_launch_count": (u64, [vp]),
         "qpzk_ctx_trim": (i, [vp]),
@@ -113,6 +113,8 @@ def load_library():
         "qpzk_selftest_mds_layer": (i, [vp, vp, u64, u32, vp]),
         "qpzk_ctx_cached_bytes": (u64, [vp]),
         "qpzk_ctx_device_allocs": (u64, [vp]),
+        "qpzk_ctx_peak_bytes": (u64, [vp]),
+        "qpzk_ctx_reset_peak": (None, [vp]),
         "qpzk_commit_from_values": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_coeffs": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_from_values_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
@@ -146,12 +148,12 @@ def load_library():
         "qpzk_partial_products": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "qpzk_partial_products_dev": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "qpzk_quotient_polys": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, vp]),
-        "qpzk_commit_quotient": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, u32, C.POINTER(vp)]),
+        "qpzk_commit_quotient": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_proof_bytes_len": (C.c_size_t, [C.POINTER(FriParams), C.POINTER(ProofShape)]),
         "qpzk_proof_to_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, vp, vp, vp, vp, vp, vp, C.c_size_t]),
         "qpzk_proof_from_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
         "qpzk_quotient_polys_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), vp]),
-        "qpzk_commit_quotient_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), u32, C.POINTER(vp)]),
+        "qpzk_commit_quotient_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), u32, vp, C.POINTER(vp)]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -217,6 +219,13 @@ class Context:
 
     def cached_bytes(self):
         return int(self.L.qpzk_ctx_cached_bytes(self.h))
+
+    def peak_bytes(self, reset=False):
+        """High-water mark of the device memory held by this context (in use + cached), in bytes."""
+        v = int(self.L.qpzk_ctx_peak_bytes(self.h))
+        if reset:
+            self.L.qpzk_ctx_reset_peak(self.h)
+        return v
 
     def poseidon_permute(self, states, mds_only_round=None):
         """PoseidonPermutation::permute on an (N, 12) array; inputs may be non-canonical, outputs are canonical.
@@ -412,17 +421,19 @@ class PolynomialBatch:
 
     @classmethod
     def commit_zs_partial_products(cls, constants_sigmas, wires, sigma_col0, num_routed, betas, gammas, cap_height,
-                                   quotient_degree_factor=8):
+                                   quotient_degree_factor=8, salt_ptr=None):
         """all_wires_permutation_partial_products + the zs/partial-products commitment on the device, from two batches
-        committed with Context.set_keep_values(True)."""
+        committed with Context.set_keep_values(True).  salt_ptr: device address of the (4, n << rate_bits) blinding
+        columns (zero-knowledge circuits blind this oracle), or None."""
         b, bp = _host(betas)
         g, gp = _host(gammas)
         h = C.c_void_p()
         ctx = wires.ctx
         _check(ctx.L.qpzk_commit_zs_partial_products(ctx.h, constants_sigmas.h, wires.h, sigma_col0, num_routed,
-                                                     quotient_degree_factor, b.size, bp, gp, cap_height, C.byref(h)))
+                                                     quotient_degree_factor, b.size, bp, gp, cap_height,
+                                                     C.c_void_p(salt_ptr) if salt_ptr else None, C.byref(h)))
         cols = b.size * ((num_routed + quotient_degree_factor - 1) // quotient_degree_factor)
-        return cls(ctx, h, wires.degree_log, cols, wires.rate_bits, cap_height, False)
+        return cls(ctx, h, wires.degree_log, cols, wires.rate_bits, cap_height, salt_ptr is not None)
 
     @classmethod
     def quotient_polys(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
@@ -437,13 +448,14 @@ class PolynomialBatch:
 
     @classmethod
     def commit_quotient(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
-                        cap_height, quotient_degree_factor=8, gate_terms_dev=None, num_gate_terms=0):
+                        cap_height, quotient_degree_factor=8, gate_terms_dev=None, num_gate_terms=0, salt_ptr=None):
         """The same, committed (from_coeffs) without leaving the device."""
         keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
                                               betas, gammas, alphas, gate_terms_dev, num_gate_terms)
         h = C.c_void_p()
-        _check(wires.ctx.L.qpzk_commit_quotient(*head, quotient_degree_factor, *tail, cap_height, C.byref(h)))
-        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, False)
+        _check(wires.ctx.L.qpzk_commit_quotient(*head, quotient_degree_factor, *tail, cap_height,
+                                                C.c_void_p(salt_ptr) if salt_ptr else None, C.byref(h)))
+        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, salt_ptr is not None)
 
     @classmethod
     def quotient_polys_prog(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
@@ -459,13 +471,14 @@ class PolynomialBatch:
 
     @classmethod
     def commit_quotient_prog(cls, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, betas, gammas, alphas,
-                             program, cap_height, quotient_degree_factor=8):
+                             program, cap_height, quotient_degree_factor=8, salt_ptr=None):
         keep, head, tail = cls._quotient_args(constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed,
                                               betas, gammas, alphas, None, 0)
         h = C.c_void_p()
         _check(wires.ctx.L.qpzk_commit_quotient_prog(*head, quotient_degree_factor, *tail[:4],
-                                                     C.byref(program) if program is not None else None, cap_height, C.byref(h)))
-        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, False)
+                                                     C.byref(program) if program is not None else None, cap_height,
+                                                     C.c_void_p(salt_ptr) if salt_ptr else None, C.byref(h)))
+        return cls(wires.ctx, h, wires.degree_log, tail[0] * quotient_degree_factor, wires.rate_bits, cap_height, salt_ptr is not None)
 
     @property
     def polynomials(self):

@@ -78,6 +78,8 @@ extern "C" {
     pub fn qpzk_poseidon_permute(ctx: *mut qpzk_ctx, states: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn qpzk_ctx_cached_bytes(ctx: *const qpzk_ctx) -> u64;
     pub fn qpzk_ctx_device_allocs(ctx: *const qpzk_ctx) -> u64;
+    pub fn qpzk_ctx_peak_bytes(ctx: *const qpzk_ctx) -> u64;
+    pub fn qpzk_ctx_reset_peak(ctx: *mut qpzk_ctx);
     pub fn qpzk_commit_from_values(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
                                    cap_height: u32, salt: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_commit_from_coeffs(ctx: *mut qpzk_ctx, cols: *const u64, log_n: u32, num_cols: u32, rate_bits: u32,
@@ -141,7 +143,7 @@ extern "C" {
     pub fn qpzk_commit_zs_partial_products(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
                                            sigma_col0: u32, num_routed: u32, chunk: u32, num_challenges: u32,
                                            betas: *const u64, gammas: *const u64, cap_height: u32,
-                                           out: *mut *mut qpzk_batch) -> c_int;
+                                           salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     // compute_quotient_polys for the permutation argument (+ caller-supplied gate terms) and the quotient commitment
     pub fn qpzk_quotient_polys(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
                                zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
@@ -151,7 +153,7 @@ extern "C" {
                                 zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
                                 quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
                                 alphas: *const u64, gate_terms_dev: *const u64, num_gate_terms: u32, cap_height: u32,
-                                out: *mut *mut qpzk_batch) -> c_int;
+                                salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_quotient_polys_prog(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, wires: *const qpzk_batch,
                                     zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
                                     quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
@@ -160,7 +162,7 @@ extern "C" {
                                      zs_partial_products: *const qpzk_batch, sigma_col0: u32, num_routed: u32,
                                      quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
                                      alphas: *const u64, prog: *const qpzk_gate_program, cap_height: u32,
-                                     out: *mut *mut qpzk_batch) -> c_int;
+                                     salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
     // ProofWithPublicInputs::to_bytes / from_bytes (host functions)
     pub fn qpzk_proof_bytes_len(p: *const qpzk_fri_params, s: *const qpzk_proof_shape) -> usize;
     pub fn qpzk_proof_to_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, wires_cap: *const u64,
