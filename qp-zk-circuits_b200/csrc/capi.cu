@@ -14,100 +14,16 @@
 #include <string>
 #include <vector>
 
-#include <nvtx3/nvToolsExt.h>
-
-#include "../../include/qpzk.h"
+#include "ctx.cuh"
 #include "goldilocks.cuh"
-#include "internal.cuh"
 
 using namespace qpzk;
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace qpzk { int wire_fail(int code, const std::string& msg) { return fail(code, msg); } }   // wire.cu
 
-#define CK(call)                                                                                       \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) {                                                                       \
-            char buf_[512];                                                                            \
-            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            return fail(e_ == cudaErrorMemoryAllocation ? QPZK_ENOMEM : QPZK_ECUDA, buf_);              \
-        }                                                                                              \
-    } while (0)
-
-// NVTX range per stage of the path (the role of the reference's phase brackets, wormhole/memprof/src/report.rs:18-54,
-// and of plonky2's TimingTree scopes): visible in nsys / ncu --nvtx, free when no tool is attached.
-struct NvtxRange {
-    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-    ~NvtxRange() { nvtxRangePop(); }
-};
-
-#define GUARD_BEGIN try {
-#define GUARD_END                                                  \
-    }                                                              \
-    catch (const std::bad_alloc&) { return fail(QPZK_ENOMEM, "host allocation failed"); } \
-    catch (const std::exception& ex) { return fail(QPZK_EINTERNAL, ex.what()); }          \
-    catch (...) { return fail(QPZK_EINTERNAL, "unknown exception"); }
-
-struct PowTables {
-    uint64_t *lo = nullptr, *hi = nullptr;  // device
-    uint64_t hi_size = 0;
-};
-struct CosetTables {
-    uint64_t *lo = nullptr, *hi = nullptr;  // device, [cosets][TW_LO_SIZE] / [cosets][hi_size]
-    uint64_t hi_size = 0;
-};
-
-struct qpzk_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int num_sms = 0;
-    int zeroize = 1;           // 0 off, 1 at release, 2 deferred until the block leaves the library (qpzk_ctx_set_zeroize)
-    std::map<void*, bool> dirty;   // mode 2: cached blocks that held secrets and have not been zeroed yet
-    bool legacy_ntt = false;   // QPZK_LEGACY_NTT=1: generic strided passes only (A/B testing of ntt_fwd.cu)
-    bool timing = false;
-    bool keep_values = false;  // from_values batches keep their input values on the device (qpzk_ctx_set_keep_values)
-    cudaStream_t copy_stream = nullptr;   // H2D of host-buffer commits, overlapped with the per-column stages
-    cudaEvent_t copy_done = nullptr;
-    cudaEvent_t h2d_done = nullptr, h2d_done2 = nullptr;   // last read of the caller's column / salt buffers (host-buffer calls wait on them before returning)
-    cudaEvent_t ev[5] = {};
-    bool ev_valid[5] = {};
-    uint64_t launches = 0;
-    uint64_t device_allocs = 0;   // cudaMalloc calls of the block cache (0 in steady state)
-    // The context stays alive until qpzk_ctx_destroy has been called AND every batch / challenger created
-    // from it has been freed, whatever order a binding's finalizers run in.
-    int refs = 1;
-    std::multimap<uint64_t, void*> cache;                              // free device blocks by size in bytes
-    std::map<void*, uint64_t> block_bytes;                             // every block this context allocated
-    uint64_t cached_bytes = 0;
-    uint64_t owned_bytes = 0, peak_owned_bytes = 0;   // device memory this context holds (in use + cached) and its high-water mark
-    std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
-    std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
-    std::map<uint32_t, PowTables> unshift_tables;                       // log_size -> powers of g^-1 (coset_ifft)
-};
-
-struct qpzk_batch {
-    qpzk_ctx* ctx = nullptr;
-    uint32_t log_n = 0, rate_bits = 0, cap_height = 0, num_cols = 0, salt_cols = 0, leaf_width = 0;
-    uint64_t num_leaves = 0;
-    uint32_t log_leaves = 0, num_levels = 0;  // levels[0] = leaf digests ... levels[num_levels-1] = cap
-    uint64_t* coeffs = nullptr;               // num_cols x n (null for a bare MerkleTree)
-    uint64_t* values = nullptr;               // num_cols x n values on the subgroup (only with keep_values)
-    uint64_t* leaves = nullptr;
-    uint64_t* digests = nullptr;
-    bool own_leaves = true;
-};
-
-struct qpzk_challenger {
-    qpzk_ctx* ctx = nullptr;
-    ChallengerDev* dev = nullptr;
-    uint64_t* scratch = nullptr;  // device staging for observed elements / drawn challenges
-    uint32_t scratch_words = 0;
-};
-
-static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
+uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++; return l; }
 
 // ---------------------------------------------------------------------------------------------
 // device memory helpers (stream-ordered pool)
@@ -120,7 +36,7 @@ static uint32_t ilog2(uint64_t x) { uint32_t l = 0; while ((1ull << l) < x) l++;
 // 0.1-3 s per commit when commits are issued back to back: its pool cannot reuse blocks whose frees are still
 // pending and keeps mapping new memory instead.)
 // zero `words` words of a block that held secret-derived data: now (mode 1) or before the block leaves the library (2)
-static void scrub(qpzk_ctx* ctx, void* p, uint64_t words) {
+void scrub(qpzk_ctx* ctx, void* p, uint64_t words) {
     if (!p || !words || !ctx->zeroize) return;
     if (ctx->zeroize == 1) launch_fill_words(p, words, 0, ctx->stream);
     else ctx->dirty[p] = true;
@@ -148,7 +64,7 @@ static void cache_trim(qpzk_ctx* ctx) {
     ctx->cache.clear();
     ctx->cached_bytes = 0;
 }
-static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
+int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
     *p = nullptr;
     if (!words) words = 1;
     uint64_t bytes = (words * sizeof(uint64_t) + 511) & ~511ull;
@@ -174,7 +90,7 @@ static int dev_alloc(qpzk_ctx* ctx, uint64_t** p, uint64_t words) {
     *p = (uint64_t*)q;
     return 0;
 }
-static void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words = 0) {
+void dev_free(qpzk_ctx* ctx, void* p, uint64_t zero_words) {
     if (!p) return;
     auto dirty = ctx->dirty.find(p);
     if (dirty != ctx->dirty.end() && ctx->zeroize == 1) {
@@ -211,7 +127,7 @@ static void fill_powers(uint64_t base, uint64_t hi_size, std::vector<uint64_t>& 
     for (uint64_t i = 0; i < hi_size; i++) { hi[i] = v; v = gl_mul_host(v, step); }
 }
 
-static int get_pow_tables(qpzk_ctx* ctx, uint32_t log_size, bool inverse, PowTables* out) {
+int get_pow_tables(qpzk_ctx* ctx, uint32_t log_size, bool inverse, PowTables* out) {
     auto key = std::make_pair(log_size, inverse ? 1 : 0);
     auto it = ctx->pow_tables.find(key);
     if (it == ctx->pow_tables.end()) {
@@ -231,7 +147,7 @@ static int get_pow_tables(qpzk_ctx* ctx, uint32_t log_size, bool inverse, PowTab
 }
 
 // coset j' (leaf block index) uses shift s = g * w_L^bitrev_r(j')
-static int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, CosetTables* out) {
+int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, CosetTables* out) {
     auto key = std::make_pair(log_n, rate_bits);
     auto it = ctx->coset_tables.find(key);
     if (it == ctx->coset_tables.end()) {
@@ -263,7 +179,6 @@ static int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, C
 extern "C" const char* qpzk_last_error(void) { return g_err.c_str(); }
 extern "C" const char* qpzk_version(void) { return "qpzk-b200 0.1 (sm_100a)"; }
 
-static void ctx_unref(qpzk_ctx* ctx);
 static int ctx_create_body(int device, void* stream, bool own, qpzk_ctx** out);
 static int ctx_create_impl(int device, void* stream, bool own, qpzk_ctx** out) {
     if (!out) return fail(QPZK_EINVAL, "out is null");
@@ -318,7 +233,7 @@ extern "C" int qpzk_ctx_create(int device, qpzk_ctx** out) {
 extern "C" int qpzk_ctx_create_on_stream(int device, void* cuda_stream, qpzk_ctx** out) {
     GUARD_BEGIN return ctx_create_impl(device, cuda_stream, false, out); GUARD_END
 }
-static void ctx_unref(qpzk_ctx* ctx) {
+void ctx_unref(qpzk_ctx* ctx) {
     if (--ctx->refs > 0) return;
     cudaSetDevice(ctx->device);
     scrub_dirty(ctx, false);
@@ -564,7 +479,7 @@ static int build_tree(qpzk_ctx* ctx, qpzk_batch* b) {
     return 0;
 }
 
-static void batch_release(qpzk_batch* b) {
+void batch_release(qpzk_batch* b) {
     if (!b) return;
     qpzk_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
@@ -1116,17 +1031,6 @@ extern "C" size_t qpzk_fri_proof_words(const qpzk_fri_params* p, uint32_t log_n,
     return w + per_q * p->num_query_rounds + ((size_t)2 << deg) + 1;
 }
 
-struct DevBufs {  // frees everything it holds on scope exit
-    qpzk_ctx* ctx;
-    std::vector<std::pair<void*, uint64_t>> ptrs;   // block, words to scrub at release (0 = holds nothing secret)
-    explicit DevBufs(qpzk_ctx* c) : ctx(c) {}
-    ~DevBufs() { for (auto& p : ptrs) dev_free(ctx, p.first, p.second); }
-    int alloc(uint64_t** p, uint64_t words, bool secret = false) {
-        int rc = dev_alloc(ctx, p, words);
-        if (!rc) ptrs.emplace_back(*p, secret ? (words ? words : 1) : 0);
-        return rc;
-    }
-};
 
 extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
                               const qpzk_fri_instance* inst, const qpzk_fri_params* p, qpzk_challenger* ch,

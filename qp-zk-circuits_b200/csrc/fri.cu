@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_ext_multi_kernel(EvalMultiA
     __shared__ ext2 red[EVAL_THREADS];
     const uint64_t n = 1ull << a.log_n;
     const uint64_t* c = a.coeffs[job] + (uint64_t)col * a.col_stride;
-    const ext2 z = ext_make(a.z[2 * job], a.z[2 * job + 1]);
+    const ext2 z = a.z_dev[job] ? ext_make(a.z_dev[job][0], a.z_dev[job][1]) : ext_make(a.z[2 * job], a.z[2 * job + 1]);
     const uint32_t T = blockDim.x, t = threadIdx.x;
     ext2 zT = ext_exp(z, T);
     ext2 acc = ext_make(0, 0);
@@ -117,6 +117,22 @@ __global__ void __launch_bounds__(EVAL_THREADS) reduce_openings_kernel(FriCombin
     if (t == 0) { a.reduced[2 * b] = red[0].a; a.reduced[2 * b + 1] = red[0].b; }
 }
 
+// the opened values in FRI-instance order (what OpeningSet holds and the challenger observes before alpha is drawn)
+__global__ void __launch_bounds__(EVAL_THREADS) openings_gather_kernel(FriCombineArgs a, uint32_t total) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    uint32_t b = 0;
+    while (b + 1 < a.num_batches && k >= a.batch_off[b + 1]) b++;
+    const uint32_t o = a.poly_oracle[k], idx = a.poly_index[k];
+    const uint64_t* ev = a.evals + 2 * ((uint64_t)a.eval_off[b * a.num_oracles + o] + idx);
+    a.openings_out[2 * k] = ev[0];
+    a.openings_out[2 * k + 1] = ev[1];
+}
+
+__global__ void ext_scale_kernel(const uint64_t* __restrict__ in, uint64_t s, uint64_t* __restrict__ out) {
+    if (threadIdx.x < 2) out[threadIdx.x] = gl_mul(in[threadIdx.x], s);
+}
+
 // One warp per 32 consecutive LDE points (leaf order).  x_p = s_j' * w_n^bitrev(r) for p = j' * n + r.
 // Phase 1: lane l inverts the denominators (x_p - z_b) of ITS point for every batch: 32 different inversions per
 // warp-instruction stream (the first version inverted the same denominator on all 32 lanes: ~5 k of the ~5.5 k
@@ -138,8 +154,11 @@ __global__ void __launch_bounds__(COMBINE_THREADS) fri_combine_kernel(FriCombine
 #pragma unroll
         for (uint32_t b = 0; b < MAX_FRI_BATCHES; b++) {
             inv[b] = ext_make(0, 0);
-            if (b < a.num_batches)
-                inv[b] = ext_inv(ext_make(gl_sub(x, a.points[2 * b]), gl_neg(a.points[2 * b + 1])));
+            if (b < a.num_batches) {
+                const uint64_t z0 = a.points_dev ? a.points_dev[2 * b] : a.points[2 * b];
+                const uint64_t z1 = a.points_dev ? a.points_dev[2 * b + 1] : a.points[2 * b + 1];
+                inv[b] = ext_inv(ext_make(gl_sub(x, z0), gl_neg(z1)));
+            }
         }
     }
     const uint32_t count = L - p0 < 32 ? (uint32_t)(L - p0) : 32u;
@@ -346,6 +365,17 @@ cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st) {
     uint64_t L = 1ull << (a.log_n + a.rate_bits);
     uint64_t blocks = (L + COMBINE_THREADS - 1) / COMBINE_THREADS;   // one warp per 32 points
     fri_combine_kernel<<<(unsigned)blocks, COMBINE_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_openings_gather(const FriCombineArgs& a, uint32_t total_polys, cudaStream_t st) {
+    if (!total_polys) return cudaSuccess;
+    openings_gather_kernel<<<(total_polys + EVAL_THREADS - 1) / EVAL_THREADS, EVAL_THREADS, 0, st>>>(a, total_polys);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ext_scale(const uint64_t* in_dev, uint64_t s, uint64_t* out_dev, cudaStream_t st) {
+    ext_scale_kernel<<<1, 32, 0, st>>>(in_dev, s, out_dev);
     return cudaGetLastError();
 }
 

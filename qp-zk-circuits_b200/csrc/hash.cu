@@ -194,28 +194,47 @@ __global__ void __launch_bounds__(32) challenger_get_kernel(ChallengerDev* c, ui
 // fri_proof_of_work: find the MINIMUM witness w such that, after observing w, the next challenge
 // (state[7] of the duplex) has >= pow_bits leading zeros.  Upstream uses rayon find_any (any valid
 // witness); the minimum is a valid choice and makes the result deterministic.
-// One launch tests the window [base, base+count): one candidate per thread, atomicMin of the hits.
-// Windows are tried in increasing order, so the first window with a hit contains the global minimum.
 // ---------------------------------------------------------------------------------------------
+// The same search in ONE launch: thread t tests the candidates t, t + T, t + 2T, ... (T = threads of the grid) in
+// increasing order and stops as soon as its next candidate is not below the smallest hit so far.  Every candidate below
+// the final minimum was therefore tested by its thread, so `found` ends as the minimum witness -- no grid barrier, no
+// host round trip per window (a window without a hit used to cost one), and the whole proof stays one stream of work
+// that a CUDA graph can replay.  `limit` bounds the search (status 2 in the finish kernel if nothing was found).
 __global__ void __launch_bounds__(HASH_THREADS)
-pow_grind_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, uint64_t base, uint64_t count,
-                 unsigned long long* found) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint64_t cand = base + i;
-    if (cand >= GL_P) return;
-    uint64_t s[12];
+pow_grind_persistent_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bits, uint64_t limit,
+                            unsigned long long* found) {
+    const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t st0[12];
 #pragma unroll
-    for (int k = 0; k < 12; k++) s[k] = c->state[k];
-    uint32_t pos = c->in_len;  // < 8 by the challenger invariant
+    for (int k = 0; k < 12; k++) st0[k] = c->state[k];
+    const uint32_t pos = c->in_len;  // < 8 by the challenger invariant
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if ((uint32_t)k < pos) s[k] = c->in[k];
-        if ((uint32_t)k == pos) s[k] = cand;
+    for (int k = 0; k < 8; k++)
+        if ((uint32_t)k < pos) st0[k] = c->in[k];
+    for (uint64_t cand = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; cand < limit; cand += T) {
+        if (cand >= *reinterpret_cast<volatile unsigned long long*>(found)) break;
+        uint64_t s[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = st0[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if ((uint32_t)k == pos) s[k] = cand;
+        poseidon_permute(s);
+        const uint64_t resp = gl_canon(s[7]);
+        if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) { atomicMin(found, (unsigned long long)cand); break; }
     }
-    poseidon_permute(s);
-    uint64_t resp = gl_canon(s[7]);
-    if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) atomicMin(found, (unsigned long long)cand);
+}
+
+// PoseidonHash::hash_no_pad of a short device vector (public inputs): one half-warp runs the overwrite-mode sponge.
+__global__ void __launch_bounds__(32) hash_no_pad_kernel(const uint64_t* __restrict__ in, uint32_t len, uint64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 15;
+    uint64_t st = 0;
+    for (uint32_t c = 0; c < len; c += 8) {
+        const uint32_t m = len - c < 8 ? len - c : 8;
+        if ((uint32_t)lane < m) st = in[c + lane];     // overwrite mode
+        st = poseidon_permute_sub<16>(st, lane);
+    }
+    if (threadIdx.x < 4) out[threadIdx.x] = gl_canon(st);
 }
 
 // Observe the witness (the ground one or a caller-supplied one), draw the PoW response, then draw the
@@ -394,15 +413,24 @@ cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t 
     return cudaGetLastError();
 }
 
+cudaError_t launch_hash_no_pad(const uint64_t* in_dev, uint32_t len, uint64_t* out_dev, cudaStream_t st) {
+    hash_no_pad_kernel<<<1, 32, 0, st>>>(in_dev, len, out_dev);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
-                       uint64_t lde_size, uint64_t window_base, uint64_t window_count,
+                       uint64_t lde_size, uint64_t max_candidates, int num_sms,
                        unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices, uint32_t* status,
                        cudaStream_t st) {
     if (forced_witness == ~0ULL) {
         cudaError_t e = launch_fill_words(found_dev, 1, ~0ULL, st);
         if (e != cudaSuccess) return e;
-        uint64_t blocks = (window_count + HASH_THREADS - 1) / HASH_THREADS;
-        pow_grind_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(c, pow_bits, window_base, window_count, found_dev);
+        // one wave of the machine (about 2^17 candidates on a B200: a hit with probability 1 - e^-2 at 16 bits);
+        // fewer blocks when the expected search is shorter than a wave
+        uint64_t want = (pow_bits < 40 ? (2ull << pow_bits) : ~0ull) / HASH_THREADS + 1;
+        uint64_t blocks = (uint64_t)(num_sms > 0 ? num_sms : 148) * 6;
+        if (want < blocks) blocks = want;
+        pow_grind_persistent_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(c, pow_bits, max_candidates < GL_P ? max_candidates : GL_P, found_dev);
     }
     pow_finish_and_indices_kernel<<<1, 32, 0, st>>>(c, found_dev, forced_witness, pow_bits, num_queries, lde_size,
                                                     witness_out, indices, status);

@@ -92,10 +92,14 @@ cudaError_t launch_merkle_levels(uint64_t* digests, uint32_t num_levels, uint64_
 uint32_t merkle_levels_launches(uint32_t num_levels, uint64_t num_leaves);
 cudaError_t launch_challenger_observe(ChallengerDev* c, const uint64_t* elems_dev, uint32_t n, cudaStream_t st);
 cudaError_t launch_challenger_get(ChallengerDev* c, uint64_t* out_dev, uint32_t n, cudaStream_t st);
+// forced_witness == ~0: grind the MINIMUM witness below `max_candidates` in one launch (no host round trip), then
+// observe it and draw the query indices; otherwise use forced_witness.  status[0]: 1 ok, 0 witness too weak, 2 none found.
 cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witness, uint32_t num_queries,
-                       uint64_t lde_size, uint64_t window_base, uint64_t window_count,
+                       uint64_t lde_size, uint64_t max_candidates, int num_sms,
                        unsigned long long* found_dev, uint64_t* witness_out, uint64_t* indices, uint32_t* status,
                        cudaStream_t st);
+// PoseidonHash::hash_no_pad of `len` device words (one warp; len == 0 gives four zeros): public_inputs_hash of prove()
+cudaError_t launch_hash_no_pad(const uint64_t* in_dev, uint32_t len, uint64_t* out_dev, cudaStream_t st);
 
 // ---- fri.cu ----
 constexpr int EVAL_THREADS = 256;
@@ -111,6 +115,7 @@ struct FriCombineArgs {
     uint32_t batch_off[MAX_FRI_BATCHES + 1];  // prefix sums of batch sizes
     uint32_t eval_off[MAX_FRI_BATCHES * MAX_ORACLES];  // ext offset of evals[b][o] inside `evals`
     uint64_t points[2 * MAX_FRI_BATCHES];
+    const uint64_t* points_dev;                // device, 2 * num_batches words; overrides `points` when not null
     const uint32_t *poly_oracle, *poly_index;  // device
     const uint64_t* apow;      // device: alpha^j, ext
     const uint64_t* evals;     // device: per (batch, oracle) evaluations of every column at the batch point
@@ -165,11 +170,17 @@ struct EvalMultiArgs {
     const uint64_t* coeffs[MAX_EVAL_JOBS];
     uint64_t* out[MAX_EVAL_JOBS];
     uint64_t z[2 * MAX_EVAL_JOBS];
+    const uint64_t* z_dev[MAX_EVAL_JOBS];    // device point of job j (2 words); overrides z when not null
     uint32_t col_begin[MAX_EVAL_JOBS + 1];   // prefix sums of the jobs' column counts
 };
 cudaError_t launch_eval_ext_multi(const EvalMultiArgs& a, cudaStream_t st);
 cudaError_t launch_alpha_powers(const uint64_t* alpha_dev, uint64_t* apow_dev, uint32_t count, cudaStream_t st);
 cudaError_t launch_fri_combine(const FriCombineArgs& a, cudaStream_t st);
+// openings_out[k] = evals[...] in FRI-instance order, without the alpha reduction (the prover observes the openings
+// BEFORE alpha is drawn; launch_fri_combine writes the same values again)
+cudaError_t launch_openings_gather(const FriCombineArgs& a, uint32_t total_polys, cudaStream_t st);
+// out (ext) = in (ext) * s:  g * zeta for the openings of Z at the next row
+cudaError_t launch_ext_scale(const uint64_t* in_dev, uint64_t s, uint64_t* out_dev, cudaStream_t st);
 cudaError_t launch_fri_fold(const FriFoldArgs& a, uint32_t arity_bits, cudaStream_t st);
 cudaError_t launch_fri_final_poly(const FriFinalArgs& a, cudaStream_t st);
 cudaError_t launch_fri_gather(const FriGatherArgs& a, uint32_t num_queries, cudaStream_t st);
@@ -190,6 +201,12 @@ struct PartialProductsArgs {
 };
 inline unsigned pp_num_blocks(uint32_t log_n) { return (unsigned)(((1ull << log_n) + 127) / 128); }
 cudaError_t launch_partial_products(const PartialProductsArgs& a, cudaStream_t st);
+// beta_k[c][j] = betas[c] * kpow[j] from device-resident challenges (kpow[j] = g^j, the coset shifts k_j)
+cudaError_t launch_perm_params(const uint64_t* betas_dev, const uint64_t* kpow_dev, uint32_t num_challenges,
+                               uint32_t num_routed, uint64_t* beta_k_dev, cudaStream_t st);
+// apow[c][t] = alphas[c]^t, t < num_terms, from device-resident challenges
+cudaError_t launch_base_powers(const uint64_t* alphas_dev, uint32_t num_challenges, uint32_t num_terms,
+                               uint64_t* apow_dev, cudaStream_t st);
 
 // ---- quotient.cu ----
 constexpr uint32_t QUOT_MAX_CHALLENGES = 4;

@@ -127,6 +127,36 @@ __global__ void __launch_bounds__(PP_THREADS) pp_finish_kernel(PartialProductsAr
     }
 }
 
+__global__ void perm_params_kernel(const uint64_t* __restrict__ betas, const uint64_t* __restrict__ kpow, uint32_t num_challenges,
+                                   uint32_t num_routed, uint64_t* __restrict__ beta_k) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_challenges * num_routed) return;
+    beta_k[t] = gl_mul(betas[t / num_routed], kpow[t % num_routed]);
+}
+
+__global__ void base_powers_kernel(const uint64_t* __restrict__ bases, uint32_t num_challenges, uint32_t num_terms,
+                                   uint64_t* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_challenges * num_terms) return;
+    out[t] = gl_exp(bases[t / num_terms], t % num_terms);
+}
+
+cudaError_t launch_perm_params(const uint64_t* betas_dev, const uint64_t* kpow_dev, uint32_t num_challenges,
+                               uint32_t num_routed, uint64_t* beta_k_dev, cudaStream_t st) {
+    const uint32_t total = num_challenges * num_routed;
+    if (!total) return cudaSuccess;
+    perm_params_kernel<<<(total + 127) / 128, 128, 0, st>>>(betas_dev, kpow_dev, num_challenges, num_routed, beta_k_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_base_powers(const uint64_t* alphas_dev, uint32_t num_challenges, uint32_t num_terms,
+                               uint64_t* apow_dev, cudaStream_t st) {
+    const uint32_t total = num_challenges * num_terms;
+    if (!total) return cudaSuccess;
+    base_powers_kernel<<<(total + 127) / 128, 128, 0, st>>>(alphas_dev, num_challenges, num_terms, apow_dev);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_partial_products(const PartialProductsArgs& a, cudaStream_t st) {
     const uint64_t n = 1ull << a.log_n;
     const unsigned blocks = pp_num_blocks(a.log_n);
