@@ -323,6 +323,58 @@ int qpzk_commit_quotient_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas,
                               const uint64_t* gammas, const uint64_t* alphas, const qpzk_gate_program* prog,
                               uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out);
 
+/* ---- prove(): the whole proof after witness generation in one call, device resident -------------------------------
+ * Replaces the body of qp-plonky2 `prove_with_partition_witness` (plonk/prover.rs) from the wires commitment to the
+ * assembled Proof (transcript Appendix A.7); what the reference's three provers
+ * call: wormhole/prover/src/lib.rs:171-175, wormhole/aggregator/src/private_batch/prover/lib.rs:326-330,
+ * wormhole/aggregator/src/public_batch/prover/lib.rs:301-305.
+ * A qpzk_prover is created once per circuit (per context) from what CircuitBuilder::build leaves behind: the committed
+ * constants/sigmas batch (committed with from_values under qpzk_ctx_set_keep_values(ctx, 1)), the numbers of wires and
+ * routed wires, the gate constraints as a qpzk_gate_program, the verifier-data digest and the FRI parameters.  Per proof
+ * the caller hands over the witness (wire values), the public inputs and -- for a zero-knowledge circuit -- the salts.
+ * The Fiat-Shamir challenges never visit the host: challenger, partial products, quotient, openings and FRI read them
+ * from device memory; after two proofs the whole sequence is replayed as ONE CUDA graph (use_graph), so a proof is one
+ * host->device copy, one graph launch, one device->host copy and one wait.  Bit-identical to the step-by-step calls.
+ * Result layout (uint64 words, qpzk_prover_get_layout): wires cap | zs_partial_products cap | quotient cap |
+ * openings (FRI-instance order: constants, sigmas, wires, zs, partial products, quotient chunks, zs at g*zeta; 2 words
+ * each) | flat FriProof of qpzk_fri_prove for the four oracles -- the pieces qpzk_proof_to_bytes takes. */
+typedef struct qpzk_prover qpzk_prover;
+typedef struct {
+    uint32_t num_wires, num_routed, sigma_col0;   /* routed wires are columns [0, num_routed); sigma_j = constants_sigmas column sigma_col0 + j */
+    uint32_t quotient_degree_factor;              /* 8 for every reference circuit (common/src/circuit.rs:378-414) */
+    uint32_t num_challenges;                      /* 2 */
+    uint32_t num_public_inputs;
+    uint32_t blinding;                            /* 1: zero-knowledge circuit, the wires / zs / quotient oracles are salted */
+    uint32_t use_graph;                           /* 1: replay the proof as a CUDA graph from the third proof on */
+    uint64_t circuit_digest[4];                   /* verifier_only.circuit_digest, observed first */
+    qpzk_fri_params fri;
+    const qpzk_gate_program* gates;               /* NULL: no gate constraints (copied to the device by qpzk_prover_create) */
+} qpzk_prover_config;
+typedef struct {
+    uint64_t cap_words;            /* 4 << cap_height */
+    uint64_t cap_offset[3];        /* wires, zs_partial_products, quotient */
+    uint64_t openings_offset, num_openings;
+    uint64_t fri_offset, fri_words;
+    uint64_t total_words;
+    uint32_t leaf_lens[4];         /* leaf lengths of the four oracles (incl. salt): the argument of qpzk_fri_proof_words */
+} qpzk_prover_layout;
+int qpzk_prover_create(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_prover_config* cfg, qpzk_prover** out);
+void qpzk_prover_free(qpzk_prover* p);
+int qpzk_prover_get_layout(const qpzk_prover* p, qpzk_prover_layout* out);
+/* wires: num_wires x 2^log_n values, column-major (host; pinned memory makes the copy asynchronous); public_inputs:
+ * num_public_inputs canonical words; salts: NULL or 3 x QPZK_SALT_SIZE x 2^(log_n+rate_bits) words (wires, zs, quotient
+ * oracle; caller RNG); pow_witness_in: QPZK_POW_SEARCH (minimum witness) or a witness to use (runs without the graph).
+ * qpzk_prover_prove_async returns when the caller's buffers have been read -- they may be zeroized at once -- and the
+ * proof is still running; qpzk_prover_finish waits for it and copies the layout.total_words result words to out_words.
+ * Several provers on several contexts may be in flight at once from one host thread (their graphs overlap on the GPU). */
+int qpzk_prover_prove_async(qpzk_prover* p, const uint64_t* wires, const uint64_t* public_inputs, const uint64_t* salts,
+                            uint64_t pow_witness_in);
+int qpzk_prover_finish(qpzk_prover* p, uint64_t* out_words);
+int qpzk_prover_prove(qpzk_prover* p, const uint64_t* wires, const uint64_t* public_inputs, const uint64_t* salts,
+                      uint64_t pow_witness_in, uint64_t* out_words);
+uint64_t qpzk_prover_launches_per_proof(const qpzk_prover* p);   /* kernels + copies enqueued (or replayed) per proof */
+int qpzk_prover_uses_graph(const qpzk_prover* p);                 /* 1 once the graph has been captured */
+
 /* ---- wire format: ProofWithPublicInputs::to_bytes / from_bytes ----------------------------------------
  * Replaces qp-plonky2 `util/serialization`: `write_proof_with_public_inputs` / `read_proof_with_public_inputs`
  * (what the reference passes between prover, aggregator and verifier:

@@ -242,6 +242,8 @@ void ctx_unref(qpzk_ctx* ctx) {
     for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (auto& kv : ctx->coset_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     for (auto& kv : ctx->unshift_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+    for (auto& kv : ctx->zh_tables) cudaFree(kv.second);
+    if (ctx->kpow) cudaFree(ctx->kpow);
     if (ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
     if (ctx->h2d_done2) cudaEventDestroy(ctx->h2d_done2);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -495,12 +497,6 @@ void batch_release(qpzk_batch* b) {
 // Where the input columns come from.  Device-resident input: `dev` is set and fetch is a no-op.  Host input: the
 // columns are copied range by range on the context's copy stream and `fetch(c0, c1)` makes the context stream wait
 // for the range, so the per-column stages (iNTT, strided LDE passes) of one range overlap the copy of the next.
-struct ColumnSource {
-    const uint64_t* dev = nullptr;
-    const uint64_t* host = nullptr;
-    uint64_t* staging = nullptr;
-    uint32_t chunks = 1;
-};
 
 static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uint32_t c0, uint32_t c1) {
     if (!src.host || c1 <= c0) return 0;
@@ -518,7 +514,7 @@ static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uin
     return 0;
 }
 
-static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols,
+int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin,
                        uint32_t coset_count, bool keep_coeffs_copy, qpzk_batch** out) {
     NvtxRange nvtx_commit(from_values ? "qpzk:from_values" : "qpzk:from_coeffs");
@@ -620,7 +616,6 @@ static int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32
     return 0;
 }
 
-static ColumnSource dev_source(const uint64_t* p) { ColumnSource s; s.dev = p; return s; }
 
 extern "C" int qpzk_commit_from_values_dev(qpzk_ctx* ctx, const uint64_t* cols, uint32_t log_n, uint32_t num_cols,
                                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
@@ -1032,16 +1027,16 @@ extern "C" size_t qpzk_fri_proof_words(const qpzk_fri_params* p, uint32_t log_n,
 }
 
 
-extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
-                              const qpzk_fri_instance* inst, const qpzk_fri_params* p, qpzk_challenger* ch,
-                              uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out) {
-    GUARD_BEGIN
+// prove_openings on the context stream, without any host synchronisation: everything it needs from the host is
+// either a kernel argument or (FriDeviceIO) already on the device, so the single-call prover (prove.cu) can capture it
+// in a CUDA graph.  Results land in device memory: the flat proof in io.proof, the opened values (instance order) in
+// io.openings, the PoW status word in io.status[0] (1 ok, 0 supplied witness too weak, 2 search exhausted).
+int fri_core(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles, const qpzk_fri_instance* inst,
+             const qpzk_fri_params* p, ChallengerDev* ch, uint64_t pow_witness_in, const FriDeviceIO& io) {
     NvtxRange nvtx_fri("qpzk:prove_openings");
-    if (!ctx || !oracles || !inst || !p || !ch || !proof_out) return fail(QPZK_EINVAL, "null argument");
     if (!num_oracles || num_oracles > MAX_ORACLES) return fail(QPZK_EINVAL, "num_oracles must be in 1..8");
     if (!inst->num_batches || inst->num_batches > MAX_FRI_BATCHES) return fail(QPZK_EINVAL, "num_batches must be in 1..8");
     if (p->num_rounds > MAX_FRI_ROUNDS) return fail(QPZK_EINVAL, "too many FRI rounds");
-    if (ch->ctx != ctx) return fail(QPZK_EINVAL, "challenger belongs to another context");
     const uint32_t log_n = oracles[0]->log_n, rate_bits = p->rate_bits, log_L = log_n + rate_bits;
     for (uint32_t o = 0; o < num_oracles; o++) {
         const qpzk_batch* b = oracles[o];
@@ -1062,16 +1057,19 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
-    // ---- instance on the device
+    // ---- instance
     uint32_t total_polys = 0, max_k = 0;
     FriCombineArgs ca{};
     for (uint32_t b = 0; b < inst->num_batches; b++) {
         ca.batch_off[b] = total_polys;
         total_polys += inst->batch_sizes[b];
         if (inst->batch_sizes[b] > max_k) max_k = inst->batch_sizes[b];
-        ca.points[2 * b] = inst->points[2 * b]; ca.points[2 * b + 1] = inst->points[2 * b + 1];
-        if (ca.points[2 * b] >= GL_P || ca.points[2 * b + 1] >= GL_P) return fail(QPZK_EINVAL, "opening point is not canonical");
+        if (!io.points) {
+            ca.points[2 * b] = inst->points[2 * b]; ca.points[2 * b + 1] = inst->points[2 * b + 1];
+            if (ca.points[2 * b] >= GL_P || ca.points[2 * b + 1] >= GL_P) return fail(QPZK_EINVAL, "opening point is not canonical");
+        }
     }
+    ca.points_dev = io.points;
     ca.batch_off[inst->num_batches] = total_polys;
     std::vector<bool> used(inst->num_batches * num_oracles, false);
     {
@@ -1085,12 +1083,16 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     }
     DevBufs bufs(ctx);
     int rc;
-    uint64_t *d_refs, *d_alpha, *d_apow, *d_evals, *d_reduced, *d_open, *d_found, *d_proof;
-    if ((rc = bufs.alloc(&d_refs, total_polys + 1))) return rc;  // two u32 arrays packed
-    uint32_t* d_po = reinterpret_cast<uint32_t*>(d_refs);
-    uint32_t* d_pi = d_po + total_polys;
-    CK(cudaMemcpyAsync(d_po, inst->poly_oracle, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_pi, inst->poly_index, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    uint64_t *d_refs = nullptr, *d_alpha, *d_apow, *d_evals, *d_reduced, *d_found;
+    const uint32_t* d_po = io.poly_refs;
+    if (!d_po) {   // the polynomial references come from caller memory: the wrapper synchronises before it returns
+        if ((rc = bufs.alloc(&d_refs, total_polys + 1))) return rc;  // two u32 arrays packed
+        uint32_t* w = reinterpret_cast<uint32_t*>(d_refs);
+        CK(cudaMemcpyAsync(w, inst->poly_oracle, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w + total_polys, inst->poly_index, total_polys * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        d_po = w;
+    }
+    const uint32_t* d_pi = d_po + total_polys;
     if ((rc = bufs.alloc(&d_alpha, 8))) return rc;             // alpha, then beta per round reuses +2
     if ((rc = bufs.alloc(&d_apow, 2ull * (max_k + 1)))) return rc;
     uint64_t eval_words = 0;
@@ -1101,12 +1103,10 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         }
     if ((rc = bufs.alloc(&d_evals, 2 * eval_words, true))) return rc;
     if ((rc = bufs.alloc(&d_reduced, 2ull * inst->num_batches))) return rc;
-    if ((rc = bufs.alloc(&d_open, 2ull * total_polys))) return rc;
-    if ((rc = bufs.alloc(&d_found, 4 + p->num_query_rounds))) return rc;  // [0]=found, [1]=witness, [2]=status, [4..]=indices
+    if ((rc = bufs.alloc(&d_found, 2))) return rc;
+    uint64_t* d_open = io.openings;
 
-    // ---- alpha and its powers; openings of every referenced oracle at every batch point
-    CK(launch_challenger_get(ch->dev, d_alpha, 2, st)); ctx->launches++;
-    CK(launch_alpha_powers(d_alpha, d_apow, max_k + 1, st)); ctx->launches++;
+    // ---- openings of every referenced oracle at every batch point; the prover observes them before alpha is drawn
     {
         EvalMultiArgs ea{};
         ea.log_n = log_n; ea.col_stride = 1ull << log_n;
@@ -1117,11 +1117,22 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
                     ea.coeffs[j] = oracles[o]->coeffs;
                     ea.out[j] = d_evals + 2ull * ca.eval_off[b * num_oracles + o];
                     ea.z[2 * j] = ca.points[2 * b]; ea.z[2 * j + 1] = ca.points[2 * b + 1];
+                    ea.z_dev[j] = io.points ? io.points + 2 * b : nullptr;
                     ea.col_begin[j + 1] = ea.col_begin[j] + oracles[o]->num_cols;
                 }
         CK(launch_eval_ext_multi(ea, st));
         ctx->launches++;
     }
+    ca.log_n = log_n; ca.rate_bits = rate_bits; ca.num_batches = inst->num_batches; ca.num_oracles = num_oracles;
+    for (uint32_t o = 0; o < num_oracles; o++) { ca.leaves[o] = oracles[o]->leaves; ca.leaf_width[o] = oracles[o]->leaf_width; }
+    ca.poly_oracle = d_po; ca.poly_index = d_pi; ca.apow = d_apow; ca.evals = d_evals; ca.reduced = d_reduced;
+    ca.openings_out = d_open;
+    if (io.observe_openings) {
+        CK(launch_openings_gather(ca, total_polys, st)); ctx->launches++;
+        CK(launch_challenger_observe(ch, d_open, 2 * total_polys, st)); ctx->launches++;
+    }
+    CK(launch_challenger_get(ch, d_alpha, 2, st)); ctx->launches++;
+    CK(launch_alpha_powers(d_alpha, d_apow, max_k + 1, st)); ctx->launches++;
 
     // ---- batch-opening polynomial, evaluated on the LDE domain in leaf order
     PowTables fwd_n, inv_L;
@@ -1132,10 +1143,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     const uint64_t L = 1ull << log_L;
     std::vector<uint64_t*> layer(p->num_rounds + 1);
     if ((rc = bufs.alloc(&layer[0], 2 * L, true))) return rc;
-    ca.log_n = log_n; ca.rate_bits = rate_bits; ca.num_batches = inst->num_batches; ca.num_oracles = num_oracles;
-    for (uint32_t o = 0; o < num_oracles; o++) { ca.leaves[o] = oracles[o]->leaves; ca.leaf_width[o] = oracles[o]->leaf_width; }
-    ca.poly_oracle = d_po; ca.poly_index = d_pi; ca.apow = d_apow; ca.evals = d_evals; ca.reduced = d_reduced;
-    ca.openings_out = d_open; ca.values = layer[0]; ca.tw_lo = fwd_n.lo; ca.tw_hi = fwd_n.hi; ca.cs_lo = cs.lo;
+    ca.values = layer[0]; ca.tw_lo = fwd_n.lo; ca.tw_hi = fwd_n.hi; ca.cs_lo = cs.lo;
     CK(launch_fri_combine(ca, st)); ctx->launches += 2;
 
     // ---- proof buffer layout
@@ -1146,7 +1154,7 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
     const size_t final_len = (size_t)1 << (log_n - total_arity);
     const size_t query_base = p->num_rounds * cap_words;
     const size_t query_words = p->num_query_rounds ? (proof_words - 1 - 2 * final_len - query_base) / p->num_query_rounds : 0;
-    if ((rc = bufs.alloc(&d_proof, proof_words, true))) return rc;
+    uint64_t* d_proof = io.proof;
 
     // ---- commit phase
     std::vector<uint64_t*> round_digests(p->num_rounds);
@@ -1162,8 +1170,8 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         CK(launch_merkle_levels(round_digests[r], levels, rows, st)); ctx->launches += merkle_levels_launches(levels, rows);
         const uint64_t* cap = round_digests[r] + digest_level_off(rows, levels - 1);
         CK(cudaMemcpyAsync(d_proof + r * cap_words, cap, cap_words * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-        CK(launch_challenger_observe(ch->dev, cap, (uint32_t)cap_words, st)); ctx->launches++;
-        CK(launch_challenger_get(ch->dev, d_beta, 2, st)); ctx->launches++;
+        CK(launch_challenger_observe(ch, cap, (uint32_t)cap_words, st)); ctx->launches++;
+        CK(launch_challenger_get(ch, d_beta, 2, st)); ctx->launches++;
         if ((rc = bufs.alloc(&layer[r + 1], 2 * rows, true))) return rc;
         FriFoldArgs fa{};
         fa.in = layer[r]; fa.out = layer[r + 1]; fa.lg = lg; fa.log_L = log_L; fa.beta = d_beta;
@@ -1186,13 +1194,9 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         cudaError_t e = launch_fri_final_poly(fa, st);
         if (e == cudaErrorInvalidValue) return fail(QPZK_EINVAL, "final FRI layer too large (reduce more rounds)");
         CK(e); ctx->launches++;
-        CK(launch_challenger_observe(ch->dev, d_final, (uint32_t)(2 * final_len), st)); ctx->launches++;
+        CK(launch_challenger_observe(ch, d_final, (uint32_t)(2 * final_len), st)); ctx->launches++;
     }
-    // ---- proof of work, query indices, query phase.  The grinder tests windows of candidates in
-    // increasing order; a window without a hit (probability e^-2 per window) is followed by the next one.
-    unsigned long long* d_foundp = reinterpret_cast<unsigned long long*>(d_found);
-    uint64_t* d_indices = d_found + 4;
-    uint32_t* d_status = reinterpret_cast<uint32_t*>(d_found + 2);
+    // ---- proof of work (minimum witness, one launch), query indices, query phase
     FriGatherArgs g{};
     for (uint32_t o = 0; o < num_oracles; o++)
         g.trees[o] = FriTreeDesc{oracles[o]->leaves, oracles[o]->digests, oracles[o]->leaf_width, log_L, p->cap_height, 0};
@@ -1201,24 +1205,48 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
         lg -= p->arity_bits[r];
         g.trees[num_oracles + r] = FriTreeDesc{layer[r], round_digests[r], 2u << p->arity_bits[r], lg, p->cap_height, p->arity_bits[r]};
     }
-    g.num_trees = num_oracles + p->num_rounds; g.num_oracles = num_oracles; g.indices = d_indices; g.status = d_status;
+    g.num_trees = num_oracles + p->num_rounds; g.num_oracles = num_oracles; g.indices = io.indices; g.status = io.status;
     g.proof = d_proof; g.query_base = query_base; g.query_words = query_words;
-    // window of 2^(bits+1) candidates: one wave of the grinder on a B200 at 16 bits (2^17 permutations, ~0.1 ms) and a
-    // hit with probability 1 - e^-2 = 86%; the next window costs one more round trip
-    const uint64_t window = 1ull << (p->proof_of_work_bits + 1 < 14 ? 14 : p->proof_of_work_bits + 1);
+    // the search gives up after 2^(bits + 10) candidates: without a hit with probability e^-1024
+    const uint64_t limit = p->proof_of_work_bits + 10 < 63 ? (1ull << (p->proof_of_work_bits + 10)) : GL_P;
+    CK(launch_pow(ch, p->proof_of_work_bits, pow_witness_in, p->num_query_rounds, L, limit, ctx->num_sms,
+                  reinterpret_cast<unsigned long long*>(d_found), d_proof + proof_words - 1, io.indices, io.status, st));
+    ctx->launches += pow_witness_in == QPZK_POW_SEARCH ? 3 : 1;
+    CK(launch_fri_gather(g, p->num_query_rounds, st)); ctx->launches++;
+    return 0;
+}
+
+extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles,
+                              const qpzk_fri_instance* inst, const qpzk_fri_params* p, qpzk_challenger* ch,
+                              uint64_t pow_witness_in, uint64_t* proof_out, uint64_t* openings_out) {
+    GUARD_BEGIN
+    if (!ctx || !oracles || !inst || !p || !ch || !proof_out) return fail(QPZK_EINVAL, "null argument");
+    if (ch->ctx != ctx) return fail(QPZK_EINVAL, "challenger belongs to another context");
+    if (!num_oracles || num_oracles > MAX_ORACLES || !oracles[0]) return fail(QPZK_EINVAL, "num_oracles must be in 1..8");
+    if (!inst->num_batches || inst->num_batches > MAX_FRI_BATCHES) return fail(QPZK_EINVAL, "num_batches must be in 1..8");
+    CK(cudaSetDevice(ctx->device));
+    uint32_t total_polys = 0;
+    for (uint32_t b = 0; b < inst->num_batches; b++) total_polys += inst->batch_sizes[b];
+    std::vector<uint32_t> leaf_lens(num_oracles);
+    for (uint32_t o = 0; o < num_oracles; o++) { if (!oracles[o]) return fail(QPZK_EINVAL, "null oracle"); leaf_lens[o] = oracles[o]->leaf_width; }
+    const size_t proof_words = qpzk_fri_proof_words(p, oracles[0]->log_n, num_oracles, leaf_lens.data());
+    DevBufs bufs(ctx);
+    int rc;
+    uint64_t *d_proof, *d_open, *d_misc;
+    if ((rc = bufs.alloc(&d_proof, proof_words, true))) return rc;
+    if ((rc = bufs.alloc(&d_open, 2ull * total_polys + 1))) return rc;
+    if ((rc = bufs.alloc(&d_misc, 2 + p->num_query_rounds))) return rc;   // [0] status, [2..] query indices
+    FriDeviceIO io{};
+    io.proof = d_proof; io.openings = d_open; io.indices = d_misc + 2; io.status = reinterpret_cast<uint32_t*>(d_misc);
+    CK(launch_fill_words(d_misc, 1, 0, ctx->stream));
+    if ((rc = fri_core(ctx, oracles, num_oracles, inst, p, ch->dev, pow_witness_in, io))) return rc;
     uint32_t status[2] = {0, 0};
-    for (uint64_t base = 0;; base += window) {
-        CK(launch_pow(ch->dev, p->proof_of_work_bits, pow_witness_in, p->num_query_rounds, L, base, window, d_foundp,
-                      d_proof + proof_words - 1, d_indices, d_status, st));
-        ctx->launches += pow_witness_in == QPZK_POW_SEARCH ? 2 : 1;
-        CK(launch_fri_gather(g, p->num_query_rounds, st)); ctx->launches++;
-        CK(cudaMemcpyAsync(proof_out, d_proof, proof_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        if (openings_out) CK(cudaMemcpyAsync(openings_out, d_open, 2ull * total_polys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(status, d_status, sizeof status, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (status[0] != 2) break;
-        if (base + window >= GL_P - window) return fail(QPZK_EPOW, "proof of work failed: no witness in the field");
-    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(proof_out, d_proof, proof_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (openings_out) CK(cudaMemcpyAsync(openings_out, d_open, 2ull * total_polys * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d_misc, sizeof status, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (status[0] == 2) return fail(QPZK_EPOW, "proof of work failed: no witness found");
     if (!status[0]) return fail(QPZK_EPOW, "proof-of-work witness does not reach the required leading zeros");
     return 0;
     GUARD_END
@@ -1227,26 +1255,48 @@ extern "C" int qpzk_fri_prove(qpzk_ctx* ctx, const qpzk_batch* const* oracles, u
 // ---------------------------------------------------------------------------------------------
 // permutation argument: Z and partial products (perm.cu)
 // ---------------------------------------------------------------------------------------------
-static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, bool host, uint32_t log_n,
-                                 uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
-                                 const uint64_t* gammas, uint64_t* out) {
+// k_j = g^j (get_unique_coset_shifts) for j < count, on the device; one table per context, grown on demand
+int get_kpow_table(qpzk_ctx* ctx, uint32_t count, const uint64_t** out) {
+    if (ctx->kpow_size < count) {
+        std::vector<uint64_t> h(count);
+        uint64_t k = 1;
+        for (uint32_t j = 0; j < count; j++) { h[j] = k; k = gl_mul_host(k, GL_GENERATOR); }
+        uint64_t* d = nullptr;
+        CK(cudaMalloc((void**)&d, count * sizeof(uint64_t)));
+        cudaError_t e = cudaMemcpyAsync(d, h.data(), count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // also: earlier kernels are done with the old table
+        if (e != cudaSuccess) { cudaFree(d); CK(e); }
+        if (ctx->kpow) cudaFree(ctx->kpow);
+        ctx->kpow = d; ctx->kpow_size = count;
+    }
+    *out = ctx->kpow;
+    return 0;
+}
+
+// betas / gammas: host challenges, or chal_dev = [betas | gammas] already on the device (the single-call prover: the
+// challenges never visit the host; beta * k_j is then computed by a kernel instead of on the host)
+int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, bool host, uint32_t log_n,
+                          uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                          const uint64_t* gammas, const uint64_t* chal_dev, uint64_t* out) {
     NvtxRange nvtx_pp("qpzk:partial_products");
-    if (!ctx || !wires || !sigmas || !betas || !gammas || !out) return fail(QPZK_EINVAL, "null argument");
+    if (!ctx || !wires || !sigmas || (!chal_dev && (!betas || !gammas)) || !out) return fail(QPZK_EINVAL, "null argument");
     if (log_n > 28) return fail(QPZK_EINVAL, "log_n must be <= 28");
     if (!num_routed || !chunk) return fail(QPZK_EINVAL, "num_routed and chunk must be positive");
     const uint32_t nchunks = (num_routed + chunk - 1) / chunk;
     if (nchunks > PP_MAX_CHUNKS) return fail(QPZK_EINVAL, "more than 32 chunks per row");
     if (!num_challenges || num_challenges > 8) return fail(QPZK_EINVAL, "num_challenges must be in 1..8");
-    for (uint32_t c = 0; c < num_challenges; c++)
+    for (uint32_t c = 0; c < num_challenges && !chal_dev; c++)
         if (betas[c] >= GL_P || gammas[c] >= GL_P) return fail(QPZK_EINVAL, "challenge is not canonical");
     CK(cudaSetDevice(ctx->device));
     const uint64_t n = 1ull << log_n, in_words = (uint64_t)num_routed * n, out_words = (uint64_t)num_challenges * nchunks * n;
     PowTables tw;
     int rc = get_pow_tables(ctx, log_n, false, &tw);
     if (rc) return rc;
+    const uint64_t* kpow = nullptr;
+    if (chal_dev && (rc = get_kpow_table(ctx, num_routed, &kpow))) return rc;
     // small parameter block: betas | gammas | beta * k_j per challenge,  k_j = g^j (get_unique_coset_shifts)
     std::vector<uint64_t> par(2 * num_challenges + (size_t)num_challenges * num_routed);
-    for (uint32_t c = 0; c < num_challenges; c++) {
+    for (uint32_t c = 0; c < num_challenges && !chal_dev; c++) {
         par[c] = betas[c]; par[num_challenges + c] = gammas[c];
         uint64_t k = 1;
         for (uint32_t j = 0; j < num_routed; j++) {
@@ -1267,11 +1317,16 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
         CK(cudaMemcpyAsync(d_w, wires, in_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_s, sigmas, in_words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (!chal_dev) CK(cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     PartialProductsArgs a{};
     a.wires = host ? d_w : wires; a.sigmas = host ? d_s : sigmas; a.col_stride = n;
     a.log_n = log_n; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = nchunks; a.num_challenges = num_challenges;
     a.betas = d_par; a.gammas = d_par + num_challenges; a.beta_k = d_par + 2 * num_challenges;
+    if (chal_dev) {
+        a.betas = chal_dev; a.gammas = chal_dev + num_challenges;
+        CK(launch_perm_params(chal_dev, kpow, num_challenges, num_routed, d_par + 2 * num_challenges, ctx->stream));
+        ctx->launches++;
+    }
     a.tw_lo = tw.lo; a.tw_hi = tw.hi;
     a.chunkprod = d_chunk; a.rowprod = d_row; a.blockprod = d_blk; a.out = host ? d_out : out;
     CK(launch_partial_products(a, ctx->stream));
@@ -1289,19 +1344,18 @@ static int partial_products_impl(qpzk_ctx* ctx, const uint64_t* wires, const uin
 extern "C" int qpzk_partial_products(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
                                      uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                                      const uint64_t* gammas, uint64_t* out) {
-    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, true, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, true, log_n, num_routed, chunk, num_challenges, betas, gammas, nullptr, out); GUARD_END
 }
 extern "C" int qpzk_partial_products_dev(qpzk_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t log_n,
                                          uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
                                          const uint64_t* gammas, uint64_t* out) {
-    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, false, log_n, num_routed, chunk, num_challenges, betas, gammas, out); GUARD_END
+    GUARD_BEGIN return partial_products_impl(ctx, wires, sigmas, false, log_n, num_routed, chunk, num_challenges, betas, gammas, nullptr, out); GUARD_END
 }
 
-extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
-                                               uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk,
-                                               uint32_t num_challenges, const uint64_t* betas, const uint64_t* gammas,
-                                               uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out) {
-    GUARD_BEGIN
+int commit_zs_impl(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires, uint32_t sigma_col0,
+                   uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                   const uint64_t* gammas, const uint64_t* chal_dev, uint32_t cap_height, const uint64_t* salt_dev,
+                   qpzk_batch** out) {
     if (!out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
     if (!ctx || !constants_sigmas || !wires) return fail(QPZK_EINVAL, "null argument");
@@ -1318,11 +1372,19 @@ extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* 
     int rc = dev_alloc(ctx, &d_out, (uint64_t)cols * n);
     if (rc) return rc;
     rc = partial_products_impl(ctx, wires->values, constants_sigmas->values + (uint64_t)sigma_col0 * n, false, wires->log_n,
-                               num_routed, chunk, num_challenges, betas, gammas, d_out);
+                               num_routed, chunk, num_challenges, betas, gammas, chal_dev, d_out);
     if (!rc) rc = commit_impl(ctx, dev_source(d_out), true, wires->log_n, cols, wires->rate_bits, cap_height, salt_dev, 0,
                               1u << wires->rate_bits, true, out);
     dev_free(ctx, d_out, (uint64_t)cols * n);
     return rc;
+}
+extern "C" int qpzk_commit_zs_partial_products(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
+                                               uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk,
+                                               uint32_t num_challenges, const uint64_t* betas, const uint64_t* gammas,
+                                               uint32_t cap_height, const uint64_t* salt_dev, qpzk_batch** out) {
+    GUARD_BEGIN
+    return commit_zs_impl(ctx, constants_sigmas, wires, sigma_col0, num_routed, chunk, num_challenges, betas, gammas, nullptr,
+                          cap_height, salt_dev, out);
     GUARD_END
 }
 
@@ -1347,13 +1409,38 @@ static int get_unshift_tables(qpzk_ctx* ctx, uint32_t log_size, PowTables* out) 
 
 // Leaves *coeffs_out (device, (num_challenges << qbits) x n words = the quotient chunks, column-major) to the caller,
 // who releases it with dev_free.
-static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, const qpzk_batch* zs,
-                         uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
-                         const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
-                         const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out) {
+// Z_H(x) = g^n w_Q^k - 1 for the Q residues k of the quotient coset, then the Q inverses; cached per (log_n, qbits)
+static int get_zh_table(qpzk_ctx* ctx, uint32_t log_n, uint32_t qbits, const uint64_t** out) {
+    auto key = std::make_pair(log_n, qbits);
+    auto it = ctx->zh_tables.find(key);
+    if (it == ctx->zh_tables.end()) {
+        const uint32_t Q = 1u << qbits;
+        std::vector<uint64_t> h;
+        const uint64_t g_pow_n = gl_exp_host(GL_GENERATOR, 1ull << log_n), wq = gl_root_of_unity_host(qbits);
+        uint64_t r = 1;
+        for (uint32_t k = 0; k < Q; k++) {
+            const uint64_t v = gl_mul_host(g_pow_n, r);
+            h.push_back(v ? v - 1 : GL_P - 1);
+            r = gl_mul_host(r, wq);
+        }
+        for (uint32_t k = 0; k < Q; k++) h.push_back(gl_inv_host(h[k]));
+        uint64_t* d = nullptr;
+        int rc = upload_words(ctx, h, &d);
+        if (rc) return rc;
+        it = ctx->zh_tables.emplace(key, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// betas / gammas / alphas: host challenges, or chal_dev = [betas | gammas | alphas] already on the device
+int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, const qpzk_batch* zs,
+                  uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
+                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, const uint64_t* chal_dev,
+                  const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out) {
     NvtxRange nvtx_q("qpzk:compute_quotient_polys");
     *coeffs_out = nullptr;
-    if (!ctx || !cs || !wires || !zs || !betas || !gammas || !alphas) return fail(QPZK_EINVAL, "null argument");
+    if (!ctx || !cs || !wires || !zs || (!chal_dev && (!betas || !gammas || !alphas))) return fail(QPZK_EINVAL, "null argument");
     if (cs->ctx != ctx || wires->ctx != ctx || zs->ctx != ctx) return fail(QPZK_EINVAL, "batch belongs to another context");
     if (!num_challenges || num_challenges > QUOT_MAX_CHALLENGES) return fail(QPZK_EINVAL, "num_challenges must be in 1..4");
     if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
@@ -1369,59 +1456,64 @@ static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* 
     const uint32_t nchunks = (num_routed + chunk - 1) / chunk;
     if (zs->num_cols < num_challenges * nchunks) return fail(QPZK_EINVAL, "zs/partial-products batch has too few columns");
     if (num_gate_terms && !gate_terms_dev) return fail(QPZK_EINVAL, "gate_terms is null");
-    for (uint32_t c = 0; c < num_challenges; c++)
+    for (uint32_t c = 0; c < num_challenges && !chal_dev; c++)
         if (betas[c] >= GL_P || gammas[c] >= GL_P || alphas[c] >= GL_P) return fail(QPZK_EINVAL, "challenge is not canonical");
     CK(cudaSetDevice(ctx->device));
-    const uint32_t log_q = log_n + qbits, Q = 1u << qbits;
+    const uint32_t log_q = log_n + qbits;
     const uint64_t n = 1ull << log_n, Lq = 1ull << log_q;
     const uint32_t T = num_challenges + num_challenges * nchunks + num_gate_terms;
     PowTables tw, un;
     int rc;
     if ((rc = get_pow_tables(ctx, log_q, false, &tw))) return rc;
     if ((rc = get_unshift_tables(ctx, log_q, &un))) return rc;
-    // parameter block: betas | gammas | beta * k_j | alpha powers | Z_H on the coset and its inverses
+    // parameter block: betas | gammas | beta * k_j | alpha powers (computed on the host from host challenges, by two
+    // small kernels from device challenges); Z_H on the coset and its inverses come from a per-context table
+    const uint64_t* d_zh = nullptr;
+    if ((rc = get_zh_table(ctx, log_n, qbits, &d_zh))) return rc;
+    const size_t off_bk = 2 * (size_t)num_challenges, off_apow = off_bk + (size_t)num_challenges * num_routed;
+    const size_t par_words = off_apow + (size_t)num_challenges * T;
     std::vector<uint64_t> par;
-    par.insert(par.end(), betas, betas + num_challenges);
-    par.insert(par.end(), gammas, gammas + num_challenges);
-    for (uint32_t c = 0; c < num_challenges; c++) {
-        uint64_t k = 1;
-        for (uint32_t j = 0; j < num_routed; j++) { par.push_back(gl_mul_host(betas[c], k)); k = gl_mul_host(k, GL_GENERATOR); }
-    }
-    const size_t off_apow = par.size();
-    for (uint32_t c = 0; c < num_challenges; c++) {
-        uint64_t v = 1;
-        for (uint32_t t = 0; t < T; t++) { par.push_back(v); v = gl_mul_host(v, alphas[c]); }
-    }
-    const size_t off_zh = par.size();
-    {
-        const uint64_t g_pow_n = gl_exp_host(GL_GENERATOR, n), wq = gl_root_of_unity_host(qbits);
-        uint64_t r = 1;
-        for (uint32_t k = 0; k < Q; k++) {
-            const uint64_t v = gl_mul_host(g_pow_n, r);
-            par.push_back(v ? v - 1 : GL_P - 1);
-            r = gl_mul_host(r, wq);
+    const uint64_t* kpow = nullptr;
+    if (chal_dev) {
+        if ((rc = get_kpow_table(ctx, num_routed, &kpow))) return rc;
+    } else {
+        par.insert(par.end(), betas, betas + num_challenges);
+        par.insert(par.end(), gammas, gammas + num_challenges);
+        for (uint32_t c = 0; c < num_challenges; c++) {
+            uint64_t k = 1;
+            for (uint32_t j = 0; j < num_routed; j++) { par.push_back(gl_mul_host(betas[c], k)); k = gl_mul_host(k, GL_GENERATOR); }
         }
-        for (uint32_t k = 0; k < Q; k++) par.push_back(gl_inv_host(par[off_zh + k]));
+        for (uint32_t c = 0; c < num_challenges; c++) {
+            uint64_t v = 1;
+            for (uint32_t t = 0; t < T; t++) { par.push_back(v); v = gl_mul_host(v, alphas[c]); }
+        }
     }
     DevBufs bufs(ctx);
     uint64_t *d_par, *d_vals, *d_coeffs;
-    if ((rc = bufs.alloc(&d_par, par.size()))) return rc;
+    if ((rc = bufs.alloc(&d_par, par_words))) return rc;
     if ((rc = bufs.alloc(&d_vals, (uint64_t)num_challenges * Lq))) return rc;
     if ((rc = dev_alloc(ctx, &d_coeffs, (uint64_t)num_challenges * Lq))) return rc;
     auto bail = [&](cudaError_t e, const char* what) {
         dev_free(ctx, d_coeffs);
         return fail(QPZK_ECUDA, std::string(what) + " failed: " + cudaGetErrorString(e));
     };
-    cudaError_t e = cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+    cudaError_t e = cudaSuccess;
+    if (chal_dev) {
+        e = launch_perm_params(chal_dev, kpow, num_challenges, num_routed, d_par + off_bk, ctx->stream);
+        if (e == cudaSuccess) e = launch_base_powers(chal_dev + 2 * num_challenges, num_challenges, T, d_par + off_apow, ctx->stream);
+        ctx->launches += 2;
+    } else {
+        e = cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e != cudaSuccess) return bail(e, "quotient parameters");
     QuotientArgs a{};
     a.cs_leaves = cs->leaves; a.w_leaves = wires->leaves; a.z_leaves = zs->leaves;
     a.cs_width = cs->leaf_width; a.w_width = wires->leaf_width; a.z_width = zs->leaf_width; a.sigma_col0 = sigma_col0;
     a.log_n = log_n; a.qbits = qbits; a.num_routed = num_routed; a.chunk = chunk; a.nchunks = nchunks;
     a.num_challenges = num_challenges; a.num_gate_terms = num_gate_terms; a.num_terms = T;
     a.gate_terms = gate_terms_dev;
-    a.betas = d_par; a.gammas = d_par + num_challenges; a.beta_k = d_par + 2 * num_challenges;
-    a.apow = d_par + off_apow; a.zh = d_par + off_zh;
+    a.betas = chal_dev ? chal_dev : d_par; a.gammas = a.betas + num_challenges; a.beta_k = d_par + off_bk;
+    a.apow = d_par + off_apow; a.zh = d_zh;
     a.n_field = n % GL_P;
     a.tw_lo = tw.lo; a.tw_hi = tw.hi;
     a.values = d_vals;
@@ -1438,18 +1530,13 @@ static int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* 
     return 0;
 }
 
-// Validates a gate program and evaluates it at every quotient-domain point: *terms_out (device, [n Q][num_terms]) is
-// left to the caller (dev_free); *num_terms_out = number of EMITs.  prog == NULL: no gates, nothing allocated.
-static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk,
-                                   const qpzk_gate_program* prog, uint64_t** terms_out, uint32_t* num_terms_out) {
-    *terms_out = nullptr; *num_terms_out = 0;
+// Validates a gate program against the column counts of the two batches it reads and copies it to the device (the copy
+// has completed when this returns: the program lives in caller memory).  num_terms = number of EMITs.
+int gate_program_upload(qpzk_ctx* ctx, uint32_t cs_cols, uint32_t wire_cols, const qpzk_gate_program* prog, GateProgramDev* out) {
+    *out = GateProgramDev{};
     if (!prog) return 0;
-    if (!ctx || !cs || !wires) return fail(QPZK_EINVAL, "null argument");
     if (!prog->code || (!prog->imm && prog->num_imm)) return fail(QPZK_EINVAL, "gate program: null code / imm");
     if (!prog->num_regs || prog->num_regs > GATE_MAX_REGS) return fail(QPZK_EINVAL, "gate program: num_regs must be in 1..256");
-    if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
-    if (ilog2(chunk) > wires->rate_bits || cs->log_n != wires->log_n || cs->rate_bits != wires->rate_bits)
-        return fail(QPZK_EINVAL, "batches must have the same degree and rate, quotient_degree_factor <= blowup");
     std::vector<bool> written(prog->num_regs, false);
     uint32_t emits = 0;
     for (uint32_t pc = 0; pc < prog->num_ops; pc++) {
@@ -1459,8 +1546,8 @@ static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qp
         auto reg_ok = [&](uint32_t r) { return r < prog->num_regs && written[r]; };
         if (op > 10 || (w0 >> 16)) return bad("unknown opcode");
         if (op != 6 && dst >= prog->num_regs) return bad("destination register out of range");
-        if (op == 0 && a >= wires->num_cols) return bad("wire column out of range");
-        if (op == 1 && a >= cs->num_cols) return bad("constants/sigmas column out of range");
+        if (op == 0 && a >= wire_cols) return bad("wire column out of range");
+        if (op == 1 && a >= cs_cols) return bad("constants/sigmas column out of range");
         if (op == 2 && a >= prog->num_imm) return bad("immediate out of range");
         if ((op == 3 || op == 4 || op == 5 || op == 7) && (!reg_ok(a) || !reg_ok(b))) return bad("source register out of range or not yet written");
         if ((op == 8 || op == 9 || op == 10) && !reg_ok(a)) return bad("source register out of range or not yet written");
@@ -1472,27 +1559,56 @@ static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qp
     for (uint32_t i = 0; i < prog->num_imm; i++) if (prog->imm[i] >= GL_P) return fail(QPZK_EINVAL, "gate program: immediate is not canonical");
     if (!emits) return 0;
     CK(cudaSetDevice(ctx->device));
-    const uint64_t points = (1ull << wires->log_n) * chunk;
-    DevBufs bufs(ctx);
-    uint64_t *d_code, *d_imm, *d_terms;
     int rc;
-    if ((rc = bufs.alloc(&d_code, 2ull * prog->num_ops + 2))) return rc;          // 4 x u32 per instruction, 16-byte aligned
-    if ((rc = bufs.alloc(&d_imm, prog->num_imm ? prog->num_imm : 1))) return rc;
-    if ((rc = dev_alloc(ctx, &d_terms, points * emits))) return rc;
-    cudaError_t e = cudaMemcpyAsync(d_code, prog->code, 16ull * prog->num_ops, cudaMemcpyHostToDevice, ctx->stream);
+    if ((rc = dev_alloc(ctx, &out->code, 2ull * prog->num_ops + 2))) return rc;          // 4 x u32 per instruction, 16-byte aligned
+    if ((rc = dev_alloc(ctx, &out->imm, prog->num_imm ? prog->num_imm : 1))) { dev_free(ctx, out->code); *out = GateProgramDev{}; return rc; }
+    cudaError_t e = cudaMemcpyAsync(out->code, prog->code, 16ull * prog->num_ops, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && prog->num_imm)
-        e = cudaMemcpyAsync(d_imm, prog->imm, 8ull * prog->num_imm, cudaMemcpyHostToDevice, ctx->stream);
-    GateProgramArgs g{};
-    g.cs_leaves = cs->leaves; g.w_leaves = wires->leaves; g.cs_width = cs->leaf_width; g.w_width = wires->leaf_width;
-    g.code = reinterpret_cast<const uint32_t*>(d_code); g.imm = d_imm; g.num_ops = prog->num_ops; g.num_terms = emits; g.num_regs = prog->num_regs;
-    g.num_points = points; g.terms = d_terms;
-    if (e == cudaSuccess) { e = launch_gate_program(g, ctx->stream); ctx->launches++; }
-    // the program came from caller memory: it must be on the device before the call returns (the scratch copies are
-    // released to the block cache, where stream order protects them until the kernel has run)
+        e = cudaMemcpyAsync(out->imm, prog->imm, 8ull * prog->num_imm, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { dev_free(ctx, d_terms); CK(e); }
-    *terms_out = d_terms; *num_terms_out = emits;
+    if (e != cudaSuccess) { gate_program_release(ctx, out); CK(e); }
+    out->num_ops = prog->num_ops; out->num_terms = emits; out->num_regs = prog->num_regs;
     return 0;
+}
+void gate_program_release(qpzk_ctx* ctx, GateProgramDev* g) {
+    dev_free(ctx, g->code); dev_free(ctx, g->imm);
+    *g = GateProgramDev{};
+}
+// Interprets an uploaded program at every quotient-domain point: *terms_out (device, [n Q][num_terms]) is left to the
+// caller (dev_free).  A program without EMITs: nothing allocated.
+int gate_terms_run(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk, const GateProgramDev& g,
+                   uint64_t** terms_out) {
+    *terms_out = nullptr;
+    if (!g.num_terms) return 0;
+    if (!chunk || (chunk & (chunk - 1))) return fail(QPZK_EINVAL, "quotient_degree_factor must be a power of two");
+    if (ilog2(chunk) > wires->rate_bits || cs->log_n != wires->log_n || cs->rate_bits != wires->rate_bits)
+        return fail(QPZK_EINVAL, "batches must have the same degree and rate, quotient_degree_factor <= blowup");
+    const uint64_t points = (1ull << wires->log_n) * chunk;
+    uint64_t* d_terms;
+    int rc;
+    if ((rc = dev_alloc(ctx, &d_terms, points * g.num_terms))) return rc;
+    GateProgramArgs ga{};
+    ga.cs_leaves = cs->leaves; ga.w_leaves = wires->leaves; ga.cs_width = cs->leaf_width; ga.w_width = wires->leaf_width;
+    ga.code = reinterpret_cast<const uint32_t*>(g.code); ga.imm = g.imm; ga.num_ops = g.num_ops; ga.num_terms = g.num_terms; ga.num_regs = g.num_regs;
+    ga.num_points = points; ga.terms = d_terms;
+    cudaError_t e = launch_gate_program(ga, ctx->stream);
+    ctx->launches++;
+    if (e != cudaSuccess) { dev_free(ctx, d_terms); CK(e); }
+    *terms_out = d_terms;
+    return 0;
+}
+static int gate_terms_from_program(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk,
+                                   const qpzk_gate_program* prog, uint64_t** terms_out, uint32_t* num_terms_out) {
+    *terms_out = nullptr; *num_terms_out = 0;
+    if (!prog) return 0;
+    if (!ctx || !cs || !wires) return fail(QPZK_EINVAL, "null argument");
+    GateProgramDev g;
+    int rc = gate_program_upload(ctx, cs->num_cols, wires->num_cols, prog, &g);
+    if (rc) return rc;
+    rc = gate_terms_run(ctx, cs, wires, chunk, g, terms_out);
+    *num_terms_out = rc ? 0 : g.num_terms;
+    gate_program_release(ctx, &g);   // back to the block cache: stream order keeps it intact until the kernel has run
+    return rc;
 }
 
 extern "C" int qpzk_quotient_polys_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
@@ -1536,7 +1652,7 @@ extern "C" int qpzk_quotient_polys(qpzk_ctx* ctx, const qpzk_batch* constants_si
     uint64_t* d;
     uint32_t qbits;
     int rc = quotient_impl(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
-                           num_challenges, betas, gammas, alphas, gate_terms_dev, num_gate_terms, &d, &qbits);
+                           num_challenges, betas, gammas, alphas, nullptr, gate_terms_dev, num_gate_terms, &d, &qbits);
     if (rc) return rc;
     const uint64_t words = ((uint64_t)num_challenges << qbits) << wires->log_n;
     cudaError_t e = cudaMemcpyAsync(out, d, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1558,7 +1674,7 @@ extern "C" int qpzk_commit_quotient(qpzk_ctx* ctx, const qpzk_batch* constants_s
     uint64_t* d;
     uint32_t qbits;
     int rc = quotient_impl(ctx, constants_sigmas, wires, zs_partial_products, sigma_col0, num_routed, quotient_degree_factor,
-                           num_challenges, betas, gammas, alphas, gate_terms_dev, num_gate_terms, &d, &qbits);
+                           num_challenges, betas, gammas, alphas, nullptr, gate_terms_dev, num_gate_terms, &d, &qbits);
     if (rc) return rc;
     const uint32_t cols = num_challenges << qbits;
     rc = commit_impl(ctx, dev_source(d), false, wires->log_n, cols, wires->rate_bits, cap_height, salt_dev, 0,

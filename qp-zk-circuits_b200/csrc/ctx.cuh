@@ -75,6 +75,9 @@ struct qpzk_ctx {
     std::map<std::pair<uint32_t, int>, PowTables> pow_tables;        // (log_size, inverse)
     std::map<std::pair<uint32_t, uint32_t>, CosetTables> coset_tables;  // (log_n, rate_bits)
     std::map<uint32_t, PowTables> unshift_tables;                       // log_size -> powers of g^-1 (coset_ifft)
+    uint64_t* kpow = nullptr;                                           // device: g^j (coset shifts k_j), kpow_size entries
+    uint32_t kpow_size = 0;
+    std::map<std::pair<uint32_t, uint32_t>, uint64_t*> zh_tables;       // (log_n, qbits) -> Z_H on the quotient coset and its inverses
 };
 
 struct qpzk_batch {
@@ -106,6 +109,45 @@ void ctx_unref(qpzk_ctx* ctx);
 void batch_release(qpzk_batch* b);
 int get_pow_tables(qpzk_ctx* ctx, uint32_t log_size, bool inverse, PowTables* out);
 int get_coset_tables(qpzk_ctx* ctx, uint32_t log_n, uint32_t rate_bits, CosetTables* out);
+
+// Device-side inputs / outputs of fri_core.  Pointers that are null fall back to the host-side instance.
+struct FriDeviceIO {
+    const uint64_t* points = nullptr;      // 2 * num_batches words: the opening points (else inst->points, host)
+    const uint32_t* poly_refs = nullptr;   // poly_oracle[total] then poly_index[total] (else copied from inst, host)
+    bool observe_openings = false;         // gather the opened values and observe them before alpha is drawn
+    uint64_t* proof = nullptr;             // flat FriProof words (required)
+    uint64_t* openings = nullptr;          // 2 * total polynomials, instance order (required)
+    uint64_t* indices = nullptr;           // num_query_rounds words (required)
+    uint32_t* status = nullptr;            // status[0]: 1 ok, 0 witness too weak, 2 search exhausted (required)
+};
+int fri_core(qpzk_ctx* ctx, const qpzk_batch* const* oracles, uint32_t num_oracles, const qpzk_fri_instance* inst,
+             const qpzk_fri_params* p, ChallengerDev* ch, uint64_t pow_witness_in, const FriDeviceIO& io);
+
+// ---- stage functions shared with the single-call prover (prove.cu) ---------------------------------------------------
+struct ColumnSource {   // where a commit's input columns come from: device-resident, or a host buffer copied in column ranges
+    const uint64_t* dev = nullptr;
+    const uint64_t* host = nullptr;
+    uint64_t* staging = nullptr;
+    uint32_t chunks = 1;
+};
+inline ColumnSource dev_source(const uint64_t* p) { ColumnSource s; s.dev = p; return s; }
+int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols, uint32_t rate_bits,
+                uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin, uint32_t coset_count,
+                bool keep_coeffs_copy, qpzk_batch** out);
+int get_kpow_table(qpzk_ctx* ctx, uint32_t count, const uint64_t** out);
+int commit_zs_impl(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires, uint32_t sigma_col0,
+                   uint32_t num_routed, uint32_t chunk, uint32_t num_challenges, const uint64_t* betas,
+                   const uint64_t* gammas, const uint64_t* chal_dev, uint32_t cap_height, const uint64_t* salt_dev,
+                   qpzk_batch** out);
+int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, const qpzk_batch* zs,
+                  uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
+                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, const uint64_t* chal_dev,
+                  const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out);
+struct GateProgramDev { uint64_t* code = nullptr; uint64_t* imm = nullptr; uint32_t num_ops = 0, num_terms = 0, num_regs = 0; };
+int gate_program_upload(qpzk_ctx* ctx, uint32_t cs_cols, uint32_t wire_cols, const qpzk_gate_program* prog, GateProgramDev* out);
+void gate_program_release(qpzk_ctx* ctx, GateProgramDev* g);
+int gate_terms_run(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk, const GateProgramDev& g,
+                   uint64_t** terms_out);
 
 struct DevBufs {  // frees everything it holds on scope exit
     qpzk_ctx* ctx;

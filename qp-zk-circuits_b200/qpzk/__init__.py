@@ -73,6 +73,20 @@ class GateProgram(C.Structure):
         return g
 
 
+class ProverConfig(C.Structure):
+    """qpzk_prover_config (see include/qpzk.h)."""
+    _fields_ = [("num_wires", C.c_uint32), ("num_routed", C.c_uint32), ("sigma_col0", C.c_uint32),
+                ("quotient_degree_factor", C.c_uint32), ("num_challenges", C.c_uint32), ("num_public_inputs", C.c_uint32),
+                ("blinding", C.c_uint32), ("use_graph", C.c_uint32), ("circuit_digest", C.c_uint64 * 4),
+                ("fri", FriParams), ("gates", C.POINTER(GateProgram))]
+
+
+class ProverLayout(C.Structure):
+    _fields_ = [("cap_words", C.c_uint64), ("cap_offset", C.c_uint64 * 3), ("openings_offset", C.c_uint64),
+                ("num_openings", C.c_uint64), ("fri_offset", C.c_uint64), ("fri_words", C.c_uint64),
+                ("total_words", C.c_uint64), ("leaf_lens", C.c_uint32 * 4)]
+
+
 class ChallengerState(C.Structure):
     _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8),
                 ("output_buffer", C.c_uint64 * 8), ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
@@ -154,6 +168,14 @@ def load_library():
         "qpzk_proof_from_bytes": (i, [C.POINTER(FriParams), C.POINTER(ProofShape), vp, C.c_size_t, vp, vp, vp, vp, vp, vp]),
         "qpzk_quotient_polys_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), vp]),
         "qpzk_commit_quotient_prog": (i, [vp, vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, C.POINTER(GateProgram), u32, vp, C.POINTER(vp)]),
+        "qpzk_prover_create": (i, [vp, vp, C.POINTER(ProverConfig), C.POINTER(vp)]),
+        "qpzk_prover_free": (None, [vp]),
+        "qpzk_prover_get_layout": (i, [vp, C.POINTER(ProverLayout)]),
+        "qpzk_prover_prove_async": (i, [vp, vp, vp, vp, u64]),
+        "qpzk_prover_finish": (i, [vp, vp]),
+        "qpzk_prover_prove": (i, [vp, vp, vp, vp, u64, vp]),
+        "qpzk_prover_launches_per_proof": (u64, [vp]),
+        "qpzk_prover_uses_graph": (i, [vp]),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }
@@ -534,6 +556,78 @@ class PolynomialBatch:
             self.ctx.L.qpzk_batch_free(self.h)
             self.h = None
             self.merkle_tree.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Prover:
+    """qpzk_prover: `prove()` after witness generation as one device-resident call (CUDA graph from the third proof).
+
+    constants_sigmas: the circuit's PolynomialBatch, committed with from_values under Context.set_keep_values(True).
+    prove(wires, public_inputs) -> dict(caps=[wires, zs_pp, quotient], openings=(k, 2), fri_proof=flat words)."""
+
+    def __init__(self, constants_sigmas, num_wires, num_routed, sigma_col0, fri_params, circuit_digest, num_public_inputs,
+                 gate_program=None, quotient_degree_factor=8, num_challenges=2, blinding=False, use_graph=True):
+        self.ctx = constants_sigmas.ctx
+        self._keep = (constants_sigmas, gate_program)
+        cfg = ProverConfig(num_wires, num_routed, sigma_col0, quotient_degree_factor, num_challenges, num_public_inputs,
+                           int(blinding), int(use_graph))
+        for k, v in enumerate(np.asarray(circuit_digest, dtype=np.uint64).reshape(4)):
+            cfg.circuit_digest[k] = int(v)
+        cfg.fri = fri_params
+        cfg.gates = C.pointer(gate_program) if gate_program is not None else None
+        h = C.c_void_p()
+        _check(self.ctx.L.qpzk_prover_create(self.ctx.h, constants_sigmas.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.layout = ProverLayout()
+        _check(self.ctx.L.qpzk_prover_get_layout(h, C.byref(self.layout)))
+        self.num_wires, self.n = num_wires, 1 << constants_sigmas.degree_log
+        self.num_public_inputs, self.blinding = num_public_inputs, blinding
+        self._pending = None
+
+    def prove_async(self, wires, public_inputs, salts=None, pow_witness=None):
+        w = np.ascontiguousarray(wires, dtype=np.uint64)
+        if w.shape != (self.num_wires, self.n):
+            raise QpzkError(-1, "wires must have shape (%d, %d)" % (self.num_wires, self.n))
+        pi = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1)
+        if pi.size != self.num_public_inputs:
+            raise QpzkError(-1, "expected %d public inputs" % self.num_public_inputs)
+        sp = None
+        if salts is not None:
+            sl = np.ascontiguousarray(salts, dtype=np.uint64)
+            sp = sl.ctypes.data_as(C.c_void_p)
+        _check(self.ctx.L.qpzk_prover_prove_async(self.h, w.ctypes.data_as(C.c_void_p), pi.ctypes.data_as(C.c_void_p) if pi.size else None,
+                                                  sp, POW_SEARCH if pow_witness is None else pow_witness))
+
+    def finish(self):
+        lay = self.layout
+        out = np.zeros(lay.total_words, np.uint64)
+        _check(self.ctx.L.qpzk_prover_finish(self.h, out.ctypes.data_as(C.c_void_p)))
+        H = lay.cap_words
+        caps = [out[lay.cap_offset[k]:lay.cap_offset[k] + H].reshape(-1, 4).copy() for k in range(3)]
+        op = out[lay.openings_offset:lay.openings_offset + 2 * lay.num_openings].reshape(-1, 2).copy()
+        return dict(caps=caps, openings=op, fri_proof=out[lay.fri_offset:lay.fri_offset + lay.fri_words].copy())
+
+    def prove(self, wires, public_inputs, salts=None, pow_witness=None):
+        self.prove_async(wires, public_inputs, salts, pow_witness)
+        return self.finish()
+
+    @property
+    def launches_per_proof(self):
+        return int(self.ctx.L.qpzk_prover_launches_per_proof(self.h))
+
+    @property
+    def uses_graph(self):
+        return bool(self.ctx.L.qpzk_prover_uses_graph(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.qpzk_prover_free(self.h)
+            self.h = None
 
     def __del__(self):
         try:

@@ -29,7 +29,7 @@ products, 16 quotient chunks; FRI rate_bits 3, cap_height 4, 16 PoW bits, 28 que
 """
 import numpy as np
 
-from . import (GENERATOR, P, Challenger, FriInstanceInfo, PolynomialBatch, fri_params, hash_no_pad,  # noqa: F401
+from . import (GENERATOR, P, Challenger, FriInstanceInfo, PolynomialBatch, Prover, fri_params, hash_no_pad,  # noqa: F401
                proof_shape, proof_to_bytes)
 
 LEAF_SHAPE = dict(log_n=13, constants_sigmas=85, wires=135, zs_partial_products=20, quotient=16, num_zs=2)
@@ -56,6 +56,17 @@ class SyntheticCircuit:
         ctx.set_keep_values(False)
         self.circuit_digest = np.arange(4, dtype=np.uint64) + 11   # stands for the verifier-data digest
         self.fri_params = fri_params(self.log_n, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, ARITY_BITS, FINAL_POLY_BITS)
+        self._provers = {}
+
+    def prover(self, num_wires, num_routed, num_public_inputs, gate_program=None, quotient_degree_factor=8, blinding=False,
+               use_graph=True):
+        """The circuit's qpzk.Prover (created once per shape and gate program, like a prover's circuit data)."""
+        key = (num_wires, num_routed, num_public_inputs, id(gate_program), quotient_degree_factor, blinding, use_graph)
+        if key not in self._provers:
+            self._provers[key] = Prover(self.constants_sigmas, num_wires, num_routed, self.sigma_col0, self.fri_params,
+                                        self.circuit_digest, num_public_inputs, gate_program, quotient_degree_factor,
+                                        self.shape["num_zs"], blinding, use_graph)
+        return self._provers[key]
 
 
 def prove_synthetic(circuit, wires, zs_partial_products, quotient_coeffs, public_inputs_hash, pow_witness=None,
@@ -127,16 +138,23 @@ def synthetic_inputs(seed, shape=LEAF_SHAPE):
                 quotient_coeffs=mk(shape["quotient"]), public_inputs_hash=rng.integers(0, P, size=4, dtype=np.uint64))
 
 
-def prove(circuit, wires, public_inputs, num_routed, gate_program=None, quotient_degree_factor=8, pow_witness=None):
+def prove(circuit, wires, public_inputs, num_routed, gate_program=None, quotient_degree_factor=8, pow_witness=None,
+          step_by_step=False):
     """`prove()` for a circuit given as data -- the committed constants/sigmas batch (sigma columns from
     circuit.sigma_col0), the number of routed wires and the gate program -- and a witness (the wire values):
     public-inputs hash, wires commitment, partial products, quotient, openings, FRI, then
-    `ProofWithPublicInputs::to_bytes`.  Returns (proof bytes, the qpzk_proof_shape they were written with)."""
+    `ProofWithPublicInputs::to_bytes`.  Returns (proof bytes, the qpzk_proof_shape they were written with).
+    Default: ONE device-resident call (qpzk.Prover = qpzk_prover_prove: challenges stay on the device, CUDA graph from
+    the third proof of a circuit); step_by_step=True drives the individual entry points instead (same bytes)."""
     ctx, sh = circuit.ctx, circuit.shape
-    pih = hash_no_pad(ctx, public_inputs)
-    sig_dummy = np.zeros((num_routed, 0), np.uint64)            # only its row count is read on the device path
-    r = prove_synthetic(circuit, wires, None, None, pih, pow_witness=pow_witness, sigmas=sig_dummy,
-                        quotient_degree_factor=quotient_degree_factor, gate_program=gate_program)
+    if step_by_step:
+        pih = hash_no_pad(ctx, public_inputs)
+        sig_dummy = np.zeros((num_routed, 0), np.uint64)            # only its row count is read on the device path
+        r = prove_synthetic(circuit, wires, None, None, pih, pow_witness=pow_witness, sigmas=sig_dummy,
+                            quotient_degree_factor=quotient_degree_factor, gate_program=gate_program)
+    else:
+        r = circuit.prover(np.asarray(wires).shape[0], num_routed, np.asarray(public_inputs).size, gate_program,
+                           quotient_degree_factor).prove(wires, public_inputs, pow_witness=pow_witness)
     nz = sh["num_zs"]
     nchunks = (num_routed + quotient_degree_factor - 1) // quotient_degree_factor
     shape = proof_shape(circuit.log_n, circuit.sigma_col0, circuit.constants_sigmas.num_cols - circuit.sigma_col0,

@@ -6,6 +6,7 @@ use core::ffi::{c_char, c_int, c_void};
 #[repr(C)] pub struct qpzk_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_challenger { _p: [u8; 0] }
+#[repr(C)] pub struct qpzk_prover { _p: [u8; 0] }
 
 pub const QPZK_POW_SEARCH: u64 = u64::MAX;
 pub const QPZK_MAX_FRI_ROUNDS: usize = 16;
@@ -53,6 +54,35 @@ pub struct qpzk_gate_program {
     pub imm: *const u64,
     pub num_imm: u32,
     pub num_regs: u32,
+}
+
+/// What `CircuitBuilder::build` leaves behind for `qpzk_prover_create` (see include/qpzk.h).
+#[repr(C)]
+pub struct qpzk_prover_config {
+    pub num_wires: u32,
+    pub num_routed: u32,
+    pub sigma_col0: u32,
+    pub quotient_degree_factor: u32,
+    pub num_challenges: u32,
+    pub num_public_inputs: u32,
+    pub blinding: u32,
+    pub use_graph: u32,
+    pub circuit_digest: [u64; 4],
+    pub fri: qpzk_fri_params,
+    pub gates: *const qpzk_gate_program,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct qpzk_prover_layout {
+    pub cap_words: u64,
+    pub cap_offset: [u64; 3],
+    pub openings_offset: u64,
+    pub num_openings: u64,
+    pub fri_offset: u64,
+    pub fri_words: u64,
+    pub total_words: u64,
+    pub leaf_lens: [u32; 4],
 }
 
 #[repr(C)]
@@ -163,6 +193,18 @@ extern "C" {
                                      quotient_degree_factor: u32, num_challenges: u32, betas: *const u64, gammas: *const u64,
                                      alphas: *const u64, prog: *const qpzk_gate_program, cap_height: u32,
                                      salt_dev: *const u64, out: *mut *mut qpzk_batch) -> c_int;
+    // prove(): the whole proof after witness generation in one device-resident call (CUDA graph replay)
+    pub fn qpzk_prover_create(ctx: *mut qpzk_ctx, constants_sigmas: *const qpzk_batch, cfg: *const qpzk_prover_config,
+                              out: *mut *mut qpzk_prover) -> c_int;
+    pub fn qpzk_prover_free(p: *mut qpzk_prover);
+    pub fn qpzk_prover_get_layout(p: *const qpzk_prover, out: *mut qpzk_prover_layout) -> c_int;
+    pub fn qpzk_prover_prove_async(p: *mut qpzk_prover, wires: *const u64, public_inputs: *const u64, salts: *const u64,
+                                   pow_witness_in: u64) -> c_int;
+    pub fn qpzk_prover_finish(p: *mut qpzk_prover, out_words: *mut u64) -> c_int;
+    pub fn qpzk_prover_prove(p: *mut qpzk_prover, wires: *const u64, public_inputs: *const u64, salts: *const u64,
+                             pow_witness_in: u64, out_words: *mut u64) -> c_int;
+    pub fn qpzk_prover_launches_per_proof(p: *const qpzk_prover) -> u64;
+    pub fn qpzk_prover_uses_graph(p: *const qpzk_prover) -> c_int;
     // ProofWithPublicInputs::to_bytes / from_bytes (host functions)
     pub fn qpzk_proof_bytes_len(p: *const qpzk_fri_params, s: *const qpzk_proof_shape) -> usize;
     pub fn qpzk_proof_to_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, wires_cap: *const u64,
