@@ -6,6 +6,8 @@
 // hash_or_noop,two_to_one}`, `Challenger` and `fri_proof_of_work` (SURVEY.md 8a rows a7, a8, a10,
 // a13; Appendix A.4-A.7).  Reached in the reference only through `prove()`
 // (wormhole/prover/src/lib.rs:171-175) and `CircuitBuilder::build` (wormhole/circuit/src/circuit.rs:206-216).
+#include <cstdio>
+#include <cstdlib>
 #include "internal.cuh"
 #include "poseidon_rc.cuh"
 #include "poseidon.cuh"
@@ -213,6 +215,7 @@ pow_grind_persistent_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bi
         if ((uint32_t)k < pos) st0[k] = c->in[k];
     for (uint64_t cand = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; cand < limit; cand += T) {
         if (cand >= *reinterpret_cast<volatile unsigned long long*>(found)) break;
+        const unsigned act = __activemask();
         uint64_t s[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) s[k] = st0[k];
@@ -221,7 +224,13 @@ pow_grind_persistent_kernel(const ChallengerDev* __restrict__ c, uint32_t pow_bi
             if ((uint32_t)k == pos) s[k] = cand;
         poseidon_permute(s);
         const uint64_t resp = gl_canon(s[7]);
-        if (pow_bits == 0 || (resp >> (64 - pow_bits)) == 0) { atomicMin(found, (unsigned long long)cand); break; }
+        const bool hit = pow_bits == 0 || (resp >> (64 - pow_bits)) == 0;
+        if (hit) atomicMin(found, (unsigned long long)cand);
+        // The lanes of a warp must not run ahead of the lane that has a hit to publish: measured on B200, the diverged
+        // rest of the warp otherwise keeps the scheduler for its whole remaining loop (590 permutations to the search
+        // limit) before the hit lane gets to issue its atomic, and `found` stays empty for everyone until then.
+        __syncwarp(act);
+        if (hit) break;
     }
 }
 

@@ -8,6 +8,11 @@
 // exactly the threading model exercised here).  Same transcript as qp-zk-circuits_b200/qpzk/prover.py.
 //
 //   prove_bench [--device D] [--devices G] [--threads T] [--proofs N] [--log-n 13] [--pinned 1] [--perm 0|1] [--zeroize 0|1|2] [--gates FILE]
+//               [--prover 1 [--inflight K] [--graph 0|1] [--routed R]]
+// --prover 1: the whole proof is ONE call (qpzk_prover_prove_async / _finish: challenges stay on the device, CUDA graph
+// replay from the third proof; always with the permutation argument and, with --gates, the gate program).  --inflight K:
+// every host thread drives K provers on K contexts and keeps K proofs in flight (their graphs overlap on the GPU) --
+// the aggregator's dispatch of independent leaf proofs without one host thread per proof.
 // --gates FILE (with --perm 1): the circuit's gate constraints as a qpzk_gate_program written by
 // tools/export_gate_program.py (upstream's PoseidonGate on every row), interpreted on the device for the quotient.
 // --devices G: one process drives G GPUs, thread t on device D + (t mod G) -- the aggregator's dispatch (independent leaf
@@ -57,6 +62,8 @@ static int g_zeroize = 1;      // qpzk_ctx_set_zeroize mode
 static std::vector<uint32_t> g_gate_code;   // --gates: program shared by all threads (read only)
 static std::vector<uint64_t> g_gate_imm;
 static uint32_t g_gate_regs = 0;
+static bool g_prover = false, g_graph = true;
+static int g_inflight = 1;
 static int g_stagger_us = 0;   // thread t starts t * g_stagger_us after the others (spreads the phases of concurrent provers)
 
 struct HostBuf {   // pinned (default) or pageable host buffer
@@ -99,8 +106,71 @@ struct Worker {
     uint64_t checksum = 0;
     uint64_t launches = 0, allocs = 0;
     double max_proof_s = 0;
+    int graph = 0;
+    uint64_t peak_bytes = 0;
+
+    // one-call prover: K contexts, K provers, K proofs in flight from this thread
+    void run_prover(std::atomic<int>* ready, std::atomic<bool>* go) {
+        const size_t n = (size_t)1 << sh.log_n;
+        const int K = g_inflight;
+        auto cs = random_columns(1, sh.constants_sigmas, n);
+        std::vector<HostBuf> wires;
+        for (int s = 0; s < 4; s++) wires.push_back(random_columns(100 + s, sh.wires, n));
+        uint64_t pi[21];
+        for (int i = 0; i < 21; i++) pi[i] = 1000 + i;
+        qpzk_prover_config cfg{};
+        cfg.num_wires = sh.wires; cfg.num_routed = sh.routed; cfg.sigma_col0 = sh.sigma_col0; cfg.quotient_degree_factor = 8;
+        cfg.num_challenges = sh.num_zs; cfg.num_public_inputs = 21; cfg.blinding = 0; cfg.use_graph = g_graph ? 1 : 0;
+        for (int i = 0; i < 4; i++) cfg.circuit_digest[i] = 11 + i;
+        QCHECK(qpzk_fri_params_constant_arity(&cfg.fri, sh.log_n, 3, 4, 16, 28, 4, 5));
+        qpzk_gate_program prog{g_gate_code.data(), (uint32_t)(g_gate_code.size() / 4), g_gate_imm.data(), (uint32_t)g_gate_imm.size(), g_gate_regs};
+        cfg.gates = g_gate_regs ? &prog : nullptr;
+        std::vector<qpzk_ctx*> ctxs(K);
+        std::vector<qpzk_batch*> csb(K);
+        std::vector<qpzk_prover*> prs(K);
+        qpzk_prover_layout lay{};
+        for (int k = 0; k < K; k++) {
+            QCHECK(qpzk_ctx_create(device, &ctxs[k]));
+            QCHECK(qpzk_ctx_set_zeroize(ctxs[k], g_zeroize));
+            QCHECK(qpzk_ctx_set_keep_values(ctxs[k], 1));
+            QCHECK(qpzk_commit_from_values(ctxs[k], cs.data(), sh.log_n, sh.constants_sigmas, 3, 4, nullptr, &csb[k]));
+            QCHECK(qpzk_ctx_set_keep_values(ctxs[k], 0));
+            QCHECK(qpzk_prover_create(ctxs[k], csb[k], &cfg, &prs[k]));
+            QCHECK(qpzk_prover_get_layout(prs[k], &lay));
+        }
+        std::vector<uint64_t> out(lay.total_words);
+        for (int k = 0; k < K; k++)
+            for (int w = 0; w < 4; w++) QCHECK(qpzk_prover_prove(prs[k], wires[w & 1].data(), pi, nullptr, QPZK_POW_SEARCH, out.data()));   // eager x2, capture, replay
+        QCHECK(qpzk_prover_prove(prs[0], wires[0].data(), pi, nullptr, QPZK_POW_SEARCH, out.data()));
+        for (size_t i = 0; i < out.size(); i++) checksum = (checksum ^ out[i]) * 0x100000001B3ULL;
+        ready->fetch_add(1);
+        while (!go->load()) std::this_thread::yield();
+        uint64_t l0 = 0, a0 = 0;
+        for (int k = 0; k < K; k++) { l0 += qpzk_ctx_launch_count(ctxs[k]); a0 += qpzk_ctx_device_allocs(ctxs[k]); }
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::chrono::steady_clock::time_point> started(K);
+        for (int i = 0; i < proofs + K; i++) {
+            const int k = i % K;
+            if (i >= K) {
+                QCHECK(qpzk_prover_finish(prs[k], out.data()));
+                const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - started[k]).count();
+                if (dt > max_proof_s) max_proof_s = dt;
+            }
+            if (i < proofs) {
+                started[k] = std::chrono::steady_clock::now();
+                QCHECK(qpzk_prover_prove_async(prs[k], wires[i & 3].data(), pi, nullptr, QPZK_POW_SEARCH));
+            }
+        }
+        seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int k = 0; k < K; k++) { launches += qpzk_ctx_launch_count(ctxs[k]); allocs += qpzk_ctx_device_allocs(ctxs[k]); }
+        launches -= l0; allocs -= a0;
+        graph = qpzk_prover_uses_graph(prs[0]);
+        peak_bytes = qpzk_ctx_peak_bytes(ctxs[0]);
+        for (int k = 0; k < K; k++) { qpzk_prover_free(prs[k]); qpzk_batch_free(csb[k]); qpzk_ctx_destroy(ctxs[k]); }
+    }
 
     void run(std::atomic<int>* ready, std::atomic<bool>* go) {
+        if (g_prover) return run_prover(ready, go);
         const size_t n = (size_t)1 << sh.log_n;
         qpzk_ctx* ctx;
         QCHECK(qpzk_ctx_create(device, &ctx));
@@ -252,6 +322,10 @@ int main(int argc, char** argv) {
         else if (k == "--perm") g_perm = v != 0;
         else if (k == "--stagger-us") g_stagger_us = v;
         else if (k == "--zeroize") g_zeroize = v;
+        else if (k == "--prover") g_prover = v != 0;
+        else if (k == "--inflight") g_inflight = v > 0 ? v : 1;
+        else if (k == "--graph") g_graph = v != 0;
+        else if (k == "--routed") sh.routed = (unsigned)v;
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     std::vector<Worker> ws(threads);
@@ -277,9 +351,10 @@ int main(int argc, char** argv) {
         if (w.max_proof_s > maxp) maxp = w.max_proof_s;
         allocs += w.allocs;
     }
-    printf("{\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"zeroize\": %d, \"gate_program_ops\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
+    printf("{\"prover\": %d, \"inflight\": %d, \"graph\": %d, \"routed\": %u, \"peak_device_MB\": %.1f, ", g_prover ? 1 : 0, g_prover ? g_inflight : 1, ws[0].graph, sh.routed, ws[0].peak_bytes / 1e6);
+    printf("\"threads\": %d, \"devices\": %d, \"proofs_per_thread\": %d, \"log_n\": %u, \"perm\": %d, \"zeroize\": %d, \"gate_program_ops\": %u, \"proofs_per_s\": %.2f, \"latency_ms\": %.3f, "
            "\"launches_per_proof\": %llu, \"proofs_identical_across_threads\": %s, \"checksum\": \"%016llx\", \"slowest_thread_s\": %.4f, \"fastest_thread_s\": %.4f, \"max_proof_ms\": %.2f, \"device_allocs_in_loop\": %llu}\n",
-           threads, devices, proofs, sh.log_n, g_perm ? 1 : 0, g_zeroize, (unsigned)(g_gate_code.size() / 4), threads * proofs / wall, 1e3 * lat / threads,
+           threads, devices, proofs, sh.log_n, (g_perm || g_prover) ? 1 : 0, g_zeroize, (unsigned)(g_gate_code.size() / 4), threads * proofs / wall, 1e3 * lat / threads,
            (unsigned long long)(ws[0].launches / proofs), same ? "true" : "false", (unsigned long long)ws[0].checksum, wall, fastest, 1e3 * maxp, (unsigned long long)allocs);
     return same ? 0 : 3;
 }

@@ -19,6 +19,20 @@ for w in $WHAT; do
               timeout 900 ncu --set full --clock-control none --import-source on -k regex:hash_rows_kernel -c 1 -f -o $O/${TAG}_hash $B > $O/${TAG}_ncu_hash.log 2>&1; echo "ncu_hash rc=$?" | tee -a $O/${TAG}_rc.txt;;
     ncu_ntt)  B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-prove --no-parity"
               timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ntt_|lde_last" -c 6 -f -o $O/${TAG}_ntt $B > $O/${TAG}_ncu_ntt.log 2>&1; echo "ncu_ntt rc=$?" | tee -a $O/${TAG}_rc.txt;;
+    prover)   timeout 900 python -m pytest tests/test_gpu_prover.py -m gpu -x -q --durations=8 > $O/${TAG}_prover.log 2>&1; echo "prover rc=$?" | tee -a $O/${TAG}_rc.txt; tail -15 $O/${TAG}_prover.log;;
+    pbench)   PB=qp-zk-circuits_b200/prove_bench; G=qp-zk-circuits_b200/host/poseidon_gate.qpgp
+              ( $PB --threads 1 --proofs 64 --perm 1 --breakdown 1
+                $PB --threads 1 --proofs 64 --perm 1 --gates $G
+                $PB --prover 1 --threads 1 --proofs 128 --graph 0
+                $PB --prover 1 --threads 1 --proofs 128
+                $PB --prover 1 --threads 1 --proofs 128 --gates $G
+                for K in 2 3 4 6 8; do $PB --prover 1 --threads 1 --inflight $K --proofs 256; done
+                for K in 2 4 8; do $PB --prover 1 --threads 1 --inflight $K --proofs 256 --gates $G; done
+                $PB --prover 1 --threads 2 --inflight 2 --proofs 256 --gates $G
+                $PB --prover 1 --threads 4 --inflight 2 --proofs 256 --gates $G
+                for LN in 15 16; do $PB --prover 1 --threads 1 --proofs 24 --log-n $LN --routed 60 --gates $G; done
+                $PB --prover 1 --threads 1 --inflight 2 --proofs 32 --log-n 15 --routed 60 --gates $G
+              ) > $O/${TAG}_pbench.jsonl 2> $O/${TAG}_pbench.err; echo "pbench rc=$?" | tee -a $O/${TAG}_rc.txt; cut -c1-330 $O/${TAG}_pbench.jsonl; tail -5 $O/${TAG}_pbench.err;;
     sanitize) for tool in memcheck racecheck synccheck; do
                 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_subset.py > $O/${TAG}_san_$tool.log 2>&1; echo "sanitize $tool rc=$?" | tee -a $O/${TAG}_rc.txt; tail -4 $O/${TAG}_san_$tool.log
               done;;
