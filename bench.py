@@ -155,29 +155,6 @@ def cpu_commit_sample(log_n_sample=16, repeats=1):
     return bytes_alg(log_n_sample) / best / 1e9, orc.num_threads(), best
 
 
-def gpu_prove_synthetic(ctx, proofs=16):
-    """Leaf-shaped synthetic prove (BASELINE.json configs 1/2): 3 commits + openings + FRI per proof
-    through the host-buffer API, sequential on one context.  Returns (ms per proof, launches per proof)."""
-    import numpy as np
-    import qpzk
-    from qpzk import prover
-    shape = prover.LEAF_SHAPE
-    rng = np.random.default_rng(1)
-    cs = rng.integers(0, P, size=(shape["constants_sigmas"], 1 << shape["log_n"]), dtype=np.uint64)
-    circuit = prover.SyntheticCircuit(ctx, cs, shape)
-    inputs = [prover.synthetic_inputs(s, shape) for s in range(4)]
-    for i in range(3):
-        prover.prove_synthetic(circuit, **inputs[i % 4])
-    ctx.synchronize()
-    l0 = ctx.launch_count()
-    t0 = time.perf_counter()
-    for i in range(proofs):
-        prover.prove_synthetic(circuit, **inputs[i % 4])
-    ctx.synchronize()
-    dt = (time.perf_counter() - t0) / proofs
-    return 1e3 * dt, (ctx.launch_count() - l0) // proofs
-
-
 def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_consts=5, nch=2, chunk=8):
     """SURVEY.md 8a rows a16/a17 at the leaf-circuit column counts: partial products + Z from device-resident routed
     wires and sigmas, then the quotient of the permutation argument from the three committed batches.  Device times
@@ -254,18 +231,16 @@ def gpu_perm_argument(ctx, dev, log_n, reps=5, routed=80, num_wires=135, num_con
             "what": "a16: qpzk_partial_products_dev; a17: qpzk_commit_quotient minus the time of its 16-column commit"}
 
 
-def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1, gates=None):
-    """The same synthetic prove driven from native code (qp-zk-circuits_b200/host/prove_bench.cpp: C++ threads on the
-    C ABI, one context per thread, pinned host buffers).  Returns the parsed JSON line or None."""
+def prove_bench(device, *opts, repeats=1):
+    """qp-zk-circuits_b200/prove_bench (host/prove_bench.cpp: the native driver of the C ABI) with the given options;
+    returns the parsed JSON line of the median run (by proofs/s) with all runs' proofs/s, or None."""
     exe = os.path.join(ROOT, "qp-zk-circuits_b200", "prove_bench")
     if not os.path.exists(exe):
         return None
     try:
         runs = []
-        for _ in range(3 if threads > 1 else 1):   # multi-threaded throughput varies from run to run: report the median
-            r = subprocess.run([exe, "--device", str(device), "--threads", str(threads), "--proofs", str(proofs), "--perm", str(perm),
-                                "--zeroize", str(zeroize)] + (["--gates", gates] if gates else []),
-                               capture_output=True, text=True, timeout=300)
+        for _ in range(repeats):
+            r = subprocess.run([exe, "--device", str(device)] + [str(o) for o in opts], capture_output=True, text=True, timeout=300)
             runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
         runs.sort(key=lambda d: d["proofs_per_s"])
         out = runs[len(runs) // 2]
@@ -276,23 +251,32 @@ def native_prove_bench(device, threads, proofs=32, perm=0, zeroize=1, gates=None
 
 
 def native_prove_suite(device, world):
-    """Leaf-shaped synthetic prove (BASELINE configs 1/2/5 stand-in) from native code: latency of one prover, throughput
-    of several on one GPU; permutation argument on the device, with and without the PoseidonGate program on every row."""
-    tmax = max(1, min(4, (os.cpu_count() or 4) // world))
+    """Leaf-shaped synthetic prove (BASELINE configs 1/2/5 stand-in) through the one-call prover
+    (qpzk_prover_prove: device-resident challenges, CUDA-graph replay), from native code:
+      latency      one proof at a time (2^13 rows, 135 wires / 80 routed, 85 constants+sigmas, 21 public inputs, FRI
+                   rate 3 / cap 4 / 16 PoW bits / 28 queries / arity 4), host buffers in, proof out, witness generation
+                   excluded; with and without upstream's PoseidonGate program on every row
+      throughput   one host thread keeping 8 proofs in flight on 8 contexts (their graphs overlap on the GPU)
+      config 5     1024 proofs sharded over the N GPUs of the job (1024 / N per rank), wall time of the slowest rank
+      private batch shapes (common/src/circuit.rs:393-402): 2^15 and 2^16 rows, 135 wires / 60 routed."""
     gp = os.path.join(ROOT, "qp-zk-circuits_b200", "host", "poseidon_gate.qpgp")   # written by __graft_entry__.build()
-    gp = gp if os.path.exists(gp) else None
-    runs = {"perm_1t": native_prove_bench(device, 1, 64, perm=1),
-            "perm_%dt" % tmax: native_prove_bench(device, tmax, 64, perm=1)}
-    if gp:
-        runs["gates_1t"] = native_prove_bench(device, 1, 64, perm=1, gates=gp)
-        runs["gates_%dt" % tmax] = native_prove_bench(device, tmax, 64, perm=1, gates=gp)
+    g = ["--gates", gp] if os.path.exists(gp) else []
+    runs = {"latency": prove_bench(device, "--prover", 1, "--proofs", 128),
+            "latency_gates": prove_bench(device, "--prover", 1, "--proofs", 128, *g),
+            "throughput": prove_bench(device, "--prover", 1, "--inflight", 8, "--proofs", 512, repeats=3),
+            "throughput_gates": prove_bench(device, "--prover", 1, "--inflight", 8, "--proofs", 512, *g, repeats=3),
+            "batch_1024": prove_bench(device, "--prover", 1, "--inflight", 8, "--proofs", 1024 // world, *g),
+            "private_batch_2p15": prove_bench(device, "--prover", 1, "--proofs", 24, "--log-n", 15, "--routed", 60, *g),
+            "private_batch_2p16": prove_bench(device, "--prover", 1, "--proofs", 16, "--log-n", 16, "--routed", 60, *g)}
     get = lambda k, f: (runs.get(k) or {}).get(f)
-    return {"threads": tmax, "runs": runs,
-            "latency_ms": get("perm_1t", "latency_ms"), "latency_ms_gates": get("gates_1t", "latency_ms"),
-            "proofs_per_s": get("perm_%dt" % tmax, "proofs_per_s"), "proofs_per_s_gates": get("gates_%dt" % tmax, "proofs_per_s"),
-            "what": "2^13 rows; commits of 135 / 20 / 16 columns, partial products + quotient (+ PoseidonGate program) on the "
-                    "device, 276 openings, FRI (rate 3, cap 4, 16 PoW bits, 28 queries, arity 4); host buffers in, proof out; "
-                    "witness generation excluded; host/prove_bench.cpp"}
+    return {"runs": runs,
+            "latency_ms": get("latency", "latency_ms"), "latency_ms_gates": get("latency_gates", "latency_ms"),
+            "proofs_per_s": get("throughput", "proofs_per_s"), "proofs_per_s_gates": get("throughput_gates", "proofs_per_s"),
+            "proofs_per_s_gates_runs": get("throughput_gates", "proofs_per_s_runs"),
+            "batch_1024_s": get("batch_1024", "slowest_thread_s"),
+            "ms_2p15_gates": get("private_batch_2p15", "latency_ms"), "ms_2p16_gates": get("private_batch_2p16", "latency_ms"),
+            "launches_per_proof": get("latency_gates", "launches_per_proof"), "graph": get("latency_gates", "graph"),
+            "what": native_prove_suite.__doc__}
 
 
 def cpu_prove_synthetic(proofs=2):
@@ -383,7 +367,7 @@ def run_reference(args):
     })))
 
 
-def compact(x, sig=5):
+def compact(x, sig=4):
     """Round floats to `sig` significant digits (the driver keeps ~1.5 kB of the line)."""
     if isinstance(x, float):
         return float("%.*g" % (sig, x))
@@ -392,6 +376,44 @@ def compact(x, sig=5):
     if isinstance(x, (list, tuple)):
         return [compact(v, sig) for v in x]
     return x
+
+
+def assemble_line(world, steps, warmup, ms_per_step, value, log_n, leaf_gbs, lde_gbs, hbm_peak, traffic, int_issue, imad_peak,
+                  perm_rate, stage, launches, clocks, e2e, parity, native, proofs_all, cpu):
+    """The contract line (kept under 1.4 kB: the driver stores about 1.5 kB; long-form strings go to the detail file)."""
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "raw commit 2^%dx%d, rate_bits %d, cap_height %d (config 3)" % (log_n, NUM_COLS, RATE_BITS, CAP_HEIGHT),
+                   "parallelism": "coset split x%d + NCCL all-gather" % world if world > 1 else "1 GPU", "l2": "inputs > L2"},
+        "roofline": {"bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": leaf_gbs / hbm_peak if leaf_gbs else None,
+                     "traffic": traffic, "kernel": "hash_rows", "int_issue": int_issue},
+        "roofline_lde": {"bound": "hbm", "achieved": lde_gbs, "frac": lde_gbs / hbm_peak if lde_gbs else None},
+        "int_pipe": {"imad_per_s": imad_peak, "perms_per_s": perm_rate},
+        "stages_ms": {"intt": stage["intt_ms"], "lde": stage["lde_ms"], "leaf_hash": stage["leaf_hash_ms"],
+                      "levels": stage["merkle_levels_ms"], "allgather": stage["allgather_ms"]},
+        "gpu_launches": int(launches), "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+    }
+    if e2e:
+        out["e2e"] = {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    if parity is not None:
+        out["parity_check"] = {"ok": parity.get("ok"), "rows": parity.get("rows_checked"), "cols": parity.get("columns"),
+                               "caps_equal": bool(parity.get("cap_timed_path_equal") and parity.get("cap_e2e_path_equal") is not False)}
+        if parity.get("error"):
+            out["parity_check"]["error"] = parity["error"][:80]
+    if native is not None:
+        out["prove"] = {k.replace("_gates", "_g"): native.get(k) for k in ("latency_ms", "latency_ms_gates", "proofs_per_s", "proofs_per_s_gates",
+                                                                           "ms_2p15_gates", "ms_2p16_gates") if native.get(k) is not None}
+        # config 5: 1024 independent proofs sharded over the job's GPUs (replicas, no data-path collective)
+        out["proofs_per_s_all_gpus"] = proofs_all[0] if proofs_all else native.get("proofs_per_s_gates")
+        out["batch_1024_proofs_s"] = proofs_all[1] if proofs_all else native.get("batch_1024_s")
+    if cpu is not None:
+        out["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"],
+                               "calibration": {"port_us_per_perm": cpu["us_perm"], "published_leaf_ms": PUBLISHED_LEAF_PROVE["ms"]}}
+        if native is not None and cpu.get("prove_ms") is not None:
+            out["prove"]["cpu_port_ms"] = cpu["prove_ms"]
+    return out
 
 
 def parity_check_commit(qpzk, ctx, dev, log_n, values_dev, cap_timed, cap_e2e, seed=22):
@@ -610,9 +632,11 @@ def main():
     # ---- independent proofs, one prover per GPU (BASELINE configs 4/5: replicas, no data-path collective) ----
     proofs_all = None
     if world > 1 and not args.no_prove:
-        v = torch.tensor([native.get("proofs_per_s", 0.0) or 0.0], device=dev, dtype=torch.float64)
-        dist.all_reduce(v)
-        proofs_all = float(v.item())
+        v = torch.tensor([native.get("proofs_per_s_gates") or 0.0, native.get("batch_1024_s") or 0.0], device=dev, dtype=torch.float64)
+        w = v.clone()
+        dist.all_reduce(v)                                  # sum of the per-GPU rates
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)            # slowest rank of the sharded batch
+        proofs_all = (float(v[0].item()), float(w[1].item()))
 
     if rank != 0:
         if world > 1:
@@ -659,49 +683,25 @@ def main():
                           "note": "integer-pipe bound, not HBM bound: int_issue = issued warp instructions / issue slots; "
                                   "HBM fraction reported because the contract asks for it"},
         "roofline_commit": {"bound": "hbm", "achieved": value, "peak": hbm_peak * world, "unit": "GB/s", "frac": value / (hbm_peak * world)},
-        "native": native,
+        "native": native, "stages_ms": stage, "e2e": e2e,
     }
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD % (log_n, C_, RATE_BITS, CAP_HEIGHT),
-                   "parallelism": "coset split x%d + NCCL all-gather of coefficients" % world if world > 1 else "single GPU",
-                   "l2": "inputs > L2"},
-        "roofline": {"bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": leaf_gbs / hbm_peak if leaf_gbs else None, "traffic": ncu.get("traffic", {}).get(str(log_n)) if world == 1 else None,
-                     "kernel": "hash_rows_kernel", "int_issue": int_issue},
-        "roofline_lde": {"bound": "hbm", "achieved": lde_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": lde_gbs / hbm_peak if lde_gbs else None},
-        "int_pipe": {"imad_wide_per_s": imad_peak, "perms_per_s_in_kernel": perm_rate_kernel,
-                     "perms_per_s_microbench": ctx.bench_poseidon(32)},
-        "stages_ms": stage, "gpu_launches": int(launches), "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons")},
-    }
-    if e2e:
-        out["e2e"] = e2e
-    if parity is not None:
-        out["parity_check"] = {k: parity.get(k) for k in ("ok", "rows_checked", "columns", "cap_timed_path_equal", "cap_e2e_path_equal", "error") if parity.get(k) is not None}
-        detail["parity_check"] = parity
-    if not args.no_prove:
-        out["prove"] = {k: native.get(k) for k in ("latency_ms", "latency_ms_gates", "proofs_per_s", "proofs_per_s_gates") if native.get(k) is not None}
-        if proofs_all is not None:
-            out["prove"]["proofs_per_s_all_gpus"] = proofs_all
-        out["prove"]["published_cpu_ms"] = PUBLISHED_LEAF_PROVE["ms"]
-    if not args.no_prove:
-        detail["perm_argument"] = [gpu_perm_argument(ctx, dev, k) for k in (13, 18)]
+    cpu = None
     if not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = orc.set_num_threads()
         us_perm = port_calibration(orc)
         k = cpu_sample_log_n(cores, 12.0)
         v, cores, secs = cpu_commit_sample(k)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "one from_values of 2^%d x %d, %.1f s" % (k, C_, secs),
-                               "calibration": {"port_us_per_perm_per_core": us_perm, "published_leaf_prove_ms": PUBLISHED_LEAF_PROVE["ms"],
-                                               "published_on": PUBLISHED_LEAF_PROVE["hardware"]}}
-        if not args.no_prove:
-            cms, _ = cpu_prove_synthetic()
-            out["prove"]["cpu_port_ms"] = cms
+        cpu = {"value": v, "cores": cores, "sample": "from_values 2^%dx%d, %.1f s" % (k, C_, secs), "us_perm": us_perm,
+               "prove_ms": cpu_prove_synthetic()[0] if not args.no_prove else None}
+    if not args.no_prove:
+        detail["perm_argument"] = [gpu_perm_argument(ctx, dev, k) for k in (13, 18)]
+    out = assemble_line(world=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, value=value, log_n=log_n,
+                        leaf_gbs=leaf_gbs, lde_gbs=lde_gbs, hbm_peak=hbm_peak, traffic=ncu.get("traffic", {}).get(str(log_n)) if world == 1 else None,
+                        int_issue=int_issue, imad_peak=imad_peak, perm_rate=perm_rate_kernel, stage=stage, launches=launches,
+                        clocks=clocks, e2e=e2e, parity=parity, native=None if args.no_prove else native, proofs_all=proofs_all, cpu=cpu)
+    if parity is not None:
+        detail["parity_check"] = parity
     path = args.detail or os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % world)
     try:
         os.makedirs(os.path.dirname(path), exist_ok=True)
