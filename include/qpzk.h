@@ -137,6 +137,19 @@ int qpzk_poseidon_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count,
  * canonical.  Lets a test drive the carry paths of the limb-domain linear layer with chosen states. */
 int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint32_t next_round, uint64_t* out);
 
+/* ---- Poseidon2: the reference's APPLICATION hash (not the FRI / Merkle hasher) -------------------------------------
+ * Replaces qp-plonky2 `hash::poseidon2::{Poseidon2Permutation, Poseidon2Hash::hash_no_pad}` / qp-poseidon-core =3.1.0
+ * (reference Cargo.toml:20-21): addresses H(H("wormhole" || secret)) (wormhole/circuit/src/unspendable_account.rs:63-95),
+ * nullifiers, zk-tree nodes (wormhole/circuit/src/zk_merkle_proof.rs:504,606), block hashes
+ * (wormhole/circuit/src/block_header/header.rs:132-141) -- SURVEY.md 8f-2.  Width 12, x^7, 4 + 22 + 4 rounds; the hash
+ * is an additive sponge of rate 8 over `x || 1 || 0*`, four words out.  PARITY PINNED by the seven vectors the
+ * reference's tests hold (tools/gen_poseidon2_constants.py; tests/golden/poseidon2_kats.json).
+ *   qpzk_poseidon2_permute      : `count` states of 12 words (any u64 representatives in, canonical out)
+ *   qpzk_poseidon2_hash_no_pad  : `count` messages of `len` canonical words each, row-major -> count x 4 words */
+int qpzk_poseidon2_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint64_t* out);
+int qpzk_poseidon2_hash_no_pad(qpzk_ctx* ctx, const uint64_t* msgs, uint64_t count, uint32_t len, uint64_t* out);
+int qpzk_poseidon2_hash_no_pad_dev(qpzk_ctx* ctx, const uint64_t* msgs_dev, uint64_t count, uint32_t len, uint64_t* out_dev);
+
 /* ---- MerkleTree::new(leaves, cap_height) / .cap / .prove / .leaves -------------------------------
  * leaves: num_leaves x leaf_len words, row-major.  num_leaves must be a power of two, cap_height <= log2. */
 int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,

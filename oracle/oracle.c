@@ -25,6 +25,7 @@
 #include "oracle.h"
 #include "goldilocks.h"
 #include "poseidon_rc.h"
+#include "poseidon2_rc.h"
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -135,6 +136,68 @@ void orc_poseidon(uint64_t s[12]) {
         for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], POSEIDON_RC[12 * r + i]));
         mds_layer(s);
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Poseidon2 (Goldilocks, width 12): the reference's APPLICATION hash `Poseidon2Hash` (addresses, nullifiers, zk-tree
+ * nodes, block hashes: wormhole/circuit/src/unspendable_account.rs:63-95, nullifier.rs:298-299, block_header/header.rs:132-141).
+ * PARITY PINNED: the parameters in poseidon2_rc.h reproduce all seven vectors the reference's tests hold
+ * (wormhole/tests/src/circuit/unspendable_account_tests.rs:9-24, wormhole/tests/test-helpers/src/lib.rs:208-219);
+ * derivation and check in tools/gen_poseidon2_constants.py.  Structure = Plonky3's Poseidon2: an initial external layer,
+ * 4 external rounds (constants, x^7 on every word, circ(2 M4, M4, M4)), 22 internal rounds (constant and x^7 on word 0,
+ * then s <- diag * s + sum(s)), 4 external rounds.
+ * ------------------------------------------------------------------------------------------ */
+static inline void p2_external_layer(uint64_t s[12]) {
+    /* M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]] on each group of four words, then every word += the sum of the
+     * words at the same position of the three groups */
+    uint64_t t[12];
+    for (int c = 0; c < 3; c++) {
+        const uint64_t a = s[4 * c], b = s[4 * c + 1], d = s[4 * c + 2], e = s[4 * c + 3];
+        const uint64_t sum = gl_add(gl_add(a, b), gl_add(d, e));
+        /* row r = sum + x_r + 2 x_{r+1} */
+        t[4 * c + 0] = gl_add(gl_add(sum, a), gl_add(b, b));
+        t[4 * c + 1] = gl_add(gl_add(sum, b), gl_add(d, d));
+        t[4 * c + 2] = gl_add(gl_add(sum, d), gl_add(e, e));
+        t[4 * c + 3] = gl_add(gl_add(sum, e), gl_add(a, a));
+    }
+    for (int k = 0; k < 4; k++) {
+        const uint64_t col = gl_add(gl_add(t[k], t[4 + k]), t[8 + k]);
+        for (int c = 0; c < 3; c++) s[4 * c + k] = gl_add(t[4 * c + k], col);
+    }
+}
+
+void orc_poseidon2(uint64_t s[12]) {
+    p2_external_layer(s);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], POSEIDON2_EXT_RC[12 * r + i]));
+        p2_external_layer(s);
+    }
+    for (int r = 0; r < 22; r++) {
+        s[0] = sbox7(gl_add(s[0], POSEIDON2_INT_RC[r]));
+        uint64_t sum = 0;
+        for (int i = 0; i < 12; i++) sum = gl_add(sum, s[i]);
+        for (int i = 0; i < 12; i++) s[i] = gl_add(gl_mul(s[i], POSEIDON2_DIAG[i]), sum);
+    }
+    for (int r = 4; r < 8; r++) {
+        for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], POSEIDON2_EXT_RC[12 * r + i]));
+        p2_external_layer(s);
+    }
+}
+
+/* Poseidon2Hash::hash_no_pad: additive sponge, rate 8, the input followed by 1 and zero-filled to a whole block
+ * (pad10_to_rate: wormhole/circuit/tests/heap_zeroization.rs:132-163), output state[0..4]. */
+void orc_hash_no_pad_p2(const uint64_t* in, size_t n, uint64_t out[4]) {
+    uint64_t st[12] = {0};
+    const size_t padded = (n + 1 + 7) / 8 * 8;
+    for (size_t off = 0; off < padded; off += 8) {
+        for (size_t i = 0; i < 8; i++) {
+            const size_t k = off + i;
+            const uint64_t v = k < n ? in[k] : (k == n ? 1 : 0);
+            st[i] = gl_add(st[i], v);
+        }
+        orc_poseidon2(st);
+    }
+    memcpy(out, st, 4 * sizeof(uint64_t));
 }
 
 /* hash_no_pad: overwrite-mode sponge, rate 8, no padding, output state[0..4]. */

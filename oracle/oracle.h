@@ -6,8 +6,9 @@
  * PARITY STATUS: "parity unpinned" for LDE values / Merkle caps / FRI transcripts -- the reference
  * tree holds no golden vector for them and the reference cannot be compiled here
  * (no cargo/rustc, the algorithm lives in the un-vendored crate qp-plonky2 =1.5.5).  What IS pinned:
- * the Goldilocks generators and the complete Poseidon-12 permutation (three upstream KATs,
- * SURVEY.md A.3), checked by tests/test_oracle_kat.py.
+ * the Goldilocks generators, the complete Poseidon-12 permutation (three upstream KATs) and the
+ * complete Poseidon2 hash of the application layer (seven vectors held by the reference's own tests), checked by
+ * tests/test_oracle_kat.py.
  */
 #ifndef ORACLE_H
 #define ORACLE_H
@@ -34,6 +35,10 @@ void orc_poseidon(uint64_t s[12]);        /* sparse partial rounds; identical fu
 void orc_hash_no_pad(const uint64_t* in, size_t n, uint64_t out[4]);
 void orc_hash_or_noop(const uint64_t* in, size_t n, uint64_t out[4]);
 void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+
+/* ---- Poseidon2 (the reference's application hash; PARITY PINNED by 7 reference-held vectors, see oracle.c) ---- */
+void orc_poseidon2(uint64_t s[12]);
+void orc_hash_no_pad_p2(const uint64_t* in, size_t n, uint64_t out[4]);
 
 /* ---- FFT: natural order in and out ---- */
 void orc_fft(uint64_t* a, unsigned log_n);

@@ -64,8 +64,9 @@ def lib():
                                          U64P, U64P, U64P, U64P, C.c_uint, U64P]
         L.orc_gate_terms.restype = C.c_int
         L.orc_gate_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, U32P, C.c_uint, U64P, U64P]
-        for f in (L.orc_hash_no_pad, L.orc_hash_or_noop):
+        for f in (L.orc_hash_no_pad, L.orc_hash_or_noop, L.orc_hash_no_pad_p2):
             f.restype = None; f.argtypes = [U64P, C.c_size_t, U64P]
+        L.orc_poseidon2.restype = None; L.orc_poseidon2.argtypes = [U64P]
         L.orc_two_to_one.restype = None; L.orc_two_to_one.argtypes = [U64P, U64P, U64P]
         for f in (L.orc_fft, L.orc_ifft):
             f.restype = None; f.argtypes = [U64P, C.c_uint]
@@ -181,6 +182,20 @@ def poseidon(state, naive=False):
 def hash_no_pad(x):
     x = _u64(x); out = np.zeros(4, np.uint64)
     lib().orc_hash_no_pad(_p64(x), x.size, _p64(out))
+    return out
+
+
+def poseidon2(state):
+    """The Poseidon2 permutation of the reference's application hash (12 words)."""
+    s = _u64(state).copy()
+    lib().orc_poseidon2(_p64(s))
+    return s
+
+
+def hash_no_pad_p2(x):
+    """Poseidon2Hash::hash_no_pad: additive sponge, rate 8, padding x || 1 || 0*, four words out."""
+    x = _u64(x).reshape(-1); out = np.zeros(4, np.uint64)
+    lib().orc_hash_no_pad_p2(_p64(x) if x.size else None, x.size, _p64(out))
     return out
 
 

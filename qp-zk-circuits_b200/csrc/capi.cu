@@ -219,6 +219,7 @@ static int ctx_create_body(int device, void* stream, bool own, qpzk_ctx** out) {
         ctx->stream = (cudaStream_t)stream;
     }
     CK(upload_poseidon_constants());
+    CK(upload_poseidon2_constants());
     for (int i = 0; i < 5; i++) CK(cudaEventCreate(&ctx->ev[i]));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
@@ -895,6 +896,55 @@ extern "C" int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, ui
     GUARD_BEGIN
     if (next_round > 30) return fail(QPZK_EINVAL, "next_round must be in 0..30");
     return permute_impl(ctx, states, count, (int)next_round, out);
+    GUARD_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poseidon2: the reference's application hash (poseidon2.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" int qpzk_poseidon2_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint64_t* out) {
+    GUARD_BEGIN
+    if (!ctx || (!states && count) || (!out && count)) return fail(QPZK_EINVAL, "null argument");
+    if (count > (1ull << 32)) return fail(QPZK_EINVAL, "too many states");
+    CK(cudaSetDevice(ctx->device));
+    DevBufs bufs(ctx);
+    uint64_t *d_in, *d_out;
+    int rc;
+    if ((rc = bufs.alloc(&d_in, 12 * count, true))) return rc;
+    if ((rc = bufs.alloc(&d_out, 12 * count, true))) return rc;
+    CK(cudaMemcpyAsync(d_in, states, 12 * count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_poseidon2_permute(d_in, count, d_out, ctx->stream)); ctx->launches++;
+    CK(cudaMemcpyAsync(out, d_out, 12 * count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_poseidon2_hash_no_pad_dev(qpzk_ctx* ctx, const uint64_t* msgs_dev, uint64_t count, uint32_t len,
+                                              uint64_t* out_dev) {
+    GUARD_BEGIN
+    if (!ctx || (!msgs_dev && count && len) || (!out_dev && count)) return fail(QPZK_EINVAL, "null argument");
+    if (len > (1u << 30)) return fail(QPZK_EINVAL, "message too long");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_poseidon2_hash(msgs_dev, count, len, len, out_dev, ctx->stream)); ctx->launches++;
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_poseidon2_hash_no_pad(qpzk_ctx* ctx, const uint64_t* msgs, uint64_t count, uint32_t len, uint64_t* out) {
+    GUARD_BEGIN
+    if (!ctx || (!msgs && count && len) || (!out && count)) return fail(QPZK_EINVAL, "null argument");
+    if (len > (1u << 30) || count > (1ull << 32)) return fail(QPZK_EINVAL, "too many / too long messages");
+    for (uint64_t i = 0; i < count * len; i++) if (msgs[i] >= GL_P) return fail(QPZK_EINVAL, "message word is not canonical");
+    CK(cudaSetDevice(ctx->device));
+    DevBufs bufs(ctx);
+    uint64_t *d_in, *d_out;
+    int rc;
+    if ((rc = bufs.alloc(&d_in, count * len, true))) return rc;    // preimages may be secret (addresses, nullifiers)
+    if ((rc = bufs.alloc(&d_out, 4 * count))) return rc;
+    if (count * len) CK(cudaMemcpyAsync(d_in, msgs, count * len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_poseidon2_hash(d_in, count, len, len, d_out, ctx->stream)); ctx->launches++;
+    if (count) CK(cudaMemcpyAsync(out, d_out, 4 * count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
     GUARD_END
 }
 

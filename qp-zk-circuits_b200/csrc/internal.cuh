@@ -101,6 +101,12 @@ cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witn
 // PoseidonHash::hash_no_pad of `len` device words (one warp; len == 0 gives four zeros): public_inputs_hash of prove()
 cudaError_t launch_hash_no_pad(const uint64_t* in_dev, uint32_t len, uint64_t* out_dev, cudaStream_t st);
 
+// ---- poseidon2.cu (the reference's application hash; not on the commitment path) ----
+cudaError_t upload_poseidon2_constants();
+cudaError_t launch_poseidon2_permute(const uint64_t* in, uint64_t count, uint64_t* out, cudaStream_t st);
+cudaError_t launch_poseidon2_hash(const uint64_t* msgs, uint64_t count, uint32_t len, uint64_t stride, uint64_t* out,
+                                  cudaStream_t st);
+
 // ---- fri.cu ----
 constexpr int EVAL_THREADS = 256;
 constexpr int COMBINE_THREADS = 256;

@@ -125,6 +125,9 @@ def load_library():
         "qpzk_pinned_free": (None, [vp]),
         "qpzk_poseidon_permute": (i, [vp, vp, u64, vp]),
         "qpzk_selftest_mds_layer": (i, [vp, vp, u64, u32, vp]),
+        "qpzk_poseidon2_permute": (i, [vp, vp, u64, vp]),
+        "qpzk_poseidon2_hash_no_pad": (i, [vp, vp, u64, u32, vp]),
+        "qpzk_poseidon2_hash_no_pad_dev": (i, [vp, vp, u64, u32, vp]),
         "qpzk_ctx_cached_bytes": (u64, [vp]),
         "qpzk_ctx_device_allocs": (u64, [vp]),
         "qpzk_ctx_peak_bytes": (u64, [vp]),
@@ -259,6 +262,23 @@ class Context:
         else:
             _check(self.L.qpzk_selftest_mds_layer(self.h, a.ctypes.data_as(C.c_void_p), a.shape[0], mds_only_round,
                                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def poseidon2_permute(self, states):
+        """The Poseidon2 permutation of the reference's application hash on an (N, 12) array."""
+        a = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 12)
+        out = np.zeros_like(a)
+        _check(self.L.qpzk_poseidon2_permute(self.h, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def poseidon2_hash_no_pad(self, msgs):
+        """Poseidon2Hash::hash_no_pad of every row of an (N, len) array of canonical felts -> (N, 4)."""
+        a = np.ascontiguousarray(msgs, dtype=np.uint64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        out = np.zeros((a.shape[0], 4), np.uint64)
+        _check(self.L.qpzk_poseidon2_hash_no_pad(self.h, a.ctypes.data_as(C.c_void_p) if a.size else None, a.shape[0], a.shape[1],
+                                                 out.ctypes.data_as(C.c_void_p)))
         return out
 
     def partial_products(self, wires, sigmas, betas, gammas, chunk=8):

@@ -149,6 +149,10 @@ extern "C" {
                                               out: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_intt_columns_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, coeffs_dev: *mut u64, log_n: u32,
                                  num_cols: u32) -> c_int;
+    // Poseidon2: the reference's application hash (addresses, nullifiers, zk-tree nodes, block hashes)
+    pub fn qpzk_poseidon2_permute(ctx: *mut qpzk_ctx, states: *const u64, count: u64, out: *mut u64) -> c_int;
+    pub fn qpzk_poseidon2_hash_no_pad(ctx: *mut qpzk_ctx, msgs: *const u64, count: u64, len: u32, out: *mut u64) -> c_int;
+    pub fn qpzk_poseidon2_hash_no_pad_dev(ctx: *mut qpzk_ctx, msgs_dev: *const u64, count: u64, len: u32, out_dev: *mut u64) -> c_int;
     pub fn qpzk_selftest_mds_layer(ctx: *mut qpzk_ctx, states: *const u64, count: u64, next_round: u32, out: *mut u64) -> c_int;
     pub fn qpzk_merkle_new_dev(ctx: *mut qpzk_ctx, leaves_dev: *const u64, num_leaves: u64, leaf_len: u32, cap_height: u32,
                                out: *mut *mut qpzk_batch) -> c_int;
