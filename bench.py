@@ -379,14 +379,14 @@ def compact(x, sig=4):
 
 
 def assemble_line(world, steps, warmup, ms_per_step, value, log_n, leaf_gbs, lde_gbs, hbm_peak, traffic, int_issue, imad_peak,
-                  perm_rate, stage, launches, clocks, e2e, parity, native, proofs_all, cpu):
+                  perm_rate, stage, launches, clocks, e2e, parity, native, proofs_all, cpu, exchange="NVLink P2P pull in LDE pass 1"):
     """The contract line (kept under 1.4 kB: the driver stores about 1.5 kB; long-form strings go to the detail file)."""
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": "raw commit 2^%dx%d, rate_bits %d, cap_height %d (config 3)" % (log_n, NUM_COLS, RATE_BITS, CAP_HEIGHT),
-                   "parallelism": "coset split x%d + NCCL all-gather" % world if world > 1 else "1 GPU", "l2": "inputs > L2"},
+                   "parallelism": ("coset split x%d, %s" % (world, exchange)) if world > 1 else "1 GPU", "l2": "inputs > L2"},
         "roofline": {"bound": "hbm", "achieved": leaf_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": leaf_gbs / hbm_peak if leaf_gbs else None,
                      "traffic": traffic, "kernel": "hash_rows", "int_issue": int_issue},
         "roofline_lde": {"bound": "hbm", "achieved": lde_gbs, "frac": lde_gbs / hbm_peak if lde_gbs else None},
@@ -453,6 +453,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the coefficient columns reach the other ranks -- p2p: the first LDE pass reads the peers' "
+                         "iNTT outputs over NVLink (fused compute + collective); nccl: all-gather, then compute")
     ap.add_argument("--detail", default=None, help="side file for the long-form record (default gpurun_out/bench_detail_n<N>.json)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -506,8 +509,18 @@ def main():
         if rank != 0 or args.no_parity:
             del full
             full = None
-    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev) if world > 1 else None
-    coeff_all = torch.empty((world * q, n), dtype=torch.int64, device=dev) if world > 1 else None
+    p2p = world > 1 and args.exchange == "p2p"
+    peers, tick = None, None
+    if p2p:
+        # this rank's iNTT output lives in an IPC-exported buffer; every peer's buffer is mapped into this process
+        peers = qpzk.PeerBuffers(ctx, q * n)
+        handles = [None] * world
+        dist.all_gather_object(handles, peers.handle)
+        peer_ptrs = peers.exchange(handles, rank)
+        tick = torch.zeros(1, device=dev)
+    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev) if world > 1 and not p2p else None
+    coeff_all = torch.empty((world * q, n), dtype=torch.int64, device=dev) if world > 1 and not p2p else None
+    coeff_mine_ptr = peers.ptr if p2p else (coeff_mine.data_ptr() if world > 1 else 0)
     cosets_per = B // world
     cap_all = torch.empty((world, (1 << CAP_HEIGHT) // world * 4), dtype=torch.int64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
@@ -520,19 +533,28 @@ def main():
             b = qpzk.PolynomialBatch.from_device(ctx, mine.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT, values=True)
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine.data_ptr(), coeff_mine.data_ptr(), log_n, q))
+            qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine.data_ptr(), coeff_mine_ptr, log_n, q))
             e0.record()
-            dist.all_gather_into_tensor(coeff_all, coeff_mine)
-            e1.record()
-            b = qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
-                                                               rank * cosets_per, cosets_per)
+            b = commit_after_intt()
+            e1.record() if not p2p else None
         if record:
             t = ctx.last_commit_timing()   # synchronises the stream
             for k in ("intt_ms", "lde_ms", "leaf_hash_ms", "merkle_levels_ms"):
                 stage[k] += t[k]
-            if world > 1:
-                stage["allgather_ms"] += e0.elapsed_time(e1)
+            if world > 1 and not p2p:
+                stage["allgather_ms"] += e0.elapsed_time(e1) - sum(t.values())   # e0..e1 brackets all-gather + commit
         return b
+
+    def commit_after_intt():
+        if p2p:
+            # every rank's iNTT has finished when this 1-element all-reduce has (stream ordered); the cap gather at the
+            # end of the step keeps a fast rank from overwriting its slice while a slow one still reads it
+            dist.all_reduce(tick)
+            return qpzk.PolynomialBatch.cosets_from_coeff_slices_device(ctx, peer_ptrs, q, log_n, C_, RATE_BITS, CAP_HEIGHT,
+                                                                        rank * cosets_per, cosets_per)
+        dist.all_gather_into_tensor(coeff_all, coeff_mine)
+        return qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
+                                                              rank * cosets_per, cosets_per)
 
     def finish(b):
         cap = b.cap                                   # tiny D2H read of this rank's cap slice
@@ -604,12 +626,10 @@ def main():
             for (a, z), ev in zip(zip(bounds[:-1], bounds[1:]), evs):
                 stream.wait_event(ev)
                 if z > a:
-                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[a:z].data_ptr(), coeff_mine[a:z].data_ptr(), log_n, z - a))
+                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[a:z].data_ptr(), coeff_mine_ptr + a * n * 8, log_n, z - a))
             if q > host.shape[0]:                      # zero padding columns of the last rank
-                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[host.shape[0]:].data_ptr(), coeff_mine[host.shape[0]:].data_ptr(), log_n, q - host.shape[0]))
-            dist.all_gather_into_tensor(coeff_all, coeff_mine)
-            finish(qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
-                                                                  rank * cosets_per, cosets_per))
+                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[host.shape[0]:].data_ptr(), coeff_mine_ptr + host.shape[0] * n * 8, log_n, q - host.shape[0]))
+            finish(commit_after_intt())
 
         for _ in range(2):
             e2e_step()
@@ -641,6 +661,8 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()                            # rank 0 finishes its parity check before NCCL goes away
+            if peers:
+                peers.close()
             dist.destroy_process_group()
         return
 
@@ -699,7 +721,8 @@ def main():
     out = assemble_line(world=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step, value=value, log_n=log_n,
                         leaf_gbs=leaf_gbs, lde_gbs=lde_gbs, hbm_peak=hbm_peak, traffic=ncu.get("traffic", {}).get(str(log_n)) if world == 1 else None,
                         int_issue=int_issue, imad_peak=imad_peak, perm_rate=perm_rate_kernel, stage=stage, launches=launches,
-                        clocks=clocks, e2e=e2e, parity=parity, native=None if args.no_prove else native, proofs_all=proofs_all, cpu=cpu)
+                        clocks=clocks, e2e=e2e, parity=parity, native=None if args.no_prove else native, proofs_all=proofs_all, cpu=cpu,
+                        exchange="NVLink P2P pull in LDE pass 1" if p2p else "NCCL all-gather")
     if parity is not None:
         detail["parity_check"] = parity
     path = args.detail or os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % world)
@@ -712,6 +735,8 @@ def main():
     print(json.dumps(compact(out), separators=(",", ":")))
     if world > 1:
         dist.barrier()
+        if peers:
+            peers.close()
         dist.destroy_process_group()
     if parity is not None and not parity.get("ok"):
         raise SystemExit("parity check FAILED: %s" % parity)

@@ -125,6 +125,24 @@ int qpzk_commit_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* cols_dev, uint32_
 int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t log_n,
                                        uint32_t num_cols, uint32_t rate_bits, uint32_t cap_height,
                                        uint32_t coset_begin, uint32_t coset_count, qpzk_batch** out);
+/* The same with the coefficient matrix spread over `num_slices` device buffers of cols_per_slice columns each (slice k
+ * holds columns [k * cols_per_slice, ...)): the per-rank iNTT outputs of a multi-GPU commitment, the other ranks' buffers
+ * mapped into this process with qpzk_peer_buffer_open.  The first LDE pass reads every slice where it lies -- over
+ * NVLink / NVSwitch for peer slices -- so the exchange step of SURVEY.md 8e is fused into the compute kernel: there is
+ * no all-gather and no assembled copy of the matrix.  Needs log_n >= 12.  The caller orders the ranks (every rank's
+ * iNTT must have finished before any rank starts, no rank may overwrite its slice before all have finished: two
+ * stream-ordered barriers, e.g. a 1-element NCCL all-reduce and the cap gather). */
+int qpzk_commit_cosets_from_coeff_slices_dev(qpzk_ctx* ctx, const uint64_t* const* slices_dev, uint32_t num_slices,
+                                             uint32_t cols_per_slice, uint32_t log_n, uint32_t num_cols,
+                                             uint32_t rate_bits, uint32_t cap_height, uint32_t coset_begin,
+                                             uint32_t coset_count, qpzk_batch** out);
+/* Exchange buffers of that path: a device buffer exported as a CUDA IPC handle (one process per GPU), and the peers'
+ * buffers mapped through their handles.  The handle bytes travel over the caller's own plumbing (torch.distributed). */
+#define QPZK_IPC_HANDLE_BYTES 64
+int qpzk_peer_buffer_create(qpzk_ctx* ctx, uint64_t words, uint64_t** dev_ptr, uint8_t handle[QPZK_IPC_HANDLE_BYTES]);
+int qpzk_peer_buffer_open(qpzk_ctx* ctx, const uint8_t handle[QPZK_IPC_HANDLE_BYTES], uint64_t** peer_ptr);
+int qpzk_peer_buffer_close(qpzk_ctx* ctx, uint64_t* peer_ptr);
+int qpzk_peer_buffer_free(qpzk_ctx* ctx, uint64_t* dev_ptr);
 /* column iNTT only (values -> coefficients), used by the coset-split path before the all-gather */
 int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint64_t* coeffs_dev, uint32_t log_n,
                           uint32_t num_cols);

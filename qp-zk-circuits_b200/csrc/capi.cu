@@ -414,8 +414,9 @@ struct LdePlan {
         }
         return 0;
     }
-    // strided passes for columns [c0, c1)
-    int run_passes(uint32_t c0, uint32_t c1) {
+    // strided passes for columns [c0, c1); first_src (optional) = where column c0 of the coefficients starts when the
+    // range does not live in `coeffs` (a peer GPU's slice, read over NVLink by the first pass itself)
+    int run_passes(uint32_t c0, uint32_t c1, const uint64_t* first_src = nullptr) {
         if (passes.empty() || c1 <= c0) return 0;
         NvtxRange nvtx_lde("qpzk:lde passes");
         const uint64_t n = 1ull << log_n;
@@ -430,7 +431,7 @@ struct LdePlan {
             a.group_stride = (uint64_t)num_cols * n;
             a.out = inter + (uint64_t)c0 * n;
             if (i == 0) {
-                a.mode = NTT_FWD_COSET_FIRST; a.in = coeffs + (uint64_t)c0 * n; a.num_groups = 1;
+                a.mode = NTT_FWD_COSET_FIRST; a.in = first_src ? first_src : coeffs + (uint64_t)c0 * n; a.num_groups = 1;
                 a.num_cosets = coset_count; a.cs_lo = cs_lo; a.cs_hi = cs_hi; a.cs_hi_size = cs.hi_size;
             } else {
                 a.mode = NTT_FWD_GENERIC; a.in = a.out; a.num_groups = coset_count; a.num_cosets = 1;
@@ -518,10 +519,12 @@ static int fetch_columns(qpzk_ctx* ctx, const ColumnSource& src, uint64_t n, uin
 int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt_dev, uint32_t coset_begin,
                        uint32_t coset_count, bool keep_coeffs_copy, qpzk_batch** out) {
+    if (src.slices && (from_values || keep_coeffs_copy || src.host || src.dev || !src.cols_per_slice))
+        return fail(QPZK_EINVAL, "coefficient slices: from_coeffs without a copy only");
     NvtxRange nvtx_commit(from_values ? "qpzk:from_values" : "qpzk:from_coeffs");
     if (!ctx || !out) return fail(QPZK_EINVAL, "null argument");
     *out = nullptr;
-    if (!src.dev && !src.host && num_cols) return fail(QPZK_EINVAL, "cols is null");
+    if (!src.dev && !src.host && !src.slices && num_cols) return fail(QPZK_EINVAL, "cols is null");
     if (log_n > 26 || rate_bits > 8) return fail(QPZK_EINVAL, "log_n > 26 or rate_bits > 8");
     uint32_t cosets = 1u << rate_bits;
     if (!coset_count || (coset_count & (coset_count - 1)) || coset_begin % coset_count || coset_begin + coset_count > cosets)
@@ -580,9 +583,21 @@ int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_
     if ((rc = lde.prepare(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count))) {
         lde.release(); return fail_out(rc);
     }
+    if (src.slices) {
+        // The coefficient matrix is spread over several buffers of cols_per_slice columns each (one per GPU of a coset-
+        // split commitment, peers mapped over NVLink): the first strided pass reads every slice where it lies, so the
+        // exchange IS the first pass -- no all-gather, no assembled copy of the matrix.
+        if (lde.passes.empty()) { lde.release(); return fail_out(fail(QPZK_EINVAL, "coefficient slices need log_n > 11")); }
+        mark(ctx, 1);
+        for (uint32_t c0 = 0, k = 0; c0 < num_cols; c0 += src.cols_per_slice, k++) {
+            const uint32_t c1 = c0 + src.cols_per_slice < num_cols ? c0 + src.cols_per_slice : num_cols;
+            if (!src.slices[k]) { lde.release(); return fail_out(fail(QPZK_EINVAL, "null coefficient slice")); }
+            if ((rc = lde.run_passes(c0, c1, src.slices[k]))) { lde.release(); return fail_out(rc); }
+        }
+    }
     const uint32_t chunks = src.host ? (src.chunks ? src.chunks : 1) : 1;
     const uint32_t per = (num_cols + chunks - 1) / chunks;
-    for (uint32_t c0 = 0; c0 < num_cols; c0 += per) {
+    for (uint32_t c0 = 0; c0 < num_cols && !src.slices; c0 += per) {
         const uint32_t c1 = c0 + per < num_cols ? c0 + per : num_cols;
         if ((rc = fetch_columns(ctx, src, n, c0, c1))) { lde.release(); return fail_out(rc); }
         if (from_values && (rc = run_intt(ctx, in_dev + (uint64_t)c0 * n, b->coeffs + (uint64_t)c0 * n, log_n, c1 - c0))) {
@@ -631,6 +646,67 @@ extern "C" int qpzk_commit_cosets_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t*
                                                   uint32_t coset_count, qpzk_batch** out) {
     GUARD_BEGIN return commit_impl(ctx, dev_source(coeffs), false, log_n, num_cols, rate_bits, cap_height, nullptr, coset_begin, coset_count, false, out); GUARD_END
 }
+extern "C" int qpzk_commit_cosets_from_coeff_slices_dev(qpzk_ctx* ctx, const uint64_t* const* slices_dev, uint32_t num_slices,
+                                                        uint32_t cols_per_slice, uint32_t log_n, uint32_t num_cols,
+                                                        uint32_t rate_bits, uint32_t cap_height, uint32_t coset_begin,
+                                                        uint32_t coset_count, qpzk_batch** out) {
+    GUARD_BEGIN
+    if (!slices_dev || !cols_per_slice || (uint64_t)num_slices * cols_per_slice < num_cols)
+        return fail(QPZK_EINVAL, "coefficient slices do not cover the columns");
+    ColumnSource src;
+    src.slices = slices_dev; src.cols_per_slice = cols_per_slice;
+    return commit_impl(ctx, src, false, log_n, num_cols, rate_bits, cap_height, nullptr, coset_begin, coset_count, false, out);
+    GUARD_END
+}
+
+// Exchange buffers for the coset split: plain cudaMalloc blocks (an IPC handle names a whole allocation, so they do not
+// come from the block cache), exported to / mapped from the other ranks' processes.
+static_assert(sizeof(cudaIpcMemHandle_t) == QPZK_IPC_HANDLE_BYTES, "IPC handle size");
+extern "C" int qpzk_peer_buffer_create(qpzk_ctx* ctx, uint64_t words, uint64_t** dev_ptr, uint8_t handle[QPZK_IPC_HANDLE_BYTES]) {
+    GUARD_BEGIN
+    if (!ctx || !dev_ptr || !handle || !words) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, words * sizeof(uint64_t)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); CK(e); }
+    memcpy(handle, &h, sizeof h);
+    *dev_ptr = (uint64_t*)p;
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_peer_buffer_open(qpzk_ctx* ctx, const uint8_t handle[QPZK_IPC_HANDLE_BYTES], uint64_t** peer_ptr) {
+    GUARD_BEGIN
+    if (!ctx || !handle || !peer_ptr) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_ptr = (uint64_t*)p;
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_peer_buffer_close(qpzk_ctx* ctx, uint64_t* peer_ptr) {
+    GUARD_BEGIN
+    if (!ctx || !peer_ptr) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+    GUARD_END
+}
+extern "C" int qpzk_peer_buffer_free(qpzk_ctx* ctx, uint64_t* dev_ptr) {
+    GUARD_BEGIN
+    if (!ctx || !dev_ptr) return fail(QPZK_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dev_ptr));
+    return 0;
+    GUARD_END
+}
+
 extern "C" int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uint32_t log_n, uint32_t num_cols) {
     GUARD_BEGIN
     if (!ctx || !values || !coeffs) return fail(QPZK_EINVAL, "null argument");

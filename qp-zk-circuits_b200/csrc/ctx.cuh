@@ -129,6 +129,8 @@ struct ColumnSource {   // where a commit's input columns come from: device-resi
     const uint64_t* host = nullptr;
     uint64_t* staging = nullptr;
     uint32_t chunks = 1;
+    const uint64_t* const* slices = nullptr;   // coefficients spread over several device buffers (peers mapped over NVLink)
+    uint32_t cols_per_slice = 0;
 };
 inline ColumnSource dev_source(const uint64_t* p) { ColumnSource s; s.dev = p; return s; }
 int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_n, uint32_t num_cols, uint32_t rate_bits,

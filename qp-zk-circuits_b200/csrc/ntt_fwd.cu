@@ -61,8 +61,12 @@ __host__ __device__ constexpr uint32_t brev_c(uint32_t x) {
 
 // Tile = 2^(SA+SB) positions of the pass x Wd = 4096 / 2^(SA+SB) consecutive low positions; 256 threads; every
 // thread handles 16 elements of each column in both phases.
-template <int SA, int SB>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
+// LEAN = true: the 16 output factors of a thread live in shared memory instead of registers and the next column is not
+// prefetched, so that the kernel fits 128 registers and TWO blocks share an SM (ncu, round 1: at 178-196 registers one
+// block of 8 warps per SM issued on 54 % of the cycles -- nothing to switch to while a warp waits; with 16 warps the
+// other block's arithmetic hides the loads the prefetch used to hide).
+template <int SA, int SB, bool LEAN>
+__global__ void __launch_bounds__(NTT_THREADS, LEAN ? 2 : 1) ntt_fwd_kernel(NttPassArgs a) {
     constexpr int S_LOG = SA + SB, A = 1 << SA, B = 1 << SB, S = 1 << S_LOG;
     constexpr int LWD = 12 - S_LOG, WD = 1 << LWD, G = NTT_THREADS / WD;   // lanes along `low`, thread groups
     constexpr int IT1 = B / G, IT2 = A / G;                                // items per thread in phase 1 / 2
@@ -71,6 +75,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
     uint64_t* buf = smem;                 // [f1][eg][w]
     uint64_t* T = smem + S * WD;          // [eg][f1]
     uint64_t* Ck = T + S;                 // [k]
+    uint64_t* Osm = Ck + A;               // LEAN: [it * B + r][thread]
     const bool coset_first = a.mode == NTT_FWD_COSET_FIRST;
     const uint32_t b_hi = a.b_lo + S_LOG;
     const uint32_t w = threadIdx.x & (WD - 1), g = threadIdx.x >> LWD;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
         T[i] = t;
     }
     if (threadIdx.x < A) Ck[threadIdx.x] = coset_first ? tw_get(clo, chi, ((uint64_t)threadIdx.x << SB) << a.b_lo) : 1;
-    uint64_t O[IT2][B];   // output factor of (f1 = g + G*it, f2 = bitrev(r)) at this thread's low position
+    uint64_t O[LEAN ? 1 : IT2][LEAN ? 1 : B];   // output factor of (f1 = g + G*it, f2 = bitrev(r)) at this thread's low position
     {
         const uint64_t pl = low0 + w;
         const uint64_t cw = coset_first ? tw_get(clo, chi, pl) : 1;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
                 const uint32_t f = f1 + A * brev_c<SB>(r);
                 uint64_t o = tw_get(a.tw_lo, a.tw_hi, ((uint64_t)f * pl) << (a.log_n - b_hi));
                 if (coset_first) o = gl_mulc(o, cw);
-                O[it][r] = o;
+                if (LEAN) Osm[(it * B + r) * NTT_THREADS + threadIdx.x] = o; else O[LEAN ? 0 : it][LEAN ? 0 : r] = o;
             }
         }
     }
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
     // loads are in flight during the exchange and the second phase (one block per SM: nothing else would hide them).
     const uint64_t in_off = (uint64_t)blockIdx.z * a.group_stride + base + w;
     uint64_t x[IT1][A];
-    if (c_begin < c_end) {
+    if (!LEAN && c_begin < c_end) {
         const uint64_t* in = a.in + c_begin * a.in_stride + in_off;
 #pragma unroll
         for (int it = 0; it < IT1; it++)
@@ -126,6 +131,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
     }
     for (uint32_t col = c_begin; col < c_end; col++) {
         uint64_t* out = a.out + col * a.out_stride + ((uint64_t)coset + blockIdx.z) * a.group_stride + base + w;
+        if (LEAN) {
+            const uint64_t* in = a.in + col * a.in_stride + in_off;
+#pragma unroll
+            for (int it = 0; it < IT1; it++)
+#pragma unroll
+                for (int k = 0; k < A; k++) x[it][k] = in[(uint64_t)(g + G * it + B * k) << a.b_lo];
+        }
 #pragma unroll
         for (int it = 0; it < IT1; it++) {
             const uint32_t eg = g + G * it;
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
                 buf[(f1 * B + eg) * WD + w] = gl_mulc(x[it][r], T[eg * A + f1]);
             }
         }
-        if (col + 1 < c_end) {
+        if (!LEAN && col + 1 < c_end) {
             const uint64_t* in = a.in + (col + 1) * a.in_stride + in_off;
 #pragma unroll
             for (int it = 0; it < IT1; it++)
@@ -157,7 +169,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(NttPassArgs a) {
             dft_regs<SB>(y);
             const uint32_t e0 = (__brev(f1) >> (32 - SA)) * B;   // slot of frequency f = f1 + A*f2 is bitrev_s(f)
 #pragma unroll
-            for (int r = 0; r < B; r++) out[(uint64_t)(e0 + r) << a.b_lo] = gl_mulc(y[r], O[it][r]);
+            for (int r = 0; r < B; r++)
+                out[(uint64_t)(e0 + r) << a.b_lo] = gl_mulc(y[r], LEAN ? Osm[(it * B + r) * NTT_THREADS + threadIdx.x] : O[LEAN ? 0 : it][LEAN ? 0 : r]);
         }
         __syncthreads();
     }
@@ -417,9 +430,16 @@ bool ntt_fwd_supported(const NttPassArgs& a) {
 template <int SA, int SB>
 static cudaError_t launch_one(const NttPassArgs& a, dim3 grid, cudaStream_t st) {
     constexpr int S = 1 << (SA + SB);
-    const size_t smem = ((size_t)4096 + S + (1 << SA)) * sizeof(uint64_t);
-
-    ntt_fwd_kernel<SA, SB><<<grid, NTT_THREADS, smem, st>>>(a);
+    static const bool lean = [] { const char* e = getenv("QPZK_NTT_LEAN"); return !e || e[0] != '0'; }();
+    const size_t smem = ((size_t)4096 + S + (1 << SA) + (lean ? 16 * NTT_THREADS : 0)) * sizeof(uint64_t);
+    if (lean) {
+        static unsigned long long done = 0;   // 65 KB of dynamic shared memory per block (two blocks per SM)
+        cudaError_t e = raise_smem_limit((const void*)ntt_fwd_kernel<SA, SB, true>, &done);
+        if (e != cudaSuccess) return e;
+        ntt_fwd_kernel<SA, SB, true><<<grid, NTT_THREADS, smem, st>>>(a);
+    } else {
+        ntt_fwd_kernel<SA, SB, false><<<grid, NTT_THREADS, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -138,6 +138,11 @@ def load_library():
         "qpzk_commit_from_coeffs_dev": (i, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
         "qpzk_commit_cosets_from_coeffs_dev": (i, [vp, vp, u32, u32, u32, u32, u32, u32, C.POINTER(vp)]),
         "qpzk_intt_columns_dev": (i, [vp, vp, vp, u32, u32]),
+        "qpzk_commit_cosets_from_coeff_slices_dev": (i, [vp, C.POINTER(vp), u32, u32, u32, u32, u32, u32, u32, u32, C.POINTER(vp)]),
+        "qpzk_peer_buffer_create": (i, [vp, u64, C.POINTER(vp), vp]),
+        "qpzk_peer_buffer_open": (i, [vp, vp, C.POINTER(vp)]),
+        "qpzk_peer_buffer_close": (i, [vp, vp]),
+        "qpzk_peer_buffer_free": (i, [vp, vp]),
         "qpzk_merkle_new": (i, [vp, vp, u64, u32, u32, C.POINTER(vp)]),
         "qpzk_merkle_new_dev": (i, [vp, vp, u64, u32, u32, C.POINTER(vp)]),
         "qpzk_batch_free": (None, [vp]),
@@ -329,6 +334,40 @@ class Context:
             pass
 
 
+class PeerBuffers:
+    """The exchange buffers of a multi-GPU commitment (one process per GPU): this rank's buffer, exported as a CUDA IPC
+    handle, and every peer's buffer mapped into this process.  `exchange(handles)` takes the list of all ranks' handle
+    bytes in rank order (gathered by the caller, e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, ctx, words):
+        self.ctx, self.words = ctx, words
+        p = C.c_void_p()
+        hb = (C.c_uint8 * 64)()
+        _check(ctx.L.qpzk_peer_buffer_create(ctx.h, words, C.byref(p), hb))
+        self.ptr, self.handle, self.peers, self._opened = p.value, bytes(hb), None, []
+
+    def exchange(self, handles, rank):
+        self.peers = []
+        for r, hb in enumerate(handles):
+            if r == rank:
+                self.peers.append(self.ptr)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+            _check(self.ctx.L.qpzk_peer_buffer_open(self.ctx.h, buf, C.byref(p)))
+            self.peers.append(p.value)
+            self._opened.append(p.value)
+        return self.peers
+
+    def close(self):
+        for p in self._opened:
+            self.ctx.L.qpzk_peer_buffer_close(self.ctx.h, C.c_void_p(p))
+        self._opened = []
+        if self.ptr:
+            self.ctx.L.qpzk_peer_buffer_free(self.ctx.h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
 class MerkleTree:
     """MerkleTree<F, PoseidonHash>: `.cap`, `.prove(i)`, `.get(i)`."""
 
@@ -447,6 +486,17 @@ class PolynomialBatch:
         h = C.c_void_p()
         _check(ctx.L.qpzk_commit_cosets_from_coeffs_dev(ctx.h, C.c_void_p(dev_ptr), log_n, num_cols, rate_bits,
                                                         cap_height, coset_begin, coset_count, C.byref(h)))
+        return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, False)
+
+    @classmethod
+    def cosets_from_coeff_slices_device(cls, ctx, slice_ptrs, cols_per_slice, log_n, num_cols, rate_bits, cap_height,
+                                        coset_begin, coset_count):
+        """Coset-split commit whose coefficient columns live in several device buffers (own + peers mapped over NVLink,
+        see PeerBuffers): the first LDE pass pulls them where they lie."""
+        arr = (C.c_void_p * len(slice_ptrs))(*[C.c_void_p(p) for p in slice_ptrs])
+        h = C.c_void_p()
+        _check(ctx.L.qpzk_commit_cosets_from_coeff_slices_dev(ctx.h, arr, len(slice_ptrs), cols_per_slice, log_n, num_cols,
+                                                              rate_bits, cap_height, coset_begin, coset_count, C.byref(h)))
         return cls(ctx, h, log_n, num_cols, rate_bits, cap_height, False)
 
     @staticmethod

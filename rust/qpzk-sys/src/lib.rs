@@ -147,6 +147,15 @@ extern "C" {
     pub fn qpzk_commit_cosets_from_coeffs_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, log_n: u32, num_cols: u32,
                                               rate_bits: u32, cap_height: u32, coset_begin: u32, coset_count: u32,
                                               out: *mut *mut qpzk_batch) -> c_int;
+    // multi-GPU coset split with the exchange fused into the first LDE pass (peer slices read over NVLink)
+    pub fn qpzk_commit_cosets_from_coeff_slices_dev(ctx: *mut qpzk_ctx, slices_dev: *const *const u64, num_slices: u32,
+                                                    cols_per_slice: u32, log_n: u32, num_cols: u32, rate_bits: u32,
+                                                    cap_height: u32, coset_begin: u32, coset_count: u32,
+                                                    out: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_peer_buffer_create(ctx: *mut qpzk_ctx, words: u64, dev_ptr: *mut *mut u64, handle: *mut u8) -> c_int;
+    pub fn qpzk_peer_buffer_open(ctx: *mut qpzk_ctx, handle: *const u8, peer_ptr: *mut *mut u64) -> c_int;
+    pub fn qpzk_peer_buffer_close(ctx: *mut qpzk_ctx, peer_ptr: *mut u64) -> c_int;
+    pub fn qpzk_peer_buffer_free(ctx: *mut qpzk_ctx, dev_ptr: *mut u64) -> c_int;
     pub fn qpzk_intt_columns_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, coeffs_dev: *mut u64, log_n: u32,
                                  num_cols: u32) -> c_int;
     // Poseidon2: the reference's application hash (addresses, nullifiers, zk-tree nodes, block hashes)

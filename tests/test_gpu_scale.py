@@ -149,4 +149,19 @@ def test_coset_split_at_scale_matches_full_commit(ctx, qpzk, sc):
                 assert r["ok"]
             part.free()
         assert (np.concatenate(caps) == cap).all()
+    # the same with the coefficient matrix left where the ranks' iNTTs wrote it (qpzk_commit_cosets_from_coeff_slices_dev:
+    # the first LDE pass reads every slice in place -- peer memory over NVLink on a multi-GPU box; here three buffers of
+    # 8 columns on one device, the last one short)
+    slices = [coeffs[c0:min(c0 + 8, C_)].clone() for c0 in range(0, C_, 8)]
+    torch.cuda.synchronize()
+    for begin, count in ((0, 8), (4, 4), (6, 2)):
+        part = qpzk.PolynomialBatch.cosets_from_coeff_slices_device(ctx, [t.data_ptr() for t in slices], 8, log_n, C_, 3, 4, begin, count)
+        assert (part.cap.reshape(-1) == cap.reshape(-1)[begin * 8:(begin + count) * 8]).all()
+        assert (part.merkle_tree.rows(5, 32) == full.merkle_tree.rows(begin * n + 5, 32)).all()
+        part.free()
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.PolynomialBatch.cosets_from_coeff_slices_device(ctx, [slices[0].data_ptr()], 8, log_n, C_, 3, 4, 0, 8)   # slices do not cover the columns
+    pb = qpzk.PeerBuffers(ctx, 1 << 12)
+    assert pb.ptr and len(pb.handle) == 64
+    pb.close()
     full.free()
