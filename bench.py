@@ -608,27 +608,50 @@ def main():
         pieces = max(1, min(8, host.shape[0]))
         bounds = [host.shape[0] * i // pieces for i in range(pieces + 1)]
 
-        def e2e_step():
+        # N > 1: the steps are a stream of commitments (the sweep, an aggregator's proofs), so the input of step k + 1
+        # is copied -- in column ranges, on a copy stream -- into a second device buffer while step k computes; every
+        # step's host->device copy is inside the timed region, but only the first one is exposed.  (On one GPU
+        # qpzk_commit_from_values overlaps the copy with the per-column stages of the same call.)
+        bufs2 = [mine, torch.empty_like(mine)] if world > 1 else None
+        if world > 1 and q > host.shape[0]:
+            bufs2[1][host.shape[0]:].zero_()                          # zero padding columns of the last rank
+        copied, consumed = [None, None], [None, None]
+
+        def e2e_prefetch(k):
+            dst = bufs2[k & 1]
+            if consumed[k & 1] is not None:
+                copy_stream.wait_event(consumed[k & 1])                # the iNTT that read this buffer two steps ago
+            else:
+                copy_stream.wait_stream(stream)
+            evs = []
+            with torch.cuda.stream(copy_stream):
+                for a, z in zip(bounds[:-1], bounds[1:]):
+                    dst[a:z].copy_(host[a:z], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    evs.append(ev)
+            copied[k & 1] = evs
+
+        def e2e_step(k=0, last=True):
             if world == 1:
                 bb = qpzk.PolynomialBatch.from_values(ctx, hnp, RATE_BITS, None, CAP_HEIGHT)
                 finish(bb)
                 return
-            # N > 1: this rank's column slice comes from pinned host memory in column ranges on a copy stream; the
-            # iNTT of one range runs while the next is in flight (what qpzk_commit_from_values does on one GPU)
-            copy_stream.wait_stream(stream)
-            evs = []
-            with torch.cuda.stream(copy_stream):
-                for a, z in zip(bounds[:-1], bounds[1:]):
-                    mine[a:z].copy_(host[a:z], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    evs.append(ev)
+            src = bufs2[k & 1]
+            if copied[k & 1] is None:
+                e2e_prefetch(k)
+            evs, copied[k & 1] = copied[k & 1], None
+            if not last:
+                e2e_prefetch(k + 1)
             for (a, z), ev in zip(zip(bounds[:-1], bounds[1:]), evs):
                 stream.wait_event(ev)
                 if z > a:
-                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[a:z].data_ptr(), coeff_mine_ptr + a * n * 8, log_n, z - a))
-            if q > host.shape[0]:                      # zero padding columns of the last rank
-                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine[host.shape[0]:].data_ptr(), coeff_mine_ptr + host.shape[0] * n * 8, log_n, q - host.shape[0]))
+                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, src[a:z].data_ptr(), coeff_mine_ptr + a * n * 8, log_n, z - a))
+            if q > host.shape[0]:
+                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, src[host.shape[0]:].data_ptr(), coeff_mine_ptr + host.shape[0] * n * 8, log_n, q - host.shape[0]))
+            done = torch.cuda.Event()
+            done.record(stream)
+            consumed[k & 1] = done
             finish(commit_after_intt())
 
         for _ in range(2):
@@ -637,8 +660,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        for k in range(args.steps):
+            e2e_step(k, last=k + 1 == args.steps)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:

@@ -416,12 +416,14 @@ struct LdePlan {
     }
     // strided passes for columns [c0, c1); first_src (optional) = where column c0 of the coefficients starts when the
     // range does not live in `coeffs` (a peer GPU's slice, read over NVLink by the first pass itself)
-    int run_passes(uint32_t c0, uint32_t c1, const uint64_t* first_src = nullptr) {
+    // which = 0: every pass, 1: only the first pass (the one that reads the coefficients), 2: every pass but the first
+    int run_passes(uint32_t c0, uint32_t c1, const uint64_t* first_src = nullptr, int which = 0) {
         if (passes.empty() || c1 <= c0) return 0;
         NvtxRange nvtx_lde("qpzk:lde passes");
         const uint64_t n = 1ull << log_n;
         uint32_t b_hi = log_n;
         for (size_t i = 0; i < passes.size(); i++) {
+            if ((which == 1 && i > 0) || (which == 2 && i == 0)) { b_hi -= passes[i]; continue; }
             NttPassArgs a{};
             a.log_n = log_n; a.s = passes[i]; a.b_lo = b_hi - passes[i];
             a.W = tile_width(a.s, a.b_lo);
@@ -439,6 +441,9 @@ struct LdePlan {
             if (!ctx->legacy_ntt && ntt_fwd_supported(a)) {
                 const uint64_t tile_cosets = (n >> 12) * coset_count;
                 uint64_t cpb = tile_cosets * (c1 - c0) / 4096;
+                // a narrow column range (a peer's slice) still amortises the per-tile factor tables over as many columns
+                // as it has, as long as the tiles alone fill the machine
+                if (which == 1 && tile_cosets >= 8ull * ctx->num_sms) cpb = c1 - c0;
                 a.cols_per_block = (uint32_t)(cpb < 1 ? 1 : cpb > 32 ? 32 : cpb);
                 CK(launch_ntt_fwd(a, ctx->stream));
             } else {
@@ -589,11 +594,19 @@ int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_
         // exchange IS the first pass -- no all-gather, no assembled copy of the matrix.
         if (lde.passes.empty()) { lde.release(); return fail_out(fail(QPZK_EINVAL, "coefficient slices need log_n > 11")); }
         mark(ctx, 1);
-        for (uint32_t c0 = 0, k = 0; c0 < num_cols; c0 += src.cols_per_slice, k++) {
+        // Every rank starts with a DIFFERENT slice (its own) and walks the ring from there: at any moment each GPU's
+        // memory serves one reader.  With all ranks starting at slice 0 the eight readers shared one GPU's NVLink
+        // egress at a time (measured at 8 GPUs: 99.8 ms per commit against 85.8 ms with an NCCL all-gather).
+        const uint32_t num_slices = (num_cols + src.cols_per_slice - 1) / src.cols_per_slice;
+        const uint32_t first = (coset_begin / coset_count) % num_slices;
+        for (uint32_t t = 0; t < num_slices; t++) {
+            const uint32_t k = (first + t) % num_slices;
+            const uint32_t c0 = k * src.cols_per_slice;
             const uint32_t c1 = c0 + src.cols_per_slice < num_cols ? c0 + src.cols_per_slice : num_cols;
             if (!src.slices[k]) { lde.release(); return fail_out(fail(QPZK_EINVAL, "null coefficient slice")); }
-            if ((rc = lde.run_passes(c0, c1, src.slices[k]))) { lde.release(); return fail_out(rc); }
+            if ((rc = lde.run_passes(c0, c1, src.slices[k], 1))) { lde.release(); return fail_out(rc); }
         }
+        if ((rc = lde.run_passes(0, num_cols, nullptr, 2))) { lde.release(); return fail_out(rc); }
     }
     const uint32_t chunks = src.host ? (src.chunks ? src.chunks : 1) : 1;
     const uint32_t per = (num_cols + chunks - 1) / chunks;
