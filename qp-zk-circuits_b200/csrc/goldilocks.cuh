@@ -192,8 +192,57 @@ __device__ __forceinline__ uint64_t reduce160(const acc160& acc) {
     return d;
 }
 
-// canonical product through the PTX path (used by the NTT / FRI kernels)
-__device__ __forceinline__ uint64_t gl_mulc(uint64_t a, uint64_t b) { return gl_canon(mulp(a, b)); }
+// ---- the multiply of the ALU-bound kernels (NTT / LDE / FRI / quotient) ------------------------------------------
+// ncu, round 2: the LDE passes keep the ALU pipe 80 % busy with the FMA pipe at 12 %, and a product is two thirds of
+// their ALU work.  mulp() above is tuned for the Poseidon kernels, where both pipes are loaded equally.  Here the
+// partial products are chained through the 64-bit addend of IMAD.WIDE (a0*b1 + hi(a0*b0) cannot overflow) and
+// w2 * (2^32 - 1) + w0 of the reduction is one more IMAD.WIDE: 16 ALU + 4 wide + 9 short FMA-pipe instructions
+// instead of 19 + 4 + 3 (tools/ubench/mulvariants.cu counts them).
+__device__ __forceinline__ u128w mul_wide_chain(uint64_t a, uint64_t b) {
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    u128w r;
+    asm("{\n\t.reg .u64 p00,y,z,h,t;\n\t.reg .u32 x1,y0,y1,z1;\n\t"
+        "mul.wide.u32 p00,%4,%6;\n\t"
+        "mov.b64 {%0,x1},p00;\n\tcvt.u64.u32 t,x1;\n\t"
+        "mad.wide.u32 y,%4,%7,t;\n\t"
+        "mov.b64 {y0,y1},y;\n\tcvt.u64.u32 t,y0;\n\t"
+        "mad.wide.u32 z,%5,%6,t;\n\t"
+        "mov.b64 {%1,z1},z;\n\tcvt.u64.u32 t,y1;\n\t"
+        "mad.wide.u32 h,%5,%7,t;\n\t"
+        "cvt.u64.u32 t,z1;\n\tadd.u64 h,h,t;\n\t"
+        "mov.b64 {%2,%3},h;\n\t}"
+        : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return r;
+}
+// (w3:w2:w1:w0) mod p as an arbitrary u64 representative:  u = w2 * EPS + w0 (< 2^64 - 2^32, exact), then
+// u + w1 * 2^32 - w3 with the carry k of the addition and the borrow of the subtraction folded into one correction
+// of (k - borrow) * EPS, which cannot wrap a second time (k = 1: the wrapped sum is <= 2^64 - 2^33; borrow without k:
+// the wrapped difference is > 2^64 - 2^32).
+__device__ __forceinline__ uint64_t reduce_fma(u128w x) {
+    uint32_t s0, s1;
+    asm("{\n\t.reg .u64 u,t;\n\t.reg .u32 u0,u1,v1,k,t0,t1,brw,c,m0,m1;\n\t"
+        "cvt.u64.u32 t,%2;\n\t"
+        "mad.wide.u32 u,%4,0xffffffff,t;\n\t"
+        "mov.b64 {u0,u1},u;\n\t"
+        "add.cc.u32 v1,u1,%3;\n\taddc.u32 k,0,0;\n\t"
+        "sub.cc.u32 t0,u0,%5;\n\tsubc.cc.u32 t1,v1,0;\n\tsubc.u32 brw,0,0;\n\t"
+        "add.u32 c,k,brw;\n\t"
+        "sub.u32 m0,0,c;\n\tshr.s32 m1,c,31;\n\t"
+        "add.cc.u32 %0,t0,m0;\n\taddc.u32 %1,t1,m1;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(x.w0), "r"(x.w1), "r"(x.w2), "r"(x.w3));
+    return ((uint64_t)s1 << 32) | s0;
+}
+#ifndef QPZK_MULC_FMA
+#define QPZK_MULC_FMA 1
+#endif
+// canonical product (used by the NTT / FRI / permutation-argument kernels)
+__device__ __forceinline__ uint64_t gl_mulc(uint64_t a, uint64_t b) {
+#if QPZK_MULC_FMA
+    return gl_canon(reduce_fma(mul_wide_chain(a, b)));
+#else
+    return gl_canon(mulp(a, b));
+#endif
+}
 __device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_mulc(a, b); }
 
 // host versions (table construction at context creation; never on the data path)
