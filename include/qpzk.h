@@ -343,6 +343,15 @@ typedef struct {
     uint32_t num_imm;
     uint32_t num_regs;
 } qpzk_gate_program;
+/* Programs of 512 steps or more are compiled at run time (NVRTC, sm_100a) into straight-line code with the program's
+ * registers in hardware registers and cached per process; shorter ones, or all of them with QPZK_GATE_JIT=0 or when NVRTC
+ * cannot be loaded, are interpreted on the device.  Both paths give the same bits.
+ * qpzk_gate_jit_available: 1 if NVRTC was found.  qpzk_gate_jit_compiled: programs compiled so far in this process. */
+int qpzk_gate_jit_available(void);
+void qpzk_gate_jit_set_mode(int mode);   /* 0 interpret, 1 compile (default, or $QPZK_GATE_JIT); process wide, applies to later uploads */
+/* compiles `prog` for sm_100a without loading it (no GPU needed; a build check of the run-time compiler path) */
+int qpzk_gate_jit_compile_check(const qpzk_gate_program* prog, uint64_t* cubin_bytes);
+uint64_t qpzk_gate_jit_compiled(void);
 /* qpzk_quotient_polys / qpzk_commit_quotient with the gate terms computed from `prog` (NULL = no gates). */
 int qpzk_quotient_polys_prog(qpzk_ctx* ctx, const qpzk_batch* constants_sigmas, const qpzk_batch* wires,
                              const qpzk_batch* zs_partial_products, uint32_t sigma_col0, uint32_t num_routed,

@@ -1707,6 +1707,7 @@ int gate_program_upload(qpzk_ctx* ctx, uint32_t cs_cols, uint32_t wire_cols, con
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { gate_program_release(ctx, out); CK(e); }
     out->num_ops = prog->num_ops; out->num_terms = emits; out->num_regs = prog->num_regs;
+    out->jit = gate_jit_get(prog->code, prog->num_ops, prog->imm, prog->num_imm, prog->num_regs);   // nullptr: interpreted
     return 0;
 }
 void gate_program_release(qpzk_ctx* ctx, GateProgramDev* g) {
@@ -1730,7 +1731,7 @@ int gate_terms_run(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires,
     ga.cs_leaves = cs->leaves; ga.w_leaves = wires->leaves; ga.cs_width = cs->leaf_width; ga.w_width = wires->leaf_width;
     ga.code = reinterpret_cast<const uint32_t*>(g.code); ga.imm = g.imm; ga.num_ops = g.num_ops; ga.num_terms = g.num_terms; ga.num_regs = g.num_regs;
     ga.num_points = points; ga.terms = d_terms;
-    cudaError_t e = launch_gate_program(ga, ctx->stream);
+    cudaError_t e = g.jit ? launch_gate_jit(g.jit, ga, ctx->stream) : launch_gate_program(ga, ctx->stream);
     ctx->launches++;
     if (e != cudaSuccess) { dev_free(ctx, d_terms); CK(e); }
     *terms_out = d_terms;

@@ -145,7 +145,14 @@ int quotient_impl(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, 
                   uint32_t sigma_col0, uint32_t num_routed, uint32_t chunk, uint32_t num_challenges,
                   const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, const uint64_t* chal_dev,
                   const uint64_t* gate_terms_dev, uint32_t num_gate_terms, uint64_t** coeffs_out, uint32_t* qbits_out);
-struct GateProgramDev { uint64_t* code = nullptr; uint64_t* imm = nullptr; uint32_t num_ops = 0, num_terms = 0, num_regs = 0; };
+struct GateProgramDev {
+    uint64_t* code = nullptr; uint64_t* imm = nullptr; uint32_t num_ops = 0, num_terms = 0, num_regs = 0;
+    cudaKernel_t jit = nullptr;   // the program compiled at run time (gate_jit.cu); nullptr = interpret
+};
+namespace qpzk {
+cudaKernel_t gate_jit_get(const uint32_t* code, uint32_t num_ops, const uint64_t* imm, uint32_t num_imm, uint32_t num_regs);
+cudaError_t launch_gate_jit(cudaKernel_t k, const GateProgramArgs& a, cudaStream_t st);
+}
 int gate_program_upload(qpzk_ctx* ctx, uint32_t cs_cols, uint32_t wire_cols, const qpzk_gate_program* prog, GateProgramDev* out);
 void gate_program_release(qpzk_ctx* ctx, GateProgramDev* g);
 int gate_terms_run(qpzk_ctx* ctx, const qpzk_batch* cs, const qpzk_batch* wires, uint32_t chunk, const GateProgramDev& g,

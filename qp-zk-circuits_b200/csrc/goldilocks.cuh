@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// JIT-BEGIN  (the text from here to JIT-END is also the prelude of run-time compiled gate programs, gate_jit.cu)
 namespace qpzk {
 
 constexpr uint64_t GL_P = 0xFFFFFFFF00000001ULL;
@@ -245,6 +246,7 @@ __device__ __forceinline__ uint64_t gl_mulc(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_mulc(a, b); }
 
+// JIT-END
 // host versions (table construction at context creation; never on the data path)
 inline uint64_t gl_mul_host(uint64_t a, uint64_t b) {
     unsigned __int128 x = (unsigned __int128)a * b;

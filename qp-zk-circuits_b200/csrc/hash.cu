@@ -437,7 +437,14 @@ cudaError_t launch_pow(ChallengerDev* c, uint32_t pow_bits, uint64_t forced_witn
         // one wave of the machine (about 2^17 candidates on a B200: a hit with probability 1 - e^-2 at 16 bits);
         // fewer blocks when the expected search is shorter than a wave
         uint64_t want = (pow_bits < 40 ? (2ull << pow_bits) : ~0ull) / HASH_THREADS + 1;
-        uint64_t blocks = (uint64_t)(num_sms > 0 ? num_sms : 148) * 6;
+        // exactly the blocks that are resident at once (5 per SM at 89 registers): a sixth block per SM used to run as a
+        // second wave after the first had finished its candidates (CUPTI trace, round 2: 294 us for a 16-bit search)
+        static const int per_sm = [] {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pow_grind_persistent_kernel, HASH_THREADS, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+            return n;
+        }();
+        uint64_t blocks = (uint64_t)(num_sms > 0 ? num_sms : 148) * per_sm;
         if (want < blocks) blocks = want;
         pow_grind_persistent_kernel<<<(unsigned)blocks, HASH_THREADS, 0, st>>>(c, pow_bits, max_candidates < GL_P ? max_candidates : GL_P, found_dev);
     }

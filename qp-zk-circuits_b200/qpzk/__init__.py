@@ -184,6 +184,10 @@ def load_library():
         "qpzk_prover_prove": (i, [vp, vp, vp, vp, u64, vp]),
         "qpzk_prover_launches_per_proof": (u64, [vp]),
         "qpzk_prover_uses_graph": (i, [vp]),
+        "qpzk_gate_jit_available": (i, []),
+        "qpzk_gate_jit_set_mode": (None, [i]),
+        "qpzk_gate_jit_compile_check": (i, [vp, vp]),
+        "qpzk_gate_jit_compiled": (u64, []),
         "qpzk_bench_imad": (i, [vp, u32, C.POINTER(C.c_double)]),
         "qpzk_bench_poseidon": (i, [vp, u32, C.POINTER(C.c_double)]),
     }

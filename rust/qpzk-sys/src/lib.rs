@@ -218,6 +218,10 @@ extern "C" {
                              pow_witness_in: u64, out_words: *mut u64) -> c_int;
     pub fn qpzk_prover_launches_per_proof(p: *const qpzk_prover) -> u64;
     pub fn qpzk_prover_uses_graph(p: *const qpzk_prover) -> c_int;
+    pub fn qpzk_gate_jit_available() -> c_int;
+    pub fn qpzk_gate_jit_set_mode(mode: c_int);
+    pub fn qpzk_gate_jit_compile_check(prog: *const qpzk_gate_program, cubin_bytes: *mut u64) -> c_int;
+    pub fn qpzk_gate_jit_compiled() -> u64;
     // ProofWithPublicInputs::to_bytes / from_bytes (host functions)
     pub fn qpzk_proof_bytes_len(p: *const qpzk_fri_params, s: *const qpzk_proof_shape) -> usize;
     pub fn qpzk_proof_to_bytes(p: *const qpzk_fri_params, s: *const qpzk_proof_shape, wires_cap: *const u64,

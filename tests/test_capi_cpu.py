@@ -7,6 +7,8 @@ import re
 import numpy as np
 import pytest
 
+P = 0xFFFFFFFF00000001
+
 
 def _declared_symbols(header):
     text = open(header).read()
@@ -55,6 +57,28 @@ def test_fri_params_and_proof_size_match_oracle(qpzk, orc):
 
 def test_challenger_state_layout_matches_header(qpzk, orc):
     assert C.sizeof(qpzk.ChallengerState) == C.sizeof(orc.ChallengerState) == 12 * 8 + 8 * 8 + 8 * 8 + 8
+
+
+def test_gate_program_compiles_for_sm_100a_without_a_gpu(qpzk, tmp_path, monkeypatch):
+    """The run-time compiler path of gate programs (csrc/gate_jit.cu): source generation + NVRTC for sm_100a need no GPU.
+    A small arithmetic program (every opcode) compiles to a cubin, lands in the disk cache and is served from there."""
+    import ctypes as C
+    lib = qpzk.load_library()
+    if not lib.qpzk_gate_jit_available():
+        pytest.skip("libnvrtc.so.12 not found")
+    monkeypatch.setenv("QPZK_JIT_CACHE_DIR", str(tmp_path))
+    code = np.array([[0, 0, 0, 0], [1, 1, 0, 0], [2, 2, 0, 0], [3, 3, 0, 1], [4, 4, 3, 2], [5, 5, 4, 3], [0x0307, 6, 5, 4],
+                     [8, 7, 6, 1], [9, 7, 7, 0], [0x060a, 7, 7, 1], [6, 0, 7, 0], [6, 0, 5, 0]], np.uint32)
+    imm = np.array([5, P - 1], np.uint64)
+    prog = qpzk.GateProgram.make(code, imm, 8)
+    size = C.c_uint64(0)
+    assert lib.qpzk_gate_jit_compile_check(C.byref(prog), C.byref(size)) == 0, lib.qpzk_last_error()
+    assert size.value > 1000
+    cached = list(tmp_path.glob("*_12.cubin"))
+    assert len(cached) == 1 and cached[0].read_bytes()[:4] == b"\x7fELF"
+    assert lib.qpzk_gate_jit_compile_check(C.byref(prog), C.byref(size)) == 0 and size.value == cached[0].stat().st_size
+    bad = qpzk.GateProgram.make(np.array([[8, 0, 0, 7]], np.uint32), imm, 8)
+    assert lib.qpzk_gate_jit_compile_check(C.byref(bad), C.byref(size)) != 0
 
 
 def test_no_cpu_fallback_without_gpu(qpzk):

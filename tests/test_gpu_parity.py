@@ -785,6 +785,39 @@ def test_poseidon_hash_chain_proved_end_to_end(ctx, qpzk, orc):
     assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
 
 
+def test_gate_program_compiled_equals_interpreted(ctx, qpzk, orc):
+    """The PoseidonGate program (2904 steps) runs as run-time compiled straight-line code (gate_jit.cu: NVRTC, sm_100a);
+    the same call with the compiler switched off runs the interpreter.  Both give the oracle's quotient, bit for bit, and
+    the counter shows that a compiled program was really used."""
+    import gen_poseidon_constants as gen
+    from qpzk import gates
+    from perm_util import poseidon_chain_circuit
+    if not ctx.L.qpzk_gate_jit_available():
+        pytest.skip("NVRTC not loadable on this box: every gate program is interpreted")
+    log_n = 6
+    rc = gen.round_constants()
+    rec = gates.Recorder()
+    gates.poseidon_gate(rec, rc, gen.derive_fast_partial(rc), selector=rec.const(0))
+    code, imm, regs = rec.finish()
+    prog = qpzk.GateProgram.make(code, imm, regs)
+    wires, consts, sigmas = poseidon_chain_circuit(log_n, 4, rc)
+    cs = np.concatenate([consts, sigmas])
+    ch = np.random.default_rng(16).integers(0, P, size=(3, 2), dtype=np.uint64)
+    zs = orc.partial_products(wires[:80], sigmas, ch[0], ch[1], 8)
+    g = [qpzk.PolynomialBatch.from_values(ctx, a, 3, None, 4) for a in (cs, wires, zs)]
+    o = [orc.PolynomialBatch.from_values(a, 3, 4) for a in (cs, wires, zs)]
+    want = orc.quotient_polys(o[0], o[1], o[2], 1, 80, ch[0], ch[1], ch[2], gate_terms=orc.gate_terms(o[0], o[1], code, imm))
+    try:
+        ctx.L.qpzk_gate_jit_set_mode(1)
+        compiled = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 1, 80, ch[0], ch[1], ch[2], prog)
+        assert ctx.L.qpzk_gate_jit_compiled() >= 1
+        ctx.L.qpzk_gate_jit_set_mode(0)
+        interpreted = qpzk.PolynomialBatch.quotient_polys_prog(g[0], g[1], g[2], 1, 80, ch[0], ch[1], ch[2], prog)
+    finally:
+        ctx.L.qpzk_gate_jit_set_mode(1)
+    assert (compiled == want).all() and (interpreted == want).all()
+
+
 def test_hash_no_pad_matches_oracle(ctx, qpzk, orc):
     rng = np.random.default_rng(17)
     for k in (0, 1, 4, 7, 8, 9, 16, 21, 135):
