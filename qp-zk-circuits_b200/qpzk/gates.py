@@ -336,3 +336,121 @@ def poseidon_gate_witness(inputs, swap, rc):
     for i in range(12):
         w[wire_output(i)] = s[i]
     return w
+
+
+# ---- Poseidon2Gate ------------------------------------------------------------------------------------------------------
+# The reference hashes inside its circuits with `builder.hash_n_to_hash_no_pad_p2::<Poseidon2Hash>` (wormhole/circuit/src/
+# nullifier.rs:298-299, unspendable_account.rs:229-231, zk_merkle_proof.rs:504,606, block_header/mod.rs:66): the gate behind
+# it lives in the un-vendored qp-plonky2 fork, so its wire layout is not in the reference tree.  What IS pinned is the
+# permutation (tests/golden/poseidon2_kats.json: the reference's 5 address and 2 block-hash vectors).  This recorder lays
+# the gate out the way upstream lays out PoseidonGate -- inputs, outputs, swap flag, deltas, one wire per S-box input so
+# that every constraint has degree <= 7 -- over the pinned permutation: same 135 wires, same 123 constraints.  A fork
+# records its own gate with its own layout; the device only ever sees the program.
+def _p2_external_layer(rec, s):
+    """circ(2 M4, M4, M4) with M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]: additions only."""
+    t = [None] * 12
+    for c in range(3):
+        a, b, d, e = s[4 * c:4 * c + 4]
+        tot = rec.add(rec.add(a, b), rec.add(d, e))
+        t[4 * c + 0] = rec.add(rec.add(tot, a), rec.add(b, b))
+        t[4 * c + 1] = rec.add(rec.add(tot, b), rec.add(d, d))
+        t[4 * c + 2] = rec.add(rec.add(tot, d), rec.add(e, e))
+        t[4 * c + 3] = rec.add(rec.add(tot, e), rec.add(a, a))
+    out = [None] * 12
+    for k in range(4):
+        col = rec.add(rec.add(t[k], t[4 + k]), t[8 + k])
+        for c in range(3):
+            out[4 * c + k] = rec.add(t[4 * c + k], col)
+    return out
+
+
+def poseidon2_gate(rec, ext_rc, int_rc, diag, selector=None):
+    """123 constraints over the PoseidonGate wire layout: swap is a bit (1), the four deltas (4), the S-box inputs of
+    external rounds 1-3 (36), of the 22 internal rounds (22) and of the last 4 external rounds (48), the outputs (12).
+    ext_rc: 96 external round constants, int_rc: 22 internal ones, diag: the 12 diagonal entries of the internal matrix
+    (tools/gen_poseidon2_constants.py: parameters())."""
+    out = (lambda c: rec.emit(rec.mul(c, selector))) if selector is not None else rec.emit
+
+    def sbox(x):
+        x2 = rec.mul(x, x); x4 = rec.mul(x2, x2); x3 = rec.mul(x, x2)
+        return rec.mul(x3, x4)
+
+    swap = rec.wire(WIRE_SWAP)
+    out(rec.mul(swap, rec.sub(swap, rec.imm(1))))
+    state = [None] * 12
+    for i in range(4):
+        lhs, rhs, delta = rec.wire(wire_input(i)), rec.wire(wire_input(i + 4)), rec.wire(wire_delta(i))
+        out(rec.sub(rec.mul(swap, rec.sub(rhs, lhs)), delta))
+        state[i], state[i + 4] = rec.add(lhs, delta), rec.sub(rhs, delta)
+    for i in range(8, 12):
+        state[i] = rec.wire(wire_input(i))
+    state = _p2_external_layer(rec, state)
+    for r in range(4):
+        state = [rec.add(state[i], rec.imm(int(ext_rc[12 * r + i]) % P)) for i in range(12)]
+        if r:
+            for i in range(12):
+                sin = rec.wire(wire_full_sbox_0(r, i))
+                out(rec.sub(state[i], sin))
+                state[i] = sin
+        state = _p2_external_layer(rec, [sbox(x) for x in state])
+    for r in range(22):
+        sin = rec.wire(wire_partial_sbox(r))
+        out(rec.sub(rec.add(state[0], rec.imm(int(int_rc[r]) % P)), sin))
+        state[0] = sbox(sin)
+        tot = state[0]
+        for i in range(1, 12):
+            tot = rec.add(tot, state[i])
+        state = [rec.add(rec.mul(state[i], rec.imm(int(diag[i]) % P)), tot) for i in range(12)]
+    for r in range(4):
+        state = [rec.add(state[i], rec.imm(int(ext_rc[12 * (4 + r) + i]) % P)) for i in range(12)]
+        for i in range(12):
+            sin = rec.wire(wire_full_sbox_1(r, i))
+            out(rec.sub(state[i], sin))
+            state[i] = sin
+        state = _p2_external_layer(rec, [sbox(x) for x in state])
+    for i in range(12):
+        out(rec.sub(state[i], rec.wire(wire_output(i))))
+
+
+def poseidon2_gate_witness(inputs, swap, ext_rc, int_rc, diag):
+    """The 135 wire values of one Poseidon2Gate row; the output wires are the permutation of the (swapped) inputs."""
+    w = [0] * POSEIDON_GATE_WIRES
+    inputs = [int(x) % P for x in inputs]
+    for i in range(12):
+        w[wire_input(i)] = inputs[i]
+    w[WIRE_SWAP] = int(swap)
+    s = list(inputs)
+    for i in range(4):
+        d = int(swap) * (inputs[i + 4] - inputs[i]) % P
+        w[wire_delta(i)] = d
+        s[i], s[i + 4] = (inputs[i] + d) % P, (inputs[i + 4] - d) % P
+
+    def ext(v):
+        t = [0] * 12
+        for c in range(3):
+            a, b, d, e = v[4 * c:4 * c + 4]
+            tot = a + b + d + e
+            t[4 * c:4 * c + 4] = [tot + a + 2 * b, tot + b + 2 * d, tot + d + 2 * e, tot + e + 2 * a]
+        return [(t[4 * c + k] + t[k] + t[4 + k] + t[8 + k]) % P for c in range(3) for k in range(4)]
+
+    s = ext(s)
+    for r in range(4):
+        s = [(x + int(c)) % P for x, c in zip(s, ext_rc[12 * r:12 * r + 12])]
+        if r:
+            for i in range(12):
+                w[wire_full_sbox_0(r, i)] = s[i]
+        s = ext([pow(x, 7, P) for x in s])
+    for r in range(22):
+        s[0] = (s[0] + int(int_rc[r])) % P
+        w[wire_partial_sbox(r)] = s[0]
+        s[0] = pow(s[0], 7, P)
+        tot = sum(s) % P
+        s = [(x * int(dg) + tot) % P for x, dg in zip(s, diag)]
+    for r in range(4):
+        s = [(x + int(c)) % P for x, c in zip(s, ext_rc[12 * (4 + r):12 * (4 + r) + 12])]
+        for i in range(12):
+            w[wire_full_sbox_1(r, i)] = s[i]
+        s = ext([pow(x, 7, P) for x in s])
+    for i in range(12):
+        w[wire_output(i)] = s[i]
+    return w

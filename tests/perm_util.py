@@ -267,10 +267,11 @@ def arithmetic_circuit(log_n, seed, inactive_rows=3):
     return u(wires), u(consts), u(sig)
 
 
-def poseidon_chain_circuit(log_n, seed, rc, routed=80, inactive_rows=2):
+def poseidon_chain_circuit(log_n, seed, rc, routed=80, inactive_rows=2, witness=None):
     """A hash chain in the reference's shape: every active row is one PoseidonGate (135 wires, the first 80 routed),
     output words 0..3 of row i are copied to input words 0..3 of row i + 1, the other input words are free.
-    Returns (wires (135, n), constants (1, n) = the gate's selector, sigmas (routed, n))."""
+    Returns (wires (135, n), constants (1, n) = the gate's selector, sigmas (routed, n)).
+    witness(inputs, swap) -> the 135 wires of a row: another gate over the same layout (Poseidon2Gate); default PoseidonGate."""
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qp-zk-circuits_b200"))
     from qpzk import gates
@@ -291,7 +292,7 @@ def poseidon_chain_circuit(log_n, seed, rc, routed=80, inactive_rows=2):
             for t in range(4):                        # out_t(i - 1) <-> in_t(i): a 2-cycle of the permutation
                 a, b = (gates.wire_output(t), i - 1), (gates.wire_input(t), i)
                 sig[a[0]][a[1]], sig[b[0]][b[1]] = ids[b[0]][b[1]], ids[a[0]][a[1]]
-        row = gates.poseidon_gate_witness(inp, i & 1, rc)
+        row = witness(inp, i & 1) if witness else gates.poseidon_gate_witness(inp, i & 1, rc)
         for j in range(gates.POSEIDON_GATE_WIRES):
             wires[j][i] = row[j]
         prev = row[12:24] if not (i & 1) else row[12:24]

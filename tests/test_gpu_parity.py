@@ -785,6 +785,42 @@ def test_poseidon_hash_chain_proved_end_to_end(ctx, qpzk, orc):
     assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
 
 
+def test_poseidon2_hash_chain_proved_end_to_end(ctx, qpzk, orc):
+    """The gate of the reference's in-circuit hashing (Poseidon2, the permutation pinned to the reference's own
+    vectors) as a gate program: a chain of Poseidon2 rows, 135 wires / 80 routed, proved on the device.  Device path =
+    oracle bit for bit, FRI accepted, the vanishing identity holds on the opened values, a wrong S-box wire is rejected."""
+    import gen_poseidon2_constants as gp
+    from qpzk import prover, gates
+    from perm_util import poseidon_chain_circuit, verify_gateless_openings
+    log_n = 6
+    ext, internal, diag = gp.parameters()
+    flat = [c for row in ext for c in row]
+    rec = gates.Recorder()
+    gates.poseidon2_gate(rec, flat, internal, diag, selector=rec.const(0))
+    code, imm, regs = rec.finish()
+    prog = qpzk.GateProgram.make(code, imm, regs)
+    wires, consts, sigmas = poseidon_chain_circuit(log_n, 14, None, witness=lambda i, s: gates.poseidon2_gate_witness(i, s, flat, internal, diag))
+    cs = np.concatenate([consts, sigmas])
+    shape = dict(prover.LEAF_SHAPE, log_n=log_n, constants_sigmas=81)
+    circuit = prover.SyntheticCircuit(ctx, cs, shape, sigma_col0=1)
+    pih = np.arange(4, dtype=np.uint64) + 11
+    got = prover.prove_synthetic(circuit, wires, None, None, pih, sigmas=sigmas, gate_program=prog)
+    ocs = orc.PolynomialBatch.from_values(cs, 3, 4)
+    want = orc.prove_synthetic(ocs, wires, None, None, pih, log_n, sigmas=sigmas, sigma_col0=1, gate_program=(code, imm))
+    for a, c in zip(got["caps"], want["caps"]):
+        assert (a == c).all()
+    assert (got["openings"] == want["openings"]).all() and (got["fri_proof"] == want["fri_proof"]).all()
+    assert orc.fri_verify(log_n, want["leaf_lens"], want["all_caps"], want["instance"], got["openings"], want["params"],
+                          want["verifier_challenger"], got["fri_proof"]) == 0
+    bg, alphas, zeta = got["challenges"]
+    assert verify_gateless_openings(log_n, got["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+    bad = wires.copy()
+    bad[gates.wire_partial_sbox(9), 5] = (int(bad[gates.wire_partial_sbox(9), 5]) + 1) % P
+    gb = prover.prove_synthetic(circuit, bad, None, None, pih, sigmas=sigmas, gate_program=prog)
+    bg, alphas, zeta = gb["challenges"]
+    assert not verify_gateless_openings(log_n, gb["openings"], 1, 80, 135, 2, 8, bg[:2], bg[2:], alphas, zeta, program=(code, imm))
+
+
 def test_gate_program_compiled_equals_interpreted(ctx, qpzk, orc):
     """The PoseidonGate program (2904 steps) runs as run-time compiled straight-line code (gate_jit.cu: NVRTC, sm_100a);
     the same call with the compiler switched off runs the interpreter.  Both give the oracle's quotient, bit for bit, and

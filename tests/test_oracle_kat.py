@@ -5,6 +5,8 @@ the three upstream Poseidon-12 permutation KATs, the round-constant self-checks,
 facts and the reference-side constants that fix the configuration
 (p at wormhole/inputs/src/lib.rs:23; FRI parameters at wormhole/circuit/src/profile.rs:168-174).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -453,6 +455,54 @@ def test_poseidon_gate_program_vanishes_on_a_correct_trace(orc):
     for inp, want in gen.KATS:
         w = gates.poseidon_gate_witness(inp, 0, rc)
         assert w[12:24] == [int(x, 16) for x in want.split()]
+
+
+def test_poseidon2_gate_program_vanishes_on_a_correct_trace(orc):
+    """The gate behind the reference's in-circuit hashing (`hash_n_to_hash_no_pad_p2::<Poseidon2Hash>`,
+    wormhole/circuit/src/nullifier.rs:298-299) over the permutation that is pinned to the reference's own vectors: all 123
+    constraints vanish on a real trace (with and without the swap), whose output wires are the oracle's -- pinned --
+    permutation; any changed wire breaks some constraint; and a trace chained the way the sponge chains permutations
+    reproduces the reference's first address vector."""
+    import json
+    import gen_poseidon2_constants as gp
+    from qpzk import gates
+    from perm_util import interpret_program
+    ext, internal, diag = gp.parameters()
+    flat = [c for row in ext for c in row]
+    rec = gates.Recorder()
+    gates.poseidon2_gate(rec, flat, internal, diag)
+    code, imm, regs = rec.finish()
+    assert (code[:, 0] == 6).sum() == 123 and regs <= 64
+    rng = np.random.default_rng(28)
+    for swap in (0, 1):
+        inp = [int(x) for x in rng.integers(0, P, size=12, dtype=np.uint64)]
+        w = gates.poseidon2_gate_witness(inp, swap, flat, internal, diag)
+        perm_in = inp if not swap else inp[4:8] + inp[0:4] + inp[8:]
+        assert w[12:24] == [int(x) for x in orc.poseidon2(np.array(perm_in, np.uint64))]
+        assert interpret_program(code, imm, w, []) == [0] * 123
+        for j in (0, 5, 24, 26, 30, 64, 65, 86, 87, 134, 12, 23):
+            bad = list(w)
+            bad[j] = (bad[j] + 1) % P
+            assert any(interpret_program(code, imm, bad, []))
+    # hash_no_pad as a chain of gate rows (what the circuit builder lays down): the reference's first address vector,
+    # secret -> H(H(salt || secret)), wormhole/tests/src/circuit/unspendable_account_tests.rs:9-24
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poseidon2_kats.json")))
+    vec = {x["name"]: x for x in G["vectors"]}
+
+    def hash_rows(felts):
+        felts = [int(x) for x in felts] + [1]
+        felts += [0] * (-len(felts) % 8)
+        st = [0] * 12
+        for off in range(0, len(felts), 8):
+            w = gates.poseidon2_gate_witness([(st[i] + felts[off + i]) % P for i in range(8)] + st[8:], 0, flat, internal, diag)
+            assert interpret_program(code, imm, w, []) == [0] * 123
+            st = w[12:24]
+        return st[:4]
+
+    inner = hash_rows(vec["unspendable_account_0_inner"]["in"])
+    assert inner == [int(x) for x in vec["unspendable_account_0_inner"]["out"]]
+    outer = hash_rows(inner)
+    assert b"".join(v.to_bytes(8, "little") for v in outer).hex() == "de68c6fcb3e38d6736b79a010e4504b98c6321f1e4d11cd8484f67c187ca090e"
 
 
 def test_recorder_register_allocation(orc):
