@@ -154,6 +154,13 @@ int qpzk_poseidon_permute(qpzk_ctx* ctx, const uint64_t* states, uint64_t count,
 /* Self-test hook (tests only): out = MDS * state + round constants of round `next_round` (0 and 30: none),
  * canonical.  Lets a test drive the carry paths of the limb-domain linear layer with chosen states. */
 int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, uint64_t count, uint32_t next_round, uint64_t* out);
+/* Device field arithmetic, one operation per element (a test hook: directed operands reach carry paths that random data
+ * does not).  op: 0 add, 1 sub (canonical operands) | any u64 operands, canonical result: 2 gl_mulc(a,b) (the NTT kernels'
+ * product), 3 mulp(a,b) (the Poseidon kernels' product), 4 a^2, 5 a*b + c, 6 the C-level product, 7 reduce(lo=a, hi=b),
+ * 8 / 9 the two PTX reductions of the 128-bit value (lo=a, hi=b) | 10 a + b with b canonical | 11 1/a | 12 a 160-bit dot
+ * product: 30 a*b + b*c + c*a | 13 extension product (a,b)*(c,a): even elements get the first coordinate, odd the second. */
+int qpzk_selftest_field_ops(qpzk_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                            uint64_t count, uint64_t* out);
 
 /* ---- Poseidon2: the reference's APPLICATION hash (not the FRI / Merkle hasher) -------------------------------------
  * Replaces qp-plonky2 `hash::poseidon2::{Poseidon2Permutation, Poseidon2Hash::hash_no_pad}` / qp-poseidon-core =3.1.0

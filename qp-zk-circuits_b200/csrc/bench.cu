@@ -37,6 +37,46 @@ __global__ void __launch_bounds__(HASH_THREADS) poseidon_bench_kernel(uint32_t p
     if (x == 0x1234567ull) sink[0] = x;
 }
 
+// ---- field arithmetic, one operation per thread (qpzk_selftest_field_ops) -------------------------------------------------
+// Every device formulation of the Goldilocks arithmetic against chosen operands: the tests drive the rare carry / borrow
+// paths of the PTX chains (probability ~2^-32 on random data) with directed values and compare with big-integer results.
+__global__ void __launch_bounds__(256) field_ops_kernel(uint32_t op, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                                                        const uint64_t* __restrict__ c, uint64_t count, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t x = a[i], y = b[i], z = c[i];
+    uint64_t r = 0;
+    switch (op) {
+        case 0: r = gl_add(x, y); break;                                   // canonical operands
+        case 1: r = gl_sub(x, y); break;
+        case 2: r = gl_mulc(x, y); break;                                  // any u64 operands from here on
+        case 3: r = gl_canon(mulp(x, y)); break;
+        case 4: r = gl_canon(sqrp(x)); break;
+        case 5: r = gl_canon(mul_addp(x, y, z)); break;
+        case 6: r = gl_canon(gl_mul_nc(x, y)); break;
+        case 7: r = gl_canon(gl_reduce128_nc(x, y)); break;                // (lo, hi)
+        case 8: { u128w w; w.w0 = (uint32_t)x; w.w1 = (uint32_t)(x >> 32); w.w2 = (uint32_t)y; w.w3 = (uint32_t)(y >> 32);
+                  r = gl_canon(reduce_fma(w)); } break;
+        case 9: { u128w w; w.w0 = (uint32_t)x; w.w1 = (uint32_t)(x >> 32); w.w2 = (uint32_t)y; w.w3 = (uint32_t)(y >> 32);
+                  r = gl_canon(reduce_w(w)); } break;
+        case 10: r = gl_canon(add_canon_p(x, y)); break;                   // x any, y canonical
+        case 11: r = gl_inv(x); break;                                     // canonical, non-zero
+        case 12: { acc160 acc = {0, 0, 0, 0, 0};                            // x*y + y*z + z*x + 29 more copies of x*y: five words in use
+                   mac160(acc, x, y); mac160(acc, y, z); mac160(acc, z, x);
+                   for (int k = 0; k < 29; k++) mac160(acc, x, y);
+                   r = gl_canon(reduce160(acc)); } break;
+        case 13: { const ext2 e = ext_mul(ext_make(x, y), ext_make(z, x)); r = (i & 1) ? e.b : e.a; } break;   // canonical operands
+        default: break;
+    }
+    out[i] = r;
+}
+
+cudaError_t launch_field_ops(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t count, uint64_t* out, cudaStream_t st) {
+    if (!count) return cudaSuccess;
+    field_ops_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(op, a, b, c, count, out);
+    return cudaGetLastError();
+}
+
 cudaError_t run_imad_bench(uint32_t iters, int num_sms, cudaStream_t st, float* ms, double* ops) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);

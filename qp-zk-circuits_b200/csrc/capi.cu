@@ -988,6 +988,26 @@ extern "C" int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, ui
     GUARD_END
 }
 
+extern "C" int qpzk_selftest_field_ops(qpzk_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                                       uint64_t count, uint64_t* out) {
+    GUARD_BEGIN
+    if (!ctx || ((!a || !b || !c || !out) && count)) return fail(QPZK_EINVAL, "null argument");
+    if (op > 13) return fail(QPZK_EINVAL, "unknown operation");
+    if (count > (1ull << 28)) return fail(QPZK_EINVAL, "too many operands");
+    CK(cudaSetDevice(ctx->device));
+    DevBufs bufs(ctx);
+    uint64_t* d[4];
+    int rc;
+    for (int k = 0; k < 4; k++) if ((rc = bufs.alloc(&d[k], count ? count : 1))) return rc;
+    const uint64_t* src[3] = {a, b, c};
+    for (int k = 0; k < 3 && count; k++) CK(cudaMemcpyAsync(d[k], src[k], count * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_field_ops(op, d[0], d[1], d[2], count, d[3], ctx->stream)); ctx->launches++;
+    if (count) CK(cudaMemcpyAsync(out, d[3], count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+    GUARD_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // Poseidon2: the reference's application hash (poseidon2.cu)
 // ---------------------------------------------------------------------------------------------

@@ -249,5 +249,6 @@ cudaError_t launch_coset_unshift(uint64_t* coeffs, uint32_t log_len, uint32_t nu
 namespace qpzk {
 // ---- bench.cu ----
 cudaError_t run_imad_bench(uint32_t iters, int num_sms, cudaStream_t st, float* ms, double* ops);
+cudaError_t launch_field_ops(uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t count, uint64_t* out, cudaStream_t st);
 cudaError_t run_poseidon_bench(uint32_t perms, int num_sms, cudaStream_t st, float* ms, double* total);
 }  // namespace qpzk

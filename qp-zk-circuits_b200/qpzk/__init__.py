@@ -184,6 +184,7 @@ def load_library():
         "qpzk_prover_prove": (i, [vp, vp, vp, vp, u64, vp]),
         "qpzk_prover_launches_per_proof": (u64, [vp]),
         "qpzk_prover_uses_graph": (i, [vp]),
+        "qpzk_selftest_field_ops": (i, [vp, u32, vp, vp, vp, u64, vp]),
         "qpzk_gate_jit_available": (i, []),
         "qpzk_gate_jit_set_mode": (None, [i]),
         "qpzk_gate_jit_compile_check": (i, [vp, vp]),
@@ -315,6 +316,15 @@ class Context:
         g, gp = _host(gammas)
         _check(self.L.qpzk_partial_products_dev(self.h, C.c_void_p(wires_ptr), C.c_void_p(sigmas_ptr), log_n, num_routed,
                                                 chunk, b.size, bp, gp, C.c_void_p(out_ptr)))
+
+    def selftest_field_ops(self, op, a, b=None, c=None):
+        """qpzk_selftest_field_ops: one device field operation per element (a test hook, see include/qpzk.h)."""
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+        b = np.zeros_like(a) if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1)
+        c = np.zeros_like(a) if c is None else np.ascontiguousarray(c, dtype=np.uint64).reshape(-1)
+        out = np.empty_like(a)
+        _check(self.L.qpzk_selftest_field_ops(self.h, op, a.ctypes.data, b.ctypes.data, c.ctypes.data, a.size, out.ctypes.data))
+        return out
 
     def bench_imad(self, iters=4096):
         v = C.c_double()

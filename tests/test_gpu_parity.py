@@ -12,6 +12,50 @@ def brev(x, bits):
     return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
 
 
+# ---- Goldilocks arithmetic on the device, operation by operation -------------------------------
+def test_field_ops_directed_and_random(ctx):
+    """Every device formulation of the field arithmetic against Python integers.  The PTX carry chains have paths that
+    uniform operands take with probability ~2^-32 (a wrapped sum that needs +EPS, a borrow that needs -EPS, both at
+    once, a 128-bit product whose top word is all ones ...): the directed operands below are all pairs and triples of
+    boundary values, which reach them; 2^17 uniform operands cover the bulk."""
+    rng = np.random.default_rng(77)
+    E = 2**32 - 1
+    edge = [0, 1, 2, E - 1, E, E + 1, E + 2, 2**33 - 1, 2**48, 2**63, 2**63 + 1, P - 2**32, P - E - 1, P - 2, P - 1, P, P + 1,
+            2**64 - 2**32, 2**64 - E, 2**64 - 2, 2**64 - 1, 0xFFFFFFFE00000001, 0xFFFFFFFF00000000, 0x00000001FFFFFFFF,
+            0xFFFFFFFEFFFFFFFF, 0x7FFFFFFF80000000, 0x8000000080000000]
+    n = len(edge)
+    ta = np.array([edge[i] for i in range(n) for j in range(n) for k in range(n)], dtype=np.uint64)
+    tb = np.array([edge[j] for i in range(n) for j in range(n) for k in range(n)], dtype=np.uint64)
+    tc = np.array([edge[k] for i in range(n) for j in range(n) for k in range(n)], dtype=np.uint64)
+    ra, rb, rc = (rng.integers(0, 2**64, size=1 << 17, dtype=np.uint64) for _ in range(3))
+    A, B, Cc = np.concatenate([ta, ra]), np.concatenate([tb, rb]), np.concatenate([tc, rc])
+    ai, bi, ci = [int(x) for x in A], [int(x) for x in B], [int(x) for x in Cc]
+    u = lambda vals: np.array(vals, dtype=np.uint64)
+    # any-representative operations, canonical result
+    for op, f in ((2, lambda x, y, z: x * y % P), (3, lambda x, y, z: x * y % P), (4, lambda x, y, z: x * x % P),
+                  (5, lambda x, y, z: (x * y + z) % P), (6, lambda x, y, z: x * y % P),
+                  (7, lambda x, y, z: (x + (y << 64)) % P), (8, lambda x, y, z: (x + (y << 64)) % P),
+                  (9, lambda x, y, z: (x + (y << 64)) % P),
+                  (12, lambda x, y, z: (30 * x * y + y * z + z * x) % P)):
+        got = ctx.selftest_field_ops(op, A, B, Cc)
+        want = u([f(x, y, z) for x, y, z in zip(ai, bi, ci)])
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, (op, hex(ai[bad[0]]), hex(bi[bad[0]]), hex(ci[bad[0]]), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
+    # canonical-operand operations
+    Ac, Bc, Zc = A % np.uint64(P), B % np.uint64(P), Cc % np.uint64(P)
+    ac, bc, zc = [x % P for x in ai], [x % P for x in bi], [x % P for x in ci]
+    assert (ctx.selftest_field_ops(0, Ac, Bc) == u([(x + y) % P for x, y in zip(ac, bc)])).all()
+    assert (ctx.selftest_field_ops(1, Ac, Bc) == u([(x - y) % P for x, y in zip(ac, bc)])).all()
+    assert (ctx.selftest_field_ops(10, A, Bc) == u([(x + y) % P for x, y in zip(ai, bc)])).all()
+    ext = ctx.selftest_field_ops(13, Ac, Bc, Zc)                      # (a + b X)(c + a X), X^2 = 7
+    want = u([((x * z + 7 * y * x) % P) if not (i & 1) else ((x * x + y * z) % P) for i, (x, y, z) in enumerate(zip(ac, bc, zc))])
+    assert (ext == want).all()
+    nz = Ac[:4096].copy()
+    nz[nz == 0] = 1
+    inv = ctx.selftest_field_ops(11, nz)
+    assert all(int(x) * int(y) % P == 1 for x, y in zip(nz, inv))
+
+
 # ---- PoseidonPermutation::permute and its linear layer -----------------------------------------------------------
 MDS_CIRC = [17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20]
 
