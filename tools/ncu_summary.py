@@ -10,6 +10,9 @@ KEYS = [
  ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
  ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_inst%"),
  ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaheavy_cyc%"),
+ ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma_cyc%"),
+ ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu_cyc%"),
+ ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "fmaheavy_inst%"),
  ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
  ("smsp__inst_executed.sum", "warp_insts"),
  ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
