@@ -510,19 +510,10 @@ def main():
             del full
             full = None
     p2p = world > 1 and args.exchange == "p2p"
-    peers, tick = None, None
-    if p2p:
-        # this rank's iNTT output lives in an IPC-exported buffer; every peer's buffer is mapped into this process
-        peers = qpzk.PeerBuffers(ctx, q * n)
-        handles = [None] * world
-        dist.all_gather_object(handles, peers.handle)
-        peer_ptrs = peers.exchange(handles, rank)
-        tick = torch.zeros(1, device=dev)
-    coeff_mine = torch.empty((q, n), dtype=torch.int64, device=dev) if world > 1 and not p2p else None
-    coeff_all = torch.empty((world * q, n), dtype=torch.int64, device=dev) if world > 1 and not p2p else None
-    coeff_mine_ptr = peers.ptr if p2p else (coeff_mine.data_ptr() if world > 1 else 0)
-    cosets_per = B // world
-    cap_all = torch.empty((world, (1 << CAP_HEIGHT) // world * 4), dtype=torch.int64, device=dev) if world > 1 else None
+    cs = None
+    if world > 1:
+        from qpzk.dist import CosetSplitCommitter        # the multi-GPU commitment lives in the library, not here
+        cs = CosetSplitCommitter(ctx, log_n, C_, RATE_BITS, CAP_HEIGHT, rank, world, dev, exchange=args.exchange)
     torch.cuda.synchronize()
 
     stage = {"intt_ms": 0.0, "lde_ms": 0.0, "leaf_hash_ms": 0.0, "merkle_levels_ms": 0.0, "allgather_ms": 0.0}
@@ -533,9 +524,9 @@ def main():
             b = qpzk.PolynomialBatch.from_device(ctx, mine.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT, values=True)
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, mine.data_ptr(), coeff_mine_ptr, log_n, q))
+            cs.intt(mine.data_ptr())
             e0.record()
-            b = commit_after_intt()
+            b = cs.commit()
             e1.record() if not p2p else None
         if record:
             t = ctx.last_commit_timing()   # synchronises the stream
@@ -545,24 +536,11 @@ def main():
                 stage["allgather_ms"] += e0.elapsed_time(e1) - sum(t.values())   # e0..e1 brackets all-gather + commit
         return b
 
-    def commit_after_intt():
-        if p2p:
-            # every rank's iNTT has finished when this 1-element all-reduce has (stream ordered); the cap gather at the
-            # end of the step keeps a fast rank from overwriting its slice while a slow one still reads it
-            dist.all_reduce(tick)
-            return qpzk.PolynomialBatch.cosets_from_coeff_slices_device(ctx, peer_ptrs, q, log_n, C_, RATE_BITS, CAP_HEIGHT,
-                                                                        rank * cosets_per, cosets_per)
-        dist.all_gather_into_tensor(coeff_all, coeff_mine)
-        return qpzk.PolynomialBatch.cosets_from_coeffs_device(ctx, coeff_all.data_ptr(), log_n, C_, RATE_BITS, CAP_HEIGHT,
-                                                              rank * cosets_per, cosets_per)
-
     def finish(b):
-        cap = b.cap                                   # tiny D2H read of this rank's cap slice
         if world > 1:
-            dist.all_gather_into_tensor(cap_all, torch.from_numpy(cap.view(np.int64).reshape(1, -1)).to(dev))
-            last_cap[0] = cap_all
+            last_cap[0] = cs.gather_cap(b)            # this rank's slice (a tiny D2H read), then the 64-byte all-gather
         else:
-            last_cap[0] = cap
+            last_cap[0] = b.cap
         b.free()
 
     # ---- device-resident timing: W warm-up, then exactly K steps between barriers + synchronize
@@ -646,13 +624,13 @@ def main():
             for (a, z), ev in zip(zip(bounds[:-1], bounds[1:]), evs):
                 stream.wait_event(ev)
                 if z > a:
-                    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, src[a:z].data_ptr(), coeff_mine_ptr + a * n * 8, log_n, z - a))
+                    cs.intt(src[a:z].data_ptr(), a, z - a)
             if q > host.shape[0]:
-                qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, src[host.shape[0]:].data_ptr(), coeff_mine_ptr + host.shape[0] * n * 8, log_n, q - host.shape[0]))
+                cs.intt(src[host.shape[0]:].data_ptr(), host.shape[0], q - host.shape[0])
             done = torch.cuda.Event()
             done.record(stream)
             consumed[k & 1] = done
-            finish(commit_after_intt())
+            finish(cs.commit())
 
         for _ in range(2):
             e2e_step()
@@ -684,8 +662,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()                            # rank 0 finishes its parity check before NCCL goes away
-            if peers:
-                peers.close()
+            cs.close()
             dist.destroy_process_group()
         return
 
@@ -758,8 +735,7 @@ def main():
     print(json.dumps(compact(out), separators=(",", ":")))
     if world > 1:
         dist.barrier()
-        if peers:
-            peers.close()
+        cs.close()
         dist.destroy_process_group()
     if parity is not None and not parity.get("ok"):
         raise SystemExit("parity check FAILED: %s" % parity)
