@@ -279,18 +279,31 @@ lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
         const uint32_t b = it & 1;
         mbar_wait(full0 + 8 * b, (it >> 1) & 1);
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // out_buf is free again
-        asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
-        for (uint32_t item = threadIdx.x; item < C * CH; item += consumers) {
-            const uint32_t c = item % C, ch = item / C;
-            const uint64_t* col = smem + b * in_words + (size_t)c * RP + ch * 32;
+        // The previous tile's bulk store still reads out_buf.  Nobody writes out_buf before the first transform of this
+        // tile has finished in registers, so the wait for that store (and the barrier that publishes it) sits between the
+        // first transform and its write-back: the store of tile i-1 overlaps the arithmetic of tile i instead of preceding it.
+        // (every consumer runs the same number of rounds, so the barrier is reached by whole warps: bar.sync is .aligned)
+        for (uint32_t base = 0; base < C * CH; base += consumers) {
+            const uint32_t item = base + threadIdx.x;
+            const bool active = item < C * CH;
+            const uint32_t c = active ? item % C : 0, ch = active ? item / C : 0;
             uint64_t x[32];
+            if (active) {
+                const uint64_t* col = smem + b * in_words + (size_t)c * RP + ch * 32;
 #pragma unroll
-            for (int k = 0; k < 32; k++) x[k] = col[k];
-            dft_regs<5>(x);
-            uint64_t* o = out_buf + (size_t)(ch * 32) * C + c;
+                for (int k = 0; k < 32; k++) x[k] = col[k];
+                dft_regs<5>(x);
+            }
+            if (base == 0) {
+                __syncwarp();   // lanes that had no item rejoin before the aligned barrier
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
+            }
+            if (active) {
+                uint64_t* o = out_buf + (size_t)(ch * 32) * C + c;
 #pragma unroll
-            for (int k = 0; k < 32; k++) o[(size_t)k * C] = x[k];
+                for (int k = 0; k < 32; k++) o[(size_t)k * C] = x[k];
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
         asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
