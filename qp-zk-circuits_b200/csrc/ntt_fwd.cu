@@ -231,7 +231,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // blockDim = consumer threads (a multiple of 32) + one producer warp (the last one).
-__global__ void __launch_bounds__(LDE_LAST32_MAX_THREADS + 32)
+// SPLIT: two threads per (column, chunk), each doing HALF of the 32-point transform -- the first DIF stage from all 32
+// inputs (sums for one thread, twiddled differences for the other), then a 16-point transform on 16 registers.  Twice the
+// consumer warps with fewer registers each: the transform phase of the unsplit kernel runs at 2.25 warps per scheduler
+// (ncu, round 2: issue 43 %, ALU 56 %) because a tile has only 270 transforms to hand out.
+constexpr int LDE_LAST32_SPLIT_MAX_THREADS = 576;
+template <bool SPLIT>
+__global__ void __launch_bounds__((SPLIT ? LDE_LAST32_SPLIT_MAX_THREADS : LDE_LAST32_MAX_THREADS) + 32)
 lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
     extern __shared__ __align__(128) uint64_t smem[];
     const uint32_t C = a.num_cols, CH = 1u << log_ch, R = 32u << log_ch, RP = R + 2;   // RP even: 16-byte aligned columns
@@ -283,16 +289,39 @@ lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
         // tile has finished in registers, so the wait for that store (and the barrier that publishes it) sits between the
         // first transform and its write-back: the store of tile i-1 overlaps the arithmetic of tile i instead of preceding it.
         // (every consumer runs the same number of rounds, so the barrier is reached by whole warps: bar.sync is .aligned)
-        for (uint32_t base = 0; base < C * CH; base += consumers) {
+        const uint32_t items = C * CH * (SPLIT ? 2u : 1u);
+        for (uint32_t base = 0; base < items; base += consumers) {
             const uint32_t item = base + threadIdx.x;
-            const bool active = item < C * CH;
-            const uint32_t c = active ? item % C : 0, ch = active ? item / C : 0;
-            uint64_t x[32];
+            const bool active = item < items;
+            // SPLIT: items [0, C*CH) are the sum halves, [C*CH, 2*C*CH) the difference halves (warps stay uniform)
+            const uint32_t half = SPLIT && active && item >= C * CH ? 1u : 0u, it2 = active ? item - half * C * CH : 0;
+            const uint32_t c = it2 % C, ch = it2 / C;
+            uint64_t x[SPLIT ? 16 : 32];
             if (active) {
                 const uint64_t* col = smem + b * in_words + (size_t)c * RP + ch * 32;
+                if (SPLIT) {
+                    uint64_t y[16];
+                    if (half == 0) {
 #pragma unroll
-                for (int k = 0; k < 32; k++) x[k] = col[k];
-                dft_regs<5>(x);
+                        for (int k = 0; k < 16; k++) y[k] = gl_add(col[k], col[k + 16]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint64_t d = gl_sub(col[k], col[k + 16]);
+                            y[k] = k == 0 ? d : gl_mulc(d, pow2_mod_p(6 * k));     // w_32^k = 2^(6k)
+                        }
+                    }
+                    dft_regs<4>(y);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) x[k] = y[k];
+                } else {
+                    uint64_t y[32];
+#pragma unroll
+                    for (int k = 0; k < 32; k++) y[k] = col[k];
+                    dft_regs<5>(y);
+#pragma unroll
+                    for (int k = 0; k < (SPLIT ? 16 : 32); k++) x[k] = y[k];
+                }
             }
             if (base == 0) {
                 __syncwarp();   // lanes that had no item rejoin before the aligned barrier
@@ -300,9 +329,11 @@ lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
                 asm volatile("bar.sync 1, %0;" :: "r"(consumers) : "memory");
             }
             if (active) {
-                uint64_t* o = out_buf + (size_t)(ch * 32) * C + c;
+                // register r of the full transform holds frequency bitrev_5(r) = leaf row r of the chunk; the sum half owns
+                // registers 0..15 (even frequencies), the difference half 16..31
+                uint64_t* o = out_buf + (size_t)(ch * 32 + (SPLIT ? 16 * half : 0)) * C + c;
 #pragma unroll
-                for (int k = 0; k < 32; k++) o[(size_t)k * C] = x[k];
+                for (int k = 0; k < (SPLIT ? 16 : 32); k++) o[(size_t)k * C] = x[k];
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
@@ -349,16 +380,20 @@ cudaError_t launch_lde_last32(const LdeLastArgs& a, cudaStream_t st, int num_sms
         if (!no_tma && lde_last32_tma_ok(a, &log_ch, &smem) &&
             (((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets) >= tiles_min) {
             const uint64_t tiles = ((1ull << a.log_n) >> (5 + log_ch)) * a.num_cosets;
-            const uint32_t items = a.num_cols << log_ch;
+            static const bool split = [] { const char* e = getenv("QPZK_LAST32_SPLIT"); return !e || e[0] != '0'; }();
+            const uint32_t items = (a.num_cols << log_ch) * (split ? 2u : 1u);
+            const uint32_t max_threads = split ? LDE_LAST32_SPLIT_MAX_THREADS : LDE_LAST32_MAX_THREADS;
             uint32_t threads = (items + 31) / 32 * 32;
-            if (threads > LDE_LAST32_MAX_THREADS) threads = LDE_LAST32_MAX_THREADS;
+            if (threads > max_threads) threads = max_threads;
             if (threads < 64) threads = 64;
-            static unsigned long long done = 0;
-            cudaError_t e = raise_smem_limit((const void*)lde_last32_tma_kernel, &done);
+            static unsigned long long done = 0, done_split = 0;
+            cudaError_t e = split ? raise_smem_limit((const void*)lde_last32_tma_kernel<true>, &done_split)
+                                  : raise_smem_limit((const void*)lde_last32_tma_kernel<false>, &done);
             if (e != cudaSuccess) return e;
             const uint64_t resident = (uint64_t)num_sms * (smem <= 110 * 1024 ? 2 : 1);   // two pipelines per SM when they fit
             const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
-            lde_last32_tma_kernel<<<grid, threads + 32, smem, st>>>(a, log_ch, (uint32_t)tiles);
+            if (split) lde_last32_tma_kernel<true><<<grid, threads + 32, smem, st>>>(a, log_ch, (uint32_t)tiles);
+            else lde_last32_tma_kernel<false><<<grid, threads + 32, smem, st>>>(a, log_ch, (uint32_t)tiles);
             return cudaGetLastError();
         }
     }
