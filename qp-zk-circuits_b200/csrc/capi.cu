@@ -392,21 +392,35 @@ struct LdePlan {
         cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
         passes.clear();
         if (log_n > s_last) {
-            // 5..8-bit passes run on the register-resident kernel (ntt_fwd.cu), which needs b_lo >= 12 - s: the pass
-            // next to the last one takes 7 or 8 bits, the ones above it 5..8 each, and what does not fit this
-            // pattern (rem = 9, 10, 11 or < 7) starts with a short pass of the generic kernel.
+            // 5..8-bit passes run on the register-resident tile kernel (ntt_fwd.cu), which needs b_lo >= 12 - s; 1..4-bit
+            // passes on its register-only sibling (b_lo >= 8); fewer than 7 bits in all go to the generic kernel.
             const uint32_t rem = log_n - s_last;
-            if (fast && rem >= 7) {
-                uint32_t top = 0, r = rem;
-                if (r >= 9 && r <= 11) { top = r - 8; r = 8; }             // generic 1..3 bits, then 8
-                std::vector<uint32_t> parts;
-                auto ok = [](uint32_t rest) { return rest == 0 || (rest >= 5 && rest != 9); };   // splittable into 5..8
-                const uint32_t last = (r >= 8 && ok(r - 8)) ? 8 : 7;
-                r -= last;
-                if (r) split_bits(r, 8, parts);
-                if (top) passes.push_back(top);
-                for (uint32_t x : parts) passes.push_back(x);
-                passes.push_back(last);
+            // QPZK_LDE_PLAN="4,5,8": the strided passes in order (experiments; used when the parts sum to the bits that
+            // remain above the last pass and every part is something a kernel takes at its position)
+            std::vector<uint32_t> forced;
+            if (const char* e = getenv("QPZK_LDE_PLAN")) {
+                uint32_t sum = 0, hi = log_n;
+                bool good = fast;
+                for (const char* q = e; *q && good;) {
+                    const uint32_t v = (uint32_t)strtoul(q, nullptr, 10);
+                    const uint32_t lo = hi >= v ? hi - v : 0;
+                    good = v >= 1 && v <= 8 && v <= hi && (v <= 4 ? lo >= 8 : lo + v >= 12);
+                    forced.push_back(v); sum += v; hi = lo;
+                    while (*q && *q != ',') q++;
+                    if (*q == ',') q++;
+                }
+                if (!good || sum != rem) forced.clear();
+            }
+            if (!forced.empty()) {
+                passes = forced;
+            } else if (fast && rem >= 7) {
+                // As many 8-bit passes as fit, the pass next to the last one always among them (it needs b_lo >= 12 - s), and
+                // what is left over as a FIRST pass: 1..4 bits on the register-only kernel (no exchange, one general
+                // product per element), 5..7 on the tile kernel.  Every pass costs two general products per element plus
+                // ~8 ALU instructions per bit, so fewer, wider passes win: measured at 2^22 x 135 (17 bits above the last
+                // pass) 5+5+7: 111.0 ms, 4+5+8: 107.7, 3+6+8: 105.5, 1+8+8: 105.2 (profiles/r2_summary.md).
+                if (rem % 8) passes.push_back(rem % 8);
+                for (uint32_t k = 0; k < rem / 8; k++) passes.push_back(8);
             } else {
                 split_bits(rem, 10, passes);
             }
