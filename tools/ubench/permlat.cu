@@ -1,7 +1,8 @@
 // dev aid: cycles of ONE warp-cooperative Poseidon permutation (single warp, clock64 around 64 permutations in a row).
 // Round 2 measurements with it (B200, 1965 MHz): 546 cycles per round as shipped (24 shuffles + 24 IMAD.WIDE per round),
 // 352 with the S-box replaced by x + 1 -- the linear layer, not the S-box, is most of a round; a shared-memory exchange
-// (one store, six broadcast loads, four accumulators) measured 585 / 320 and was not kept.
+// (one store, six broadcast loads, four accumulators) measured 585 / 320 and was not kept; two accumulator chains of six in
+// the shuffle version: 580.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I qp-zk-circuits_b200/csrc -o permlat tools/ubench/permlat.cu
 #include <cstdio>
 #include "internal.cuh"
