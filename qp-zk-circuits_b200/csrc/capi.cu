@@ -743,7 +743,7 @@ extern "C" int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values, uint
     GUARD_END
 }
 
-// Host-buffer commit: the input is copied in column ranges of >= 32 MB (at most 8) so that the copy of one range
+// Host-buffer commit: the input is copied in column ranges of >= 32 MB (at most 16) so that the copy of one range
 // overlaps the iNTT and the strided LDE passes of the previous one; small inputs go in one piece.
 static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, uint32_t log_n, uint32_t num_cols,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, qpzk_batch** out) {
@@ -765,7 +765,8 @@ static int commit_host(qpzk_ctx* ctx, const uint64_t* cols, bool from_values, ui
     src.host = cols;
     uint64_t bytes = (uint64_t)num_cols * n * sizeof(uint64_t);
     src.chunks = (uint32_t)(bytes >> 25);
-    if (src.chunks > 8) src.chunks = 8;
+    static const uint32_t max_chunks = [] { const char* e = getenv("QPZK_H2D_CHUNKS"); const int v = e ? atoi(e) : 16; return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }();   // measured at 2^22 x 135: 1: 696.6 ms, 2: 655.4, 4: 638.2, 8: 629.2, 16: 626.4, 32: 634.2 (device resident: 613)
+    if (src.chunks > max_chunks) src.chunks = max_chunks;
     if (src.chunks < 1) src.chunks = 1;
     if (!num_cols) { src.host = nullptr; src.dev = nullptr; }
     rc = commit_impl(ctx, src, from_values, log_n, num_cols, rate_bits, cap_height, d_salt, 0, 1u << rate_bits, true, out);
