@@ -158,7 +158,8 @@ int qpzk_selftest_mds_layer(qpzk_ctx* ctx, const uint64_t* states, uint64_t coun
  * does not).  op: 0 add, 1 sub (canonical operands) | any u64 operands, canonical result: 2 gl_mulc(a,b) (the NTT kernels'
  * product), 3 mulp(a,b) (the Poseidon kernels' product), 4 a^2, 5 a*b + c, 6 the C-level product, 7 reduce(lo=a, hi=b),
  * 8 / 9 the two PTX reductions of the 128-bit value (lo=a, hi=b) | 10 a + b with b canonical | 11 1/a | 12 a 160-bit dot
- * product: 30 a*b + b*c + c*a | 13 extension product (a,b)*(c,a): even elements get the first coordinate, odd the second. */
+ * product: 30 a*b + b*c + c*a | 13 extension product (a,b)*(c,a): even elements get the first coordinate, odd the second |
+ * 14 canonical a times 2^(6 (b mod 16)) by shifts (the in-register twiddles of the NTT kernels). */
 int qpzk_selftest_field_ops(qpzk_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, const uint64_t* c,
                             uint64_t count, uint64_t* out);
 

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) field_ops_kernel(uint32_t op, const uint6
                    for (int k = 0; k < 29; k++) mac160(acc, x, y);
                    r = gl_canon(reduce160(acc)); } break;
         case 13: { const ext2 e = ext_mul(ext_make(x, y), ext_make(z, x)); r = (i & 1) ? e.b : e.a; } break;   // canonical operands
+        case 14: r = gl_mul_pow2_6j(x, 6u * (unsigned)(y % 16)); break;    // canonical x times 2^(6 (y mod 16)): every in-register twiddle
         default: break;
     }
     out[i] = r;

@@ -1007,7 +1007,7 @@ extern "C" int qpzk_selftest_field_ops(qpzk_ctx* ctx, uint32_t op, const uint64_
                                        uint64_t count, uint64_t* out) {
     GUARD_BEGIN
     if (!ctx || ((!a || !b || !c || !out) && count)) return fail(QPZK_EINVAL, "null argument");
-    if (op > 13) return fail(QPZK_EINVAL, "unknown operation");
+    if (op > 14) return fail(QPZK_EINVAL, "unknown operation");
     if (count > (1ull << 28)) return fail(QPZK_EINVAL, "too many operands");
     CK(cudaSetDevice(ctx->device));
     DevBufs bufs(ctx);

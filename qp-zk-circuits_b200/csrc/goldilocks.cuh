@@ -246,6 +246,67 @@ __device__ __forceinline__ uint64_t gl_mulc(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_mulc(a, b); }
 
+// ---- x * 2^K for a compile-time K < 96 (the in-register twiddles of the NTT kernels: roots of unity of order <= 64 are
+// powers of two) ----------------------------------------------------------------------------------------------------
+// K = 32 q + r.  (v2 : v1 : v0) = x << r comes from two IMAD.WIDE by 2^r (the multiplier is read from constant memory:
+// as an immediate ptxas turns the product into shifts on the ALU pipe, which is the pipe these kernels are bound by);
+// then with 2^64 = EPS, 2^96 = -1, 2^128 = -2^32 (mod p):
+//   q = 0:  (v1 : v0) + v2 * EPS          -> one IMAD.WIDE (v2 * EPS + v0, exact), one add with carry, one +EPS on wrap
+//   q = 1:  v0 * 2^32 + v1 * EPS - v2     -> the general 128-bit reduction of (v2 : v1 : v0 : 0)
+//   q = 2:  v0 * EPS - (v2 : v1)          -> one IMAD.WIDE, one 64-bit subtraction, -EPS on borrow
+// 9 / 14 / 9 ALU-pipe instructions and 3 wide multiplies instead of 16 + 5 for the general product (canonical in and out).
+__constant__ uint32_t c_pow2_shift[32] = {1u << 0, 1u << 1, 1u << 2, 1u << 3, 1u << 4, 1u << 5, 1u << 6, 1u << 7, 1u << 8, 1u << 9, 1u << 10,
+                                          1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20,
+                                          1u << 21, 1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30,
+                                          1u << 31};
+template <unsigned K>
+__device__ __forceinline__ uint64_t gl_mul_pow2c(uint64_t x) {
+    static_assert(K < 96, "2^96 = -1: fold the sign first");
+    constexpr unsigned r = K % 32, q = K / 32;
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    uint32_t v0, v1, v2;
+    if (r == 0) {
+        v0 = x0; v1 = x1; v2 = 0;
+    } else {
+        const uint32_t R = c_pow2_shift[r];
+        asm("{\n\t.reg .u64 t,u,a;\n\t.reg .u32 t1;\n\t"
+            "mul.wide.u32 t,%3,%5;\n\tmov.b64 {%0,t1},t;\n\tcvt.u64.u32 a,t1;\n\t"
+            "mad.wide.u32 u,%4,%5,a;\n\tmov.b64 {%1,%2},u;\n\t}"
+            : "=r"(v0), "=r"(v1), "=r"(v2) : "r"(x0), "r"(x1), "r"(R));
+    }
+    uint32_t s0, s1;
+    if (q == 0) {
+        asm("{\n\t.reg .u64 w,a;\n\t.reg .u32 w0,w1,k,m;\n\t"
+            "cvt.u64.u32 a,%2;\n\tmad.wide.u32 w,%4,0xffffffff,a;\n\tmov.b64 {w0,w1},w;\n\t"
+            "add.cc.u32 w1,w1,%3;\n\taddc.u32 k,0,0;\n\tsub.u32 m,0,k;\n\t"
+            "add.cc.u32 %0,w0,m;\n\taddc.u32 %1,w1,0;\n\t}"
+            : "=r"(s0), "=r"(s1) : "r"(v0), "r"(v1), "r"(v2));
+        return gl_canon(((uint64_t)s1 << 32) | s0);
+    } else if (q == 1) {
+        u128w w; w.w0 = 0; w.w1 = v0; w.w2 = v1; w.w3 = v2;
+        return gl_canon(reduce_fma(w));
+    } else {
+        asm("{\n\t.reg .u64 w;\n\t.reg .u32 w0,w1,b;\n\t"
+            "mul.wide.u32 w,%2,0xffffffff;\n\tmov.b64 {w0,w1},w;\n\t"
+            "sub.cc.u32 w0,w0,%3;\n\tsubc.cc.u32 w1,w1,%4;\n\tsubc.u32 b,0,0;\n\t"      // b = borrow ? 0xffffffff : 0
+            "sub.cc.u32 %0,w0,b;\n\tsubc.u32 %1,w1,0;\n\t}"                           // - EPS on borrow (= + p mod 2^64)
+            : "=r"(s0), "=r"(s1) : "r"(v0), "r"(v1), "r"(v2));
+        return gl_canon(((uint64_t)s1 << 32) | s0);
+    }
+}
+// the same for a K that is a constant only after loop unrolling (multiples of 6 below 96: every twiddle of an in-register
+// transform of up to 32 points)
+__device__ __forceinline__ uint64_t gl_mul_pow2_6j(uint64_t x, unsigned K) {
+    switch (K) {
+        case 0: return x;
+        case 6: return gl_mul_pow2c<6>(x);   case 12: return gl_mul_pow2c<12>(x); case 18: return gl_mul_pow2c<18>(x);
+        case 24: return gl_mul_pow2c<24>(x); case 30: return gl_mul_pow2c<30>(x); case 36: return gl_mul_pow2c<36>(x);
+        case 42: return gl_mul_pow2c<42>(x); case 48: return gl_mul_pow2c<48>(x); case 54: return gl_mul_pow2c<54>(x);
+        case 60: return gl_mul_pow2c<60>(x); case 66: return gl_mul_pow2c<66>(x); case 72: return gl_mul_pow2c<72>(x);
+        case 78: return gl_mul_pow2c<78>(x); case 84: return gl_mul_pow2c<84>(x); case 90: return gl_mul_pow2c<90>(x);
+        default: return gl_mulc(x, K < 64 ? (1ull << K) : ((1ull << (K - 32)) - (1ull << (K - 64))));
+    }
+}
 // JIT-END
 // host versions (table construction at context creation; never on the data path)
 inline uint64_t gl_mul_host(uint64_t a, uint64_t b) {

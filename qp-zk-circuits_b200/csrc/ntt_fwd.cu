@@ -25,6 +25,10 @@
 #include "goldilocks.cuh"
 #include "ntt_local.cuh"
 
+#ifndef QPZK_POW2_SHIFT
+#define QPZK_POW2_SHIFT 1
+#endif
+
 namespace qpzk {
 
 __host__ __device__ constexpr uint64_t pow2_mod_p(unsigned t) {   // 2^t mod p for t < 96, as a canonical constant
@@ -47,7 +51,11 @@ __device__ __forceinline__ void dft_regs(uint64_t (&x)[1 << LOG]) {
             const uint64_t a = x[k], b = x[k + half];
             x[k] = gl_add(a, b);
             const uint64_t d = gl_sub(a, b);
+#if QPZK_POW2_SHIFT
+            x[k + half] = j == 0 ? d : gl_mul_pow2_6j(d, (96 / half) * j);     // shifts instead of a general product
+#else
             x[k + half] = j == 0 ? d : gl_mulc(d, pow2_mod_p((96 / half) * j));
+#endif
         }
     }
 }
@@ -308,7 +316,11 @@ lde_last32_tma_kernel(LdeLastArgs a, uint32_t log_ch, uint32_t total_tiles) {
 #pragma unroll
                         for (int k = 0; k < 16; k++) {
                             const uint64_t d = gl_sub(col[k], col[k + 16]);
+#if QPZK_POW2_SHIFT
+                            y[k] = k == 0 ? d : gl_mul_pow2_6j(d, 6 * k);          // w_32^k = 2^(6k)
+#else
                             y[k] = k == 0 ? d : gl_mulc(d, pow2_mod_p(6 * k));     // w_32^k = 2^(6k)
+#endif
                         }
                     }
                     dft_regs<4>(y);

@@ -50,6 +50,14 @@ def test_field_ops_directed_and_random(ctx):
     ext = ctx.selftest_field_ops(13, Ac, Bc, Zc)                      # (a + b X)(c + a X), X^2 = 7
     want = u([((x * z + 7 * y * x) % P) if not (i & 1) else ((x * x + y * z) % P) for i, (x, y, z) in enumerate(zip(ac, bc, zc))])
     assert (ext == want).all()
+    # x * 2^(6 j), j < 16, by shifts: every twiddle of the in-register transforms (w_32 = 2^6); all boundary values x every j
+    ea = np.array([e % P for e in edge for j in range(16)], dtype=np.uint64)
+    ej = np.array([j for e in edge for j in range(16)], dtype=np.uint64)
+    pa, pj = np.concatenate([ea, Ac]), np.concatenate([ej, B % np.uint64(16)])
+    got = ctx.selftest_field_ops(14, pa, pj)
+    want = u([int(x) * pow(2, 6 * int(j), P) % P for x, j in zip(pa, pj)])
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (hex(int(pa[bad[0]])), int(pj[bad[0]]), hex(int(got[bad[0]])), hex(int(want[bad[0]])))
     nz = Ac[:4096].copy()
     nz[nz == 0] = 1
     inv = ctx.selftest_field_ops(11, nz)

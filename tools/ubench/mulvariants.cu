@@ -31,7 +31,7 @@ __device__ __forceinline__ u128w wide_chain_ptx(uint64_t a, uint64_t b) {
     return r;
 }
 // reduction with w2 * EPS + w0 as one IMAD.WIDE
-__device__ __forceinline__ uint64_t reduce_fma(u128w x) {
+__device__ __forceinline__ uint64_t reduce_fma_local(u128w x) {
     uint32_t s0, s1;
     asm("{\n\t.reg .u64 u,t;\n\t.reg .u32 u0,u1,v1,k,t0,t1,brw,c,m0,m1;\n\t"
         "cvt.u64.u32 t,%2;\n\t"
@@ -56,12 +56,16 @@ __device__ __forceinline__ uint64_t canon_add(uint64_t r) {
 K2(k_mulc_old, gl_canon(mulp(a, b)))
 K2(k_v1_chainC_oldred, gl_canon(reduce_w(wide_chain(a, b))))
 K2(k_v2_chainP_oldred, gl_canon(reduce_w(wide_chain_ptx(a, b))))
-K2(k_v3_old_fmared, gl_canon(reduce_fma(mul_wide_w(a, b))))
-K2(k_v4_chainP_fmared, gl_canon(reduce_fma(wide_chain_ptx(a, b))))
-K2(k_v5_chainP_fmared_canon2, canon_add(reduce_fma(wide_chain_ptx(a, b))))
-K2(k_v6_nocanon, reduce_fma(wide_chain_ptx(a, b)))
+K2(k_v3_old_fmared, gl_canon(reduce_fma_local(mul_wide_w(a, b))))
+K2(k_v4_chainP_fmared, gl_canon(reduce_fma_local(wide_chain_ptx(a, b))))
+K2(k_v5_chainP_fmared_canon2, canon_add(reduce_fma_local(wide_chain_ptx(a, b))))
+K2(k_v6_nocanon, reduce_fma_local(wide_chain_ptx(a, b)))
 extern "C" __global__ void k_addsub(uint64_t* p) {
     uint64_t a = p[threadIdx.x], b = p[threadIdx.x + 32];
     p[threadIdx.x] = gl_add(a, b);
     p[threadIdx.x + 32] = gl_sub(a, b);
 }
+// x * 2^K: general product by the constant vs the shift formulation (goldilocks.cuh: gl_mul_pow2c)
+#define KP(name, K) extern "C" __global__ void name(uint64_t* p) { p[threadIdx.x] = gl_mul_pow2c<K>(p[threadIdx.x]); }
+KP(k_pow2_12, 12) KP(k_pow2_48, 48) KP(k_pow2_72, 72)
+extern "C" __global__ void k_pow2_12_general(uint64_t* p) { p[threadIdx.x] = gl_mulc(p[threadIdx.x], 1ull << 12); }
