@@ -373,8 +373,9 @@ struct LdePlan {
     const uint64_t *cs_lo = nullptr, *cs_hi = nullptr;
     std::vector<uint32_t> passes;
 
+    // remote_first: the first pass reads coefficient slices of peer GPUs over NVLink (coset-split commitment)
     int prepare(qpzk_ctx* c, const uint64_t* coeffs_, uint64_t* leaves_, uint32_t log_n_, uint32_t num_cols_,
-                uint32_t leaf_width_, uint32_t rate_bits, uint32_t coset_begin, uint32_t coset_count_) {
+                uint32_t leaf_width_, uint32_t rate_bits, uint32_t coset_begin, uint32_t coset_count_, bool remote_first = false) {
         ctx = c; coeffs = coeffs_; leaves = leaves_; log_n = log_n_; num_cols = num_cols_; leaf_width = leaf_width_;
         coset_count = coset_count_;
         if (!num_cols) return 0;
@@ -419,8 +420,17 @@ struct LdePlan {
                 // product per element), 5..7 on the tile kernel.  Every pass costs two general products per element plus
                 // ~8 ALU instructions per bit, so fewer, wider passes win: measured at 2^22 x 135 (17 bits above the last
                 // pass) 5+5+7: 111.0 ms, 4+5+8: 107.7, 3+6+8: 105.5, 1+8+8: 105.2 (profiles/r2_summary.md).
-                if (rem % 8) passes.push_back(rem % 8);
-                for (uint32_t k = 0; k < rem / 8; k++) passes.push_back(8);
+                // When the first pass pulls its input over NVLink it should be a wide one, so that its arithmetic covers the
+                // transfer: the short pass goes second (2 GPUs, 2^22: 8+1+8 311.3 ms per commit, 1+8+8 315.0; on one GPU
+                // 1+8+8 is the better order, 101.6 against 107.1 ms of LDE).
+                if (remote_first && rem % 8 && rem / 8 >= 2) {
+                    passes.push_back(8);
+                    passes.push_back(rem % 8);
+                    for (uint32_t k = 1; k < rem / 8; k++) passes.push_back(8);
+                } else {
+                    if (rem % 8) passes.push_back(rem % 8);
+                    for (uint32_t k = 0; k < rem / 8; k++) passes.push_back(8);
+                }
             } else {
                 split_bits(rem, 10, passes);
             }
@@ -599,7 +609,7 @@ int commit_impl(qpzk_ctx* ctx, ColumnSource src, bool from_values, uint32_t log_
     }
     if ((rc = dev_alloc(ctx, &b->leaves, b->num_leaves * b->leaf_width))) return fail_out(rc);
     LdePlan lde;
-    if ((rc = lde.prepare(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count))) {
+    if ((rc = lde.prepare(ctx, coeffs, b->leaves, log_n, num_cols, b->leaf_width, rate_bits, coset_begin, coset_count, src.slices != nullptr))) {
         lde.release(); return fail_out(rc);
     }
     if (src.slices) {

@@ -121,6 +121,29 @@ def test_host_buffer_commit_equals_device_commit(ctx, qpzk, sc, log_n, C_, salte
     d.free()
 
 
+def test_coefficient_slices_at_2p22_use_the_wide_first_pass(ctx, qpzk):
+    """At 2^22 the slice path (first pass reads the ranks' buffers in place) orders its strided passes 8 + 1 + 8 instead of
+    the 1 + 8 + 8 of a single-buffer commit; both must give the same leaves and cap."""
+    import torch
+    log_n, C_ = 22, 10
+    n = 1 << log_n
+    x = _device_columns(2222, C_, n)
+    full = qpzk.PolynomialBatch.from_device(ctx, x.data_ptr(), log_n, C_, 3, 4, values=True)
+    coeffs = torch.empty_like(x)
+    qpzk._check(ctx.L.qpzk_intt_columns_dev(ctx.h, x.data_ptr(), coeffs.data_ptr(), log_n, C_))
+    ctx.synchronize()                                          # the context has its own stream: torch must not clone before the iNTT has run
+    slices = [coeffs[c0:min(c0 + 4, C_)].clone() for c0 in range(0, C_, 4)]
+    torch.cuda.synchronize()
+    cap = full.cap
+    for begin, count in ((0, 8), (6, 2)):
+        part = qpzk.PolynomialBatch.cosets_from_coeff_slices_device(ctx, [t.data_ptr() for t in slices], 4, log_n, C_, 3, 4, begin, count)
+        assert (part.cap.reshape(-1) == cap.reshape(-1)[begin * 8:(begin + count) * 8]).all()
+        for row in (0, 12345, n - 40):
+            assert (part.merkle_tree.rows(row, 32) == full.merkle_tree.rows(begin * n + row, 32)).all()
+        part.free()
+    full.free()
+
+
 def test_coset_split_at_scale_matches_full_commit(ctx, qpzk, sc):
     """The multi-GPU decomposition at a size with the multi-pass plans: iNTT on column slices, the
     coefficient matrix assembled as the all-gather would, every coset range committed separately -- the cap slices
