@@ -5,10 +5,12 @@
 // (qp-plonky2 =1.5.5 plonk/vanishing_poly.rs).
 //
 // Why: the interpreter spends 52 instructions per program step, half of them on fetch/dispatch and on a register file
-// that lives in local memory (profiles/r1_summary.md: long-scoreboard 9.1 per issue).  Compiled, upstream's PoseidonGate
-// (2904 steps) is 71 k SASS instructions with every program register in a real register (84 registers, no local
-// memory); the field arithmetic is the same text as the library's own (goldilocks.cuh between its JIT markers), so
-// the results are bit-identical by construction and the tests compare both paths.
+// that lives in local memory (profiles/r1_summary.md: long-scoreboard 9.1 per issue).  Compiled, every program register
+// is a hardware register (68 for upstream's PoseidonGate, 2904 steps; no local memory, no stack) and the field arithmetic
+// is the same text as the library's own (goldilocks.cuh between its JIT markers), so the results are bit-identical by
+// construction and the tests compare both paths.  Fully inlined the kernel is 71 k instructions = 1.1 MB and runs at the
+// instruction-fetch rate of an SM (520 us at 2^13 rows against 864 us interpreted); with the products as calls of two
+// shared functions 20 k instructions stream and the product bodies stay in the instruction cache: 400 us.
 //
 // NVRTC is loaded with dlopen (no link-time dependency); when it is missing, when compilation fails, for short
 // programs, or with QPZK_GATE_JIT=0, the interpreter runs -- on the device, like everything else.  Compiled programs are
@@ -85,10 +87,15 @@ std::atomic<int> g_mode{[] { const char* e = getenv("QPZK_GATE_JIT"); return e ?
 // streams the whole program through the instruction cache on its own and the kernel is bound by instruction fetch
 // (measured: 0.24 instructions per cycle per scheduler).  With a barrier every few dozen steps the warps of a block stay
 // inside a window that fits the instruction cache and one fetch serves all of them.
-struct JitOptions { uint32_t block, sync_every; };
+struct JitOptions { uint32_t block, sync_every, calls; };
 JitOptions jit_options() {
     static const JitOptions o = [] {
-        JitOptions r{256, 48};
+        JitOptions r{128, 48, 1};
+        // calls = 1: products are calls of two small functions instead of inline code.  The straight-line kernel is bound
+        // by instruction fetch (1.1 MB for PoseidonGate); with the 24-instruction product bodies shared, 323 KB stream
+        // through the instruction cache and the bodies stay in it (the compiler keeps every program register in a
+        // hardware register across the calls: 64 registers, no stack).
+        if (const char* e = getenv("QPZK_GATE_JIT_CALLS")) r.calls = atoi(e) ? 1u : 0u;
         if (const char* e = getenv("QPZK_GATE_JIT_BLOCK")) { const int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) r.block = (uint32_t)v; }
         if (const char* e = getenv("QPZK_GATE_JIT_SYNC")) { const int v = atoi(e); r.sync_every = v > 0 ? (uint32_t)v : 0; }
         return r;
@@ -160,8 +167,12 @@ std::string gate_jit_source(const uint32_t* code, uint32_t num_ops, const uint64
     s.reserve((size_t)num_ops * 48 + 16384);
     s += "typedef unsigned long long uint64_t;\ntypedef unsigned int uint32_t;\ntypedef unsigned short uint16_t;\n";
     s += kPrelude;
-    s += "\n}  // namespace qpzk\nusing namespace qpzk;\n"
-         "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(jit_options().block) + ") qpzk_gate_jit(const uint64_t* __restrict__ w_leaves, uint32_t w_width,\n"
+    const bool calls = jit_options().calls != 0;
+    s += "\n}  // namespace qpzk\nusing namespace qpzk;\n";
+    if (calls)
+        s += "__device__ __noinline__ uint64_t qj_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }\n"
+             "__device__ __noinline__ uint64_t qj_ma(uint64_t a, uint64_t b, uint64_t c) { return gl_canon(mul_addp(a, b, c)); }\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(jit_options().block) + ") qpzk_gate_jit(const uint64_t* __restrict__ w_leaves, uint32_t w_width,\n"
          "    const uint64_t* __restrict__ cs_leaves, uint32_t cs_width, uint64_t* __restrict__ terms, uint32_t num_terms, uint64_t num_points) {\n"
          "  const uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;\n"
          "  const bool live = j0 < num_points;\n  const uint64_t j = live ? j0 : num_points - 1;   // every thread reaches every barrier\n"
@@ -180,11 +191,11 @@ std::string gate_jit_source(const uint32_t* code, uint32_t num_ops, const uint64
             case 2: s += R(d) + "="; append_u64(s, imm[a]); s += ";"; break;
             case 3: s += R(d) + "=gl_add(" + R(a) + "," + R(b) + ");"; break;
             case 4: s += R(d) + "=gl_sub(" + R(a) + "," + R(b) + ");"; break;
-            case 5: s += R(d) + "=gl_mul(" + R(a) + "," + R(b) + ");"; break;
-            case 7: s += R(d) + "=gl_canon(mul_addp(" + R(a) + "," + R(b) + "," + R(cc) + "));"; break;
-            case 8: s += R(d) + "=gl_mul(" + R(a) + ","; append_u64(s, imm[b]); s += ");"; break;
+            case 5: s += R(d) + (calls ? "=qj_mul(" : "=gl_mul(") + R(a) + "," + R(b) + ");"; break;
+            case 7: s += R(d) + (calls ? "=qj_ma(" : "=gl_canon(mul_addp(") + R(a) + "," + R(b) + "," + R(cc) + (calls ? ");" : "));"); break;
+            case 8: s += R(d) + (calls ? "=qj_mul(" : "=gl_mul(") + R(a) + ","; append_u64(s, imm[b]); s += ");"; break;
             case 9: s += R(d) + "=gl_add(" + R(a) + ","; append_u64(s, imm[b]); s += ");"; break;
-            case 10: s += R(d) + "=gl_canon(mul_addp(" + R(a) + ","; append_u64(s, imm[b]); s += "," + R(cc) + "));"; break;
+            case 10: s += R(d) + (calls ? "=qj_ma(" : "=gl_canon(mul_addp(") + R(a) + ","; append_u64(s, imm[b]); s += "," + R(cc) + (calls ? ");" : "));"); break;
             default: s += "if(live)o[" + std::to_string(emitted++) + "]=" + R(a) + ";"; break;
         }
         s += "\n";
