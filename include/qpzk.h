@@ -143,6 +143,12 @@ int qpzk_peer_buffer_create(qpzk_ctx* ctx, uint64_t words, uint64_t** dev_ptr, u
 int qpzk_peer_buffer_open(qpzk_ctx* ctx, const uint8_t handle[QPZK_IPC_HANDLE_BYTES], uint64_t** peer_ptr);
 int qpzk_peer_buffer_close(qpzk_ctx* ctx, uint64_t* peer_ptr);
 int qpzk_peer_buffer_free(qpzk_ctx* ctx, uint64_t* dev_ptr);
+/* The pass plan of the coset LDE for a shape (a pure host function; a test hook and a description of what a commit of
+ * this shape launches): passes_out[0..*num_passes) = position bits taken by the strided passes, top down (1..4: the
+ * register-only kernel, 5..8: the tile kernel, more: the generic kernel), *last_pass_bits = bits of the pass that writes
+ * whole leaf rows.  peer_slices != 0: the plan of qpzk_commit_cosets_from_coeff_slices_dev (wide pass first). */
+int qpzk_lde_pass_plan(uint32_t log_n, uint32_t num_cols, int peer_slices, uint32_t* passes_out, uint32_t* num_passes,
+                       uint32_t* last_pass_bits);
 /* column iNTT only (values -> coefficients), used by the coset-split path before the all-gather */
 int qpzk_intt_columns_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint64_t* coeffs_dev, uint32_t log_n,
                           uint32_t num_cols);

@@ -362,6 +362,75 @@ static int run_intt(qpzk_ctx* ctx, const uint64_t* values, uint64_t* coeffs, uin
 // The strided passes work column by column, so they can run on a column range as soon as those columns are on the
 // device (the host-buffer commit overlaps them with the H2D copy of the next range); the last pass needs every
 // column of its rows and runs once.
+// The pass plan of one coset LDE: which position bits every strided pass takes, top down, and how many bits the last
+// pass (the one that writes whole leaf rows) keeps.  A pure function of the shape (qpzk_lde_pass_plan exposes it for
+// tests); QPZK_LDE_PLAN can force the strided part for experiments.
+static void lde_pass_plan(uint32_t log_n, uint32_t num_cols, bool legacy_ntt, bool remote_first, std::vector<uint32_t>& passes,
+                          uint32_t* s_last_out) {
+    passes.clear();
+    // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
+    uint32_t s_last = 0;
+    while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
+    // preferred: the 32-point in-register last pass (ntt_fwd.cu) whenever the polynomial is long enough
+    const bool fast = !legacy_ntt && log_n > 5 && (size_t)num_cols * 33 * 8 <= 160 * 1024;
+    if (fast) s_last = 5;
+    *s_last_out = s_last;
+    if (log_n <= s_last) return;
+    // 5..8-bit passes run on the register-resident tile kernel (ntt_fwd.cu), which needs b_lo >= 12 - s; 1..4-bit
+    // passes on its register-only sibling (b_lo >= 8); fewer than 7 bits in all go to the generic kernel.
+    const uint32_t rem = log_n - s_last;
+    // QPZK_LDE_PLAN="4,5,8": the strided passes in order (experiments; used when the parts sum to the bits that
+    // remain above the last pass and every part is something a kernel takes at its position)
+    std::vector<uint32_t> forced;
+    if (const char* e = getenv("QPZK_LDE_PLAN")) {
+        uint32_t sum = 0, hi = log_n;
+        bool good = fast;
+        for (const char* q = e; *q && good;) {
+            const uint32_t v = (uint32_t)strtoul(q, nullptr, 10);
+            const uint32_t lo = hi >= v ? hi - v : 0;
+            good = v >= 1 && v <= 8 && v <= hi && (v <= 4 ? lo >= 8 : lo + v >= 12);
+            forced.push_back(v); sum += v; hi = lo;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        if (!good || sum != rem) forced.clear();
+    }
+    if (!forced.empty()) {
+        passes = forced;
+    } else if (fast && rem >= 7) {
+        // As many 8-bit passes as fit, the pass next to the last one always among them (it needs b_lo >= 12 - s), and
+        // what is left over as a FIRST pass: 1..4 bits on the register-only kernel (no exchange, one general
+        // product per element), 5..7 on the tile kernel.  Every pass costs two general products per element plus
+        // ~8 ALU instructions per bit, so fewer, wider passes win: measured at 2^22 x 135 (17 bits above the last
+        // pass) 5+5+7: 111.0 ms, 4+5+8: 107.7, 3+6+8: 105.5, 1+8+8: 105.2 (profiles/r2_summary.md).
+        // When the first pass pulls its input over NVLink it should be a wide one, so that its arithmetic covers the
+        // transfer: the short pass goes second (2 GPUs, 2^22: 8+1+8 311.3 ms per commit, 1+8+8 315.0; on one GPU
+        // 1+8+8 is the better order, 101.6 against 107.1 ms of LDE).
+        if (remote_first && rem % 8 && rem / 8 >= 2) {
+            passes.push_back(8);
+            passes.push_back(rem % 8);
+            for (uint32_t k = 1; k < rem / 8; k++) passes.push_back(8);
+        } else {
+            if (rem % 8) passes.push_back(rem % 8);
+            for (uint32_t k = 0; k < rem / 8; k++) passes.push_back(8);
+        }
+    } else {
+        split_bits(rem, 10, passes);
+    }
+}
+extern "C" int qpzk_lde_pass_plan(uint32_t log_n, uint32_t num_cols, int peer_slices, uint32_t* passes_out, uint32_t* num_passes,
+                                  uint32_t* last_pass_bits) {
+    if (!passes_out || !num_passes || !last_pass_bits) return fail(QPZK_EINVAL, "null argument");
+    if (log_n > 26 || !num_cols || num_cols > 65535) return fail(QPZK_EINVAL, "log_n > 26 or num_cols not in 1..65535");
+    std::vector<uint32_t> passes;
+    static const bool legacy = [] { const char* e = getenv("QPZK_LEGACY_NTT"); return e && e[0] == '1'; }();
+    lde_pass_plan(log_n, num_cols, legacy, peer_slices != 0, passes, last_pass_bits);
+    if (passes.size() > 8) return fail(QPZK_EINTERNAL, "more than 8 strided passes");
+    for (size_t i = 0; i < passes.size(); i++) passes_out[i] = passes[i];
+    *num_passes = (uint32_t)passes.size();
+    return 0;
+}
+
 struct LdePlan {
     qpzk_ctx* ctx = nullptr;
     const uint64_t* coeffs = nullptr;
@@ -383,57 +452,10 @@ struct LdePlan {
         if (rc) return rc;
         if ((rc = get_coset_tables(ctx, log_n, rate_bits, &cs))) return rc;
         if (num_cols > 65535) return fail(QPZK_EINVAL, "num_cols > 65535");
-        // rows per block of the last pass: all columns resident in ~40 KB of shared memory (4-5 blocks per SM)
-        s_last = 0;
-        while (s_last < 10 && s_last < log_n && ((uint64_t)num_cols << (s_last + 1)) <= 4608) s_last++;
-        // preferred: the 32-point in-register last pass (ntt_fwd.cu) whenever the polynomial is long enough
-        const bool fast = !ctx->legacy_ntt && log_n > 5 && (size_t)num_cols * 33 * 8 <= 160 * 1024;
-        if (fast) s_last = 5;
+        lde_pass_plan(log_n, num_cols, ctx->legacy_ntt, remote_first, passes, &s_last);
         cs_lo = cs.lo + (size_t)coset_begin * TW_LO_SIZE;
         cs_hi = cs.hi + (size_t)coset_begin * cs.hi_size;
-        passes.clear();
         if (log_n > s_last) {
-            // 5..8-bit passes run on the register-resident tile kernel (ntt_fwd.cu), which needs b_lo >= 12 - s; 1..4-bit
-            // passes on its register-only sibling (b_lo >= 8); fewer than 7 bits in all go to the generic kernel.
-            const uint32_t rem = log_n - s_last;
-            // QPZK_LDE_PLAN="4,5,8": the strided passes in order (experiments; used when the parts sum to the bits that
-            // remain above the last pass and every part is something a kernel takes at its position)
-            std::vector<uint32_t> forced;
-            if (const char* e = getenv("QPZK_LDE_PLAN")) {
-                uint32_t sum = 0, hi = log_n;
-                bool good = fast;
-                for (const char* q = e; *q && good;) {
-                    const uint32_t v = (uint32_t)strtoul(q, nullptr, 10);
-                    const uint32_t lo = hi >= v ? hi - v : 0;
-                    good = v >= 1 && v <= 8 && v <= hi && (v <= 4 ? lo >= 8 : lo + v >= 12);
-                    forced.push_back(v); sum += v; hi = lo;
-                    while (*q && *q != ',') q++;
-                    if (*q == ',') q++;
-                }
-                if (!good || sum != rem) forced.clear();
-            }
-            if (!forced.empty()) {
-                passes = forced;
-            } else if (fast && rem >= 7) {
-                // As many 8-bit passes as fit, the pass next to the last one always among them (it needs b_lo >= 12 - s), and
-                // what is left over as a FIRST pass: 1..4 bits on the register-only kernel (no exchange, one general
-                // product per element), 5..7 on the tile kernel.  Every pass costs two general products per element plus
-                // ~8 ALU instructions per bit, so fewer, wider passes win: measured at 2^22 x 135 (17 bits above the last
-                // pass) 5+5+7: 111.0 ms, 4+5+8: 107.7, 3+6+8: 105.5, 1+8+8: 105.2 (profiles/r2_summary.md).
-                // When the first pass pulls its input over NVLink it should be a wide one, so that its arithmetic covers the
-                // transfer: the short pass goes second (2 GPUs, 2^22: 8+1+8 311.3 ms per commit, 1+8+8 315.0; on one GPU
-                // 1+8+8 is the better order, 101.6 against 107.1 ms of LDE).
-                if (remote_first && rem % 8 && rem / 8 >= 2) {
-                    passes.push_back(8);
-                    passes.push_back(rem % 8);
-                    for (uint32_t k = 1; k < rem / 8; k++) passes.push_back(8);
-                } else {
-                    if (rem % 8) passes.push_back(rem % 8);
-                    for (uint32_t k = 0; k < rem / 8; k++) passes.push_back(8);
-                }
-            } else {
-                split_bits(rem, 10, passes);
-            }
             if ((rc = dev_alloc(ctx, &inter, (uint64_t)coset_count * num_cols << log_n))) return rc;
         }
         return 0;

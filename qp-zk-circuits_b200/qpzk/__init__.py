@@ -184,6 +184,7 @@ def load_library():
         "qpzk_prover_prove": (i, [vp, vp, vp, vp, u64, vp]),
         "qpzk_prover_launches_per_proof": (u64, [vp]),
         "qpzk_prover_uses_graph": (i, [vp]),
+        "qpzk_lde_pass_plan": (i, [u32, u32, i, vp, vp, vp]),
         "qpzk_selftest_field_ops": (i, [vp, u32, vp, vp, vp, u64, vp]),
         "qpzk_gate_jit_available": (i, []),
         "qpzk_gate_jit_set_mode": (None, [i]),

@@ -218,6 +218,7 @@ extern "C" {
                              pow_witness_in: u64, out_words: *mut u64) -> c_int;
     pub fn qpzk_prover_launches_per_proof(p: *const qpzk_prover) -> u64;
     pub fn qpzk_prover_uses_graph(p: *const qpzk_prover) -> c_int;
+    pub fn qpzk_lde_pass_plan(log_n: u32, num_cols: u32, peer_slices: c_int, passes_out: *mut u32, num_passes: *mut u32, last_pass_bits: *mut u32) -> c_int;
     pub fn qpzk_selftest_field_ops(ctx: *mut qpzk_ctx, op: u32, a: *const u64, b: *const u64, c: *const u64, count: u64, out: *mut u64) -> c_int;
     pub fn qpzk_gate_jit_available() -> c_int;
     pub fn qpzk_gate_jit_set_mode(mode: c_int);

@@ -81,6 +81,37 @@ def test_gate_program_compiles_for_sm_100a_without_a_gpu(qpzk, tmp_path, monkeyp
     assert lib.qpzk_gate_jit_compile_check(C.byref(bad), C.byref(size)) != 0
 
 
+def test_lde_pass_plan_for_every_size(qpzk):
+    """The pass planner of the coset LDE (capi.cu: lde_pass_plan) is a pure host function: for every size of the sweep the
+    passes cover exactly the bits above the last pass, every pass is one a kernel takes at its position (1..4 bits need
+    b_lo >= 8, 5..8 bits need b_lo >= 12 - s), the pass next to the last one is wide, and the benchmarked shapes get the
+    measured-best orders (2^22: 1+8+8 on one GPU, 8+1+8 when the first pass reads peer slices)."""
+    import ctypes as C
+    lib = qpzk.load_library()
+    passes, n, last = (C.c_uint32 * 8)(), C.c_uint32(0), C.c_uint32(0)
+
+    def plan(log_n, cols=135, peer=0):
+        assert lib.qpzk_lde_pass_plan(log_n, cols, peer, passes, C.byref(n), C.byref(last)) == 0
+        return list(passes[:n.value]), last.value
+
+    for peer in (0, 1):
+        for log_n in range(12, 27):
+            p, s_last = plan(log_n, 135, peer)
+            assert s_last == 5 and sum(p) == log_n - 5 and len(p) <= 4
+            b_hi = log_n
+            for s in p:
+                b_lo = b_hi - s
+                assert 1 <= s <= 8 and (b_lo >= 8 if s <= 4 else b_lo >= 12 - s), (log_n, p)
+                b_hi = b_lo
+            assert p[-1] >= 7
+    assert plan(22)[0] == [1, 8, 8] and plan(22, peer=1)[0] == [8, 1, 8]
+    assert plan(20)[0] == [7, 8] and plan(21)[0] == [8, 8] and plan(13)[0] == [8] and plan(16)[0] == [3, 8]
+    assert plan(23, peer=1)[0] == [8, 2, 8] and plan(21, peer=1)[0] == [8, 8]
+    p, s_last = plan(8, 6)                         # a short polynomial: everything in the last pass or one generic pass
+    assert sum(p) + s_last == 8
+    assert lib.qpzk_lde_pass_plan(30, 135, 0, passes, C.byref(n), C.byref(last)) != 0
+
+
 def test_no_cpu_fallback_without_gpu(qpzk):
     import torch
     if torch.cuda.is_available():
